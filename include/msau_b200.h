@@ -1,0 +1,168 @@
+/* msau_b200 -- C ABI of the B200-native engine for the datvo06/MSAU hot path.
+ *
+ * The reference (pure Python / PyTorch / NumPy / SciPy) has NO native or FFI layer: its hot path sits
+ * behind Python classes and functions.  This header is therefore the boundary a
+ * maintainer binds with ctypes; every entry point names the reference symbol whose
+ * arithmetic it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MSAU_ERR_* code otherwise; msau_last_error() gives
+ *     a thread-local human-readable message;
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name starts with `h_`
+ *     (host pointer); the library never frees or retains caller memory past the call (the only retained
+ *     memory is the small descriptor table inside an MsauPlan);
+ *   - every call takes the CUDA stream to enqueue on (`void*` = cudaStream_t) and is asynchronous on
+ *     it: no hidden synchronisation, no hidden allocation on the data path;
+ *   - activations are fp32; the network runs channels-last (NHWC) internally, the API tensors keep the
+ *     reference's NCHW layout unless stated otherwise.
+ */
+#ifndef MSAU_B200_H
+#define MSAU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSAU_OK 0
+#define MSAU_ERR_ARG (-1)
+#define MSAU_ERR_CUDA (-2)
+#define MSAU_ERR_UNSUPPORTED (-3)
+#define MSAU_ERR_WORKSPACE (-4)
+
+const char* msau_last_error(void);
+int msau_version(void);
+/* number of kernels this library has launched in the calling process so far (bench.py `gpu_launches`) */
+long long msau_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model: MSAUWrapper / MSAUNet            model/model.py:347-459 (kwargs :406-419)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct MsauConfig {
+  int channels;         /* input channels (chargrid: n_token, BERT-grid: 768)          model.py:400 */
+  int n_class;          /* logits channels                                              model.py:400 */
+  int scale_space_num;  /* S: levels per U-Net block                                    model.py:406 */
+  int res_depth;        /* R: convs per residual block                                  model.py:407 */
+  int feat_root;        /* featRoot                                                     model.py:408 */
+  int filter_size;      /* 3 (only value supported)                                     model.py:409 */
+  int pool_size;        /* 2 (only value supported)                                     model.py:410 */
+  int num_blocks;       /* 3, hard-coded in the reference                               model.py:354 */
+} MsauConfig;
+
+typedef struct MsauPlan MsauPlan;
+
+/* Builds the launch plan for a fixed (batch, height, width).  Parameter order inside the flat
+ * parameter / gradient buffers is the reference's state_dict() iteration order. */
+int msau_plan_create(const MsauConfig* cfg, int batch, int height, int width, MsauPlan** plan);
+void msau_plan_destroy(MsauPlan* plan);
+long long msau_param_count(const MsauPlan* plan);
+/* offset (in floats) and element count of the idx-th state_dict tensor; returns MSAU_ERR_ARG past the end */
+int msau_param_info(const MsauPlan* plan, int idx, long long* offset, long long* numel);
+int msau_workspace_bytes(const MsauPlan* plan, int training, size_t* bytes);
+
+/* MSAUWrapper.forward (model/model.py:435-437) = MSAUNet.forward (:378-396) + Softmax(dim=1).
+ *   x            [B, channels, H, W] fp32 (x_layout 0, NCHW) or [B, H, W, round_up(channels,4)] (1, NHWC)
+ *   params       flat fp32 parameter buffer (msau_param_count floats)
+ *   logits, aux  [B, n_class, H, W] fp32 NCHW, either may be NULL
+ *   probs        [B, n_class, H, W] softmax over classes, or NULL
+ *   argmax       [B, H, W] uint8 (first maximum wins; train...py:135, kv_model.py:162), or NULL
+ * With training != 0 every activation needed by msau_loss_backward stays in `workspace`. */
+int msau_forward(MsauPlan* plan, const float* x, int x_layout, const float* params, void* workspace,
+                 size_t workspace_bytes, int training, float* logits, float* aux, float* probs,
+                 uint8_t* argmax, void* stream);
+
+/* MSAUWrapper.loss (model/model.py:446-459) averaged over the pages of the batch +
+ * loss.backward() (train_chargrid_funsd_msau.py:56-57).  Must follow msau_forward(training=1) on the
+ * same plan / workspace / x.
+ *   labels       [B, H, W]; label_dtype 0 = uint8, 1 = int64; 0 = ignored pixel
+ *   loss_scale   multiplies every gradient (1/world_size for data-parallel averaging); `loss` itself
+ *                is reported unscaled
+ *   loss         1 float (device)
+ *   grads        flat fp32 gradient buffer (same layout as params); overwritten */
+int msau_loss_backward(MsauPlan* plan, const float* x, int x_layout, const void* labels, int label_dtype,
+                       float loss_scale, void* workspace, size_t workspace_bytes, float* loss,
+                       float* grads, void* stream);
+
+/* nn.utils.clip_grad_norm(params, 1.0) + torch.optim.Adam.step()   train...py:24-26,58-59.
+ * `scratch` >= 4 KiB; total_norm (device float, pre-clip norm) may be NULL. */
+int msau_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
+                        int step, float lr, float beta1, float beta2, float eps, float max_norm,
+                        float* scratch, float* total_norm, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rasterisers (CSR batches of pages; all coordinates fp64, arithmetic bit-exact with the reference)
+ * ------------------------------------------------------------------------------------------------ */
+/* Grid geometry of every page: get_min_max_x_y_w_h (data_generator_funsd_bert.py:49-61) + grid extent
+ * (:72-73 / :154-155) + min_scale (:156-160).  page_ptr [n_pages+1] int32 CSR over boxes;
+ * n_chars [n_boxes] int32 (characters per word; NULL for R2).  geom [n_pages][8] fp64 =
+ * {min_x, min_y, min_w, min_h, min_scale, Hn, Wn, 0}. */
+int msau_raster_geometry(const double* x, const double* y, const double* w, const double* h,
+                         const int32_t* n_chars, const int32_t* page_ptr, int n_pages, double* geom,
+                         void* stream);
+
+/* R1 get_box_mask_box_label_word (data_generator_funsd_bert.py:149-186) and
+ * R2 get_box_mask_box_label      (data_generator_funsd_bert.py:64-93).
+ *   boxes          x,y,w,h fp64 [n_boxes]; page_ptr CSR [n_pages+1]
+ *   char_ptr       [n_boxes+1] int32 CSR over characters, char_feat [n_chars_total] int32 = row of
+ *                  feat_table per character (R1).  NULL for R2, where box i uses row feat_row[i].
+ *   feat_row       [n_boxes] int32 (R2) or NULL
+ *   feat_table     [n_rows, D] fp64 (charset one-hot rows / BERT embeddings); converted to fp32 by
+ *                  round-to-nearest exactly like torch.Tensor(float64 ndarray)
+ *   geom           from msau_raster_geometry of the WORD boxes (R1) / CELL boxes (R2)
+ *   use_min_scale  1 = R1 word fill (x by min_scale), 0 = R2 box fill (x by min_w)
+ *   out_h, out_w   allocated page extent; pages whose (Hn,Wn) differ are clipped / zero-filled
+ *   grid           fp32, layout 0: [n_pages, D, out_h, out_w]  1: [n_pages, out_h, out_w, round_up(D,4)]
+ *   owner_scratch  int32 [n_pages*out_h*out_w] */
+int msau_raster_features(const double* x, const double* y, const double* w, const double* h,
+                         const int32_t* page_ptr, int n_pages, int n_boxes, const int32_t* char_ptr,
+                         const int32_t* char_feat, const int32_t* feat_row, const double* feat_table,
+                         int feat_dim, const double* geom, int use_min_scale, int out_h, int out_w,
+                         int layout, float* grid, int32_t* owner_scratch, void* stream);
+/* label mask of R1/R2: label_mask[ny:ny+nh, nx:nx+nw] = label+1 (uint8), boxes scaled by min_w/min_h. */
+int msau_raster_labels(const double* x, const double* y, const double* w, const double* h,
+                       const int32_t* labels, const int32_t* page_ptr, int n_pages, int n_boxes,
+                       const double* geom, int out_h, int out_w, uint8_t* label_mask, int32_t* owner_scratch, void* stream);
+
+/* R3 KVModel._generate_masks_from_label (inference/kv_model.py:83-148).
+ *   boxes [n_lines,4] fp64 x1,y1,x2,y2; char_ptr/char_ids CSR of token ids per line (after the host-side
+ *   digit folding and tok_to_id lookup, :126,:140).  geom3 [n_pages][8] fp64 out =
+ *   {min_x - bg_pad, min_y - bg_pad, scale, bg_pad, H, W, median_h, 0}; scaled_boxes [n_lines,4] int32.
+ *   input/line/char masks uint16 [n_pages, out_h, out_w]. */
+int msau_raster_kv_geometry(const double* boxes, const int32_t* page_ptr, int n_pages, double* geom3,
+                            void* stream);
+int msau_raster_kv(const double* boxes, const int32_t* page_ptr, int n_pages, int n_lines,
+                   const int32_t* char_ptr, const int32_t* char_ids, const double* geom3, int out_h, int out_w,
+                   uint16_t* input_mask, uint16_t* line_mask, uint16_t* char_mask, int32_t* scaled_boxes,
+                   int32_t* owner_scratch, void* stream);
+/* to_categorical + transposes (inference/generic_util.py:94-95, kv_model.py:274-278):
+ * ids uint16 [n, H, W] -> one-hot fp32, layout 0: [n, n_token, H, W], 1: [n, H, W, round_up(n_token,4)] */
+int msau_one_hot(const uint16_t* ids, int n_pages, int height, int width, int n_token, int layout,
+                 float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Post-process: inference/morph_util.py:13-22,65-84 (SciPy ndimage semantics), kv_model.py:162-177
+ * ------------------------------------------------------------------------------------------------ */
+/* r_dilation / r_erosion: rectangular max / min filter, mode='constant' (zeros outside), SciPy origin. */
+int msau_rect_filter(const uint8_t* in, uint8_t* out, int n_maps, int height, int width, int size_h,
+                     int size_w, int origin_h, int origin_w, int is_max, void* stream);
+/* out = (class_map == cls) as uint8 0/1 (kv_model.py:175) */
+int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int cls, void* stream);
+/* connected_components: scipy.ndimage.label (4-connectivity, labels ordered by first raster pixel)
+ * + find_objects.  labels int32 [n_maps,H,W]; n_labels int32 [n_maps]; bboxes int32
+ * [n_maps, max_labels, 4] = y0,y1,x0,x1 half-open (labels beyond max_labels are counted, not boxed).
+ * scratch int32 [n_maps*H*W + n_maps*(H*W/1024+2)] */
+int msau_ccl4(const uint8_t* binary, int n_maps, int height, int width, int32_t* labels, int32_t* n_labels,
+              int32_t* bboxes, int max_labels, int32_t* scratch, void* stream);
+
+/* Debugging aids used by the parity tests: workspace layout = [packed weights | activations |
+ * activation gradients (training) | scratch], all in floats; tensor `id` (allocation order) lives at
+ * activations + off as [B, H, W, C] fp32. */
+int msau_debug_layout(const MsauPlan* plan, long long* packed_floats, long long* act_floats, int* n_tensors);
+int msau_debug_tensor(const MsauPlan* plan, int id, long long* off, int* channels, int* height, int* width);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSAU_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of ``libmsau_b200.so`` (the C ABI declared in ``include/msau_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the caller gets an
+exception.  PyTorch tensors are only buffer carriers here (``data_ptr()``), never compute.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmsau_b200.so")
+
+SYMBOLS = [
+    "msau_last_error", "msau_version", "msau_launch_count",
+    "msau_plan_create", "msau_plan_destroy", "msau_param_count", "msau_param_info", "msau_workspace_bytes",
+    "msau_forward", "msau_loss_backward", "msau_clip_adam_step",
+    "msau_raster_geometry", "msau_raster_features", "msau_raster_labels",
+    "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
+    "msau_rect_filter", "msau_class_equals", "msau_ccl4",
+    "msau_debug_layout", "msau_debug_tensor",
+]
+
+
+class MsauConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("channels", "n_class", "scale_space_num", "res_depth", "feat_root",
+                                       "filter_size", "pool_size", "num_blocks")]
+
+
+class MsauError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the library; raises if it has not been built (``make`` / ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MsauError(f"{LIB_PATH} not found: build the CUDA extension first (make, or __graft_entry__.build()). "
+                        "msau_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+    L.msau_last_error.restype = C.c_char_p
+    L.msau_last_error.argtypes = []
+    L.msau_version.restype = i32
+    L.msau_launch_count.restype = i64
+    L.msau_plan_create.argtypes = [C.POINTER(MsauConfig), i32, i32, i32, C.POINTER(vp)]
+    L.msau_plan_destroy.argtypes = [vp]
+    L.msau_plan_destroy.restype = None
+    L.msau_param_count.argtypes = [vp]
+    L.msau_param_count.restype = i64
+    L.msau_param_info.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.msau_workspace_bytes.argtypes = [vp, i32, C.POINTER(sz)]
+    L.msau_forward.argtypes = [vp, vp, i32, vp, vp, sz, i32, vp, vp, vp, vp, vp]
+    L.msau_loss_backward.argtypes = [vp, vp, i32, vp, i32, f32, vp, sz, vp, vp, vp]
+    L.msau_clip_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, f32, vp, vp, vp]
+    L.msau_raster_geometry.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    L.msau_raster_features.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]
+    L.msau_raster_labels.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, vp]
+    L.msau_raster_kv_geometry.argtypes = [vp, vp, i32, vp, vp]
+    L.msau_raster_kv.argtypes = [vp, vp, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.msau_one_hot.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
+    L.msau_rect_filter.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
+    L.msau_class_equals.argtypes = [vp, vp, i64, i32, vp]
+    L.msau_ccl4.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
+    L.msau_debug_layout.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
+    L.msau_debug_tensor.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    for name in SYMBOLS:
+        getattr(L, name)   # every symbol the header declares must be exported
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = lib().msau_last_error()
+        raise MsauError(f"msau_b200 error {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (or 0 for None)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().msau_launch_count())

@@ -1,0 +1,85 @@
+// Shared helpers for the msau_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define MSAU_OK 0
+#define MSAU_ERR_ARG (-1)
+#define MSAU_ERR_CUDA (-2)
+#define MSAU_ERR_UNSUPPORTED (-3)
+#define MSAU_ERR_WORKSPACE (-4)
+
+namespace msau {
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define MSAU_CUDA_TRY(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::msau::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return MSAU_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+#define MSAU_TRY(expr)            \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != MSAU_OK) return _r; \
+  } while (0)
+
+#define MSAU_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::msau::set_error(__VA_ARGS__);  \
+      return MSAU_ERR_ARG;             \
+    }                                  \
+  } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int sm_count();
+void count_launch(int n);   // bench.py's gpu_launches counter
+
+// ------------------------------------------------------------------ kernel argument blocks
+// A 4-D activation in HBM: NHWC fp32, `pitch` floats per pixel (>= channels used, multiple of 4).
+// nchw=1 (network input only): planar [B, c_logical, H, W].
+
+struct ConvArgs {
+  const float* src1; int c1; int p1; int src1_nchw; int c1_logical;
+  const float* mask1; int pm1;     // optional: src1 is zeroed where mask1 <= 0 (same pixel, same channel)
+  int relu1;                       // relu applied to src1 on load
+  const float* src2; int c2; int p2;  // optional second source (channel concat [src1 | src2])
+  const float* w;                  // packed [taps][c1+c2][coutp]
+  const float* bias;               // [coutp] or nullptr
+  float* out; int po; int coutp;
+  int B, Hin, Win;                 // source extent
+  int Hq, Wq;                      // iteration extent (virtual output grid)
+  int kh, kw, dil, stride, pad_t, pad_l;   // in_y = q_y*stride - pad_t + ky*dil
+  int Hout, Wout, osy, oy0, ox0;   // physical output: (q_y*osy + oy0, q_x*osy + ox0) inside [Hout, Wout]
+  int relu;                        // relu after bias
+  const float* res; int pr;        // + res (after relu)
+  int relu2;                       // relu after the residual add
+  const float* omask; int pom;     // * (omask > 0)
+  const float* add; int pa; const float* addmask; int pam;   // + add * (addmask > 0 if addmask)
+  int accumulate;                  // out += value
+};
+
+struct WgradArgs {
+  // dW[tap][ca][cb] += sum_q A[b, sa*qy + ty*dila - pada_t, ..][ca] * Bm[b, sb*qy + ty*dilb - padb_t, ..][cb]
+  const float* A; int ca; int pa; int a_nchw; int ca_logical; int reluA;
+  int Ha, Wa, sa, dila, pada_t, pada_l;
+  const float* Bm; int cb; int pb; const float* maskB; int pmb;
+  int Hb, Wb, sb, dilb, padb_t, padb_l;
+  int B, Hq, Wq, kh, kw;
+  float* dW; long s_ca, s_cb; int ca_lim, cb_lim;   // dW index = ca*s_ca + cb*s_cb + (ty*kw+tx)
+  float* dbias;                                     // += sum_q Bm (tap-independent B only) or nullptr
+};
+
+int launch_conv(const ConvArgs& a, cudaStream_t st);
+int launch_wgrad(const WgradArgs& a, cudaStream_t st);
+
+}  // namespace msau

@@ -1,0 +1,786 @@
+// MsauPlan: the launch plan of the MSAU network for a fixed (B, H, W).
+//
+// Walks the reference architecture (model/model.py:53-396) once on the host, assigning every activation
+// an offset in a caller-provided workspace and every parameter tensor its offset in the flat
+// state_dict-ordered parameter buffer, then replays the walk as kernel launches:
+//   msau_forward        MSAUNet.forward model.py:378-396 (down tower :129-164, up tower :224-259,
+//                       residual block :37-50, attention attention.py:152-162, 4x4 heads :375-376,390)
+//   msau_loss_backward  MSAUWrapper.loss model.py:446-459 + the hand-derived gradient of the above
+// Concats are never materialised (two-source convs), F.pad never runs (bounds-checked tiles), ReLU /
+// residual add / ReLU-backward masks live in conv epilogues and operand loaders.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/msau_b200.h"
+#include "attention.cuh"
+#include "common.cuh"
+#include "optim.cuh"
+#include "pointwise.cuh"
+
+namespace msau {
+
+// ------------------------------------------------------------------ error / runtime helpers
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct Tensor {
+  long off = -1;  // floats, inside the activation arena (and, mirrored, inside the gradient arena)
+  int C = 0, H = 0, W = 0;
+  int id = -1;
+};
+
+struct ConvLayer {
+  long w_off = 0, b_off = 0;
+  int cout = 0, cin1 = 0, cin2 = 0, k = 1, dil = 1;   // logical dims; cin2 = second concat source
+  int coutp = 0, c1p = 0, c2p = 0;                      // padded dims
+  long pk_w = -1, pk_b = -1, pk_d1 = -1, pk_d2 = -1;    // packed: fwd weights, bias, dgrad wrt src1 / src2
+  int pad() const { return ((k - 1) * dil) / 2; }       // SAME "before" padding, model/layers/utils.py:13-18
+};
+
+struct DeconvLayer {
+  long w_off = 0, b_off = 0;
+  int cin = 0, cout = 0, cinp = 0, coutp = 0;
+  long pk_phase[4] = {-1, -1, -1, -1}, pk_b = -1, pk_d = -1;
+};
+
+struct AttnLayer {
+  ConvLayer fg;   // f | g fused into one 1x1 conv with cout = 2d (its w_off/b_off are f's)
+  long g_w_off = 0, g_b_off = 0;
+  ConvLayer h;
+  int C = 0, d = 0;
+};
+
+struct Level {
+  ConvLayer conv1, coupl;
+  std::vector<ConvLayer> res;
+  Tensor z1, y1, rr, cc, pooled;
+  std::vector<Tensor> a;
+};
+
+struct UpLevel {
+  DeconvLayer deconv;
+  ConvLayer conv1, coupl;
+  std::vector<ConvLayer> res;
+  Tensor d, u, ur, uc;
+  std::vector<Tensor> a;
+};
+
+struct Block {
+  std::vector<Level> down;
+  std::vector<UpLevel> up;
+  AttnLayer attn;
+  bool has_attn = false;   // blocks 0 .. num_blocks-2; the last block's attention output is never read
+  Tensor fg, hh, att, mrow, zinv, dvec;
+  ConvLayer end;
+  Tensor logits;
+};
+
+}  // namespace msau
+
+using namespace msau;
+
+struct MsauPlan {
+  MsauConfig cfg;
+  int B, H, W;
+  std::vector<int> Hl, Wl;
+  std::vector<Block> blocks;
+  std::vector<std::pair<long, long>> params;   // (offset, numel) in state_dict order
+  long n_params = 0;
+  long packed_floats = 0;
+  long act_floats = 0;
+  int n_tensors = 0;
+  std::vector<PackDesc> descs;
+  PackDesc* d_descs = nullptr;
+  long pack_blocks = 0;
+  long misc_floats = 0;
+  // runtime state (set per call)
+  float* pk = nullptr;
+  float* act = nullptr;
+  float* grad = nullptr;
+  float* misc = nullptr;
+  float* gparams = nullptr;
+  std::vector<char> written;
+  std::vector<Tensor> all_tensors;
+  cudaStream_t st = nullptr;
+
+  Tensor alloc(int C, int Hh, int Ww) {
+    Tensor t;
+    t.off = act_floats; t.C = C; t.H = Hh; t.W = Ww; t.id = n_tensors++;
+    const long n = (long)B * Hh * Ww * C;
+    act_floats += (n + 63) / 64 * 64;
+    all_tensors.push_back(t);
+    return t;
+  }
+  long alloc_packed(long n) {
+    const long o = packed_floats;
+    packed_floats += (n + 63) / 64 * 64;
+    return o;
+  }
+  long add_param(long numel) {
+    const long o = n_params;
+    params.push_back({o, numel});
+    n_params += numel;
+    return o;
+  }
+  float* A(const Tensor& t) const { return act + t.off; }
+  float* G(const Tensor& t) const { return grad + t.off; }
+  long npix(const Tensor& t) const { return (long)B * t.H * t.W; }
+  // whether the gradient of `t` already holds a contribution; marks it written
+  int touch(const Tensor& t) {
+    const int w = written[t.id];
+    written[t.id] = 1;
+    return w;
+  }
+};
+
+namespace msau {
+
+static int pad4(int c) { return round_up(c, 4); }
+static int pad8(int c) { return round_up(c, 8); }
+
+// ------------------------------------------------------------------ pack descriptors
+static void add_desc(MsauPlan* p, long dst, int TH, int TW, int I, int O, int i_dst0, int o_dst0, int I_log, int O_log, long src,
+                     int i_off, int o_off, long s_i, long s_o, int ky0, int kys, int kx0, int kxs, int KW) {
+  PackDesc d;
+  d.dst_off = dst; d.src_off = src; d.TH = TH; d.TW = TW; d.I = I; d.O = O; d.i_dst0 = i_dst0; d.o_dst0 = o_dst0;
+  d.I_log = I_log; d.O_log = O_log; d.i_off = i_off; d.o_off = o_off; d.s_i = s_i; d.s_o = s_o;
+  d.ky0 = ky0; d.kys = kys; d.kx0 = kx0; d.kxs = kxs; d.KW = KW;
+  d.blk0 = p->pack_blocks;
+  p->pack_blocks += cdiv((long)TH * TW * I_log * O_log, 256);
+  p->descs.push_back(d);
+}
+
+// torch Conv2d weight [cout][cin1+cin2][k][k]:
+//   fwd   [tap][c1p + c2p][coutp]                     rows = input channels of [src1 | src2]
+//   dgrad [flipped tap][coutp][c_s p] per source s     rows = output channels, cols = that source's channels
+static void setup_conv(MsauPlan* p, ConvLayer& L, int cout, int cin1, int cin2, int k, int dil, bool need_d1, bool need_d2,
+                       int c1p_override = 0) {
+  L.cout = cout; L.cin1 = cin1; L.cin2 = cin2; L.k = k; L.dil = dil;
+  L.coutp = pad8(cout);
+  L.c1p = c1p_override ? c1p_override : pad4(cin1);
+  L.c2p = cin2 ? pad4(cin2) : 0;
+  const int cin = cin1 + cin2;
+  const long kk = (long)k * k;
+  L.w_off = p->add_param((long)cout * cin * kk);
+  L.b_off = p->add_param(cout);
+  const int cinp = L.c1p + L.c2p;
+  L.pk_w = p->alloc_packed(kk * cinp * L.coutp);
+  add_desc(p, L.pk_w, k, k, cinp, L.coutp, 0, 0, cin1, cout, L.w_off, 0, 0, kk, cin * kk, 0, 1, 0, 1, k);
+  if (cin2) add_desc(p, L.pk_w, k, k, cinp, L.coutp, L.c1p, 0, cin2, cout, L.w_off, cin1, 0, kk, cin * kk, 0, 1, 0, 1, k);
+  L.pk_b = p->alloc_packed(L.coutp);
+  add_desc(p, L.pk_b, 1, 1, 1, L.coutp, 0, 0, 1, cout, L.b_off, 0, 0, 0, 1, 0, 1, 0, 1, 1);
+  if (need_d1) {
+    L.pk_d1 = p->alloc_packed(kk * L.coutp * L.c1p);
+    add_desc(p, L.pk_d1, k, k, L.coutp, L.c1p, 0, 0, cout, cin1, L.w_off, 0, 0, cin * kk, kk, k - 1, -1, k - 1, -1, k);
+  }
+  if (need_d2 && cin2) {
+    L.pk_d2 = p->alloc_packed(kk * L.coutp * L.c2p);
+    add_desc(p, L.pk_d2, k, k, L.coutp, L.c2p, 0, 0, cout, cin2, L.w_off, 0, cin1, cin * kk, kk, k - 1, -1, k - 1, -1, k);
+  }
+}
+
+// torch ConvTranspose2d(cin, cout, 3, stride 2, padding 1) weight [cin][cout][3][3]; out[2 iy - 1 + ky] += x[iy] W[ky]
+static void setup_deconv(MsauPlan* p, DeconvLayer& L, int cin, int cout) {
+  L.cin = cin; L.cout = cout; L.cinp = pad4(cin); L.coutp = pad8(cout);
+  L.w_off = p->add_param((long)cin * cout * 9);
+  L.b_off = p->add_param(cout);
+  // sub-pixel phases: even output rows use ky=1 (input row q); odd rows use ky=2 (row q) and ky=0 (row q+1)
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      const int th = py ? 2 : 1, tw = px ? 2 : 1;
+      L.pk_phase[py * 2 + px] = p->alloc_packed((long)th * tw * L.cinp * L.coutp);
+      add_desc(p, L.pk_phase[py * 2 + px], th, tw, L.cinp, L.coutp, 0, 0, cin, cout, L.w_off, 0, 0, (long)cout * 9, 9,
+               py ? 2 : 1, py ? -2 : 0, px ? 2 : 1, px ? -2 : 0, 3);
+    }
+  L.pk_b = p->alloc_packed(L.coutp);
+  add_desc(p, L.pk_b, 1, 1, 1, L.coutp, 0, 0, 1, cout, L.b_off, 0, 0, 0, 1, 0, 1, 0, 1, 1);
+  // dgrad: d_in[iy] = sum_ky dOut[2 iy - 1 + ky] W[ci][co][ky]: stride-2 conv over dOut (rows = co, cols = ci)
+  L.pk_d = p->alloc_packed(9L * L.coutp * L.cinp);
+  add_desc(p, L.pk_d, 3, 3, L.coutp, L.cinp, 0, 0, cout, cin, L.w_off, 0, 0, 9, (long)cout * 9, 0, 1, 0, 1, 3);
+}
+
+static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
+  const int d = C / 8;
+  at.C = C; at.d = d;
+  ConvLayer& L = at.fg;
+  L.cout = 2 * d; L.cin1 = C; L.cin2 = 0; L.k = 1; L.dil = 1; L.coutp = pad8(2 * d); L.c1p = C; L.c2p = 0;
+  L.w_off = p->add_param((long)d * C); L.b_off = p->add_param(d);          // f.conv.{weight,bias}
+  at.g_w_off = p->add_param((long)d * C); at.g_b_off = p->add_param(d);    // g.conv.{weight,bias}
+  setup_conv(p, at.h, C, C, 0, 1, 1, true, false);                          // h.conv.{weight,bias}
+  L.pk_w = p->alloc_packed((long)C * L.coutp);
+  add_desc(p, L.pk_w, 1, 1, C, L.coutp, 0, 0, C, d, L.w_off, 0, 0, 1, C, 0, 1, 0, 1, 1);
+  add_desc(p, L.pk_w, 1, 1, C, L.coutp, 0, d, C, d, at.g_w_off, 0, 0, 1, C, 0, 1, 0, 1, 1);
+  L.pk_b = p->alloc_packed(L.coutp);
+  add_desc(p, L.pk_b, 1, 1, 1, L.coutp, 0, 0, 1, d, L.b_off, 0, 0, 0, 1, 0, 1, 0, 1, 1);
+  add_desc(p, L.pk_b, 1, 1, 1, L.coutp, 0, d, 1, d, at.g_b_off, 0, 0, 0, 1, 0, 1, 0, 1, 1);
+  L.pk_d1 = p->alloc_packed((long)L.coutp * C);
+  add_desc(p, L.pk_d1, 1, 1, L.coutp, C, 0, 0, d, C, L.w_off, 0, 0, C, 1, 0, 1, 0, 1, 1);
+  add_desc(p, L.pk_d1, 1, 1, L.coutp, C, d, 0, d, C, at.g_w_off, 0, 0, C, 1, 0, 1, 0, 1, 1);
+}
+
+// ------------------------------------------------------------------ launch helpers
+struct ConvOpt {
+  bool relu1 = false, relu = false, relu2 = false;
+  int accumulate = 0;
+  const float* mask1 = nullptr; int pm1 = 0;
+  const float* res = nullptr; int pr = 0;
+  const float* omask = nullptr; int pom = 0;
+  const float* add = nullptr; int pa = 0;
+  const float* addmask = nullptr; int pam = 0;
+};
+
+// same-size stride-1 convolution (forward of a layer, or a dgrad with flipped packed weights)
+static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, int c1_logical, const float* src2, int c2, int p2,
+                     const float* w, const float* bias, float* out, int po, int coutp, int H, int W, int k, int dil, int pad,
+                     const ConvOpt& o) {
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src1 = src1; a.c1 = c1; a.p1 = p1; a.src1_nchw = nchw; a.c1_logical = c1_logical;
+  a.mask1 = o.mask1; a.pm1 = o.pm1; a.relu1 = o.relu1;
+  a.src2 = src2; a.c2 = c2; a.p2 = p2;
+  a.w = w; a.bias = bias; a.out = out; a.po = po; a.coutp = coutp;
+  a.B = p->B; a.Hin = H; a.Win = W; a.Hq = H; a.Wq = W;
+  a.kh = k; a.kw = k; a.dil = dil; a.stride = 1; a.pad_t = pad; a.pad_l = pad;
+  a.Hout = H; a.Wout = W; a.osy = 1; a.oy0 = 0; a.ox0 = 0;
+  a.relu = o.relu; a.res = o.res; a.pr = o.pr; a.relu2 = o.relu2;
+  a.omask = o.omask; a.pom = o.pom; a.add = o.add; a.pa = o.pa; a.addmask = o.addmask; a.pam = o.pam;
+  a.accumulate = o.accumulate;
+  count_launch(1);
+  return launch_conv(a, p->st);
+}
+
+static int layer_fwd(MsauPlan* p, const ConvLayer& L, const Tensor& s1, const Tensor* s2, const Tensor& out, const ConvOpt& o) {
+  return conv_same(p, p->A(s1), L.c1p, s1.C, 0, L.c1p, s2 ? p->A(*s2) : nullptr, s2 ? L.c2p : 0, s2 ? s2->C : 0, p->pk + L.pk_w,
+                   p->pk + L.pk_b, p->A(out), out.C, L.coutp, out.H, out.W, L.k, L.dil, L.pad(), o);
+}
+
+// data gradient of a conv layer wrt source `which` (1 or 2): dY (channels coutp) -> dX
+static int layer_dgrad(MsauPlan* p, const ConvLayer& L, int which, const float* dy, int pdy, const float* dymask, int pm,
+                       const Tensor& dst, ConvOpt o) {
+  const int cs = which == 1 ? L.c1p : L.c2p;
+  const long pkd = which == 1 ? L.pk_d1 : L.pk_d2;
+  if (pkd < 0) { set_error("internal: dgrad weights missing"); return MSAU_ERR_ARG; }
+  o.mask1 = dymask; o.pm1 = pm;
+  o.accumulate = p->touch(dst);
+  const int padd = (L.k - 1) * L.dil - L.pad();
+  return conv_same(p, dy, L.coutp, pdy, 0, L.coutp, nullptr, 0, 0, p->pk + pkd, nullptr, p->G(dst), dst.C, cs, dst.H, dst.W, L.k,
+                   L.dil, padd, o);
+}
+
+// weight (+bias) gradient of a conv layer wrt source `which`
+static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* src, int psrc, int nchw, int c_logical, bool reluA,
+                       const float* dy, int pdy, const float* dymask, int pm, int H, int W, long w_off_override = -1,
+                       long b_off_override = -1, int cb_off = 0, int cb = -1, int cb_lim = -1) {
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  const int cin = L.cin1 + L.cin2;
+  const long kk = (long)L.k * L.k;
+  a.A = src; a.ca = which == 1 ? L.c1p : L.c2p; a.pa = psrc; a.a_nchw = nchw; a.ca_logical = c_logical; a.reluA = reluA;
+  a.Ha = H; a.Wa = W; a.sa = 1; a.dila = L.dil; a.pada_t = L.pad(); a.pada_l = L.pad();
+  a.Bm = dy + cb_off; a.cb = cb < 0 ? L.coutp : cb; a.pb = pdy; a.maskB = dymask ? dymask + cb_off : nullptr; a.pmb = pm;
+  a.Hb = H; a.Wb = W; a.sb = 1; a.dilb = 0; a.padb_t = 0; a.padb_l = 0;
+  a.B = p->B; a.Hq = H; a.Wq = W; a.kh = L.k; a.kw = L.k;
+  const long w_off = w_off_override >= 0 ? w_off_override : L.w_off;
+  a.dW = p->gparams + w_off + (which == 2 ? (long)L.cin1 * kk : 0);
+  a.s_ca = kk; a.s_cb = cin * kk;
+  a.ca_lim = which == 1 ? L.cin1 : L.cin2;
+  a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
+  a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
+  count_launch(1);
+  return launch_wgrad(a, p->st);
+}
+
+// MultiConvResidualBlock forward, model/model.py:37-50
+static int res_fwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor& in, const std::vector<Tensor>& a, const Tensor& out) {
+  const int R = (int)res.size();
+  for (int r = 0; r < R; ++r) {
+    ConvOpt o;
+    const Tensor& src = r == 0 ? in : a[r - 1];
+    o.relu1 = (r == 0);
+    if (r < R - 1) {
+      o.relu = true;
+      MSAU_TRY(layer_fwd(p, res[r], src, nullptr, a[r], o));
+    } else {
+      o.res = p->A(in); o.pr = in.C; o.relu2 = true;
+      MSAU_TRY(layer_fwd(p, res[r], src, nullptr, out, o));
+    }
+  }
+  return MSAU_OK;
+}
+
+// backward of the residual block: G(out) -> G(in) (overwritten: `in` has no other consumer) + weight grads
+static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor& in, const std::vector<Tensor>& a, const Tensor& out) {
+  const int R = (int)res.size();
+  for (int r = R - 1; r >= 0; --r) {
+    const bool last = (r == R - 1);
+    // dY of conv r: last conv -> G(out) masked by relu(out); inner convs -> G(a[r]) (already masked when produced)
+    const float* dy = last ? p->G(out) : p->G(a[r]);
+    const int pdy = last ? out.C : a[r].C;
+    const float* dymask = last ? p->A(out) : nullptr;
+    const Tensor& src = r == 0 ? in : a[r - 1];
+    MSAU_TRY(layer_wgrad(p, res[r], 1, p->A(src), src.C, 0, res[r].c1p, r == 0, dy, pdy, dymask, out.C, in.H, in.W));
+    ConvOpt o;
+    if (r > 0) {
+      o.omask = p->A(a[r - 1]); o.pom = a[r - 1].C;          // relu after conv r-1
+      MSAU_TRY(layer_dgrad(p, res[r], 1, dy, pdy, dymask, out.C, a[r - 1], o));
+    } else {
+      o.omask = p->A(in); o.pom = in.C;                       // relu applied to the block input
+      o.add = p->G(out); o.pa = out.C; o.addmask = p->A(out); o.pam = out.C;   // identity skip path
+      MSAU_TRY(layer_dgrad(p, res[r], 1, dy, pdy, dymask, out.C, in, o));
+    }
+  }
+  return MSAU_OK;
+}
+
+// coupling 1x1 conv on cat[prev, cur] + ReLU (model/model.py:143-148, 246-252)
+static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const Tensor& cur, const Tensor& out) {
+  const float* dy = p->G(out);
+  const float* mask = p->A(out);
+  MSAU_TRY(layer_wgrad(p, L, 1, p->A(prev), prev.C, 0, L.c1p, false, dy, out.C, mask, out.C, out.H, out.W));
+  MSAU_TRY(layer_wgrad(p, L, 2, p->A(cur), cur.C, 0, L.c2p, false, dy, out.C, mask, out.C, out.H, out.W));
+  ConvOpt o;
+  MSAU_TRY(layer_dgrad(p, L, 1, dy, out.C, mask, out.C, prev, o));
+  MSAU_TRY(layer_dgrad(p, L, 2, dy, out.C, mask, out.C, cur, o));
+  return MSAU_OK;
+}
+
+static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out) {
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      ConvArgs a;
+      memset(&a, 0, sizeof(a));
+      a.src1 = p->A(in); a.c1 = L.cinp; a.p1 = in.C; a.c1_logical = L.cinp;
+      a.w = p->pk + L.pk_phase[py * 2 + px]; a.bias = p->pk + L.pk_b;
+      a.out = p->A(out); a.po = out.C; a.coutp = L.coutp;
+      a.B = p->B; a.Hin = in.H; a.Win = in.W;
+      a.Hq = (out.H - py + 1) / 2; a.Wq = (out.W - px + 1) / 2;
+      if (a.Hq <= 0 || a.Wq <= 0) continue;
+      a.kh = py ? 2 : 1; a.kw = px ? 2 : 1; a.dil = 1; a.stride = 1; a.pad_t = 0; a.pad_l = 0;
+      a.Hout = out.H; a.Wout = out.W; a.osy = 2; a.oy0 = py; a.ox0 = px;
+      count_launch(1);
+      MSAU_TRY(launch_conv(a, p->st));
+    }
+  return MSAU_OK;
+}
+
+static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out) {
+  // weights: dW[ci][co][ky][kx] = sum_q x[q][ci] * dOut[2q - 1 + (ky,kx)][co]
+  for (int pass = 0; pass < 1; ++pass) {
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = p->A(in); a.ca = L.cinp; a.pa = in.C; a.ca_logical = L.cinp;
+    a.Ha = in.H; a.Wa = in.W; a.sa = 1; a.dila = 0; a.pada_t = 0; a.pada_l = 0;
+    a.Bm = p->G(out); a.cb = L.coutp; a.pb = out.C;
+    a.Hb = out.H; a.Wb = out.W; a.sb = 2; a.dilb = 1; a.padb_t = 1; a.padb_l = 1;
+    a.B = p->B; a.Hq = in.H; a.Wq = in.W; a.kh = 3; a.kw = 3;
+    a.dW = p->gparams + L.w_off; a.s_ca = (long)L.cout * 9; a.s_cb = 9; a.ca_lim = L.cin; a.cb_lim = L.cout;
+    a.dbias = nullptr;
+    count_launch(1);
+    MSAU_TRY(launch_wgrad(a, p->st));
+  }
+  count_launch(1);
+  MSAU_TRY(launch_colsum(p->G(out), p->npix(out), out.C, L.cout, p->gparams + L.b_off, p->st));
+  // data: stride-2 gather over dOut
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.src1 = p->G(out); a.c1 = L.coutp; a.p1 = out.C; a.c1_logical = L.coutp;
+  a.w = p->pk + L.pk_d; a.bias = nullptr;
+  a.out = p->G(in); a.po = in.C; a.coutp = L.cinp;
+  a.B = p->B; a.Hin = out.H; a.Win = out.W; a.Hq = in.H; a.Wq = in.W;
+  a.kh = 3; a.kw = 3; a.dil = 1; a.stride = 2; a.pad_t = 1; a.pad_l = 1;
+  a.Hout = in.H; a.Wout = in.W; a.osy = 1;
+  a.accumulate = p->touch(in);
+  count_launch(1);
+  return launch_conv(a, p->st);
+}
+
+static size_t ws_bytes(const MsauPlan* p, int training) {
+  const long floats = p->packed_floats + p->act_floats * (training ? 2 : 1) + p->misc_floats;
+  return (size_t)floats * sizeof(float);
+}
+
+static int bind(MsauPlan* p, void* ws, size_t bytes, int training, void* stream) {
+  MSAU_CHECK_ARG(ws != nullptr, "workspace is null");
+  if (bytes < ws_bytes(p, training)) {
+    set_error("workspace too small: %zu < %zu bytes", bytes, ws_bytes(p, training));
+    return MSAU_ERR_WORKSPACE;
+  }
+  MSAU_CHECK_ARG(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
+  p->pk = reinterpret_cast<float*>(ws);
+  p->act = p->pk + p->packed_floats;
+  p->grad = training ? p->act + p->act_floats : nullptr;
+  p->misc = p->act + p->act_floats * (training ? 2 : 1);
+  p->st = reinterpret_cast<cudaStream_t>(stream);
+  return MSAU_OK;
+}
+
+}  // namespace msau
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" const char* msau_last_error(void) { return msau::get_error(); }
+extern "C" int msau_version(void) { return 100; }
+extern "C" long long msau_launch_count(void) { return msau::g_launches.load(); }
+
+extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, int width, MsauPlan** out) {
+  MSAU_CHECK_ARG(cfg && out, "plan_create: null argument");
+  MSAU_CHECK_ARG(batch >= 1 && height >= 1 && width >= 1, "plan_create: bad shape %dx%dx%d", batch, height, width);
+  MSAU_CHECK_ARG(cfg->filter_size == 3 && cfg->pool_size == 2, "plan_create: only filter_size=3, pool_size=2 are supported");
+  MSAU_CHECK_ARG(cfg->num_blocks >= 2 && cfg->num_blocks <= 8, "plan_create: num_blocks must be in [2,8]");
+  MSAU_CHECK_ARG(cfg->scale_space_num >= 2 && cfg->res_depth >= 1, "plan_create: need scale_space_num >= 2, res_depth >= 1");
+  MSAU_CHECK_ARG(cfg->feat_root >= 8 && cfg->feat_root % 8 == 0, "plan_create: feat_root must be a multiple of 8");
+  MSAU_CHECK_ARG(cfg->n_class >= 2 && cfg->n_class <= 8, "plan_create: n_class must be in [2,8]");
+  MSAU_CHECK_ARG(cfg->channels >= 1, "plan_create: channels must be >= 1");
+  const int S = cfg->scale_space_num, R = cfg->res_depth, NB = cfg->num_blocks;
+  const int fa = cfg->feat_root << (S - 1), da = fa / 8;
+  if (!attn_supported(fa, da)) {
+    set_error("plan_create: attention at %d channels (d=%d) is not supported yet (supported: 64/8, 32/4)", fa, da);
+    return MSAU_ERR_UNSUPPORTED;
+  }
+  for (int l = 0; l < S; ++l) {
+    const int f = cfg->feat_root << l;
+    if (!(f == 8 || f == 16 || f == 32 || f == 64)) {
+      set_error("plan_create: level %d has %d channels; LRN kernels cover 8/16/32/64", l, f);
+      return MSAU_ERR_UNSUPPORTED;
+    }
+  }
+  MsauPlan* p = new MsauPlan();
+  p->cfg = *cfg; p->B = batch; p->H = height; p->W = width;
+  p->Hl.resize(S); p->Wl.resize(S);
+  p->Hl[0] = height; p->Wl[0] = width;
+  for (int l = 1; l < S; ++l) { p->Hl[l] = (p->Hl[l - 1] + 1) / 2; p->Wl[l] = (p->Wl[l - 1] + 1) / 2; }
+  p->blocks.resize(NB);
+  // ---- parameters in state_dict order (down tower conv_res_list, conv1s, conv1_1s,
+  //      layer_attentions f,g,h; up tower conv_res_list, conv1s, conv1_1s, deconvs; then end_convs) ----
+  for (int b = 0; b < NB; ++b) {
+    Block& blk = p->blocks[b];
+    blk.down.resize(S); blk.up.resize(S - 1);
+    blk.has_attn = b < NB - 1;
+    const int cin0 = b == 0 ? cfg->channels : cfg->n_class;
+    for (int l = 0; l < S; ++l) {
+      const int f = cfg->feat_root << l;
+      blk.down[l].res.resize(R);
+      for (int r = 0; r < R; ++r) setup_conv(p, blk.down[l].res[r], f, f, 0, 3, 1, true, false);
+    }
+    for (int l = 0; l < S; ++l) {
+      const int f = cfg->feat_root << l;
+      const int cin = l == 0 ? cin0 : (cfg->feat_root << (l - 1));
+      // blocks >= 1 read the previous block's logits, stored with pitch 8
+      setup_conv(p, blk.down[l].conv1, f, cin, 0, 3, 1 << l, !(b == 0 && l == 0), false, (b > 0 && l == 0) ? 8 : 0);
+    }
+    if (b > 0)
+      for (int l = 0; l < S; ++l) {
+        const int f = cfg->feat_root << l;
+        setup_conv(p, blk.down[l].coupl, f, f, f, 1, 1, true, true);
+      }
+    setup_attn(p, blk.attn, fa);
+    for (int l = 0; l < S - 1; ++l) {
+      const int f = cfg->feat_root << l;
+      blk.up[l].res.resize(R);
+      for (int r = 0; r < R; ++r) setup_conv(p, blk.up[l].res[r], f, f, 0, 3, 1, true, false);
+    }
+    for (int l = 0; l < S - 1; ++l) {
+      const int f = cfg->feat_root << l;
+      setup_conv(p, blk.up[l].conv1, f, f, f, 3, 1, true, true);
+    }
+    if (b > 0)
+      for (int l = 0; l < S - 1; ++l) {
+        const int f = cfg->feat_root << l;
+        setup_conv(p, blk.up[l].coupl, f, f, f, 1, 1, true, true);
+      }
+    for (int l = 0; l < S - 1; ++l) {
+      const int f = cfg->feat_root << l;
+      setup_deconv(p, blk.up[l].deconv, 2 * f, f);
+    }
+  }
+  for (int b = 0; b < NB; ++b) setup_conv(p, p->blocks[b].end, cfg->n_class, cfg->feat_root, 0, 4, 1, true, false);
+
+  // ---- activations ----
+  for (int b = 0; b < NB; ++b) {
+    Block& blk = p->blocks[b];
+    for (int l = 0; l < S; ++l) {
+      Level& L = blk.down[l];
+      const int f = cfg->feat_root << l, Hh = p->Hl[l], Ww = p->Wl[l];
+      L.z1 = p->alloc(f, Hh, Ww); L.y1 = p->alloc(f, Hh, Ww);
+      for (int r = 0; r + 1 < R; ++r) L.a.push_back(p->alloc(f, Hh, Ww));
+      L.rr = p->alloc(f, Hh, Ww);
+      L.cc = b > 0 ? p->alloc(f, Hh, Ww) : L.rr;
+      if (l < S - 1) L.pooled = p->alloc(f, p->Hl[l + 1], p->Wl[l + 1]);
+    }
+    if (blk.has_attn) {
+      const int Hh = p->Hl[S - 1], Ww = p->Wl[S - 1];
+      blk.fg = p->alloc(blk.attn.fg.coutp, Hh, Ww);
+      blk.hh = p->alloc(fa, Hh, Ww);
+      blk.att = p->alloc(fa, Hh, Ww);
+      blk.mrow = p->alloc(1, Hh, Ww); blk.zinv = p->alloc(1, Hh, Ww); blk.dvec = p->alloc(1, Hh, Ww);
+    }
+    for (int l = S - 2; l >= 0; --l) {
+      UpLevel& U = blk.up[l];
+      const int f = cfg->feat_root << l, Hh = p->Hl[l], Ww = p->Wl[l];
+      U.d = p->alloc(f, Hh, Ww); U.u = p->alloc(f, Hh, Ww);
+      for (int r = 0; r + 1 < R; ++r) U.a.push_back(p->alloc(f, Hh, Ww));
+      U.ur = p->alloc(f, Hh, Ww);
+      U.uc = b > 0 ? p->alloc(f, Hh, Ww) : U.ur;
+    }
+    blk.logits = p->alloc(8, height, width);
+  }
+  p->written.assign(p->n_tensors, 0);
+  p->misc_floats = round_up(loss_partial_count(batch, (long)height * width) + 2 * batch + 2048, 64);
+  // descriptor table: the only device memory the plan owns
+  cudaError_t e = cudaMalloc(&p->d_descs, sizeof(PackDesc) * p->descs.size());
+  if (e == cudaSuccess) e = cudaMemcpy(p->d_descs, p->descs.data(), sizeof(PackDesc) * p->descs.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("plan_create: descriptor upload failed: %s", cudaGetErrorString(e));
+    if (p->d_descs) cudaFree(p->d_descs);
+    delete p;
+    return MSAU_ERR_CUDA;
+  }
+  *out = p;
+  return MSAU_OK;
+}
+
+extern "C" void msau_plan_destroy(MsauPlan* p) {
+  if (!p) return;
+  if (p->d_descs) cudaFree(p->d_descs);
+  delete p;
+}
+
+extern "C" long long msau_param_count(const MsauPlan* p) { return p ? p->n_params : 0; }
+
+extern "C" int msau_param_info(const MsauPlan* p, int idx, long long* offset, long long* numel) {
+  MSAU_CHECK_ARG(p && idx >= 0 && idx < (int)p->params.size(), "param_info: index %d out of range", idx);
+  if (offset) *offset = p->params[idx].first;
+  if (numel) *numel = p->params[idx].second;
+  return MSAU_OK;
+}
+
+extern "C" int msau_workspace_bytes(const MsauPlan* p, int training, size_t* bytes) {
+  MSAU_CHECK_ARG(p && bytes, "workspace_bytes: null argument");
+  *bytes = ws_bytes(p, training);
+  return MSAU_OK;
+}
+
+extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const float* params, void* workspace, size_t workspace_bytes,
+                            int training, float* logits, float* aux, float* probs, uint8_t* argmax, void* stream) {
+  MSAU_CHECK_ARG(p && x && params, "forward: null argument");
+  MSAU_TRY(bind(p, workspace, workspace_bytes, training, stream));
+  const MsauConfig& cfg = p->cfg;
+  const int S = cfg.scale_space_num, NB = cfg.num_blocks;
+  // repack the (possibly just updated) parameters into kernel layouts
+  MSAU_CUDA_TRY(cudaMemsetAsync(p->pk, 0, sizeof(float) * p->packed_floats, p->st));
+  count_launch(1);
+  MSAU_TRY(launch_pack(params, p->pk, p->d_descs, (int)p->descs.size(), p->pack_blocks, p->st));
+
+  for (int b = 0; b < NB; ++b) {
+    Block& blk = p->blocks[b];
+    Block* prev = b > 0 ? &p->blocks[b - 1] : nullptr;
+    // ---- down tower, model/model.py:129-164 ----
+    for (int l = 0; l < S; ++l) {
+      Level& L = blk.down[l];
+      ConvOpt o;
+      if (b == 0 && l == 0) {
+        const int c1 = pad4(cfg.channels);
+        MSAU_TRY(conv_same(p, x, c1, c1, x_layout == 0, cfg.channels, nullptr, 0, 0, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b,
+                           p->A(L.z1), L.z1.C, L.conv1.coutp, p->H, p->W, 3, 1, 1, o));
+      } else {
+        const Tensor& src = l == 0 ? prev->logits : blk.down[l - 1].pooled;
+        MSAU_TRY(layer_fwd(p, L.conv1, src, nullptr, L.z1, o));
+      }
+      count_launch(1);
+      MSAU_TRY(launch_lrn_fwd(p->A(L.z1), p->A(L.y1), p->npix(L.z1), L.z1.C, p->st));
+      MSAU_TRY(res_fwd(p, L.res, L.y1, L.a, L.rr));
+      if (b > 0) {
+        const Tensor& pd = (l == S - 1) ? prev->att : prev->down[l].cc;
+        ConvOpt oc; oc.relu = true;
+        MSAU_TRY(layer_fwd(p, L.coupl, pd, &L.rr, L.cc, oc));
+      }
+      if (l == S - 1) {
+        if (blk.has_attn) {
+          ConvOpt oa;
+          MSAU_TRY(layer_fwd(p, blk.attn.fg, L.cc, nullptr, blk.fg, oa));
+          MSAU_TRY(layer_fwd(p, blk.attn.h, L.cc, nullptr, blk.hh, oa));
+          count_launch(2);
+          MSAU_TRY(launch_attn_fwd(p->A(blk.fg), p->A(blk.hh), p->A(L.cc), p->B, L.cc.H * L.cc.W, blk.attn.C, blk.attn.d,
+                                   p->A(blk.mrow), p->A(blk.zinv), p->A(blk.att), p->st));
+        }
+      } else {
+        count_launch(1);
+        MSAU_TRY(launch_pool_fwd(p->A(L.cc), p->A(L.pooled), p->B, L.cc.H, L.cc.W, L.cc.C, p->st));
+      }
+    }
+    // ---- up tower, model/model.py:224-259 ----
+    for (int l = S - 2; l >= 0; --l) {
+      UpLevel& U = blk.up[l];
+      const Tensor& xin = (l == S - 2) ? blk.down[S - 1].cc : blk.up[l + 1].uc;
+      MSAU_TRY(deconv_fwd(p, U.deconv, xin, U.d));
+      ConvOpt o;
+      MSAU_TRY(layer_fwd(p, U.conv1, blk.down[l].cc, &U.d, U.u, o));
+      MSAU_TRY(res_fwd(p, U.res, U.u, U.a, U.ur));
+      if (b > 0) {
+        ConvOpt oc; oc.relu = true;
+        MSAU_TRY(layer_fwd(p, U.coupl, prev->up[l].uc, &U.ur, U.uc, oc));
+      }
+    }
+    ConvOpt oe;
+    MSAU_TRY(layer_fwd(p, blk.end, blk.up[0].uc, nullptr, blk.logits, oe));
+  }
+  const long npp = (long)p->H * p->W;
+  if (aux) {
+    count_launch(1);
+    MSAU_TRY(launch_head(p->A(p->blocks[NB - 2].logits), 8, cfg.n_class, p->B, npp, aux, nullptr, nullptr, p->st));
+  }
+  if (logits || probs || argmax) {
+    count_launch(1);
+    MSAU_TRY(launch_head(p->A(p->blocks[NB - 1].logits), 8, cfg.n_class, p->B, npp, logits, probs, argmax, p->st));
+  }
+  return MSAU_OK;
+}
+
+extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, const void* labels, int label_dtype, float loss_scale,
+                                  void* workspace, size_t workspace_bytes, float* loss, float* grads, void* stream) {
+  MSAU_CHECK_ARG(p && x && labels && loss && grads, "loss_backward: null argument");
+  MSAU_TRY(bind(p, workspace, workspace_bytes, 1, stream));
+  const MsauConfig& cfg = p->cfg;
+  const int S = cfg.scale_space_num, NB = cfg.num_blocks;
+  p->gparams = grads;
+  std::fill(p->written.begin(), p->written.end(), 0);
+  MSAU_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p->n_params, p->st));
+  const long npp = (long)p->H * p->W;
+  {
+    Block& last = p->blocks[NB - 1];
+    Block& auxb = p->blocks[NB - 2];
+    int* counts = reinterpret_cast<int*>(p->misc);
+    float* partial = p->misc + round_up(p->B, 64);
+    count_launch(3);
+    MSAU_TRY(launch_loss(p->A(last.logits), p->A(auxb.logits), cfg.n_class, labels, label_dtype, p->B, npp, loss_scale,
+                         p->G(last.logits), p->G(auxb.logits), counts, partial, loss, p->st));
+    p->touch(last.logits); p->touch(auxb.logits);
+  }
+  for (int b = NB - 1; b >= 0; --b) {
+    Block& blk = p->blocks[b];
+    Block* prev = b > 0 ? &p->blocks[b - 1] : nullptr;
+    // ---- 4x4 head ----
+    {
+      const Tensor& src = blk.up[0].uc;
+      MSAU_TRY(layer_wgrad(p, blk.end, 1, p->A(src), src.C, 0, blk.end.c1p, false, p->G(blk.logits), 8, nullptr, 0, p->H, p->W));
+      ConvOpt o;
+      MSAU_TRY(layer_dgrad(p, blk.end, 1, p->G(blk.logits), 8, nullptr, 0, src, o));
+    }
+    // ---- up tower (forward ran l = S-2..0, so backward runs l = 0..S-2) ----
+    for (int l = 0; l <= S - 2; ++l) {
+      UpLevel& U = blk.up[l];
+      const Tensor& xin = (l == S - 2) ? blk.down[S - 1].cc : blk.up[l + 1].uc;
+      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc));
+      MSAU_TRY(res_bwd(p, U.res, U.u, U.a, U.ur));
+      p->touch(U.u);
+      // conv1s on cat[dw[l], deconv]
+      const Tensor& skip = blk.down[l].cc;
+      MSAU_TRY(layer_wgrad(p, U.conv1, 1, p->A(skip), skip.C, 0, U.conv1.c1p, false, p->G(U.u), U.u.C, nullptr, 0, U.u.H, U.u.W));
+      MSAU_TRY(layer_wgrad(p, U.conv1, 2, p->A(U.d), U.d.C, 0, U.conv1.c2p, false, p->G(U.u), U.u.C, nullptr, 0, U.u.H, U.u.W));
+      ConvOpt o;
+      MSAU_TRY(layer_dgrad(p, U.conv1, 1, p->G(U.u), U.u.C, nullptr, 0, skip, o));
+      MSAU_TRY(layer_dgrad(p, U.conv1, 2, p->G(U.u), U.u.C, nullptr, 0, U.d, o));
+      MSAU_TRY(deconv_bwd(p, U.deconv, xin, U.d));
+    }
+    // ---- down tower, deepest level first ----
+    for (int l = S - 1; l >= 0; --l) {
+      Level& L = blk.down[l];
+      if (l == S - 1 && blk.has_attn) {
+        if (p->written[blk.att.id]) {   // only the next block's coupling reads the attention output
+          const AttnLayer& at = blk.attn;
+          const int N = L.cc.H * L.cc.W;
+          count_launch(3);
+          MSAU_TRY(launch_attn_bwd(p->A(blk.fg), p->A(blk.hh), p->G(blk.att), p->A(blk.mrow), p->A(blk.zinv), p->B, N, at.C, at.d,
+                                   p->A(blk.dvec), p->G(blk.fg), p->G(blk.hh), p->st));
+          // residual path out = x + o
+          count_launch(1);
+          MSAU_TRY(launch_add(p->G(L.cc), p->G(blk.att), p->npix(L.cc) * L.cc.C, p->touch(L.cc), p->st));
+          // h conv
+          MSAU_TRY(layer_wgrad(p, at.h, 1, p->A(L.cc), L.cc.C, 0, at.h.c1p, false, p->G(blk.hh), blk.hh.C, nullptr, 0, L.cc.H, L.cc.W));
+          ConvOpt o;
+          MSAU_TRY(layer_dgrad(p, at.h, 1, p->G(blk.hh), blk.hh.C, nullptr, 0, L.cc, o));
+          // f | g conv: two parameter tensors, column windows [0,d) and [d,2d) of the fused output
+          MSAU_TRY(layer_wgrad(p, at.fg, 1, p->A(L.cc), L.cc.C, 0, at.fg.c1p, false, p->G(blk.fg), blk.fg.C, nullptr, 0, L.cc.H, L.cc.W,
+                               at.fg.w_off, at.fg.b_off, 0, at.d, at.d));
+          MSAU_TRY(layer_wgrad(p, at.fg, 1, p->A(L.cc), L.cc.C, 0, at.fg.c1p, false, p->G(blk.fg), blk.fg.C, nullptr, 0, L.cc.H, L.cc.W,
+                               at.g_w_off, at.g_b_off, at.d, at.d, at.d));
+          MSAU_TRY(layer_dgrad(p, at.fg, 1, p->G(blk.fg), blk.fg.C, nullptr, 0, L.cc, o));
+        }
+      }
+      if (l < S - 1) {
+        count_launch(1);
+        MSAU_TRY(launch_pool_bwd(p->A(L.cc), p->G(L.pooled), p->G(L.cc), p->B, L.cc.H, L.cc.W, L.cc.C, p->touch(L.cc), p->st));
+      }
+      if (b > 0) {
+        const Tensor& pd = (l == S - 1) ? prev->att : prev->down[l].cc;
+        MSAU_TRY(coupl_bwd(p, L.coupl, pd, L.rr, L.cc));
+      }
+      MSAU_TRY(res_bwd(p, L.res, L.y1, L.a, L.rr));
+      count_launch(1);
+      MSAU_TRY(launch_lrn_bwd(p->A(L.z1), p->G(L.y1), p->G(L.z1), p->npix(L.z1), L.z1.C, p->st));
+      if (b == 0 && l == 0) {
+        const int c1 = pad4(cfg.channels);
+        MSAU_TRY(layer_wgrad(p, L.conv1, 1, x, c1, x_layout == 0, cfg.channels, false, p->G(L.z1), L.z1.C, nullptr, 0, p->H, p->W));
+      } else {
+        const Tensor& src = l == 0 ? prev->logits : blk.down[l - 1].pooled;
+        MSAU_TRY(layer_wgrad(p, L.conv1, 1, p->A(src), src.C, 0, L.conv1.c1p, false, p->G(L.z1), L.z1.C, nullptr, 0, L.z1.H, L.z1.W));
+        ConvOpt o;
+        MSAU_TRY(layer_dgrad(p, L.conv1, 1, p->G(L.z1), L.z1.C, nullptr, 0, src, o));
+      }
+    }
+  }
+  return MSAU_OK;
+}
+
+extern "C" int msau_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr,
+                                   float beta1, float beta2, float eps, float max_norm, float* scratch, float* total_norm,
+                                   void* stream) {
+  MSAU_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && scratch, "clip_adam_step: null argument");
+  count_launch(2);
+  return launch_clip_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, max_norm, scratch, total_norm,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- debugging aids (tests/test_model_gpu.py compares every internal activation / activation gradient
+//      with the oracle's traced forward); not part of the reference-facing surface ----
+extern "C" int msau_debug_layout(const MsauPlan* p, long long* packed_floats, long long* act_floats, int* n_tensors) {
+  MSAU_CHECK_ARG(p, "debug_layout: null plan");
+  if (packed_floats) *packed_floats = p->packed_floats;
+  if (act_floats) *act_floats = p->act_floats;
+  if (n_tensors) *n_tensors = p->n_tensors;
+  return MSAU_OK;
+}
+
+extern "C" int msau_debug_tensor(const MsauPlan* p, int id, long long* off, int* Cc, int* Hh, int* Ww) {
+  MSAU_CHECK_ARG(p && id >= 0 && id < p->n_tensors, "debug_tensor: bad id");
+  const Tensor& t = p->all_tensors[id];
+  if (off) *off = t.off;
+  if (Cc) *Cc = t.C;
+  if (Hh) *Hh = t.H;
+  if (Ww) *Ww = t.W;
+  return MSAU_OK;
+}

@@ -1,0 +1,401 @@
+// Pixel-wise kernels: LRN fwd/bwd, 2x2 SAME max-pool fwd/bwd, logits head (NHWC->NCHW, softmax, argmax),
+// masked cross-entropy loss + dlogits.  All are HBM-bound streaming kernels: one thread per pixel (or per
+// pixel x channel-quad), float4 accesses, no shared-memory reuse needed.
+//
+// Reference semantics:
+//   LRN  : torch.nn.LocalResponseNorm(size=C) as used at model/layers/layers.py:145,161-162
+//          y_c = z_c / (1 + (1e-4/C) * sum_{c' in [c-C/2, c+(C-1)/2]} z_c'^2)^0.75
+//   pool : pad_2d(...,'pool2d') + MaxPool2d(2,2)   model/model.py:87-94,158-160
+//   loss : MSAUWrapper.loss model/model.py:446-459 per page, averaged over pages
+//   head : Softmax(dim=1) model/model.py:426-427,437 ; argmax train_chargrid_funsd_msau.py:135, kv_model.py:162
+#include "common.cuh"
+#include "pointwise.cuh"
+
+namespace msau {
+
+static constexpr float kLrnAlpha = 1e-4f;
+static constexpr float kLrnBeta = 0.75f;
+
+// ------------------------------------------------------------------------------------------- LRN
+// d^-0.75 = rsqrt(d) * sqrt(rsqrt(d)); d is in [1, ~1.1] so this is accurate to ~2 ulp.
+__device__ __forceinline__ float pow_m075(float d) {
+  const float r = rsqrtf(d);
+  return r * sqrtf(r);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) lrn_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, long npix) {
+  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float v[C];
+  const float4* src = reinterpret_cast<const float4*>(z + pix * C);
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) {
+    const float4 t = __ldg(src + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+  constexpr int LO = C / 2, HI = (C - 1) / 2;
+  float out[C];
+  // sliding window over channels: the first half of the channels only gains terms, the second half
+  // only loses them, so the running sum never cancels catastrophically.
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k <= HI; ++k) s = fmaf(v[k], v[k], s);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    if (c > 0) {
+      if (c + HI < C) s = fmaf(v[c + HI < C ? c + HI : 0], v[c + HI < C ? c + HI : 0], s);
+      if (c - LO - 1 >= 0) s -= v[c - LO - 1 >= 0 ? c - LO - 1 : 0] * v[c - LO - 1 >= 0 ? c - LO - 1 : 0];
+    }
+    const float d = fmaf(s, kLrnAlpha / C, 1.f);
+    out[c] = v[c] * pow_m075(d);
+  }
+  float4* dst = reinterpret_cast<float4*>(y + pix * C);
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+}
+
+// dz_j = g_j d_j^-b - (2ab/C) z_j * sum_{c : j in win(c)} g_c z_c d_c^(-b-1),  {c : j in win(c)} = [j-HI, j+LO]
+template <int C>
+__global__ void __launch_bounds__(256) lrn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gy,
+                                                       float* __restrict__ gz, long npix) {
+  const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  float v[C], g[C];
+  const float4* sz = reinterpret_cast<const float4*>(z + pix * C);
+  const float4* sg = reinterpret_cast<const float4*>(gy + pix * C);
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) {
+    const float4 t = __ldg(sz + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    const float4 u = __ldg(sg + i);
+    g[4 * i] = u.x; g[4 * i + 1] = u.y; g[4 * i + 2] = u.z; g[4 * i + 3] = u.w;
+  }
+  constexpr int LO = C / 2, HI = (C - 1) / 2;
+  float pw[C], tt[C];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k <= HI; ++k) s = fmaf(v[k], v[k], s);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    if (c > 0) {
+      if (c + HI < C) s = fmaf(v[c + HI < C ? c + HI : 0], v[c + HI < C ? c + HI : 0], s);
+      if (c - LO - 1 >= 0) s -= v[c - LO - 1 >= 0 ? c - LO - 1 : 0] * v[c - LO - 1 >= 0 ? c - LO - 1 : 0];
+    }
+    const float d = fmaf(s, kLrnAlpha / C, 1.f);
+    pw[c] = pow_m075(d);
+    tt[c] = g[c] * v[c] * pw[c] / d;
+  }
+  float out[C];
+  // {c : j in win(c)} = [j-HI, j+LO]: second sliding window, over tt
+  float u = 0.f;
+#pragma unroll
+  for (int c = 0; c <= LO && c < C; ++c) u += tt[c];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    if (j > 0) {
+      if (j + LO < C) u += tt[j + LO < C ? j + LO : 0];
+      if (j - HI - 1 >= 0) u -= tt[j - HI - 1 >= 0 ? j - HI - 1 : 0];
+    }
+    out[j] = g[j] * pw[j] - (2.f * kLrnAlpha * kLrnBeta / C) * v[j] * u;
+  }
+  float4* dst = reinterpret_cast<float4*>(gz + pix * C);
+#pragma unroll
+  for (int i = 0; i < C / 4; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+}
+
+template <bool BWD>
+static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, cudaStream_t st) {
+  const int grid = cdiv(npix, 256);
+#define MSAU_LRN(CV)                                                             \
+  case CV:                                                                       \
+    if (BWD) lrn_bwd_kernel<CV><<<grid, 256, 0, st>>>(z, gy, out, npix);         \
+    else lrn_fwd_kernel<CV><<<grid, 256, 0, st>>>(z, out, npix);                 \
+    break;
+  switch (C) {
+    MSAU_LRN(4) MSAU_LRN(8) MSAU_LRN(16) MSAU_LRN(32) MSAU_LRN(64)
+    default:
+      set_error("lrn: unsupported channel count %d (supported 4,8,16,32,64)", C);
+      return MSAU_ERR_UNSUPPORTED;
+  }
+#undef MSAU_LRN
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+int launch_lrn_fwd(const float* z, float* y, long npix, int C, cudaStream_t st) { return lrn_dispatch<false>(z, nullptr, y, npix, C, st); }
+int launch_lrn_bwd(const float* z, const float* gy, float* gz, long npix, int C, cudaStream_t st) { return lrn_dispatch<true>(z, gy, gz, npix, C, st); }
+
+// ------------------------------------------------------------------------------------------- pool
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
+                                                        int Ho, int Wo, int C4) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Ho * Wo * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long r = idx / C4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  const float4* src = reinterpret_cast<const float4*>(x);
+  const int y0 = 2 * oy, x0 = 2 * ox;
+  float4 m = __ldg(src + (((long)b * H + y0) * W + x0) * C4 + c4);
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);   // SAME zero padding takes part in the max
+  const float4 v01 = (x0 + 1 < W) ? __ldg(src + (((long)b * H + y0) * W + x0 + 1) * C4 + c4) : zero;
+  const float4 v10 = (y0 + 1 < H) ? __ldg(src + (((long)b * H + y0 + 1) * W + x0) * C4 + c4) : zero;
+  const float4 v11 = (y0 + 1 < H && x0 + 1 < W) ? __ldg(src + (((long)b * H + y0 + 1) * W + x0 + 1) * C4 + c4) : zero;
+  m.x = fmaxf(fmaxf(m.x, v01.x), fmaxf(v10.x, v11.x));
+  m.y = fmaxf(fmaxf(m.y, v01.y), fmaxf(v10.y, v11.y));
+  m.z = fmaxf(fmaxf(m.z, v01.z), fmaxf(v10.z, v11.z));
+  m.w = fmaxf(fmaxf(m.w, v01.w), fmaxf(v10.w, v11.w));
+  reinterpret_cast<float4*>(y)[idx] = m;
+}
+
+__device__ __forceinline__ void pool_route(float a, float b, float c, float d, float g, float& ga, float& gb, float& gc, float& gd) {
+  // torch max_pool2d backward: the FIRST maximum in row-major window order receives the gradient.
+  // b/c/d may be the SAME zero pad (then their gradient is dropped by the caller's bounds check).
+  int k = 0; float m = a;
+  if (b > m) { m = b; k = 1; }
+  if (c > m) { m = c; k = 2; }
+  if (d > m) { m = d; k = 3; }
+  ga = k == 0 ? g : 0.f; gb = k == 1 ? g : 0.f; gc = k == 2 ? g : 0.f; gd = k == 3 ? g : 0.f;
+}
+
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
+                                                        int B, int H, int W, int Ho, int Wo, int C4, int accumulate) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Ho * Wo * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long r = idx / C4;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int b = (int)(r / Ho);
+  const float4* src = reinterpret_cast<const float4*>(x);
+  const int y0 = 2 * oy, x0 = 2 * ox;
+  const bool hx = x0 + 1 < W, hy = y0 + 1 < H;
+  const long i00 = (((long)b * H + y0) * W + x0) * C4 + c4;
+  const long i01 = i00 + C4, i10 = i00 + (long)W * C4, i11 = i10 + C4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = __ldg(src + i00);
+  const float4 v01 = hx ? __ldg(src + i01) : zero;
+  const float4 v10 = hy ? __ldg(src + i10) : zero;
+  const float4 v11 = (hx && hy) ? __ldg(src + i11) : zero;
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gy) + idx);
+  float4 g00, g01, g10, g11;
+  pool_route(a.x, v01.x, v10.x, v11.x, g.x, g00.x, g01.x, g10.x, g11.x);
+  pool_route(a.y, v01.y, v10.y, v11.y, g.y, g00.y, g01.y, g10.y, g11.y);
+  pool_route(a.z, v01.z, v10.z, v11.z, g.z, g00.z, g01.z, g10.z, g11.z);
+  pool_route(a.w, v01.w, v10.w, v11.w, g.w, g00.w, g01.w, g10.w, g11.w);
+  float4* dst = reinterpret_cast<float4*>(gx);
+  auto put = [&](long i, float4 v) {
+    if (accumulate) { const float4 o = dst[i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    dst[i] = v;
+  };
+  put(i00, g00);
+  if (hx) put(i01, g01);
+  if (hy) put(i10, g10);
+  if (hx && hy) put(i11, g11);
+}
+
+int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long total = (long)B * Ho * Wo * (C / 4);
+  pool_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, y, B, H, W, Ho, Wo, C / 4);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long total = (long)B * Ho * Wo * (C / 4);
+  pool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- misc streaming
+__global__ void __launch_bounds__(256) add_kernel(float4* __restrict__ dst, const float4* __restrict__ src, long n4, int accumulate) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = __ldg(src + i);
+  if (accumulate) { const float4 o = dst[i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+  dst[i] = v;
+}
+
+int launch_add(float* dst, const float* src, long n, int accumulate, cudaStream_t st) {
+  add_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n / 4, accumulate);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+// per-channel sum over pixels (bias gradient of the transposed conv): out[c] += sum_p g[p][c], c < c_lim
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, long npix, int C, int c_lim, float* __restrict__ out) {
+  // thread t owns channel (t % C) of pixels t / C, t / C + 256 / C, ...   (C divides 256 for C in 8..64)
+  const int c = threadIdx.x % C;
+  const int ppb = 256 / C;
+  float s = 0.f;
+  for (long pix = (long)blockIdx.x * ppb + threadIdx.x / C; pix < npix; pix += (long)gridDim.x * ppb) s += __ldg(g + pix * C + c);
+  __shared__ float sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+    for (int k = 0; k < ppb; ++k) t += sh[k * C + threadIdx.x];
+    if (threadIdx.x < c_lim) atomicAdd(out + threadIdx.x, t);
+  }
+}
+
+int launch_colsum(const float* g, long npix, int C, int c_lim, float* out, cudaStream_t st) {
+  MSAU_CHECK_ARG(C >= 4 && C <= 256 && 256 % C == 0, "colsum: unsupported pitch %d", C);
+  const int ppb = 256 / C;
+  int grid = cdiv(npix, (long)ppb * 16);
+  if (grid > 4 * sm_count()) grid = 4 * sm_count();
+  if (grid < 1) grid = 1;
+  colsum_kernel<<<grid, 256, 0, st>>>(g, npix, C, c_lim, out);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- head
+// logits NHWC (pitch P, n_class <= 8 used) -> NCHW logits / softmax probabilities / uint8 argmax.
+// One thread per pixel: reads 32 B, writes n_class strided planes (coalesced across the warp).
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ lg, int P, int n_class, long npix_per_page, int B,
+                                                    float* __restrict__ logits_nchw, float* __restrict__ probs_nchw,
+                                                    uint8_t* __restrict__ argmax) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix_per_page * B) return;
+  const int b = (int)(idx / npix_per_page);
+  const long p = idx - (long)b * npix_per_page;
+  float v[8];
+  const float4 a = __ldg(reinterpret_cast<const float4*>(lg + idx * P));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(lg + idx * P) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  float m = v[0]; int am = 0;
+#pragma unroll
+  for (int k = 1; k < 8; ++k)
+    if (k < n_class && v[k] > m) { m = v[k]; am = k; }   // first maximum wins (numpy / torch argmax)
+  if (argmax) argmax[idx] = (uint8_t)am;
+  float* lo = logits_nchw ? logits_nchw + (long)b * n_class * npix_per_page + p : nullptr;
+  if (lo) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n_class) lo[k * npix_per_page] = v[k];
+  }
+  if (probs_nchw) {
+    float e[8]; float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = k < n_class ? expf(v[k] - m) : 0.f; s += e[k]; }
+    const float inv = 1.f / s;
+    float* po = probs_nchw + (long)b * n_class * npix_per_page + p;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (k < n_class) po[k * npix_per_page] = e[k] * inv;
+  }
+}
+
+int launch_head(const float* lg, int P, int n_class, int B, long npix_per_page, float* logits_nchw, float* probs_nchw, uint8_t* argmax, cudaStream_t st) {
+  MSAU_CHECK_ARG(P == 8 && n_class <= 8, "head: logits pitch must be 8 and n_class <= 8 (got %d, %d)", P, n_class);
+  head_kernel<<<cdiv(npix_per_page * B, 256), 256, 0, st>>>(lg, P, n_class, npix_per_page, B, logits_nchw, probs_nchw, argmax);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+// ------------------------------------------------------------------------------------------- loss
+// stage 1: kept-pixel count per page ; stage 2: per-pixel log-softmax NLL for both heads + dlogits,
+// per-block partial sums ; stage 3: fixed-order final sum (deterministic).
+template <typename LT>
+__global__ void __launch_bounds__(256) count_kept_kernel(const LT* __restrict__ labels, long npix_per_page, int* __restrict__ counts) {
+  const int b = blockIdx.y;
+  const LT* l = labels + (long)b * npix_per_page;
+  int c = 0;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix_per_page; i += (long)gridDim.x * blockDim.x) c += (l[i] != 0);
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + b, c);
+}
+
+__device__ __forceinline__ float ce_head(const float* __restrict__ src, long idx, int n_class, int lab, float scale,
+                                         float gscale, float4& g0, float4& g1) {
+  float v[8];
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src + idx * 8));
+  const float4 c = __ldg(reinterpret_cast<const float4*>(src + idx * 8) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  float m = v[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) if (k < n_class) m = fmaxf(m, v[k]);
+  float e[8]; float s = 0.f; float vl = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { e[k] = k < n_class ? expf(v[k] - m) : 0.f; s += e[k]; if (k == lab) vl = v[k]; }
+  const float gs = scale * gscale;
+  const float inv = gs / s;
+  float gq[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gq[k] = e[k] * inv - (k == lab ? gs : 0.f);
+  g0 = make_float4(gq[0], gq[1], gq[2], gq[3]);
+  g1 = make_float4(gq[4], gq[5], gq[6], gq[7]);
+  return (logf(s) + m - vl) * scale;
+}
+
+template <typename LT>
+__global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ lg, const float* __restrict__ la, int n_class,
+                                                  const LT* __restrict__ labels, const int* __restrict__ counts, long npix_per_page, int B,
+                                                  float gscale, float* __restrict__ dlg, float* __restrict__ dla, float* __restrict__ partial) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  float loss = 0.f;
+  if (idx < npix_per_page * B) {
+    const int b = (int)(idx / npix_per_page);
+    const int lab = (int)labels[idx];
+    float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0, y0 = z0, y1 = z0;
+    if (lab != 0) {
+      const float scale = 1.f / ((float)counts[b] * (float)B);
+      loss += ce_head(lg, idx, n_class, lab, scale, gscale, z0, z1);
+      loss += ce_head(la, idx, n_class, lab, scale, gscale, y0, y1);
+    }
+    reinterpret_cast<float4*>(dlg + idx * 8)[0] = z0; reinterpret_cast<float4*>(dlg + idx * 8)[1] = z1;
+    reinterpret_cast<float4*>(dla + idx * 8)[0] = y0; reinterpret_cast<float4*>(dla + idx * 8)[1] = y1;
+  }
+  __shared__ float ws[8];
+  for (int o = 16; o; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = loss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < 8; ++i) s += ws[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) final_sum_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) s += (double)partial[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)sh[0];
+}
+
+int loss_partial_count(int B, long npix_per_page) { return cdiv(npix_per_page * B, 256); }
+
+int launch_loss(const float* lg, const float* la, int n_class, const void* labels, int label_is_i64, int B, long npix_per_page,
+                float gscale, float* dlg, float* dla, int* counts, float* partial, float* loss_out, cudaStream_t st) {
+  MSAU_CHECK_ARG(n_class <= 8, "loss: n_class <= 8 supported");
+  MSAU_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * B, st));
+  const int nblk = loss_partial_count(B, npix_per_page);
+  dim3 cg(min(cdiv(npix_per_page, 256), 64), B);
+  if (label_is_i64) {
+    count_kept_kernel<long long><<<cg, 256, 0, st>>>((const long long*)labels, npix_per_page, counts);
+    ce_kernel<long long><<<nblk, 256, 0, st>>>(lg, la, n_class, (const long long*)labels, counts, npix_per_page, B, gscale, dlg, dla, partial);
+  } else {
+    count_kept_kernel<uint8_t><<<cg, 256, 0, st>>>((const uint8_t*)labels, npix_per_page, counts);
+    ce_kernel<uint8_t><<<nblk, 256, 0, st>>>(lg, la, n_class, (const uint8_t*)labels, counts, npix_per_page, B, gscale, dlg, dla, partial);
+  }
+  final_sum_kernel<<<1, 1024, 0, st>>>(partial, nblk, loss_out);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+}  // namespace msau

@@ -296,3 +296,88 @@ def clip_adam_step(sd, grads, m, v, step: int, lr: float = 1e-4, b1: float = 0.9
         denom = (v[k].sqrt() / math.sqrt(bc2)).add_(eps)
         sd[k].addcdiv_(m[k], denom, value=-(lr / bc1))
     return total
+
+
+# ----------------------------------------------------------------------------- traced forward (debugging aid)
+def msau_forward_trace(sd, cfg: MsauConfig, x: Tensor, retain_grad: bool = False):
+    """Same arithmetic as ``msau_forward`` but also returns every intermediate activation, in the order the
+    CUDA plan allocates them (msau_b200/csrc/plan.cu), as a list of (name, tensor NCHW).  Entries that the
+    engine allocates but that have no oracle counterpart (soft-max row statistics) are (name, None)."""
+    S, R, NB = cfg.scale_space_num, cfg.res_depth, cfg.num_blocks
+    trace = []
+
+    def rec(name, t):
+        if retain_grad and t is not None and t.requires_grad:
+            t.retain_grad()
+        trace.append((name, t))
+        return t
+
+    def res(prefix, name, t):
+        o = t
+        cur = F.relu(t)
+        for r in range(R):
+            p = f"{prefix}.conv_res_list.{r}.custom_conv"
+            cur = conv_same(cur, sd[p + ".weight"], sd[p + ".bias"])
+            if r < R - 1:
+                cur = rec(f"{name}.a{r}", F.relu(cur))
+        return rec(f"{name}.rr", F.relu(cur + o))
+
+    prev_dw = prev_up = None
+    inp = x
+    aux = None
+    for b in range(NB):
+        dn = f"msau_net.blocks.{b}.downsamplingblock"
+        dw = {}
+        cur_in = inp
+        for l in range(S):
+            p = f"{dn}.conv1s.{l}.conv"
+            z = rec(f"b{b}.d{l}.z1", conv_same(cur_in, sd[p + ".weight"], sd[p + ".bias"], dilation=2 ** l))
+            t = rec(f"b{b}.d{l}.y1", lrn_full(z))
+            t = res(f"{dn}.conv_res_list.{l}", f"b{b}.d{l}", t)
+            if b > 0:
+                p = f"{dn}.conv1_1s.{l}.custom_conv"
+                t = rec(f"b{b}.d{l}.cc", F.relu(F.conv2d(torch.cat([prev_dw[l], t], 1), sd[p + ".weight"], sd[p + ".bias"])))
+            dw[l] = t
+            if l < S - 1:
+                cur_in = rec(f"b{b}.d{l}.pooled",
+                             F.max_pool2d(_pad_same(t, cfg.pool_size, cfg.pool_size, cfg.pool_size), cfg.pool_size))
+        deep = t
+        if b < NB - 1:
+            ap = f"{dn}.layer_attentions.attention_block"
+            f_ = F.conv2d(deep, sd[ap + ".f.conv.weight"], sd[ap + ".f.conv.bias"])
+            g_ = F.conv2d(deep, sd[ap + ".g.conv.weight"], sd[ap + ".g.conv.bias"])
+            rec(f"b{b}.fg", torch.cat([f_, g_], 1))
+            h_ = rec(f"b{b}.hh", F.conv2d(deep, sd[ap + ".h.conv.weight"], sd[ap + ".h.conv.bias"]))
+            B_, C_, H_, W_ = deep.shape
+            s = torch.matmul(g_.reshape(B_, -1, H_ * W_).transpose(1, 2), f_.reshape(B_, -1, H_ * W_))
+            beta = torch.softmax(s, dim=-1)
+            o = torch.matmul(h_.reshape(B_, C_, H_ * W_), beta).reshape(B_, C_, H_, W_)
+            dw[S - 1] = rec(f"b{b}.att", o + deep)
+            for nm in ("mrow", "zinv", "dvec"):
+                trace.append((f"b{b}.{nm}", None))
+        up = {}
+        xx = deep
+        un = f"msau_net.blocks.{b}.upsamplingblock"
+        for l in range(S - 2, -1, -1):
+            skip = dw[l]
+            p = f"{un}.deconvs.{l}.conv"
+            hin, win = xx.shape[2:]
+            hout, wout = skip.shape[2:]
+            opad = (hout - (2 * hin - 1), wout - (2 * win - 1))
+            d = rec(f"b{b}.u{l}.d", F.conv_transpose2d(xx, sd[p + ".weight"], sd[p + ".bias"], stride=2, padding=1,
+                                                      output_padding=opad))
+            p = f"{un}.conv1s.{l}.custom_conv"
+            t = rec(f"b{b}.u{l}.u", conv_same(torch.cat([skip, d], 1), sd[p + ".weight"], sd[p + ".bias"]))
+            t = res(f"{un}.conv_res_list.{l}", f"b{b}.u{l}", t)
+            if b > 0:
+                p = f"{un}.conv1_1s.{l}.custom_conv"
+                t = rec(f"b{b}.u{l}.uc", F.relu(F.conv2d(torch.cat([prev_up[l], t], 1), sd[p + ".weight"], sd[p + ".bias"])))
+            up[l] = t
+            xx = t
+        p = f"msau_net.end_convs.{b}.custom_conv"
+        out = rec(f"b{b}.logits", conv_same(xx, sd[p + ".weight"], sd[p + ".bias"]))
+        prev_dw, prev_up = dw, up
+        inp = out
+        if b == NB - 2:
+            aux = out
+    return out, aux, trace

@@ -1,0 +1,178 @@
+"""Parity of the CUDA engine (through the C ABI / MSAUWrapper) with the oracle and the golden fixtures.
+
+Tolerances (fp32 engine vs fp32 reference, different summation order): |dlogit| <= 5e-4 absolute,
+arg-max agreement >= 99.9 % (BASELINE.json north_star); gradients 2e-3 relative to the tensor's max."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import msau_b200
+from msau_b200 import _lib
+from oracle import model as om
+from oracle.synth import synth_input
+
+pytestmark = pytest.mark.gpu
+LOGIT_ATOL = 5e-4
+FIXTURES = ["model_s3r2_c12", "model_s4r2_c96", "model_s2r3_c8"]
+
+
+def load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    return z, meta, om.MsauConfig(**meta["cfg"])
+
+
+def build(cfg, sd):
+    m = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=cfg.feat_root,
+                                                              scale_space_num=cfg.scale_space_num, res_depth=cfg.res_depth))
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def plan_tensors(m, pl):
+    """Every internal activation (and its gradient) of the last training forward, as NCHW CPU tensors."""
+    L = _lib.lib()
+    pk, act, n = C.c_longlong(), C.c_longlong(), C.c_int()
+    _lib.check(L.msau_debug_layout(pl.handle, C.byref(pk), C.byref(act), C.byref(n)))
+    base, _ = pl.ws_ptr(True)
+    ws = pl.workspace(True)
+    shift = (base - ws.data_ptr())
+    fl = ws[shift:shift + (ws.numel() - shift) // 4 * 4].view(torch.float32)
+    out = []
+    for i in range(n.value):
+        off, c, h, w = C.c_longlong(), C.c_int(), C.c_int(), C.c_int()
+        _lib.check(L.msau_debug_tensor(pl.handle, i, C.byref(off), C.byref(c), C.byref(h), C.byref(w)))
+        cnt = pl.B * h.value * w.value * c.value
+        a = fl[pk.value + off.value: pk.value + off.value + cnt].view(pl.B, h.value, w.value, c.value).permute(0, 3, 1, 2).cpu()
+        g = fl[pk.value + act.value + off.value: pk.value + act.value + off.value + cnt].view(pl.B, h.value, w.value, c.value).permute(0, 3, 1, 2).cpu()
+        out.append((a, g))
+    return out
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_forward_matches_golden(golden_dir, name):
+    z, meta, cfg = load(golden_dir, name)
+    sd = om.init_state_dict(cfg, meta["seed"])
+    x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
+    m = build(cfg, sd).eval()
+    with torch.no_grad():
+        probs, logits, aux = m(x.cuda())
+    lg, ax, pr = logits.cpu().numpy(), aux.cpu().numpy(), probs.cpu().numpy()
+    assert np.abs(lg - z["logits"]).max() <= LOGIT_ATOL
+    assert np.abs(ax - z["aux"]).max() <= LOGIT_ATOL
+    assert np.abs(pr - z["probs"]).max() <= 1e-4
+    agree = (lg.argmax(1) == z["logits"].argmax(1)).mean()
+    assert agree >= 0.999
+    am = m.predict_classes(x.cuda()).cpu().numpy()
+    assert (am == lg.argmax(1)).all()
+    # channels-last input (what the device rasteriser produces) gives the identical result
+    cp = (cfg.channels + 3) // 4 * 4
+    xn = torch.zeros(meta["B"], meta["H"], meta["W"], cp)
+    xn[..., :cfg.channels] = x.permute(0, 2, 3, 1)
+    am2 = m.predict_classes(xn.cuda(), layout=1).cpu().numpy()
+    assert (am2 == am).all()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_every_activation_and_gradient_matches_oracle(golden_dir, name):
+    """Walks the engine's workspace tensor by tensor against the oracle's traced forward/backward: the first
+    mismatch names the kernel at fault."""
+    z, meta, cfg = load(golden_dir, name)
+    sd = om.init_state_dict(cfg, meta["seed"])
+    x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
+    m = build(cfg, sd).train()
+    _, logits, aux = m(x.cuda())
+    loss = m.loss(logits, aux, labels.cuda())
+    pl = m._last[0]
+    torch.cuda.synchronize()
+    got = plan_tensors(m, pl)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out, axo, trace = om.msau_forward_trace(leaves, cfg, x, retain_grad=True)
+    ref_loss = om.batch_loss(out, axo, labels)
+    ref_loss.backward()
+    assert len(trace) == len(got)
+    bad = []
+    for (nm, t), (a, g) in zip(trace, got):
+        if t is None:
+            continue
+        c = t.shape[1]
+        err = (a[:, :c] - t.detach()).abs().max().item()
+        scale = max(1.0, t.detach().abs().max().item())
+        if not err <= 2e-4 * scale:
+            bad.append(("act", nm, err))
+        if t.grad is not None and not nm.endswith(".logits_dead"):
+            gs = max(t.grad.abs().max().item(), 1e-12)
+            gerr = (g[:, :c] - t.grad).abs().max().item()
+            if not gerr <= 2e-3 * gs:
+                bad.append(("grad", nm, gerr / gs))
+    assert not bad, bad[:12]
+    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * max(1.0, abs(float(ref_loss)))
+    assert abs(float(loss) - z["page_losses"].mean()) <= 1e-4 * z["page_losses"].mean()
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_param_grads_and_train_step_match_golden(golden_dir, name):
+    z, meta, cfg = load(golden_dir, name)
+    sd = om.init_state_dict(cfg, meta["seed"])
+    x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
+    m = build(cfg, sd).train()
+    # ---- the reference's own loop shape: forward -> loss -> backward -> clip -> Adam (train...py:46-59)
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, m.parameters()), lr=0.0001)
+    m.zero_grad()
+    _, ypred, ypred_aux = m(x.cuda())
+    loss = m.loss(ypred, ypred_aux, labels.cuda())
+    loss.backward()
+    keys = [k for k, _ in om.param_schema(cfg)]
+    named = dict(m.named_parameters())
+    none = np.array([named[k].grad is None for k in keys])
+    assert (none == z["grad_is_none"]).all()
+    norms = np.array([0.0 if named[k].grad is None else float(named[k].grad.double().norm()) for k in keys])
+    np.testing.assert_allclose(norms, z["grad_norms"], rtol=2e-3, atol=1e-6)
+    for k in z.files:
+        if k.startswith("grad::"):
+            want = z[k]
+            np.testing.assert_allclose(named[k[6:]].grad.cpu().numpy(), want, rtol=0, atol=2e-3 * np.abs(want).max())
+    total = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+    assert abs(float(total) - float(z["total_norm"])) <= 2e-3 * float(z["total_norm"])
+    opt.step()
+    sums = np.array([float(named[k].detach().double().sum()) for k in keys])
+    np.testing.assert_allclose(sums, z["param_sums_after_step"], rtol=1e-4, atol=2e-4)
+    for k in z.files:
+        if k.startswith("param_after::"):
+            # Adam's first step moves every weight by ~lr*sign(g): elements with |g| ~ 0 may flip, so bound by lr
+            assert np.abs(named[k[13:]].detach().cpu().numpy() - z[k]).max() <= 2.1e-4
+
+    # ---- fused path: same numbers from train_step (forward+loss+backward+clip+Adam in the engine)
+    m2 = build(cfg, sd).train()
+    l2 = m2.train_step(x.cuda(), labels.cuda())
+    assert abs(float(l2) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+    torch.cuda.synchronize()
+    live = torch.tensor(m2._live_mask())
+    for (k, p2), p1 in zip(m2.named_parameters(), m.parameters()):
+        assert (p2.detach() - p1.detach()).abs().max().item() <= 2e-6, k
+    assert abs(float(m2._adam[4]) - float(z["total_norm"])) <= 2e-3 * float(z["total_norm"])
+    # dead attention params untouched
+    dead = [k for k, lv in zip(keys, m2._live_mask()) if not lv]
+    for k in dead:
+        assert torch.equal(dict(m2.named_parameters())[k].detach().cpu(), sd[k])
+
+
+def test_full_size_page_properties():
+    """512x512 chargrid page at the train-script config: finite outputs, soft-max rows sum to 1, loss decreases
+    over a few fused steps (size-independent sanity at BASELINE.json's full page size)."""
+    cfg = om.MsauConfig()
+    sd = om.init_state_dict(cfg, 0)
+    x, labels = synth_input(cfg.channels, cfg.n_class, 2, 512, 512, 5)
+    m = build(cfg, sd).train()
+    xc, lc = x.cuda(), labels.cuda()
+    losses = [float(m.train_step(xc, lc, lr=1e-3)) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+    m.eval()
+    with torch.no_grad():
+        probs, logits, aux = m(xc)
+    assert torch.isfinite(logits).all() and torch.isfinite(aux).all()
+    assert (probs.sum(1) - 1).abs().max().item() < 1e-5

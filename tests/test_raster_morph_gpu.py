@@ -1,0 +1,171 @@
+"""Bit-exact parity of the rasterisers / morphology / CCL kernels (through the C ABI) with the numpy oracle
+and the golden fixtures generated from the reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from msau_b200 import morph, raster
+from oracle import morph as omo
+from oracle import raster as orr
+from oracle.synth import class_map
+
+pytestmark = pytest.mark.gpu
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def page(mp):
+    words, lines = orr.synth_page(mp["seed"], mp["gh"], mp["gw"], mp["n_words"])
+    if mp["tag"] == "odd":
+        words["chars"][3] = np.zeros(0, np.int32)
+        words["chars"][7] = np.zeros(0, np.int32)
+    return words, lines
+
+
+@pytest.fixture(scope="module")
+def rgold(golden_dir):
+    z = np.load(os.path.join(golden_dir, "raster.npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+def kv_inputs(words, charset):
+    boxes = np.stack([words["x"], words["y"], words["x"] + words["w"], words["y"] + words["h"]], 1)
+    tok = {t: i for i, t in enumerate(" $" + charset)}
+    ids = []
+    for ch in words["chars"]:
+        text = "".join(charset[c - 2] for c in ch)
+        text = "".join(c if not c.isdigit() else "0" for c in text)
+        ids.append(np.array([tok.get(c, 1) for c in text], np.int32))
+    return boxes, ids
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_rasterisers_match_golden(rgold, idx):
+    z, meta = rgold
+    mp = meta["pages"][idx]
+    tag = mp["tag"]
+    words, lines = page(mp)
+    grid, label, geom = raster.rasterize_word_chargrid([words], [lines], np.eye(96))
+    g = geom.cpu().numpy()[0]
+    assert (int(g[5]), int(g[6])) == (mp["gh"], mp["gw"])
+    assert sha(grid[0].cpu().numpy()) == str(z[f"{tag}::r1_sha"])
+    assert sha(label[0].cpu().numpy()) == str(z[f"{tag}::r1_label_sha"])
+    # channels-last output holds the same values
+    grid_l, _, _ = raster.rasterize_word_chargrid([words], [lines], np.eye(96), layout="nhwc")
+    assert torch.equal(grid_l[0].permute(2, 0, 1)[:96], grid[0])
+    feats = np.random.RandomState(mp["seed"] + 100).randn(len(lines["x"]), mp["feat_dim"])
+    grid2, label2, _ = raster.rasterize_box_grid([lines], [feats])
+    assert sha(grid2[0].cpu().numpy()) == str(z[f"{tag}::r2_sha"])
+    assert sha(label2[0].cpu().numpy()) == str(z[f"{tag}::r2_label_sha"])
+    boxes, ids = kv_inputs(words, meta["charset"])
+    r3 = raster.rasterize_kv([boxes], [ids])
+    assert tuple(z[f"{tag}::r3_shape"]) == tuple(r3["input_mask"].shape[1:])
+    for nm, key in (("input", "input_mask"), ("line", "line_id_mask"), ("char", "character_id_mask")):
+        assert sha(r3[key][0].cpu().numpy().view(np.uint16)) == str(z[f"{tag}::r3_{nm}_sha"]), nm
+    assert (r3["scaled_boxes"].cpu().numpy() == z[f"{tag}::r3_boxes"]).all()
+    g3 = r3["geom3"].cpu().numpy()[0]
+    assert g3[2] == z[f"{tag}::r3_scale_pad"][0] and g3[3] == z[f"{tag}::r3_scale_pad"][1]
+    if tag == "small":
+        oh = raster.one_hot(r3["input_mask"], int(z["small::r3_n_token"]))
+        assert sha(oh.cpu().numpy()) == str(z["small::r3_onehot_sha"])
+
+
+def test_raster_batch_matches_oracle():
+    """A ragged batch (different page sizes, empty words) against the numpy oracle, page by page."""
+    specs = [(3, 48, 40, 24), (9, 37, 53, 30), (12, 64, 64, 60), (13, 20, 33, 5)]
+    wp, lp, fe = [], [], []
+    for seed, gh, gw, n in specs:
+        w, l = orr.synth_page(seed, gh, gw, n)
+        if seed == 9:
+            w["chars"][2] = np.zeros(0, np.int32)
+        wp.append(w); lp.append(l)
+        fe.append(np.random.RandomState(seed).randn(len(l["x"]), 20))
+    grid, label, geom = raster.rasterize_word_chargrid(wp, lp, np.eye(96), out_hw=(64, 64))
+    grid2, label2, _ = raster.rasterize_box_grid(lp, fe, out_hw=(64, 64))
+    boxes_ids = [kv_inputs(w, "".join(chr(c) for c in range(33, 127) if chr(c) != "$") + chr(161)) for w in wp]
+    r3 = raster.rasterize_kv([b for b, _ in boxes_ids], [i for _, i in boxes_ids])
+    for p, (seed, gh, gw, n) in enumerate(specs):
+        og, ol = orr.raster_word_chargrid(wp[p], lp[p], np.eye(96))
+        want = np.zeros((96, 64, 64), np.float32); want[:, :gh, :gw] = og
+        assert np.array_equal(grid[p].cpu().numpy(), want)
+        wl = np.zeros((64, 64), np.uint8); wl[:gh, :gw] = ol
+        assert np.array_equal(label[p].cpu().numpy(), wl)
+        og2, ol2 = orr.raster_box_grid(lp[p], fe[p])
+        want2 = np.zeros((20, 64, 64), np.float32); want2[:, :gh, :gw] = torch.Tensor(og2).numpy()
+        assert np.array_equal(grid2[p].cpu().numpy(), want2)
+        o3 = orr.raster_kv_chargrid(*boxes_ids[p])
+        h3, w3 = o3["input_mask"].shape
+        for key in ("input_mask", "line_id_mask", "character_id_mask"):
+            got = r3[key][p].cpu().numpy().view(np.uint16)
+            assert np.array_equal(got[:h3, :w3], o3[key]), (p, key)
+            assert got[h3:].sum() == 0 and got[:, w3:].sum() == 0
+
+
+@pytest.fixture(scope="module")
+def mgold(golden_dir):
+    z = np.load(os.path.join(golden_dir, "morph.npz"))
+    return z, json.loads(str(z["meta"]))
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_closing_ccl_match_golden(mgold, idx):
+    z, meta = mgold
+    mp = meta[idx]
+    tag, H, W = mp["tag"], mp["H"], mp["W"]
+    m = class_map(mp["seed"], H, W)
+    for c in range(2, 5):
+        closed = morph.r_closing(m == c, (1, 3))
+        want = np.unpackbits(z[f"{tag}::{c}::closed"])[:H * W].reshape(H, W).astype(bool)
+        assert closed.dtype == np.bool_ and (closed == want).all()
+        labels, objs = morph.connected_components(closed)
+        assert labels.dtype == np.int32
+        assert sha(labels) == str(z[f"{tag}::{c}::labels_sha"])
+        bb = np.array([[o[0].start, o[0].stop, o[1].start, o[1].stop] for o in objs], np.int32).reshape(-1, 4)
+        assert (bb == z[f"{tag}::{c}::bboxes"]).all()
+    fns = dict(dil=morph.r_dilation, ero=morph.r_erosion, open=morph.r_opening)
+    n = 0
+    for key in z.files:
+        parts = key.split("::")
+        if parts[0] != tag or parts[1] not in fns:
+            continue
+        sh_, sw_ = (int(v) for v in parts[2].split("x"))
+        got = fns[parts[1]](m > 2, (sh_, sw_), eval(parts[3]))
+        want = np.unpackbits(z[key])[:H * W].reshape(H, W).astype(bool)
+        assert (got == want).all(), key
+        n += 1
+    assert n == 15
+
+
+def test_ccl_batch_against_scipy_full_size():
+    """256 x 3 class maps at 512x512 (BASELINE.json config 4): every label map equals scipy.ndimage.label's,
+    plus the size-independent properties (labels are 1..n, bbox tight)."""
+    from scipy import ndimage
+    maps = np.stack([class_map(100 + i, 512, 512) for i in range(16)])
+    t = torch.from_numpy(maps).cuda()
+    for c in (2, 3, 4):
+        closed = morph.closing_batch(morph.class_equals(t, c), (1, 3))
+        labels, n_labels, bboxes = morph.ccl_batch(closed)
+        lab = labels.cpu().numpy(); nl = n_labels.cpu().numpy(); bb = bboxes.cpu().numpy(); cl = closed.cpu().numpy()
+        for i in range(maps.shape[0]):
+            want_closed = ndimage.minimum_filter(ndimage.maximum_filter(maps[i] == c, (1, 3), mode="constant"), (1, 3), mode="constant")
+            assert (cl[i].astype(bool) == want_closed).all()
+            want, n = ndimage.label(want_closed)
+            assert nl[i] == n and (lab[i] == want).all()
+            objs = ndimage.find_objects(want)
+            got = morph.objects_from_bboxes(n, bb[i])
+            assert got == objs
+
+
+def test_degenerate_maps():
+    for img in (np.zeros((7, 9), bool), np.ones((7, 9), bool), np.eye(8, dtype=bool)):
+        labels, objs = morph.connected_components(img)
+        wl, wo = omo.connected_components(img)
+        assert (labels == wl).all() and objs == wo
+        assert (morph.r_closing(img, (1, 3)) == omo.r_closing(img, (1, 3))).all()
+        assert (morph.r_erosion(img, (3, 3)) == omo.r_erosion(img, (3, 3))).all()
