@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- pages/sec of the MSAU train step (fwd + loss + bwd + clip + Adam) on 512x512 chargrid pages.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[1]): batch 16 of synthetic 512x512 chargrid pages PER GPU (weak scaling),
+MSAUWrapper(96, 5, featRoot=8, scale_space_num=4, res_depth=2), random-init weights, synthetic pages from the
+SURVEY.md section 8(d) generator (198 words + 2 anchors, one-hot D=96).
+
+One JSON line on stdout (rank 0):
+  value     whole-job pages/s with the dense fp32 [16,96,512,512] batch already resident in HBM
+  e2e       same step driven from HOST page records through the public API: pinned CSR boxes -> H2D -> device
+            rasterisation (R1) -> train step -> loss read back, every step inside the timed region
+  roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference step timed on the host cores (bounded sample)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(channels=96, n_class=5, scale_space_num=4, res_depth=2, feat_root=8)
+PAGES_PER_GPU = 16
+H = W = 512
+METRIC = "pages/sec MSAU fwd+bwd 512x512 chargrid"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, tf=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def synth_records(first_seed, n):
+    from oracle import raster as orr
+    wp, lp = [], []
+    for i in range(n):
+        w, l = orr.synth_page(first_seed + i, H, W, 198)
+        wp.append(w); lp.append(l)
+    return wp, lp
+
+
+# --------------------------------------------------------------------------------------------- reference arm
+def cpu_train_pages(n_pages, warm, threads=None):
+    """The reference step (train_chargrid_funsd_msau.py:46-59 restated in oracle/model.py) page by page on the host."""
+    import numpy as np
+    import torch
+    from oracle import model as om
+    from oracle import raster as orr
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = om.MsauConfig(**CFG)
+    sd = om.init_state_dict(cfg, 0)
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v = {k: torch.zeros_like(t) for k, t in sd.items()}
+    times = []
+    for i in range(warm + n_pages):
+        words, lines = orr.synth_page(1000 + i, H, W, 198)
+        t0 = time.perf_counter()
+        grid, label = orr.raster_word_chargrid(words, lines, np.eye(CFG["channels"]))     # R1, as dataset.getitem does
+        x = torch.Tensor(grid).unsqueeze(0)
+        lab = torch.from_numpy(label.astype(np.int64)).unsqueeze(0)
+        loss, _, _, grads = om.loss_and_grads(sd, cfg, x, lab)
+        dead = f"msau_net.blocks.{cfg.num_blocks - 1}.downsamplingblock.layer_attentions."
+        grads = {k: (None if k.startswith(dead) else g) for k, g in grads.items()}
+        om.clip_adam_step(sd, grads, m, v, step=i + 1)
+        dt = time.perf_counter() - t0
+        if i >= warm:
+            times.append(dt)
+    return times, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    times, threads = cpu_train_pages(args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    val = 1e3 / ms
+    sample = "1 page per step (rasterise R1 + fwd + loss + bwd + clip + Adam), torch-CPU fp32 oracle port of the reference step"
+    print(json.dumps(dict(
+        impl="reference", metric=METRIC, value=val, unit="pages/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload="MSAU chargrid training step, synthetic 512x512 pages (configs[1])", model_kwargs=CFG,
+                    pages_per_step=1, note="reference = pure-Python/PyTorch; no installable package, oracle port timed"),
+        cpu_baseline=dict(value=val, unit="pages/s", cores=threads, kind="port", sample=sample),
+        e2e=dict(value=val, unit="pages/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+
+
+# --------------------------------------------------------------------------------------------- native arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--pages", type=int, default=PAGES_PER_GPU, help="pages per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e-dense", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import msau_b200
+    from msau_b200 import _lib, raster
+    from oracle import model as om
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, Wm, P = args.steps, max(args.warmup, 3), args.pages
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t)
+        return ms
+
+    cfg = om.MsauConfig(**CFG)
+    model = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=cfg.feat_root,
+                                                                  scale_space_num=cfg.scale_space_num, res_depth=cfg.res_depth))
+    model.load_state_dict(om.init_state_dict(cfg, 0))     # identical replicas on every rank
+    model = model.to(dev).train()
+    pg = dist.group.WORLD if world > 1 else None
+
+    # ---- synthetic pages for this rank: records on the host, dense grid rasterised once for the resident run
+    words, lines = synth_records(rank * P, P)
+    table = torch.eye(cfg.channels, dtype=torch.float64, device=dev)
+    grid, label, _ = raster.rasterize_word_chargrid(words, lines, table, out_hw=(H, W), layout="nchw", device=dev)
+    labels64 = label.long()
+
+    def step_resident():
+        return model.train_step(grid, labels64, process_group=pg, world_size=world)
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    for _ in range(Wm):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(step_resident, K)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = world * P / (ms_step * 1e-3)
+
+    # ---- e2e: host page records -> device every step (public API: raster.rasterize_word_chargrid + train_step)
+    h2d = [0]
+
+    def step_e2e():
+        wb = raster.BoxBatch(words, dev, with_chars=True)
+        lb = raster.BoxBatch(lines, dev, with_chars=False, with_labels=True)
+        geom = wb.geometry()
+        g = raster.raster_features(wb, geom, table, (H, W), True, "nhwc")
+        lab = raster.raster_labels(lb, geom, (H, W))
+        h2d[0] = wb.h_bytes + lb.h_bytes
+        loss = model.train_step(g, lab, layout=1, process_group=pg, world_size=world)
+        return float(loss)            # D2H read of the step's result
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, K) / K
+    e2e = dict(value=world * P / (ms_e2e * 1e-3), unit="pages/s", h2d_bytes_per_step=h2d[0], d2h_bytes_per_step=4,
+               input="host page records (CSR boxes + char ids, pinned) rasterised on the device (R1) every step")
+
+    # ---- e2e with the reference's literal input format: dense fp32 NCHW page tensor in pinned host memory
+    e2e_dense = None
+    if not args.no_e2e_dense:
+        host_x = torch.empty(grid.shape, dtype=torch.float32).pin_memory()
+        host_x.copy_(grid)
+        host_l = torch.empty(labels64.shape, dtype=torch.int64).pin_memory()
+        host_l.copy_(labels64)
+
+        def step_dense():
+            xd = host_x.to(dev, non_blocking=True)
+            ld = host_l.to(dev, non_blocking=True)
+            return float(model.train_step(xd, ld, process_group=pg, world_size=world))
+
+        step_dense()
+        ms_d = timed(step_dense, max(2, K // 2)) / max(2, K // 2)
+        e2e_dense = dict(value=world * P / (ms_d * 1e-3), unit="pages/s",
+                         h2d_bytes_per_step=host_x.numel() * 4 + host_l.numel() * 8, d2h_bytes_per_step=4,
+                         input="dense fp32 [B,96,512,512] + int64 labels from pinned host memory (PCIe-bound)")
+        del host_x, host_l
+
+    # ---- per-kernel pass (CUDA events around every launch) -> roofline of the dominant kernel
+    roof, breakdown = None, None
+    if rank == 0 or world == 1:
+        pk = peaks()
+        _lib.profile_enable(True)
+        for _ in range(K):
+            step_resident()
+        rep = _lib.profile_report()
+        _lib.profile_enable(False)
+        tot = sum(v["ms"] for v in rep.values())
+        breakdown = {k: dict(share=round(v["ms"] / tot, 4), ms_per_step=round(v["ms"] / K, 4), launches_per_step=v["launches"] // K,
+                             gbs=round(v["bytes"] / v["ms"] / 1e6, 1), tflops=round(v["flops"] / v["ms"] / 1e9, 2))
+                     for k, v in sorted(rep.items(), key=lambda kv: -kv[1]["ms"])}
+        top, tv = max(rep.items(), key=lambda kv: kv[1]["ms"])
+        t_hbm = tv["bytes"] / (pk["hbm_gbs"] * 1e9)
+        t_ten = tv["flops"] / (pk["tf"] * 1e12)
+        if t_hbm >= t_ten:
+            ach = tv["bytes"] / (tv["ms"] * 1e-3) / 1e9
+            roof = dict(bound="hbm", achieved=ach, peak=pk["hbm_gbs"], unit="GB/s", frac=ach / pk["hbm_gbs"], traffic=None)
+        else:
+            ach = tv["flops"] / (tv["ms"] * 1e-3) / 1e12
+            roof = dict(bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=None)
+        roof.update(kernel=top, peak_source=pk["src"], launches=tv["launches"], avg_launch_ms=tv["ms"] / tv["launches"],
+                    share_of_step=tv["ms"] / tot, pass_="separate K-step pass with CUDA events around every launch")
+    barrier()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        times, threads = cpu_train_pages(3, 1)
+        cpu = dict(value=len(times) / sum(times), unit="pages/s", cores=threads, kind="port",
+                   sample="3 pages (after 1 warm-up) of the same workload: R1 rasterise + fwd + loss + bwd + clip + Adam, "
+                          "torch-CPU fp32 oracle port of train_chargrid_funsd_msau.py:46-59")
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit="pages/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms_step,
+                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                   config=dict(workload="MSAU chargrid training step, batch 16 synthetic 512x512 pages per GPU (BASELINE.json configs[1])",
+                               model_kwargs=CFG, pages_per_gpu=P, global_batch=world * P, parallelism=f"dp{world}",
+                               l2="inputs (1.6 GB) and activations (>30 GB) are larger than L2; no flush needed",
+                               step="fwd + masked CE (main+aux) + bwd + NCCL all-reduce (N>1) + clip_grad_norm(1.0) + Adam(1e-4)"),
+                   e2e=e2e, e2e_dense=e2e_dense, gpu_launches=int(launches), roofline=roof, kernel_breakdown=breakdown,
+                   cpu_baseline=cpu, clocks=clocks)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

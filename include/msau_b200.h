@@ -156,6 +156,12 @@ int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int c
 int msau_ccl4(const uint8_t* binary, int n_maps, int height, int width, int32_t* labels, int32_t* n_labels,
               int32_t* bboxes, int max_labels, int32_t* scratch, void* stream);
 
+/* Per-kernel timing for bench.py's roofline report: when enabled every launch is bracketed by CUDA events on
+ * its stream; msau_profile_report synchronises the device and writes a JSON object
+ * {"<kernel>": {"launches", "ms", "flops", "bytes"}} (algorithmic work) into buf, then clears. */
+int msau_profile_enable(int on);
+int msau_profile_report(char* h_buf, size_t capacity);
+
 /* Debugging aids used by the parity tests: workspace layout = [packed weights | activations |
  * activation gradients (training) | scratch], all in floats; tensor `id` (allocation order) lives at
  * activations + off as [B, H, W, C] fp32. */

@@ -18,7 +18,7 @@ SYMBOLS = [
     "msau_raster_geometry", "msau_raster_features", "msau_raster_labels",
     "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
     "msau_rect_filter", "msau_class_equals", "msau_ccl4",
-    "msau_debug_layout", "msau_debug_tensor",
+    "msau_debug_layout", "msau_debug_tensor", "msau_profile_enable", "msau_profile_report",
 ]
 
 
@@ -69,6 +69,8 @@ def lib() -> C.CDLL:
     L.msau_ccl4.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     L.msau_debug_layout.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.msau_debug_tensor.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.msau_profile_enable.argtypes = [i32]
+    L.msau_profile_report.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
         getattr(L, name)   # every symbol the header declares must be exported
     _lib = L
@@ -93,3 +95,14 @@ def current_stream() -> int:
 
 def launch_count() -> int:
     return int(lib().msau_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().msau_profile_enable(int(on)))
+
+
+def profile_report() -> dict:
+    import json
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().msau_profile_report(buf, len(buf)))
+    return json.loads(buf.value.decode())

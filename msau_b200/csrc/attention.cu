@@ -17,6 +17,7 @@
 // exp/FMA-bound on the CUDA cores, not tensor-bound.
 #include "common.cuh"
 #include "attention.cuh"
+#include "prof.cuh"
 
 namespace msau {
 
@@ -310,6 +311,8 @@ bool attn_supported(int C, int d) { return (C == 64 && d == 8) || (C == 32 && d 
 int launch_attn_fwd(const float* FG, const float* Hh, const float* X, int B, int N, int C, int d, float* mrow, float* zinv,
                     float* out, cudaStream_t st) {
   dim3 grid(cdiv(N, TR), B);
+  // two sweeps over the N x N relation map: stats (d MACs) + output (d + C MACs); 1 exp per entry per sweep
+  ProfScope ps("attn_fwd_kernels", 2.0 * B * (double)N * N * (2 * d + C), (double)B * N * (2 * d + 3 * C + 2) * 4.0, st);
   if (C == 64 && d == 8) {
     attn_stats_kernel<8><<<grid, TR, 0, st>>>(FG, N, mrow, zinv);
     attn_out_kernel<8, 64><<<grid, TR, 0, st>>>(FG, Hh, X, mrow, zinv, N, out);
@@ -327,6 +330,7 @@ int launch_attn_fwd(const float* FG, const float* Hh, const float* X, int B, int
 int launch_attn_bwd(const float* FG, const float* Hh, const float* dO, const float* mrow, const float* zinv, int B, int N, int C,
                     int d, float* Dvec, float* dFG, float* dHh, cudaStream_t st) {
   dim3 grid(cdiv(N, TR), B);
+  ProfScope ps("attn_bwd_kernels", 2.0 * B * (double)N * N * (5 * d + 3 * C), (double)B * N * (4 * d + 3 * C + 3) * 4.0, st);
   if (C == 64 && d == 8) {
     attn_bwd_h_kernel<8, 64><<<grid, TR, 0, st>>>(FG, Hh, dO, mrow, zinv, N, dHh, Dvec);
     attn_bwd_g_kernel<8, 64><<<grid, TR, 0, st>>>(FG, Hh, dO, mrow, zinv, Dvec, N, dFG);

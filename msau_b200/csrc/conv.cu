@@ -12,6 +12,7 @@
 // Reference semantics: model/layers/layers.py:10-164,207-260 (conv / dilated conv / transposed conv),
 // model/layers/utils.py:5-28 (SAME padding -> pad_t/pad_l here), model/model.py:37-50 (residual epilogue).
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace msau {
 
@@ -208,6 +209,12 @@ int launch_conv(const ConvArgs& a, cudaStream_t st) {
   MSAU_CHECK_ARG(smem <= 220 * 1024, "conv: tile does not fit shared memory (%zu B)", smem);
   dim3 grid(cdiv(a.Wq, 32), cdiv(a.Hq, t.TH), a.B * t.ncb);
   MSAU_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "conv: grid too large");
+  // algorithmic work: every operand tensor crosses HBM once; 2 flops per multiply-add
+  const double npix_in = (double)a.B * a.Hin * a.Win, npix_out = (double)a.B * a.Hq * a.Wq;
+  double bytes = npix_in * ((a.src1_nchw ? a.c1_logical : a.c1) + a.c2 + (a.mask1 ? a.c1 : 0)) * 4.0;
+  bytes += npix_out * a.coutp * 4.0 * (1 + (a.res ? 1 : 0) + (a.omask ? 1 : 0) + (a.add ? 1 : 0) + (a.addmask ? 1 : 0) + (a.accumulate ? 1 : 0));
+  const double flops = 2.0 * npix_out * a.kh * a.kw * (a.c1 + a.c2) * a.coutp;
+  ProfScope ps(co16 ? "conv_kernel<16,4>" : "conv_kernel<8,4>", flops, bytes, st);
   if (co16) {
     static bool attr = false;
     if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
@@ -377,6 +384,10 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
   const int ny = (int)((rows + t.rows_per_block - 1) / t.rows_per_block);
   dim3 grid(outblocks, ny);
   const size_t smem = ((size_t)a.kw * t.MB * t.NB + t.NB) * 4;
+  const double npq = (double)a.B * a.Hq * a.Wq;
+  const double wbytes = ((double)a.B * a.Ha * a.Wa * (a.a_nchw ? a.ca_logical : a.ca) + (double)a.B * a.Hb * a.Wb * a.cb * (a.maskB ? 2 : 1)) * 4.0;
+  const double wflops = 2.0 * npq * a.kh * a.kw * a.ca * a.cb;
+  ProfScope ps(btap ? "wgrad_kernel<3,btap>" : (a.kw == 1 ? "wgrad_kernel<1>" : (a.kw == 3 ? "wgrad_kernel<3>" : "wgrad_kernel<4>")), wflops, wbytes, st);
 #define MSAU_WG(KWV, BT)                                                                                    \
   {                                                                                                         \
     static bool attr = false;                                                                               \

@@ -8,6 +8,7 @@
 // Parameters whose grad is None in the reference (the dead last-block attention) have an all-zero
 // gradient here; with zero-initialised moments Adam's update for them is exactly 0, as in torch's skip.
 #include "optim.cuh"
+#include "prof.cuh"
 
 namespace msau {
 
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
 }
 
 int launch_pack(const float* params, float* packed, const PackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st) {
+  ProfScope ps("pack_kernel", 0, (double)total_blocks * 256 * 8.0, st);
   pack_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(params, packed, d_descs, n_desc);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
 int launch_clip_adam(float* params, float* grads, float* m, float* v, long n, int step, float lr, float b1, float b2, float eps,
                      float max_norm, float* partial, float* total_norm_out, cudaStream_t st) {
   MSAU_CHECK_ARG(step >= 1, "adam: step must be >= 1");
+  ProfScope ps("clip_adam_kernels", 0, (double)n * 4.0 * 8, st);
   sumsq_kernel<<<kNormBlocks, 256, 0, st>>>(grads, n, partial);
   const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
   adam_kernel<<<kNormBlocks, 256, 0, st>>>(params, grads, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps, max_norm,

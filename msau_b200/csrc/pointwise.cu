@@ -10,6 +10,7 @@
 //   head : Softmax(dim=1) model/model.py:426-427,437 ; argmax train_chargrid_funsd_msau.py:135, kv_model.py:162
 #include "common.cuh"
 #include "pointwise.cuh"
+#include "prof.cuh"
 
 namespace msau {
 
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(256) lrn_bwd_kernel(const float* __restrict__ 
 template <bool BWD>
 static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, cudaStream_t st) {
   const int grid = cdiv(npix, 256);
+  ProfScope ps(BWD ? "lrn_bwd_kernel" : "lrn_fwd_kernel", (double)npix * C * (BWD ? 12 : 6), (double)npix * C * 4.0 * (BWD ? 3 : 2), st);
 #define MSAU_LRN(CV)                                                             \
   case CV:                                                                       \
     if (BWD) lrn_bwd_kernel<CV><<<grid, 256, 0, st>>>(z, gy, out, npix);         \
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
 int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long total = (long)B * Ho * Wo * (C / 4);
+  ProfScope ps("pool_fwd_kernel", 0, ((double)B * H * W + (double)B * Ho * Wo) * C * 4.0, st);
   pool_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, y, B, H, W, Ho, Wo, C / 4);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -209,6 +212,7 @@ int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaSt
 int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long total = (long)B * Ho * Wo * (C / 4);
+  ProfScope ps("pool_bwd_kernel", 0, ((double)B * H * W * (accumulate ? 3 : 2) + (double)B * Ho * Wo) * C * 4.0, st);
   pool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -224,6 +228,7 @@ __global__ void __launch_bounds__(256) add_kernel(float4* __restrict__ dst, cons
 }
 
 int launch_add(float* dst, const float* src, long n, int accumulate, cudaStream_t st) {
+  ProfScope ps("add_kernel", 0, (double)n * 4.0 * (accumulate ? 3 : 2), st);
   add_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n / 4, accumulate);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -252,6 +257,7 @@ int launch_colsum(const float* g, long npix, int C, int c_lim, float* out, cudaS
   int grid = cdiv(npix, (long)ppb * 16);
   if (grid > 4 * sm_count()) grid = 4 * sm_count();
   if (grid < 1) grid = 1;
+  ProfScope ps("colsum_kernel", 0, (double)npix * C * 4.0, st);
   colsum_kernel<<<grid, 256, 0, st>>>(g, npix, C, c_lim, out);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -296,6 +302,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ lg,
 
 int launch_head(const float* lg, int P, int n_class, int B, long npix_per_page, float* logits_nchw, float* probs_nchw, uint8_t* argmax, cudaStream_t st) {
   MSAU_CHECK_ARG(P == 8 && n_class <= 8, "head: logits pitch must be 8 and n_class <= 8 (got %d, %d)", P, n_class);
+  ProfScope ps("head_kernel", 0, (double)npix_per_page * B * (32.0 + 4.0 * n_class * ((logits_nchw ? 1 : 0) + (probs_nchw ? 1 : 0)) + (argmax ? 1 : 0)), st);
   head_kernel<<<cdiv(npix_per_page * B, 256), 256, 0, st>>>(lg, P, n_class, npix_per_page, B, logits_nchw, probs_nchw, argmax);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -384,6 +391,7 @@ int launch_loss(const float* lg, const float* la, int n_class, const void* label
                 float gscale, float* dlg, float* dla, int* counts, float* partial, float* loss_out, cudaStream_t st) {
   MSAU_CHECK_ARG(n_class <= 8, "loss: n_class <= 8 supported");
   MSAU_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * B, st));
+  ProfScope ps("loss_kernels", 0, (double)npix_per_page * B * (4 * 32.0 + 2.0 * (label_is_i64 ? 8 : 1)), st);
   const int nblk = loss_partial_count(B, npix_per_page);
   dim3 cg(min(cdiv(npix_per_page, 256), 64), B);
   if (label_is_i64) {

@@ -23,9 +23,38 @@ def _dev(device=None) -> torch.device:
     return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
 
 
+_STAGING: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
 def _h2d(a: np.ndarray, device) -> torch.Tensor:
     t = torch.from_numpy(np.ascontiguousarray(a))
     return t.pin_memory().to(device, non_blocking=True)
+
+
+def _h2d_packed(arrays: List[np.ndarray], device) -> Tuple[List[torch.Tensor], int]:
+    """One pinned staging buffer + ONE async copy for a list of small arrays; returns device views."""
+    offs, total = [], 0
+    for a in arrays:
+        offs.append(total)
+        total += (a.nbytes + 15) // 16 * 16
+    total = max(total, 16)
+    cap = 1 << max(12, (total - 1).bit_length())
+    key = (cap, torch.device(device).index or 0)
+    host = _STAGING.get(key)
+    if host is None:
+        host = torch.empty(cap, dtype=torch.uint8).pin_memory()
+        _STAGING[key] = host
+    else:
+        torch.cuda.current_stream(device).synchronize()   # the previous copy out of this buffer must be done
+    hv = host.numpy()
+    for a, o in zip(arrays, offs):
+        hv[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+    dev_buf = torch.empty(total, dtype=torch.uint8, device=device)
+    dev_buf.copy_(host[:total], non_blocking=True)
+    out = []
+    for a, o in zip(arrays, offs):
+        out.append(dev_buf[o:o + a.nbytes].view(getattr(torch, str(a.dtype))).reshape(a.shape))
+    return out, total
 
 
 class BoxBatch:
@@ -34,30 +63,28 @@ class BoxBatch:
     def __init__(self, pages: Sequence[Dict], device=None, with_chars: bool = True, with_labels: bool = False):
         dev = _dev(device)
         self.n_pages = len(pages)
-        xs, ys, ws, hs, ptr, nch, cptr, cfeat, labels = [], [], [], [], [0], [], [0], [], []
-        for pg in pages:
-            n = len(pg["x"])
-            xs.append(np.asarray(pg["x"], np.float64)); ys.append(np.asarray(pg["y"], np.float64))
-            ws.append(np.asarray(pg["w"], np.float64)); hs.append(np.asarray(pg["h"], np.float64))
-            ptr.append(ptr[-1] + n)
-            if with_chars:
-                for ch in pg["chars"]:
-                    nch.append(len(ch)); cptr.append(cptr[-1] + len(ch)); cfeat.append(np.asarray(ch, np.int32))
-            if with_labels:
-                labels.append(np.asarray(pg["label"], np.int32))
-        self.n_boxes = ptr[-1]
-        self.h_bytes = 0
-
-        def up(a):
-            self.h_bytes += a.nbytes
-            return _h2d(a, dev)
-
-        self.x, self.y, self.w, self.h = (up(np.concatenate(v)) for v in (xs, ys, ws, hs))
-        self.page_ptr = up(np.asarray(ptr, np.int32))
-        self.n_chars = up(np.asarray(nch, np.int32)) if with_chars else None
-        self.char_ptr = up(np.asarray(cptr, np.int32)) if with_chars else None
-        self.char_feat = up(np.concatenate(cfeat).astype(np.int32) if cfeat else np.zeros(0, np.int32)) if with_chars else None
-        self.labels = up(np.concatenate(labels)) if with_labels else None
+        ptr = np.zeros(len(pages) + 1, np.int32)
+        ptr[1:] = np.cumsum([len(pg["x"]) for pg in pages])
+        self.n_boxes = int(ptr[-1])
+        arrays = [np.concatenate([np.asarray(pg[k], np.float64) for pg in pages]) for k in "xywh"] + [ptr]
+        if with_chars:
+            lens = np.fromiter((len(ch) for pg in pages for ch in pg["chars"]), np.int32, self.n_boxes)
+            cptr = np.zeros(self.n_boxes + 1, np.int32)
+            cptr[1:] = np.cumsum(lens)
+            allc = [np.asarray(ch, np.int32) for pg in pages for ch in pg["chars"] if len(ch)]
+            cfeat = np.concatenate(allc) if allc else np.zeros(1, np.int32)
+            arrays += [lens, cptr, cfeat]
+        if with_labels:
+            arrays.append(np.concatenate([np.asarray(pg["label"], np.int32) for pg in pages]))
+        dv, self.h_bytes = _h2d_packed(arrays, dev)
+        self.x, self.y, self.w, self.h, self.page_ptr = dv[:5]
+        k = 5
+        self.n_chars = self.char_ptr = self.char_feat = self.labels = None
+        if with_chars:
+            self.n_chars, self.char_ptr, self.char_feat = dv[5:8]
+            k = 8
+        if with_labels:
+            self.labels = dv[k]
         self.device = dev
 
     def geometry(self) -> torch.Tensor:
