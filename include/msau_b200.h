@@ -156,6 +156,10 @@ int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int c
 int msau_ccl4(const uint8_t* binary, int n_maps, int height, int width, int32_t* labels, int32_t* n_labels,
               int32_t* bboxes, int max_labels, int32_t* scratch, void* stream);
 
+/* Engine options.  "tensor_core_conv" (default 1): run the convolutions that fit on the tcgen05 implicit-GEMM
+ * kernel; 0 = every convolution on the fp32 CUDA-core kernel (used by the parity tests to cross-check). */
+int msau_set_option(const char* name, int value);
+
 /* Per-kernel timing for bench.py's roofline report: when enabled every launch is bracketed by CUDA events on
  * its stream; msau_profile_report synchronises the device and writes a JSON object
  * {"<kernel>": {"launches", "ms", "flops", "bytes"}} (algorithmic work) into buf, then clears. */

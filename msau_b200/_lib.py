@@ -19,6 +19,7 @@ SYMBOLS = [
     "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
     "msau_rect_filter", "msau_class_equals", "msau_ccl4",
     "msau_debug_layout", "msau_debug_tensor", "msau_profile_enable", "msau_profile_report",
+    "msau_set_option",
 ]
 
 
@@ -69,6 +70,7 @@ def lib() -> C.CDLL:
     L.msau_ccl4.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     L.msau_debug_layout.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.msau_debug_tensor.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.msau_set_option.argtypes = [C.c_char_p, i32]
     L.msau_profile_enable.argtypes = [i32]
     L.msau_profile_report.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
@@ -106,3 +108,7 @@ def profile_report() -> dict:
     buf = C.create_string_buffer(1 << 16)
     check(lib().msau_profile_report(buf, len(buf)))
     return json.loads(buf.value.decode())
+
+
+def set_option(name: str, value: int) -> None:
+    check(lib().msau_set_option(name.encode(), int(value)))

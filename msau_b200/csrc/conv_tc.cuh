@@ -1,0 +1,14 @@
+#pragma once
+#include "common.cuh"
+namespace msau {
+struct TcPackDesc {
+  long src_off;   // floats, into the fp32 packed buffer: [taps][cin][coutp]
+  long dst_off;   // bf16 elements, into the tensor-core weight buffer
+  int taps, cin, coutp, N;
+  long blk0;
+};
+bool conv_tc_supported(const ConvArgs& a);
+int tc_weight_floats_equiv(int taps, int cin, int coutp);
+int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st);
+int launch_pack_tc(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st);
+}  // namespace msau

@@ -17,6 +17,7 @@
 #include "../../include/msau_b200.h"
 #include "attention.cuh"
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "optim.cuh"
 #include "pointwise.cuh"
 
@@ -57,6 +58,7 @@ struct ConvLayer {
   int cout = 0, cin1 = 0, cin2 = 0, k = 1, dil = 1;   // logical dims; cin2 = second concat source
   int coutp = 0, c1p = 0, c2p = 0;                      // padded dims
   long pk_w = -1, pk_b = -1, pk_d1 = -1, pk_d2 = -1;    // packed: fwd weights, bias, dgrad wrt src1 / src2
+  long tc_w = -1, tc_d1 = -1, tc_d2 = -1;               // bf16 tensor-core weight images (bf16 element offsets)
   int pad() const { return ((k - 1) * dil) / 2; }       // SAME "before" padding, model/layers/utils.py:13-18
 };
 
@@ -116,6 +118,11 @@ struct MsauPlan {
   PackDesc* d_descs = nullptr;
   long pack_blocks = 0;
   long misc_floats = 0;
+  std::vector<TcPackDesc> tc_descs;
+  TcPackDesc* d_tc_descs = nullptr;
+  long tc_blocks = 0;
+  long tc_elems = 0;      // bf16 elements
+  uint16_t* pktc = nullptr;
   // runtime state (set per call)
   float* pk = nullptr;
   float* act = nullptr;
@@ -173,6 +180,19 @@ static void add_desc(MsauPlan* p, long dst, int TH, int TW, int I, int O, int i_
   p->descs.push_back(d);
 }
 
+static long add_tc(MsauPlan* p, long src_off, int taps, int cin, int coutp) {
+  if (cin % 8 != 0 || coutp > 128) return -1;
+  TcPackDesc d;
+  d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = taps; d.cin = cin; d.coutp = coutp;
+  d.N = coutp < 16 ? 16 : round_up(coutp, 16);
+  const long elems = (long)(cin / 8) * (taps + (taps + 1) / 2) * d.N * 16;
+  d.blk0 = p->tc_blocks;
+  p->tc_blocks += cdiv(elems, 256);
+  p->tc_elems += (elems + 127) / 128 * 128;
+  p->tc_descs.push_back(d);
+  return d.dst_off;
+}
+
 // torch Conv2d weight [cout][cin1+cin2][k][k]:
 //   fwd   [tap][c1p + c2p][coutp]                     rows = input channels of [src1 | src2]
 //   dgrad [flipped tap][coutp][c_s p] per source s     rows = output channels, cols = that source's channels
@@ -200,6 +220,9 @@ static void setup_conv(MsauPlan* p, ConvLayer& L, int cout, int cin1, int cin2, 
     L.pk_d2 = p->alloc_packed(kk * L.coutp * L.c2p);
     add_desc(p, L.pk_d2, k, k, L.coutp, L.c2p, 0, 0, cout, cin2, L.w_off, 0, cin1, cin * kk, kk, k - 1, -1, k - 1, -1, k);
   }
+  L.tc_w = add_tc(p, L.pk_w, k * k, cinp, L.coutp);
+  if (L.pk_d1 >= 0) L.tc_d1 = add_tc(p, L.pk_d1, k * k, L.coutp, L.c1p);
+  if (L.pk_d2 >= 0) L.tc_d2 = add_tc(p, L.pk_d2, k * k, L.coutp, L.c2p);
 }
 
 // torch ConvTranspose2d(cin, cout, 3, stride 2, padding 1) weight [cin][cout][3][3]; out[2 iy - 1 + ky] += x[iy] W[ky]
@@ -239,6 +262,8 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
   L.pk_d1 = p->alloc_packed((long)L.coutp * C);
   add_desc(p, L.pk_d1, 1, 1, L.coutp, C, 0, 0, d, C, L.w_off, 0, 0, C, 1, 0, 1, 0, 1, 1);
   add_desc(p, L.pk_d1, 1, 1, L.coutp, C, d, 0, d, C, at.g_w_off, 0, 0, C, 1, 0, 1, 0, 1, 1);
+  L.tc_w = add_tc(p, L.pk_w, 1, C, L.coutp);
+  L.tc_d1 = add_tc(p, L.pk_d1, 1, L.coutp, C);
 }
 
 // ------------------------------------------------------------------ launch helpers
@@ -253,9 +278,11 @@ struct ConvOpt {
 };
 
 // same-size stride-1 convolution (forward of a layer, or a dgrad with flipped packed weights)
+static bool g_use_tc = true;
+
 static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, int c1_logical, const float* src2, int c2, int p2,
                      const float* w, const float* bias, float* out, int po, int coutp, int H, int W, int k, int dil, int pad,
-                     const ConvOpt& o) {
+                     const ConvOpt& o, long tc_off = -1) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.src1 = src1; a.c1 = c1; a.p1 = p1; a.src1_nchw = nchw; a.c1_logical = c1_logical;
@@ -269,12 +296,13 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.omask = o.omask; a.pom = o.pom; a.add = o.add; a.pa = o.pa; a.addmask = o.addmask; a.pam = o.pam;
   a.accumulate = o.accumulate;
   count_launch(1);
+  if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
   return launch_conv(a, p->st);
 }
 
 static int layer_fwd(MsauPlan* p, const ConvLayer& L, const Tensor& s1, const Tensor* s2, const Tensor& out, const ConvOpt& o) {
   return conv_same(p, p->A(s1), L.c1p, s1.C, 0, L.c1p, s2 ? p->A(*s2) : nullptr, s2 ? L.c2p : 0, s2 ? s2->C : 0, p->pk + L.pk_w,
-                   p->pk + L.pk_b, p->A(out), out.C, L.coutp, out.H, out.W, L.k, L.dil, L.pad(), o);
+                   p->pk + L.pk_b, p->A(out), out.C, L.coutp, out.H, out.W, L.k, L.dil, L.pad(), o, L.tc_w);
 }
 
 // data gradient of a conv layer wrt source `which` (1 or 2): dY (channels coutp) -> dX
@@ -287,7 +315,7 @@ static int layer_dgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   o.accumulate = p->touch(dst);
   const int padd = (L.k - 1) * L.dil - L.pad();
   return conv_same(p, dy, L.coutp, pdy, 0, L.coutp, nullptr, 0, 0, p->pk + pkd, nullptr, p->G(dst), dst.C, cs, dst.H, dst.W, L.k,
-                   L.dil, padd, o);
+                   L.dil, padd, o, which == 1 ? L.tc_d1 : L.tc_d2);
 }
 
 // weight (+bias) gradient of a conv layer wrt source `which`
@@ -418,7 +446,7 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
 }
 
 static size_t ws_bytes(const MsauPlan* p, int training) {
-  const long floats = p->packed_floats + p->act_floats * (training ? 2 : 1) + p->misc_floats;
+  const long floats = p->packed_floats + (p->tc_elems + 1) / 2 + 64 + p->act_floats * (training ? 2 : 1) + p->misc_floats;
   return (size_t)floats * sizeof(float);
 }
 
@@ -430,7 +458,8 @@ static int bind(MsauPlan* p, void* ws, size_t bytes, int training, void* stream)
   }
   MSAU_CHECK_ARG(((uintptr_t)ws & 255) == 0, "workspace must be 256-byte aligned");
   p->pk = reinterpret_cast<float*>(ws);
-  p->act = p->pk + p->packed_floats;
+  p->pktc = reinterpret_cast<uint16_t*>(p->pk + p->packed_floats);
+  p->act = p->pk + p->packed_floats + ((p->tc_elems + 1) / 2 + 63) / 64 * 64;
   p->grad = training ? p->act + p->act_floats : nullptr;
   p->misc = p->act + p->act_floats * (training ? 2 : 1);
   p->st = reinterpret_cast<cudaStream_t>(stream);
@@ -553,9 +582,15 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   // descriptor table: the only device memory the plan owns
   cudaError_t e = cudaMalloc(&p->d_descs, sizeof(PackDesc) * p->descs.size());
   if (e == cudaSuccess) e = cudaMemcpy(p->d_descs, p->descs.data(), sizeof(PackDesc) * p->descs.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !p->tc_descs.empty()) {
+    e = cudaMalloc(&p->d_tc_descs, sizeof(TcPackDesc) * p->tc_descs.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_tc_descs, p->tc_descs.data(), sizeof(TcPackDesc) * p->tc_descs.size(), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     set_error("plan_create: descriptor upload failed: %s", cudaGetErrorString(e));
     if (p->d_descs) cudaFree(p->d_descs);
+    if (p->d_tc_descs) cudaFree(p->d_tc_descs);
     delete p;
     return MSAU_ERR_CUDA;
   }
@@ -566,6 +601,7 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
 extern "C" void msau_plan_destroy(MsauPlan* p) {
   if (!p) return;
   if (p->d_descs) cudaFree(p->d_descs);
+  if (p->d_tc_descs) cudaFree(p->d_tc_descs);
   delete p;
 }
 
@@ -594,6 +630,10 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
   MSAU_CUDA_TRY(cudaMemsetAsync(p->pk, 0, sizeof(float) * p->packed_floats, p->st));
   count_launch(1);
   MSAU_TRY(launch_pack(params, p->pk, p->d_descs, (int)p->descs.size(), p->pack_blocks, p->st));
+  if (g_use_tc) {
+    count_launch(1);
+    MSAU_TRY(launch_pack_tc(p->pk, p->pktc, p->d_tc_descs, (int)p->tc_descs.size(), p->tc_blocks, p->st));
+  }
 
   for (int b = 0; b < NB; ++b) {
     Block& blk = p->blocks[b];
@@ -605,7 +645,7 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
         MSAU_TRY(conv_same(p, x, c1, c1, x_layout == 0, cfg.channels, nullptr, 0, 0, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b,
-                           p->A(L.z1), L.z1.C, L.conv1.coutp, p->H, p->W, 3, 1, 1, o));
+                           p->A(L.z1), L.z1.C, L.conv1.coutp, p->H, p->W, 3, 1, 1, o, L.conv1.tc_w));
       } else {
         const Tensor& src = l == 0 ? prev->logits : blk.down[l - 1].pooled;
         MSAU_TRY(layer_fwd(p, L.conv1, src, nullptr, L.z1, o));
@@ -769,7 +809,7 @@ extern "C" int msau_clip_adam_step(float* params, float* grads, float* exp_avg, 
 //      with the oracle's traced forward); not part of the reference-facing surface ----
 extern "C" int msau_debug_layout(const MsauPlan* p, long long* packed_floats, long long* act_floats, int* n_tensors) {
   MSAU_CHECK_ARG(p, "debug_layout: null plan");
-  if (packed_floats) *packed_floats = p->packed_floats;
+  if (packed_floats) *packed_floats = p->packed_floats + ((p->tc_elems + 1) / 2 + 63) / 64 * 64;
   if (act_floats) *act_floats = p->act_floats;
   if (n_tensors) *n_tensors = p->n_tensors;
   return MSAU_OK;
@@ -783,4 +823,11 @@ extern "C" int msau_debug_tensor(const MsauPlan* p, int id, long long* off, int*
   if (Hh) *Hh = t.H;
   if (Ww) *Ww = t.W;
   return MSAU_OK;
+}
+
+extern "C" int msau_set_option(const char* name, int value) {
+  MSAU_CHECK_ARG(name, "set_option: null name");
+  if (!strcmp(name, "tensor_core_conv")) { g_use_tc = value != 0; return MSAU_OK; }
+  set_error("set_option: unknown option '%s'", name);
+  return MSAU_ERR_ARG;
 }

@@ -17,6 +17,15 @@ from oracle.synth import synth_input
 
 pytestmark = pytest.mark.gpu
 LOGIT_ATOL = 5e-4
+
+
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "fp32core"])
+def tc(request):
+    """Run every model test on both convolution paths: the tcgen05 implicit-GEMM kernels (bf16 hi/lo split, the
+    default) and the fp32 CUDA-core kernels."""
+    _lib.set_option("tensor_core_conv", request.param)
+    yield request.param
+    _lib.set_option("tensor_core_conv", 1)
 FIXTURES = ["model_s3r2_c12", "model_s4r2_c96", "model_s2r3_c8"]
 
 
@@ -54,7 +63,7 @@ def plan_tensors(m, pl):
 
 
 @pytest.mark.parametrize("name", FIXTURES)
-def test_forward_matches_golden(golden_dir, name):
+def test_forward_matches_golden(golden_dir, name, tc):
     z, meta, cfg = load(golden_dir, name)
     sd = om.init_state_dict(cfg, meta["seed"])
     x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
@@ -78,7 +87,7 @@ def test_forward_matches_golden(golden_dir, name):
 
 
 @pytest.mark.parametrize("name", FIXTURES)
-def test_every_activation_and_gradient_matches_oracle(golden_dir, name):
+def test_every_activation_and_gradient_matches_oracle(golden_dir, name, tc):
     """Walks the engine's workspace tensor by tensor against the oracle's traced forward/backward: the first
     mismatch names the kernel at fault."""
     z, meta, cfg = load(golden_dir, name)
@@ -109,16 +118,24 @@ def test_every_activation_and_gradient_matches_oracle(golden_dir, name):
             # output (already multiplied by the ReLU mask), the oracle w.r.t. the ReLU output
             want = t.grad * (t.detach() > 0) if nm.rsplit(".", 1)[-1].startswith("a") and nm.rsplit(".", 1)[-1] != "att" else t.grad
             gs = max(want.abs().max().item(), 1e-12)
-            gerr = (g[:, :c] - want).abs().max().item()
-            if not gerr <= 2e-3 * gs:
-                bad.append(("grad", nm, gerr / gs))
+            diff = (g[:, :c] - want).abs()
+            if tc:
+                # bf16 hi/lo-split convs perturb pre-activations by ~1e-5: a handful of ReLU masks flip w.r.t. the
+                # oracle; each flip changes one pixel's gradient completely and diffuses through the convs upstream.
+                # Demand agreement in L2 (<= 3 %) and that >= 99.5 % of the elements are within 2 % of the max.
+                frac = (diff <= 2e-2 * gs).float().mean().item()
+                l2 = (diff.double().norm() / max(want.double().norm().item(), 1e-30)).item()
+                if not (frac >= 0.995 and l2 <= 0.03):
+                    bad.append(("grad", nm, frac, l2))
+            elif not diff.max().item() <= 2e-3 * gs:
+                bad.append(("grad", nm, diff.max().item() / gs))
     assert not bad, bad[:12]
     assert abs(float(loss) - float(ref_loss)) <= 1e-4 * max(1.0, abs(float(ref_loss)))
     assert abs(float(loss) - z["page_losses"].mean()) <= 1e-4 * z["page_losses"].mean()
 
 
 @pytest.mark.parametrize("name", FIXTURES)
-def test_param_grads_and_train_step_match_golden(golden_dir, name):
+def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
     z, meta, cfg = load(golden_dir, name)
     sd = om.init_state_dict(cfg, meta["seed"])
     x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
@@ -134,16 +151,16 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name):
     none = np.array([named[k].grad is None for k in keys])
     assert (none == z["grad_is_none"]).all()
     norms = np.array([0.0 if named[k].grad is None else float(named[k].grad.double().norm()) for k in keys])
-    np.testing.assert_allclose(norms, z["grad_norms"], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(norms, z["grad_norms"], rtol=3e-2 if tc else 2e-3, atol=1e-6)
     for k in z.files:
         if k.startswith("grad::"):
             want = z[k]
-            np.testing.assert_allclose(named[k[6:]].grad.cpu().numpy(), want, rtol=0, atol=2e-3 * np.abs(want).max())
+            np.testing.assert_allclose(named[k[6:]].grad.cpu().numpy(), want, rtol=0, atol=(3e-2 if tc else 2e-3) * np.abs(want).max())
     total = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
-    assert abs(float(total) - float(z["total_norm"])) <= 2e-3 * float(z["total_norm"])
+    assert abs(float(total) - float(z["total_norm"])) <= (2e-2 if tc else 2e-3) * float(z["total_norm"])
     opt.step()
     sums = np.array([float(named[k].detach().double().sum()) for k in keys])
-    np.testing.assert_allclose(sums, z["param_sums_after_step"], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(sums, z["param_sums_after_step"], rtol=1e-4, atol=1e-2 if tc else 2e-4)
     for k in z.files:
         if k.startswith("param_after::"):
             # Adam's first step moves every weight by ~lr*sign(g): elements with |g| ~ 0 may flip, so bound by lr
@@ -157,7 +174,7 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name):
     live = torch.tensor(m2._live_mask())
     for (k, p2), p1 in zip(m2.named_parameters(), m.parameters()):
         assert (p2.detach() - p1.detach()).abs().max().item() <= 2e-6, k
-    assert abs(float(m2._adam[4]) - float(z["total_norm"])) <= 2e-3 * float(z["total_norm"])
+    assert abs(float(m2._adam[4]) - float(z["total_norm"])) <= (2e-2 if tc else 2e-3) * float(z["total_norm"])
     # dead attention params untouched
     dead = [k for k, lv in zip(keys, m2._live_mask()) if not lv]
     for k in dead:
