@@ -267,6 +267,8 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 }
 
 // ------------------------------------------------------------------ launch helpers
+static bool g_use_tc = true;
+
 struct ConvOpt {
   bool relu1 = false, relu = false, relu2 = false;
   int accumulate = 0;
@@ -278,8 +280,6 @@ struct ConvOpt {
 };
 
 // same-size stride-1 convolution (forward of a layer, or a dgrad with flipped packed weights)
-static bool g_use_tc = true;
-
 static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, int c1_logical, const float* src2, int c2, int p2,
                      const float* w, const float* bias, float* out, int po, int coutp, int H, int W, int k, int dil, int pad,
                      const ConvOpt& o, long tc_off = -1) {
@@ -338,6 +338,7 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
   count_launch(1);
+  if (g_use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->st);
   return launch_wgrad(a, p->st);
 }
 

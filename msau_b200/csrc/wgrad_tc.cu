@@ -1,0 +1,339 @@
+// Weight gradient on the tensor cores (tcgen05.mma, MN-major operands, accumulators resident in TMEM).
+//
+//     dW[ky][kx][ci][co] = sum_pixels X[pixel + offset(ky,kx)][ci] * dY[pixel][co]
+// The reduction (K) dimension is the pixel index, so both operands are "MN-major": 8 channels contiguous
+// (16 B) and 8 consecutive pixels stacked at 16-B pitch = exactly the planar bf16 tile that conv_tc.cu
+// builds ([8-channel plane][row][col][8 ch]).  One instruction consumes 16 consecutive pixels of one image row.
+//   M = 128 = 16 row-groups of 8 input channels (one channel plane); group i reads the tile shifted by i*dil
+//       pixels, so groups 0..kw-1 ARE the kx taps of one kernel row (groups kw..15 are ignored padding of
+//       the M=128 shape: the tensor pipe is far from being the bound here, HBM is)
+//   N = cout (padded to 16)       K = 16 pixels
+//   one TMEM accumulator per kernel row ky; a CTA keeps its kh accumulators resident over ALL the pixel tiles
+//   it visits and reduces them into dW with fp32 atomics once, at the end.
+// fp32 accuracy from bf16: X = Xh + Xl, dY = Yh + Yl, three instructions per chunk: Xh*Yh + Xl*Yh + Xh*Yl.
+// grid = (pixel-tile ranges, input-channel planes).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "prof.cuh"
+
+namespace msau {
+
+// ---- PTX wrappers (same protocol as conv_tc.cu) ----
+__device__ __forceinline__ uint32_t wsmem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void wmbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wsmem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void wmbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = wsmem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void wtc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(wsmem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wtc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// no-swizzle descriptor; for MN-major operands LBO = stride between 8-row K groups, SBO = stride between MN groups
+__device__ __forceinline__ uint64_t wmake_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void wtmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void wsplit8(const float* x, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct WgTile {
+  int TR, TC, HHx, HWx, N, ny_planes;       // tile rows/cols, X halo extent, MMA N, dY channel planes
+  int tiles_x, tiles_y, n_tiles, tiles_per_cta;
+  uint32_t x_plane_bytes, y_plane_bytes, stage_bytes, tmem_cols;
+};
+
+static constexpr int WG_THREADS = 256;
+
+__global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a, const WgTile t) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_free[2];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int plane = blockIdx.y;               // input-channel plane (8 channels) of this CTA
+  const int tile0 = blockIdx.x * t.tiles_per_cta;
+  const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
+  const bool do_bias = a.dbias != nullptr && plane == 0;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    wmbar_init(&bar_free[0], 1);
+    wmbar_init(&bar_free[1], 1);
+    wmbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 128) sbias[tid] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  if (tile0 >= tile1) {       // nothing to do (grid rounding): still free TMEM
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+    return;
+  }
+
+  // bf16 x bf16 -> fp32, A and B both MN-major, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(t.N >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  const int x_px = t.HHx * t.HWx;
+  const int y_px = t.TR * t.TC;
+  const int ca0 = plane << 3;
+  float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+  int it = 0;
+  for (int tile = tile0; tile < tile1; ++tile, ++it) {
+    const int s = it & 1;
+    uint8_t* st = smem + (size_t)s * t.stage_bytes;
+    if (it >= 2) wmbar_wait(&bar_free[s], ((it >> 1) - 1) & 1);
+    const int tx = tile % t.tiles_x;
+    const int rest = tile / t.tiles_x;
+    const int ty = rest % t.tiles_y;
+    const int b = rest / t.tiles_y;
+    const int qy0 = ty * t.TR, qx0 = tx * t.TC;
+    // ---- X halo tile of this plane: [hi][lo], (HHx x HWx) pixels of 16 B ----
+    {
+      const int in_y0 = qy0 - a.pada_t, in_x0 = qx0 - a.pada_l;
+      uint8_t* xh = st;
+      uint8_t* xl = st + t.x_plane_bytes;
+      for (int e = tid; e < x_px; e += WG_THREADS) {
+        const int iy = e / t.HWx, ix = e - iy * t.HWx;
+        const int gy = in_y0 + iy, gx = in_x0 + ix;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gy >= 0 && gy < a.Ha && gx >= 0 && gx < a.Wa) {
+          if (a.a_nchw) {
+            const long pl = (long)a.Ha * a.Wa;
+            const float* sp = a.A + ((long)b * a.ca_logical + ca0) * pl + (long)gy * a.Wa + gx;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (ca0 + k < a.ca_logical) v[k] = __ldg(sp + k * pl);
+          } else {
+            const float* sp = a.A + (((long)b * a.Ha + gy) * a.Wa + gx) * a.pa + ca0;
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(sp));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+          }
+          if (a.reluA) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+        }
+        uint4 hi, lo;
+        wsplit8(v, hi, lo);
+        *reinterpret_cast<uint4*>(xh + (size_t)e * 16) = hi;
+        *reinterpret_cast<uint4*>(xl + (size_t)e * 16) = lo;
+      }
+    }
+    // ---- dY tile: [hi: planes][lo: planes], each plane TR x TC pixels of 16 B ----
+    {
+      uint8_t* yh = st + 2 * t.x_plane_bytes;
+      uint8_t* yl = yh + (size_t)t.ny_planes * t.y_plane_bytes;
+      const int total = y_px * t.ny_planes;
+      for (int e = tid; e < total; e += WG_THREADS) {
+        const int pl = e % t.ny_planes;          // constant per thread (256 % ny_planes == 0)
+        const int px = e / t.ny_planes;
+        const int r = px / t.TC, c = px - r * t.TC;
+        const int gy = qy0 + r, gx = qx0 + c;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (gy < a.Hb && gx < a.Wb) {
+          const long pix = ((long)b * a.Hb + gy) * a.Wb + gx;
+          const float* sp = a.Bm + pix * a.pb + (pl << 3);
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(sp));
+          const float4 q1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
+          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+          if (a.maskB) {
+            const float* mp = a.maskB + pix * a.pmb + (pl << 3);
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp));
+            const float4 m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
+            const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = m[k] > 0.f ? v[k] : 0.f;
+          }
+          if (do_bias) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bacc[k] += v[k];
+          }
+        }
+        uint4 hi, lo;
+        wsplit8(v, hi, lo);
+        *reinterpret_cast<uint4*>(yh + (size_t)pl * t.y_plane_bytes + (size_t)px * 16) = hi;
+        *reinterpret_cast<uint4*>(yl + (size_t)pl * t.y_plane_bytes + (size_t)px * 16) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t xh = wsmem_u32(st), xl = xh + t.x_plane_bytes;
+      const uint32_t yh = xh + 2 * t.x_plane_bytes, yl = yh + (uint32_t)t.ny_planes * t.y_plane_bytes;
+      const uint32_t sbo_a = (uint32_t)a.dila * 16;
+      const int chunks = t.TC >> 4;
+      for (int ky = 0; ky < a.kh; ++ky) {
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ky * t.N);
+        uint32_t first = (it == 0) ? 0u : 1u;
+        for (int r = 0; r < t.TR; ++r) {
+          const uint32_t xoff = (uint32_t)((r + ky * a.dila) * t.HWx) * 16;
+          const uint32_t yoff = (uint32_t)(r * t.TC) * 16;
+          for (int cc = 0; cc < chunks; ++cc) {
+            const uint64_t ah = wmake_desc(xh + xoff + cc * 256, 128, sbo_a);
+            const uint64_t al = wmake_desc(xl + xoff + cc * 256, 128, sbo_a);
+            const uint64_t bh = wmake_desc(yh + yoff + cc * 256, 128, t.y_plane_bytes);
+            const uint64_t bl = wmake_desc(yl + yoff + cc * 256, 128, t.y_plane_bytes);
+            wtc_mma(d_tmem, ah, bh, idesc, first);
+            wtc_mma(d_tmem, al, bh, idesc, 1u);
+            wtc_mma(d_tmem, ah, bl, idesc, 1u);
+            first = 1u;
+          }
+        }
+      }
+      wtc_commit(&bar_free[s]);
+      if (tile == tile1 - 1) wtc_commit(&bar_done);
+    }
+  }
+  // ---- bias gradient partials ----
+  if (do_bias) {
+    const int pl = tid % t.ny_planes;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&sbias[pl * 8 + k], bacc[k]);
+  }
+  // ---- reduce the resident accumulators into dW ----
+  wmbar_wait(&bar_done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp == 0) {
+    // accumulator lane = (kx group) * 8 + channel-in-plane ; groups 0..kw-1 are the taps (kw <= 4)
+    const int kx = lane >> 3, ci = ca0 + (lane & 7);
+    for (int ky = 0; ky < a.kh; ++ky) {
+      for (int c0 = 0; c0 < a.cb; c0 += 16) {
+        float v[16];
+        wtmem_ld16(tmem_base + (uint32_t)(ky * t.N + c0), v);
+        if (kx < a.kw && ci < a.ca_lim) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = c0 + j;
+            if (co < a.cb_lim) atomicAdd(a.dW + (long)ci * a.s_ca + (long)co * a.s_cb + (ky * a.kw + kx), v[j]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (do_bias && tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+}
+
+bool wgrad_tc_supported(const WgradArgs& a) {
+  if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
+  if (a.Ha != a.Hq || a.Wa != a.Wq || a.Hb != a.Hq || a.Wb != a.Wq) return false;
+  if ((a.ca & 7) || (a.cb & 7) || a.cb > 128 || a.kw > 4 || a.kh > 4) return false;
+  const int nyp = a.cb >> 3;
+  if (256 % nyp) return false;
+  if (!a.a_nchw && (a.pa & 3)) return false;
+  if (a.pb & 3) return false;
+  if (a.dila < 1) return false;
+  return true;
+}
+
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
+  MSAU_CHECK_ARG(wgrad_tc_supported(a), "wgrad_tc: unsupported shape");
+  WgTile t;
+  t.N = a.cb < 16 ? 16 : round_up(a.cb, 16);
+  t.ny_planes = a.cb >> 3;
+  int px_budget = 8192 / a.cb;          // dY tile <= 32 KB of bf16 hi+lo
+  if (px_budget > 512) px_budget = 512;
+  t.TC = round_up(a.Wq, 16);
+  if (t.TC > 64) t.TC = 64;
+  while (t.TC > 16 && t.TC * 2 > px_budget * 2 && t.TC > px_budget) t.TC -= 16;
+  t.TR = px_budget / t.TC;
+  if (t.TR < 1) t.TR = 1;
+  if (t.TR > 8) t.TR = 8;
+  if (t.TR > a.Hq) t.TR = a.Hq;
+  t.HHx = t.TR + (a.kh - 1) * a.dila;
+  t.HWx = t.TC + (a.kw - 1) * a.dila;
+  const int slack_px = 15 * a.dila + 16;                  // M groups kw..15 read past the useful columns
+  t.x_plane_bytes = (uint32_t)((t.HHx * t.HWx + slack_px) * 16 + 127) / 128 * 128;
+  t.y_plane_bytes = (uint32_t)(t.TR * t.TC * 16);
+  // N-groups beyond the real planes (cb = 8 -> N = 16) read one plane further: keep that inside the stage
+  const uint32_t y_bytes = 2u * t.ny_planes * t.y_plane_bytes + ((t.N >> 3) > t.ny_planes ? t.y_plane_bytes : 0u);
+  t.stage_bytes = (2 * t.x_plane_bytes + y_bytes + 1023) / 1024 * 1024;
+  t.tiles_x = cdiv(a.Wq, t.TC);
+  t.tiles_y = cdiv(a.Hq, t.TR);
+  t.n_tiles = t.tiles_x * t.tiles_y * a.B;
+  const int planes = a.ca >> 3;
+  int ctas = (2 * sm_count() + planes - 1) / planes;
+  if (ctas > t.n_tiles) ctas = t.n_tiles;
+  if (ctas < 1) ctas = 1;
+  t.tiles_per_cta = cdiv(t.n_tiles, ctas);
+  ctas = cdiv(t.n_tiles, t.tiles_per_cta);
+  int cols = a.kh * t.N;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
+  const size_t smem = (size_t)t.stage_bytes * 2 + 1024;
+  MSAU_CHECK_ARG(smem <= 200 * 1024 && t.tmem_cols <= 512, "wgrad_tc: tile does not fit (smem %zu B, tmem %u cols)", smem, t.tmem_cols);
+  static bool attr = false;
+  if (!attr) {
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid(ctas, planes);
+  const double npq = (double)a.B * a.Hq * a.Wq;
+  const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + npq * a.cb * (a.maskB ? 2 : 1)) * 4.0;
+  ProfScope ps("wgrad_tc_kernel", 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(a, t);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+}  // namespace msau
