@@ -109,12 +109,14 @@ struct TcTile {
 };
 
 static constexpr int TC_THREADS = 256;
+static constexpr int LD_U = 2;        // halo pixels whose global loads are in flight per thread
 
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const TcTile t) {
+__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const TcTile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_free[2];     // stage s may be overwritten (its MMAs retired)
   __shared__ uint64_t bar_done;        // all MMAs retired -> epilogue
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t tap_off16[16];   // smem offset of every tap, in 16-B units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.z;
@@ -125,6 +127,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, c
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(t.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid < 16 && tid < a.kh * a.kw) {
+    const int ky = tid / a.kw, kx = tid - ky * a.kw;
+    tap_off16[tid] = (uint32_t)(ky * a.dil * t.HW + kx * a.dil);
   }
   if (tid == 0) {
     mbar_init(&bar_free[0], 1);
@@ -150,45 +156,64 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, c
     // ---- load + split this 8-channel plane of the halo tile ----
     const bool from1 = p < planes1;
     const int cg = from1 ? (p << 3) : ((p - planes1) << 3);
-    for (int e = tid; e < halo_px; e += TC_THREADS) {
-      const int iy = e / t.HW, ix = e - iy * t.HW;
-      const int gy = in_y0 + iy, gx = in_x0 + ix;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win) {
-        const long pix = ((long)b * a.Hin + gy) * a.Win + gx;
-        if (from1) {
-          if (a.src1_nchw) {
-            const long plane = (long)a.Hin * a.Win;
-            const float* sp = a.src1 + ((long)b * a.c1_logical + cg) * plane + (long)gy * a.Win + gx;
+    for (int e0 = tid; e0 < halo_px; e0 += TC_THREADS * LD_U) {
+      float v[LD_U][8];
+      float4 mk[LD_U][2];
+      bool inb[LD_U];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (cg + k < a.c1_logical) v[k] = __ldg(sp + k * plane);
+      for (int u = 0; u < LD_U; ++u) {
+        const int e = e0 + u * TC_THREADS;
+        const int iy = e / t.HW, ix = e - iy * t.HW;
+        const int gy = in_y0 + iy, gx = in_x0 + ix;
+        inb[u] = e < halo_px && gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
+        mk[u][0] = mk[u][1] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (inb[u]) {
+          const long pix = ((long)b * a.Hin + gy) * a.Win + gx;
+          if (from1) {
+            if (a.src1_nchw) {
+              const long plane = (long)a.Hin * a.Win;
+              const float* sp = a.src1 + ((long)b * a.c1_logical + cg) * plane + (long)gy * a.Win + gx;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                if (cg + k < a.c1_logical) v[u][k] = __ldg(sp + k * plane);
+            } else {
+              const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.p1 + cg));
+              const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.p1 + cg) + 1);
+              v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+              v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+            }
+            if (a.mask1) {
+              mk[u][0] = __ldg(reinterpret_cast<const float4*>(a.mask1 + pix * a.pm1 + cg));
+              mk[u][1] = __ldg(reinterpret_cast<const float4*>(a.mask1 + pix * a.pm1 + cg) + 1);
+            }
           } else {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.p1 + cg));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.p1 + cg) + 1);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.p2 + cg));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.p2 + cg) + 1);
+            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
           }
-          if (a.mask1) {
-            const float4 m0 = __ldg(reinterpret_cast<const float4*>(a.mask1 + pix * a.pm1 + cg));
-            const float4 m1 = __ldg(reinterpret_cast<const float4*>(a.mask1 + pix * a.pm1 + cg) + 1);
-            const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = m[k] > 0.f ? v[k] : 0.f;
-          }
-          if (a.relu1) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-          }
-        } else {
-          const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.p2 + cg));
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.p2 + cg) + 1);
-          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
         }
       }
-      uint4 hi, lo;
-      split_bf16x8(v, hi, lo);
-      *reinterpret_cast<uint4*>(st + (size_t)e * 16) = hi;
-      *reinterpret_cast<uint4*>(st + plane_bytes + (size_t)e * 16) = lo;
+#pragma unroll
+      for (int u = 0; u < LD_U; ++u) {
+        const int e = e0 + u * TC_THREADS;
+        if (e >= halo_px) break;
+        if (from1 && a.mask1) {
+          const float m[8] = {mk[u][0].x, mk[u][0].y, mk[u][0].z, mk[u][0].w, mk[u][1].x, mk[u][1].y, mk[u][1].z, mk[u][1].w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[u][k] = m[k] > 0.f ? v[u][k] : 0.f;
+        }
+        if (from1 && a.relu1) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
+        }
+        uint4 hi, lo;
+        split_bf16x8(v[u], hi, lo);
+        *reinterpret_cast<uint4*>(st + (size_t)e * 16) = hi;
+        *reinterpret_cast<uint4*>(st + plane_bytes + (size_t)e * 16) = lo;
+      }
     }
     // ---- this plane's weight image (already bf16, already in UMMA layout) ----
     {
@@ -203,26 +228,25 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvArgs a, c
       tc_fence_after();
       const uint32_t in_addr = smem_u32(st);
       const uint32_t w_addr = in_addr + t.in_bytes;
-      const uint32_t wimg = (uint32_t)t.N * 32;          // bytes of one B image: 2 K-chunks x N rows x 16 B
+      const uint32_t wimg16 = (uint32_t)t.N * 2;          // one B image (2 K-chunks x N rows x 16 B) in 16-B units
+      // descriptors differ only in their start-address field: build them once, then add (bytes >> 4)
+      const uint64_t a1_base = make_desc(in_addr, plane_bytes, row_pitch);
+      const uint64_t b_base = make_desc(w_addr, (uint32_t)t.N * 16, 128);
+      const uint64_t a3_hi = ((uint64_t)((row_pitch >> 4) & 0x3FFF) << 32) | (1ull << 46);
       for (int tile = 0; tile < t.T; ++tile) {
         const uint32_t d_tmem = tmem_base + (uint32_t)(tile * t.N);
-        const uint32_t tile_addr = in_addr + (uint32_t)tile * 128;       // 8 pixels to the right
+        const uint32_t tile16 = (uint32_t)tile * 8;       // 8 pixels to the right, in 16-B units
+        uint32_t acc = (p > 0) ? 1u : 0u;
         for (int tap = 0; tap < t.n1; ++tap) {
-          const int ky = tap / a.kw, kx = tap - ky * a.kw;
-          const uint32_t off = (uint32_t)(ky * a.dil * t.HW + kx * a.dil) * 16;
-          const uint64_t ad = make_desc(tile_addr + off, plane_bytes, row_pitch);
-          const uint64_t bd = make_desc(w_addr + (uint32_t)tap * wimg, (uint32_t)t.N * 16, 128);
-          tc_mma(d_tmem, ad, bd, idesc, (p > 0 || tap > 0) ? 1u : 0u);
+          tc_mma(d_tmem, a1_base + tile16 + tap_off16[tap], b_base + (uint32_t)tap * wimg16, idesc, acc);
+          acc = 1u;
         }
         for (int j = 0; j < t.n3; ++j) {
           const int ta = 2 * j, tb = (2 * j + 1 < t.n1) ? 2 * j + 1 : 2 * j;
-          const int kya = ta / a.kw, kxa = ta - kya * a.kw, kyb = tb / a.kw, kxb = tb - kyb * a.kw;
-          const uint32_t offa = (uint32_t)(kya * a.dil * t.HW + kxa * a.dil) * 16;
-          const uint32_t offb = (uint32_t)(kyb * a.dil * t.HW + kxb * a.dil) * 16;
-          const uint32_t lbo = tb == ta ? 16u : offb - offa;             // dummy second chunk multiplies zero weights
-          const uint64_t ad = make_desc(tile_addr + offa, lbo, row_pitch);
-          const uint64_t bd = make_desc(w_addr + (uint32_t)(t.n1 + j) * wimg, (uint32_t)t.N * 16, 128);
-          tc_mma(d_tmem, ad, bd, idesc, 1u);
+          const uint32_t offa = tap_off16[ta], offb = tap_off16[tb];
+          const uint32_t lbo16 = tb == ta ? 1u : offb - offa;           // dummy second chunk multiplies zero weights
+          const uint64_t ad = a3_hi | (uint64_t)(((in_addr >> 4) + tile16 + offa) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16);
+          tc_mma(d_tmem, ad, b_base + (uint32_t)(t.n1 + j) * wimg16, idesc, 1u);
         }
       }
       tc_commit(&bar_free[s]);                 // arrives when every MMA issued so far has retired
