@@ -21,6 +21,7 @@
 // streamed through a 2-stage shared-memory ring (mbarrier + tcgen05.commit), the epilogue reads TMEM with
 // tcgen05.ld (one thread = one pixel, all couts) and applies bias / ReLU / residual / masks like conv.cu.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_tc.cuh"
@@ -38,14 +39,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 // bounded wait: a protocol bug must surface as a trap, never as a hung GPU
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  // try_wait with a suspend-time hint parks the thread in hardware instead of spinning on issue slots
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
   }
@@ -70,6 +72,49 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
+// exactly one lane of a converged warp (the compiler then emits straight-line UTCHMMA without per-lane election loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// same instruction with the descriptors given as (lo, hi) halves: only the low word (start address, LBO) changes between
+// the instructions of a plane, so the issuing thread does one 32-bit add per MMA
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// all T tiles of one (tap | tap pair): same B image, A shifted by 8 pixels (= 8 x 16 B) per tile, one accumulator per tile
+template <int TT>
+__device__ __forceinline__ void issue_tiles(uint32_t acc_base, uint32_t N, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+#pragma unroll
+  for (int tile = 0; tile < TT; ++tile) tc_mma2(acc_base + tile * N, a_lo + tile * 8, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+
+__device__ __forceinline__ void issue_tiles_rt(int T, uint32_t acc_base, uint32_t N, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  switch (T) {
+    case 8: issue_tiles<8>(acc_base, N, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); break;
+    case 4: issue_tiles<4>(acc_base, N, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); break;
+    case 2: issue_tiles<2>(acc_base, N, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); break;
+    default: issue_tiles<1>(acc_base, N, a_lo, a_hi, b_lo, b_hi, idesc, accumulate); break;
+  }
+}
+
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
@@ -88,40 +133,186 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): two packed converts, two logic ops and two subtractions per pair
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);          // cvt.rn.bf16x2.f32 (x0 -> low half)
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split_bf16x8(const float* x, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-    const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-    h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-    l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
+  split_pair(x[0], x[1], hi.x, lo.x);
+  split_pair(x[2], x[3], hi.y, lo.y);
+  split_pair(x[4], x[5], hi.z, lo.z);
+  split_pair(x[6], x[7], hi.w, lo.w);
 }
 
 struct TcTile {
-  int T, N, HH, HW, P, stages;      // tiles per CTA, MMA N, halo extent, input planes, ring depth
+  int T, N, HH, HW, P, stages;      // tiles per super-tile, MMA N, halo extent, input planes, smem ring depth
   int n1, n3;                       // type-1 / type-3 instructions per plane (= taps, ceil(taps/2))
+  int tiles_x, tiles_y, n_super;    // super-tile grid (16 rows x 8T columns each)
+  int step_q, step_r;               // PROD_THREADS = step_q * HW + step_r
+  int dbg;                          // MSAU_TC_DEBUG experiments: 1 = no MMAs, 2 = no producer loads, 4 = no epilogue stores
   uint32_t in_bytes, w_bytes, stage_bytes, tmem_cols;
 };
 
-static constexpr int TC_THREADS = 256;
-static constexpr int LD_U = 2;        // halo pixels whose global loads are in flight per thread
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 
-__global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const TcTile t) {
+// extra epilogue operands of one work item (one pixel x 8 output channels = 2 float4 groups)
+struct EpiOps { float4 res[2], om[2], ad[2], am[2], ou[2]; };
+
+__device__ __forceinline__ void epi_load(EpiOps& o, const ConvArgs& a, long pix, int co, bool valid) {
+  if (!valid) return;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int c = co + g * 4;
+    if (a.res) o.res[g] = __ldg(reinterpret_cast<const float4*>(a.res + pix * a.pr + c));
+    if (a.omask) o.om[g] = __ldg(reinterpret_cast<const float4*>(a.omask + pix * a.pom + c));
+    if (a.add) o.ad[g] = __ldg(reinterpret_cast<const float4*>(a.add + pix * a.pa + c));
+    if (a.addmask) o.am[g] = __ldg(reinterpret_cast<const float4*>(a.addmask + pix * a.pam + c));
+    if (a.accumulate) o.ou[g] = *reinterpret_cast<const float4*>(a.out + pix * a.po + c);
+  }
+}
+
+__device__ __forceinline__ void epi_apply(const EpiOps& o, const ConvArgs& a, long pix, int co, const float* v) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    const int c = co + g * 4;
+    float4 r4 = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    if (a.bias) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+      r4.x += bv.x; r4.y += bv.y; r4.z += bv.z; r4.w += bv.w;
+    }
+    if (a.relu) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
+    if (a.res) { r4.x += o.res[g].x; r4.y += o.res[g].y; r4.z += o.res[g].z; r4.w += o.res[g].w; }
+    if (a.relu2) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
+    if (a.omask) {
+      r4.x = o.om[g].x > 0.f ? r4.x : 0.f; r4.y = o.om[g].y > 0.f ? r4.y : 0.f;
+      r4.z = o.om[g].z > 0.f ? r4.z : 0.f; r4.w = o.om[g].w > 0.f ? r4.w : 0.f;
+    }
+    if (a.add) {
+      float4 r = o.ad[g];
+      if (a.addmask) {
+        r.x = o.am[g].x > 0.f ? r.x : 0.f; r.y = o.am[g].y > 0.f ? r.y : 0.f;
+        r.z = o.am[g].z > 0.f ? r.z : 0.f; r.w = o.am[g].w > 0.f ? r.w : 0.f;
+      }
+      r4.x += r.x; r4.y += r.y; r4.z += r.z; r4.w += r.w;
+    }
+    if (a.accumulate) { r4.x += o.ou[g].x; r4.y += o.ou[g].y; r4.z += o.ou[g].z; r4.w += o.ou[g].w; }
+    *reinterpret_cast<float4*>(a.out + pix * a.po + c) = r4;
+  }
+}
+
+// Warp roles of the persistent CTA (one CTA per SM, grid-stride over super-tiles):
+//   warps 0..6   producers : fp32 halo plane -> bf16 hi/lo planar image + weight image, into a 2..3-stage ring
+//   warp  7      MMA issuer: one lane feeds the tensor core, tcgen05.commit recycles ring slots / publishes tiles
+//   warps 8..15  epilogue  : TMEM -> registers -> bias/ReLU/residual/masks -> global (double-buffered accumulators)
+static constexpr int PROD_WARPS = 7;     // 7 + 1 + 8 = 16 warps -> 128 registers per thread
+static constexpr int PROD_THREADS = PROD_WARPS * 32;
+static constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes every other tile
+static constexpr int TC_THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
+static constexpr int LD_U = 4;        // halo pixels whose global loads are in flight per producer thread
+static constexpr int W_U = 4;         // weight-image uint4s prefetched per producer thread per plane (the rest is copied late)
+static constexpr int MAX_STAGES = 3;
+
+enum { SRC_PLAIN = 0, SRC_RELU = 1, SRC_MASK = 2, SRC_NCHW = 3 };
+
+// One 8-channel plane of the halo tile: fp32 global -> bf16 hi/lo planar image in shared memory.
+// `src` / `mask` already point at (batch b, channel cg); indices stay 32-bit (tensors < 2^31 floats).
+template <int MODE>
+__device__ __forceinline__ void produce_plane(const float* __restrict__ src, int pitch, const float* __restrict__ mask, int pm,
+                                              int plane_stride, int n_valid, int in_x0, int in_y0, int Hin, int Win,
+                                              const TcTile& t, uint8_t* __restrict__ stg, uint32_t plane_bytes, int tid) {
+  const int halo_px = t.HH * t.HW;
+  int iy_c = tid / t.HW, ix_c = tid - iy_c * t.HW;          // halo coordinates of element e, advanced incrementally
+  for (int e0 = tid; e0 < halo_px; e0 += PROD_THREADS * LD_U) {
+    float v[LD_U][8];
+    float4 mk[LD_U][2];
+#pragma unroll
+    for (int u = 0; u < LD_U; ++u) {
+      const int e = e0 + u * PROD_THREADS;
+      const int gy = in_y0 + iy_c, gx = in_x0 + ix_c;
+      iy_c += t.step_q; ix_c += t.step_r;                     // e += PROD_THREADS
+      if (ix_c >= t.HW) { ix_c -= t.HW; ++iy_c; }
+      const bool inb = e < halo_px && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win && !(t.dbg & 2);
+      const int lin = gy * Win + gx;
+      if (MODE == SRC_NCHW) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = (inb && k < n_valid) ? __ldg(src + lin + k * plane_stride) : 0.f;
+      } else {
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* sp = reinterpret_cast<const float4*>(src + lin * pitch);
+        const float4 q0 = inb ? __ldg(sp) : z4;
+        const float4 q1 = inb ? __ldg(sp + 1) : z4;
+        v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+        v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+        if (MODE == SRC_MASK) {
+          const float4* mp = reinterpret_cast<const float4*>(mask + lin * pm);
+          mk[u][0] = inb ? __ldg(mp) : z4;
+          mk[u][1] = inb ? __ldg(mp + 1) : z4;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < LD_U; ++u) {
+      const int e = e0 + u * PROD_THREADS;
+      if (e >= halo_px) break;
+      if (MODE == SRC_MASK) {
+        const float m[8] = {mk[u][0].x, mk[u][0].y, mk[u][0].z, mk[u][0].w, mk[u][1].x, mk[u][1].y, mk[u][1].z, mk[u][1].w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = m[k] > 0.f ? v[u][k] : 0.f;
+      }
+      if (MODE == SRC_RELU) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
+      }
+      uint4 hi, lo;
+      split_bf16x8(v[u], hi, lo);
+      *reinterpret_cast<uint4*>(stg + e * 16) = hi;
+      *reinterpret_cast<uint4*>(stg + plane_bytes + e * 16) = lo;
+    }
+  }
+}
+
+template <bool GENERAL>
+__device__ __forceinline__ void epi_store(const EpiOps& o, const ConvArgs& a, float* __restrict__ dst, const float* __restrict__ bias8,
+                                          bool relu, const float* v) {
+  // fast path: bias (+ReLU) only -- two 16-byte stores per item
+  if (!GENERAL) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      float4 r4 = make_float4(v[g * 4] + bias8[g * 4], v[g * 4 + 1] + bias8[g * 4 + 1], v[g * 4 + 2] + bias8[g * 4 + 2],
+                              v[g * 4 + 3] + bias8[g * 4 + 3]);
+      if (relu) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
+      reinterpret_cast<float4*>(dst)[g] = r4;
+    }
+  }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int SRC_MODE, bool EPI_GENERAL>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const TcTile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_free[2];     // stage s may be overwritten (its MMAs retired)
-  __shared__ uint64_t bar_done;        // all MMAs retired -> epilogue
+  __shared__ uint64_t bar_full[MAX_STAGES];    // producers -> MMA : stage holds plane data
+  __shared__ uint64_t bar_empty[MAX_STAGES];   // MMA -> producers : the MMAs reading the stage have retired
+  __shared__ uint64_t bar_acc_full[2];         // MMA -> epilogue  : accumulator set complete
+  __shared__ uint64_t bar_acc_empty[2];        // epilogue -> MMA  : accumulator set drained
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t tap_off16[16];   // smem offset of every tap, in 16-B units
+  __shared__ uint32_t tap_off16[16];           // smem offset of every tap, in 16-B units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.z;
-  const int x0 = blockIdx.x * (8 * t.T), y0 = blockIdx.y * 16;
-  const int in_x0 = x0 - a.pad_l, in_y0 = y0 - a.pad_t;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -132,181 +323,173 @@ __global__ void __launch_bounds__(TC_THREADS, 3) conv_tc_kernel(const ConvArgs a
     const int ky = tid / a.kw, kx = tid - ky * a.kw;
     tap_off16[tid] = (uint32_t)(ky * a.dil * t.HW + kx * a.dil);
   }
-  if (tid == 0) {
-    mbar_init(&bar_free[0], 1);
-    mbar_init(&bar_free[1], 1);
-    mbar_init(&bar_done, 1);
+  if (tid == 32) {
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bar_full[i], PROD_THREADS); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(t.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   const uint32_t plane_bytes = (uint32_t)t.HH * t.HW * 16;       // one of {hi, lo}
-  const uint32_t row_pitch = (uint32_t)t.HW * 16;
-  const int halo_px = t.HH * t.HW;
-  const int planes1 = a.c1 >> 3;
+  const int S = t.stages;
 
-  for (int p = 0; p < t.P; ++p) {
-    const int s = p % t.stages;
-    uint8_t* st = smem + (size_t)s * t.stage_bytes;
-    if (p >= t.stages) mbar_wait(&bar_free[s], ((p / t.stages) - 1) & 1);
-    // ---- load + split this 8-channel plane of the halo tile ----
-    const bool from1 = p < planes1;
-    const int cg = from1 ? (p << 3) : ((p - planes1) << 3);
-    for (int e0 = tid; e0 < halo_px; e0 += TC_THREADS * LD_U) {
-      float v[LD_U][8];
-      float4 mk[LD_U][2];
-      bool inb[LD_U];
+  if (warp < PROD_WARPS) {
+    // =============================================================== producers
+    const int planes1 = a.c1 >> 3;
+    uint32_t c = 0;                                               // (super-tile, plane) chunk counter
+    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
+      const int sx = st_i % t.tiles_x;
+      const int rest = st_i / t.tiles_x;
+      const int sy = rest % t.tiles_y;
+      const int b = rest / t.tiles_y;
+      const int in_x0 = sx * (8 * t.T) - a.pad_l, in_y0 = sy * 16 - a.pad_t;
+      for (int p = 0; p < t.P; ++p, ++c) {
+        const int s = c % S;
+        uint8_t* stg = smem + (size_t)s * t.stage_bytes;
+        if (c >= (uint32_t)S) {
+          if (lane == 0) mbar_wait(&bar_empty[s], ((c / S) - 1) & 1);
+          __syncwarp();
+        }
+        const bool from1 = p < planes1;
+        const int cg = from1 ? (p << 3) : ((p - planes1) << 3);
+        // request this plane's weight image first so its latency hides behind the pixel loads
+        uint4 wreg[W_U];
+        const uint4* wsrc = reinterpret_cast<const uint4*>(wtc) + (size_t)p * (t.w_bytes >> 4);
+        const int w16 = (int)(t.w_bytes >> 4);
 #pragma unroll
-      for (int u = 0; u < LD_U; ++u) {
-        const int e = e0 + u * TC_THREADS;
-        const int iy = e / t.HW, ix = e - iy * t.HW;
-        const int gy = in_y0 + iy, gx = in_x0 + ix;
-        inb[u] = e < halo_px && gy >= 0 && gy < a.Hin && gx >= 0 && gx < a.Win;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
-        mk[u][0] = mk[u][1] = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (inb[u]) {
-          const long pix = ((long)b * a.Hin + gy) * a.Win + gx;
-          if (from1) {
-            if (a.src1_nchw) {
-              const long plane = (long)a.Hin * a.Win;
-              const float* sp = a.src1 + ((long)b * a.c1_logical + cg) * plane + (long)gy * a.Win + gx;
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (cg + k < a.c1_logical) v[u][k] = __ldg(sp + k * plane);
-            } else {
-              const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.p1 + cg));
-              const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.src1 + pix * a.p1 + cg) + 1);
-              v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
-              v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
-            }
-            if (a.mask1) {
-              mk[u][0] = __ldg(reinterpret_cast<const float4*>(a.mask1 + pix * a.pm1 + cg));
-              mk[u][1] = __ldg(reinterpret_cast<const float4*>(a.mask1 + pix * a.pm1 + cg) + 1);
-            }
+        for (int u = 0; u < W_U; ++u)
+          if (tid + u * PROD_THREADS < w16) wreg[u] = __ldg(wsrc + tid + u * PROD_THREADS);
+        if (from1) {
+          if (SRC_MODE == SRC_NCHW) {
+            const int plane_stride = a.Hin * a.Win;
+            produce_plane<SRC_NCHW>(a.src1 + ((long)b * a.c1_logical + cg) * plane_stride, 0, nullptr, 0, plane_stride,
+                                    a.c1_logical - cg, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
           } else {
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.p2 + cg));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.src2 + pix * a.p2 + cg) + 1);
-            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
-            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+            const long boff = (long)b * a.Hin * a.Win;
+            produce_plane<SRC_MODE>(a.src1 + boff * a.p1 + cg, a.p1, SRC_MODE == SRC_MASK ? a.mask1 + boff * a.pm1 + cg : nullptr,
+                                    a.pm1, 0, 8, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
           }
+        } else {
+          const long boff = (long)b * a.Hin * a.Win;
+          produce_plane<SRC_PLAIN>(a.src2 + boff * a.p2 + cg, a.p2, nullptr, 0, 0, 8, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
         }
-      }
+        {   // this plane's weight image (already bf16, already in UMMA layout)
+          uint4* dst = reinterpret_cast<uint4*>(stg + t.in_bytes);
 #pragma unroll
-      for (int u = 0; u < LD_U; ++u) {
-        const int e = e0 + u * TC_THREADS;
-        if (e >= halo_px) break;
-        if (from1 && a.mask1) {
-          const float m[8] = {mk[u][0].x, mk[u][0].y, mk[u][0].z, mk[u][0].w, mk[u][1].x, mk[u][1].y, mk[u][1].z, mk[u][1].w};
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[u][k] = m[k] > 0.f ? v[u][k] : 0.f;
+          for (int u = 0; u < W_U; ++u)
+            if (tid + u * PROD_THREADS < w16) dst[tid + u * PROD_THREADS] = wreg[u];
+          for (int e = tid + W_U * PROD_THREADS; e < w16; e += PROD_THREADS) dst[e] = __ldg(wsrc + e);
         }
-        if (from1 && a.relu1) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
-        }
-        uint4 hi, lo;
-        split_bf16x8(v[u], hi, lo);
-        *reinterpret_cast<uint4*>(st + (size_t)e * 16) = hi;
-        *reinterpret_cast<uint4*>(st + plane_bytes + (size_t)e * 16) = lo;
+        fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&bar_full[s]);
       }
     }
-    // ---- this plane's weight image (already bf16, already in UMMA layout) ----
+  } else if (warp == PROD_WARPS) {
+    // =============================================================== MMA issuer
+    // The whole warp walks the loops (warp-uniform control flow); one elected lane issues the MMAs / commits.
     {
-      const uint4* src = reinterpret_cast<const uint4*>(wtc) + (size_t)p * (t.w_bytes >> 4);
-      uint4* dst = reinterpret_cast<uint4*>(st + t.in_bytes);
-      for (int e = tid; e < (int)(t.w_bytes >> 4); e += TC_THREADS) dst[e] = __ldg(src + e);
-    }
-    fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    // ---- one thread issues every MMA of this plane ----
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t in_addr = smem_u32(st);
-      const uint32_t w_addr = in_addr + t.in_bytes;
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(t.N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t row_pitch = (uint32_t)t.HW * 16;
       const uint32_t wimg16 = (uint32_t)t.N * 2;          // one B image (2 K-chunks x N rows x 16 B) in 16-B units
-      // descriptors differ only in their start-address field: build them once, then add (bytes >> 4)
-      const uint64_t a1_base = make_desc(in_addr, plane_bytes, row_pitch);
-      const uint64_t b_base = make_desc(w_addr, (uint32_t)t.N * 16, 128);
-      const uint64_t a3_hi = ((uint64_t)((row_pitch >> 4) & 0x3FFF) << 32) | (1ull << 46);
-      for (int tile = 0; tile < t.T; ++tile) {
-        const uint32_t d_tmem = tmem_base + (uint32_t)(tile * t.N);
-        const uint32_t tile16 = (uint32_t)tile * 8;       // 8 pixels to the right, in 16-B units
-        uint32_t acc = (p > 0) ? 1u : 0u;
-        for (int tap = 0; tap < t.n1; ++tap) {
-          tc_mma(d_tmem, a1_base + tile16 + tap_off16[tap], b_base + (uint32_t)tap * wimg16, idesc, acc);
-          acc = 1u;
-        }
-        for (int j = 0; j < t.n3; ++j) {
-          const int ta = 2 * j, tb = (2 * j + 1 < t.n1) ? 2 * j + 1 : 2 * j;
-          const uint32_t offa = tap_off16[ta], offb = tap_off16[tb];
-          const uint32_t lbo16 = tb == ta ? 1u : offb - offa;           // dummy second chunk multiplies zero weights
-          const uint64_t ad = a3_hi | (uint64_t)(((in_addr >> 4) + tile16 + offa) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16);
-          tc_mma(d_tmem, ad, b_base + (uint32_t)(t.n1 + j) * wimg16, idesc, 1u);
-        }
-      }
-      tc_commit(&bar_free[s]);                 // arrives when every MMA issued so far has retired
-      if (p == t.P - 1) tc_commit(&bar_done);
-    }
-  }
-  // ---- epilogue: TMEM -> registers -> global ----
-  mbar_wait(&bar_done, 0);
-  tc_fence_after();
-  {
-    const int q = warp & 3;                    // TMEM lane quarter this warp may read
-    const int row = q * 4 + (lane >> 3);       // lane i of the accumulator = pixel (i / 8, i % 8) of the tile
-    const int colx = lane & 7;
-    const int oy = y0 + row;
-    const int half = warp >> 2;                // warps 0-3: first half of the tiles, 4-7: second half
-    const int t_lo = half ? (t.T + 1) / 2 : 0, t_hi = half ? t.T : (t.T + 1) / 2;
-    for (int tile = t_lo; tile < t_hi; ++tile) {
-      const int ox = x0 + tile * 8 + colx;
-      const bool valid = oy < a.Hout && ox < a.Wout;
-      const long pix = ((long)b * a.Hout + oy) * a.Wout + ox;
-      for (int c0 = 0; c0 < a.coutp; c0 += 16) {
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tile * t.N + c0), v);   // warp-collective
-        if (!valid) continue;
-        const int nq = min(4, (a.coutp - c0) >> 2);
-        for (int g = 0; g < nq; ++g) {
-          const int co = c0 + g * 4;
-          float4 r4 = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-          if (a.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + co));
-            r4.x += bv.x; r4.y += bv.y; r4.z += bv.z; r4.w += bv.w;
-          }
-          if (a.relu) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
-          if (a.res) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(a.res + pix * a.pr + co));
-            r4.x += r.x; r4.y += r.y; r4.z += r.z; r4.w += r.w;
-          }
-          if (a.relu2) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
-          if (a.omask) {
-            const float4 m = __ldg(reinterpret_cast<const float4*>(a.omask + pix * a.pom + co));
-            r4.x = m.x > 0.f ? r4.x : 0.f; r4.y = m.y > 0.f ? r4.y : 0.f;
-            r4.z = m.z > 0.f ? r4.z : 0.f; r4.w = m.w > 0.f ? r4.w : 0.f;
-          }
-          if (a.add) {
-            float4 r = __ldg(reinterpret_cast<const float4*>(a.add + pix * a.pa + co));
-            if (a.addmask) {
-              const float4 m = __ldg(reinterpret_cast<const float4*>(a.addmask + pix * a.pam + co));
-              r.x = m.x > 0.f ? r.x : 0.f; r.y = m.y > 0.f ? r.y : 0.f;
-              r.z = m.z > 0.f ? r.z : 0.f; r.w = m.w > 0.f ? r.w : 0.f;
+      const uint32_t a_hi = ((row_pitch >> 4) & 0x3FFF) | (1u << 14);          // bits 32..45 SBO, bit 46 version
+      const uint32_t b_hi = (128u >> 4) | (1u << 14);
+      const uint32_t a1_lbo = ((plane_bytes >> 4) & 0x3FFF) << 16;
+      const uint32_t b_lbo = (((uint32_t)t.N * 16 >> 4) & 0x3FFF) << 16;
+      uint32_t c = 0, tcount = 0;
+      for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
+        const uint32_t as = tcount & 1;
+        if (tcount >= 2) mbar_wait(&bar_acc_empty[as], ((tcount >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N);
+        for (int p = 0; p < t.P; ++p, ++c) {
+          const int s = c % S;
+          mbar_wait(&bar_full[s], (c / S) & 1);
+          tc_fence_after();
+          const uint32_t in_addr = smem_u32(smem + (size_t)s * t.stage_bytes);
+          const uint32_t in16 = in_addr >> 4, w16a = (in_addr + t.in_bytes) >> 4;
+          if (elect_one()) {
+            if (!(t.dbg & 1)) {
+              // tap-major / tile-minor order: consecutive instructions hit different accumulators (no RAW chain)
+              for (int tap = 0; tap < t.n1; ++tap) {
+                issue_tiles_rt(t.T, acc_base, (uint32_t)t.N, ((in16 + tap_off16[tap]) & 0x3FFF) | a1_lbo, a_hi,
+                               ((w16a + (uint32_t)tap * wimg16) & 0x3FFF) | b_lbo, b_hi, idesc, (p > 0 || tap > 0) ? 1u : 0u);
+              }
+              for (int j = 0; j < t.n3; ++j) {
+                const int ta = 2 * j, tb = (2 * j + 1 < t.n1) ? 2 * j + 1 : 2 * j;
+                const uint32_t offa = tap_off16[ta], offb = tap_off16[tb];
+                const uint32_t lbo16 = tb == ta ? 1u : offb - offa;         // dummy second chunk multiplies zero weights
+                issue_tiles_rt(t.T, acc_base, (uint32_t)t.N, ((in16 + offa) & 0x3FFF) | ((lbo16 & 0x3FFF) << 16), a_hi,
+                               ((w16a + (uint32_t)(t.n1 + j) * wimg16) & 0x3FFF) | b_lbo, b_hi, idesc, 1u);
+              }
             }
-            r4.x += r.x; r4.y += r.y; r4.z += r.z; r4.w += r.w;
+            tc_commit(&bar_empty[s]);                 // ring slot reusable once these MMAs have retired
+            if (p == t.P - 1) tc_commit(&bar_acc_full[as]);   // accumulator set complete
           }
-          float4* dst = reinterpret_cast<float4*>(a.out + pix * a.po + co);
-          if (a.accumulate) {
-            const float4 o = *dst;
-            r4.x += o.x; r4.y += o.y; r4.z += o.z; r4.w += o.w;
-          }
-          *dst = r4;
+          __syncwarp();
         }
       }
+    }
+  } else {
+    // =============================================================== epilogue
+    // Work item = (tile, 8 output channels).  The extra operands of item k+1 (residual / masks / skip-path
+    // add / previous output) are requested from HBM before item k is computed, and the first item's operands
+    // before the accumulator is even complete, so a warp exposes at most one memory latency per super-tile.
+    const int ew = warp - (PROD_WARPS + 1);         // 0..7
+    const int q = warp & 3;                         // TMEM lane quarter this warp may read
+    const int sub = ew >> 2;                        // 0/1: which half of the tiles
+    const int row = q * 4 + (lane >> 3);            // lane i of the accumulator = pixel (i / 8, i % 8) of the tile
+    const int colx = lane & 7;
+    const int chunks = a.coutp >> 3;                // 8-channel chunks per pixel
+    const int tiles_mine = (t.T - sub + 1) >> 1;    // tiles sub, sub+2, ...
+    const int n_items = tiles_mine * chunks;
+    uint32_t tcount = 0;
+    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
+      const int sx = st_i % t.tiles_x;
+      const int rest = st_i / t.tiles_x;
+      const int sy = rest % t.tiles_y;
+      const int b = rest / t.tiles_y;
+      const int x0 = sx * (8 * t.T), oy = sy * 16 + row;
+      const uint32_t as = tcount & 1;
+      const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N) + ((uint32_t)(q * 32) << 16);
+      const long rowpix = ((long)b * a.Hout + oy) * a.Wout;
+      const bool row_ok = oy < a.Hout;
+      EpiOps cur, nxt;
+      if (EPI_GENERAL && n_items > 0) epi_load(cur, a, rowpix + x0 + sub * 8 + colx, 0, row_ok && (x0 + sub * 8 + colx) < a.Wout);
+      if (lane == 0) mbar_wait(&bar_acc_full[as], (tcount >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+      int tile = sub, ch = 0;
+      for (int k = 0; k < n_items; ++k) {
+        int ntile = tile, nch = ch + 1;
+        if (nch == chunks) { nch = 0; ntile += 2; }
+        if (EPI_GENERAL && k + 1 < n_items)
+          epi_load(nxt, a, rowpix + x0 + ntile * 8 + colx, nch * 8, row_ok && (x0 + ntile * 8 + colx) < a.Wout);
+        float v[8];
+        tmem_ld8(acc_base + (uint32_t)(tile * t.N + ch * 8), v);        // warp-collective
+        const int ox = x0 + tile * 8 + colx;
+        if (row_ok && ox < a.Wout && !(t.dbg & 4)) {
+          if (EPI_GENERAL) {
+            epi_apply(cur, a, rowpix + ox, ch * 8, v);
+          } else {
+            float b8[8];
+            if (a.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8) + 1);
+              b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) b8[i] = 0.f;
+            }
+            epi_store<false>(cur, a, a.out + (rowpix + ox) * a.po + ch * 8, b8, a.relu != 0, v);
+          }
+        }
+        if (EPI_GENERAL) cur = nxt;
+        tile = ntile; ch = nch;
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acc_empty[as]);              // every epilogue thread has finished reading this accumulator set
     }
   }
   tc_fence_before();
@@ -335,34 +518,58 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   MSAU_CHECK_ARG(conv_tc_supported(a), "conv_tc: unsupported shape");
   TcTile t;
   t.N = a.coutp < 16 ? 16 : round_up(a.coutp, 16);
-  t.T = t.N <= 32 ? 8 : (t.N <= 64 ? 4 : 2);
-  while (t.T > 1 && 8 * (t.T / 2) >= a.Wout) t.T /= 2;       // narrow maps: do not pay for columns that do not exist
+  t.T = t.N <= 32 ? 8 : (t.N <= 64 ? 4 : 2);               // 2 accumulator sets x T x N columns <= 512
+  while (t.T > 1 && 8 * (t.T / 2) >= a.Wout) t.T /= 2;     // narrow maps: do not pay for columns that do not exist
   const int taps = a.kh * a.kw;
   t.n1 = taps; t.n3 = (taps + 1) / 2;
   t.HH = 16 + (a.kh - 1) * a.dil;
   t.HW = 8 * t.T + (a.kw - 1) * a.dil;
+  t.step_q = PROD_THREADS / t.HW; t.step_r = PROD_THREADS % t.HW;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
   t.P = (a.c1 + a.c2) / 8;
   t.in_bytes = (uint32_t)t.HH * t.HW * 32;
   t.w_bytes = (uint32_t)(t.n1 + t.n3) * t.N * 32;
   t.stage_bytes = (t.in_bytes + t.w_bytes + 127) / 128 * 128;
-  t.stages = t.P >= 2 ? 2 : 1;
-  int cols = t.T * t.N;
+  t.stages = MAX_STAGES;
+  while (t.stages > 2 && (size_t)t.stage_bytes * t.stages > 200 * 1024) --t.stages;
+  t.tiles_x = cdiv(a.Wout, 8 * t.T);
+  t.tiles_y = cdiv(a.Hout, 16);
+  t.n_super = t.tiles_x * t.tiles_y * a.B;
+  const int cols = 2 * t.T * t.N;
   t.tmem_cols = 32;
   while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
   const size_t smem = (size_t)t.stage_bytes * t.stages + 1024;
   MSAU_CHECK_ARG(smem <= 220 * 1024 && t.tmem_cols <= 512, "conv_tc: tile does not fit (smem %zu B, tmem %u cols)", smem, t.tmem_cols);
-  static bool attr = false;
-  if (!attr) {
-    MSAU_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr = true;
-  }
-  dim3 grid(cdiv(a.Wout, 8 * t.T), cdiv(a.Hout, 16), a.B);
-  MSAU_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "conv_tc: grid too large");
+  int grid = t.n_super < sm_count() ? t.n_super : sm_count();   // persistent: one CTA per SM
+  const int src_mode = a.src1_nchw ? SRC_NCHW : (a.mask1 ? SRC_MASK : (a.relu1 ? SRC_RELU : SRC_PLAIN));
+  MSAU_CHECK_ARG(!(a.mask1 && a.relu1), "conv_tc: mask1 and relu1 together are not supported");
+  const bool general = a.res || a.omask || a.add || a.accumulate || a.relu2;
   const double npix = (double)a.B * a.Hin * a.Win;
   double bytes = npix * ((a.src1_nchw ? a.c1_logical : a.c1) + a.c2 + (a.mask1 ? a.c1 : 0)) * 4.0;
   bytes += npix * a.coutp * 4.0 * (1 + (a.res ? 1 : 0) + (a.omask ? 1 : 0) + (a.add ? 1 : 0) + (a.addmask ? 1 : 0) + (a.accumulate ? 1 : 0));
-  ProfScope ps("conv_tc_kernel", 2.0 * npix * taps * (a.c1 + a.c2) * a.coutp, bytes, st);
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(a, wtc, t);
+  ProfScope ps("conv_tc_kernel", a.c1 + a.c2, a.coutp, a.kh, a.dil, a.Wout, src_mode * 2 + (general ? 1 : 0), 2.0 * npix * taps * (a.c1 + a.c2) * a.coutp, bytes, st);
+#define MSAU_TC_LAUNCH(SM, EG)                                                                                          \
+  {                                                                                                                    \
+    static bool attr = false;                                                                                          \
+    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<SM, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    conv_tc_kernel<SM, EG><<<grid, TC_THREADS, smem, st>>>(a, wtc, t);                                                 \
+  }
+  if (general) {
+    switch (src_mode) {
+      case SRC_PLAIN: MSAU_TC_LAUNCH(SRC_PLAIN, true) break;
+      case SRC_RELU: MSAU_TC_LAUNCH(SRC_RELU, true) break;
+      case SRC_MASK: MSAU_TC_LAUNCH(SRC_MASK, true) break;
+      default: MSAU_TC_LAUNCH(SRC_NCHW, true) break;
+    }
+  } else {
+    switch (src_mode) {
+      case SRC_PLAIN: MSAU_TC_LAUNCH(SRC_PLAIN, false) break;
+      case SRC_RELU: MSAU_TC_LAUNCH(SRC_RELU, false) break;
+      case SRC_MASK: MSAU_TC_LAUNCH(SRC_MASK, false) break;
+      default: MSAU_TC_LAUNCH(SRC_NCHW, false) break;
+    }
+  }
+#undef MSAU_TC_LAUNCH
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

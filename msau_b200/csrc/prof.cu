@@ -1,6 +1,7 @@
 #include "prof.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -14,7 +15,7 @@
 namespace msau {
 
 struct ProfRec {
-  const char* kernel;
+  std::string kernel;
   double flops, bytes;
   cudaEvent_t e0, e1;
 };
@@ -25,6 +26,11 @@ static std::vector<ProfRec> g_recs;
 static std::vector<cudaEvent_t> g_pool;
 
 bool prof_enabled() { return g_on; }
+bool prof_detail() {
+  static int d = -1;
+  if (d < 0) { const char* e = getenv("MSAU_PROF_DETAIL"); d = (e && atoi(e)) ? 1 : 0; }
+  return d == 1;
+}
 
 static cudaEvent_t get_event() {
   if (!g_pool.empty()) {

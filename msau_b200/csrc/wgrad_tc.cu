@@ -30,14 +30,15 @@ __device__ __forceinline__ void wmbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void wmbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = wsmem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 26); ++it) {
+  // try_wait with a suspend-time hint parks the thread in hardware instead of spinning on issue slots
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
     if (ok) return;
   }
@@ -52,6 +53,26 @@ __device__ __forceinline__ void wtc_mma(uint32_t d_tmem, uint64_t a_desc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool welect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void wtc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // no-swizzle descriptor; for MN-major operands LBO = stride between 8-row K groups, SBO = stride between MN groups
@@ -144,7 +165,10 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   for (int tile = tile0; tile < tile1; ++tile, ++it) {
     const int s = it & 1;
     uint8_t* st = smem + (size_t)s * t.stage_bytes;
-    if (it >= 2) wmbar_wait(&bar_free[s], ((it >> 1) - 1) & 1);
+    if (it >= 2) {
+      if (tid == 0) wmbar_wait(&bar_free[s], ((it >> 1) - 1) & 1);
+      __syncthreads();
+    }
     const int tx = tile % t.tiles_x;
     const int rest = tile / t.tiles_x;
     const int ty = rest % t.tiles_y;
@@ -213,29 +237,43 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    // one issuing thread per kernel row (warps 0..kh-1, lane 0): each owns its own TMEM accumulator
-    if (warp < a.kh && lane == 0) {
+    // one issuing warp per kernel row (warps 0..kh-1, one elected lane each): each owns its own TMEM accumulator
+    if (warp < a.kh) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int ky = warp;
-      const uint32_t xh = wsmem_u32(st);
-      const uint32_t yh = xh + t.x_plane_bytes;
-      const uint32_t sbo_a = (uint32_t)a.dila * 16;
-      const int chunks = t.TC >> 4;
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ky * t.N);
-      uint32_t first = (it == 0) ? 0u : 1u;
-      uint64_t ah = wmake_desc(xh + (uint32_t)(ky * a.dila * t.HWx) * 16, 128, sbo_a);
-      uint64_t bh = wmake_desc(yh, 128, t.y_plane_bytes);
-      const uint32_t xrow16 = (uint32_t)t.HWx - (uint32_t)chunks * 16;   // row advance after the chunks, 16-B units
-      for (int r = 0; r < t.TR; ++r) {
-        for (int cc = 0; cc < chunks; ++cc) {
-          wtc_mma(d_tmem, ah, bh, idesc, first);
-          first = 1u;
-          ah += 16; bh += 16;                             // next 16 pixels = 256 B
+      if (welect_one()) {
+        const int ky = warp;
+        const uint32_t xh = wsmem_u32(st);
+        const uint32_t yh = xh + t.x_plane_bytes;
+        const int chunks = t.TC >> 4;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ky * t.N);
+        uint32_t first = (it == 0) ? 0u : 1u;
+        const uint32_t lbo = (128u >> 4) << 16;
+        const uint32_t a_hi = (((uint32_t)a.dila * 16 >> 4) & 0x3FFF) | (1u << 14);
+        const uint32_t b_hi = ((t.y_plane_bytes >> 4) & 0x3FFF) | (1u << 14);
+        uint32_t a_lo = (((xh >> 4) + (uint32_t)(ky * a.dila * t.HWx)) & 0x3FFF) | lbo;
+        uint32_t b_lo = ((yh >> 4) & 0x3FFF) | lbo;
+        const uint32_t xrow16 = (uint32_t)t.HWx - (uint32_t)chunks * 16;   // row advance after the chunks, 16-B units
+        for (int r = 0; r < t.TR; ++r) {
+          if (chunks == 4) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              wtc_mma2(d_tmem, a_lo + cc * 16, a_hi, b_lo + cc * 16, b_hi, idesc, cc == 0 ? first : 1u);
+            }
+            first = 1u;
+            a_lo += 64; b_lo += 64;
+          } else {
+            for (int cc = 0; cc < chunks; ++cc) {
+              wtc_mma2(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+              first = 1u;
+              a_lo += 16; b_lo += 16;                       // next 16 pixels = 256 B
+            }
+          }
+          a_lo += xrow16;                                   // dY rows are dense: b_lo already points at the next row
         }
-        ah += xrow16;                                     // dY rows are dense: bh already points at the next row
+        wtc_commit(&bar_free[s]);
+        if (tile == tile1 - 1) wtc_commit(&bar_done);
       }
-      wtc_commit(&bar_free[s]);
-      if (tile == tile1 - 1) wtc_commit(&bar_done);
+      __syncwarp();
     }
   }
   // ---- bias gradient partials ----
@@ -245,7 +283,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
     for (int k = 0; k < 8; ++k) atomicAdd(&sbias[pl * 8 + k], bacc[k]);
   }
   // ---- reduce the resident accumulators into dW ----
-  wmbar_wait(&bar_done, 0);
+  if (tid == 0) wmbar_wait(&bar_done, 0);
+  __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   if (warp < 2) {
     // M = 64 accumulator: row m lives in TMEM lane (m % 16) + 32 * (m / 16)  (cute tmem_frg, "half subpartition"
@@ -328,7 +367,7 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   dim3 grid(ctas, planes);
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + npq * a.cb * (a.maskB ? 2 : 1)) * 4.0;
-  ProfScope ps("wgrad_tc_kernel", 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  ProfScope ps("wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
   wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(a, t);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
