@@ -72,6 +72,16 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // exactly one lane of a converged warp (the compiler then emits straight-line UTCHMMA without per-lane election loops)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -154,7 +164,7 @@ struct TcTile {
   int tiles_x, tiles_y, n_super;    // super-tile grid (16 rows x 8T columns each)
   int step_q, step_r;               // PROD_THREADS = step_q * HW + step_r
   int dbg;                          // MSAU_TC_DEBUG experiments: 1 = no MMAs, 2 = no producer loads, 4 = no epilogue stores
-  uint32_t in_bytes, w_bytes, stage_bytes, tmem_cols;
+  uint32_t in_bytes, w_bytes, stage_bytes, raw_bytes, tmem_cols;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -167,48 +177,50 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// extra epilogue operands of one work item (one pixel x 8 output channels = 2 float4 groups)
-struct EpiOps { float4 res[2], om[2], ad[2], am[2], ou[2]; };
+// Extra epilogue operands of one work item (one pixel x 8 output channels), compact enough to keep several
+// items in flight: `a` = residual (forward) or skip-path add (backward), `o` = previous output (accumulate),
+// `m` = 8 ReLU-mask bits taken from the masking activation.
+struct EpiItem { float4 a[2]; float4 o[2]; uint32_t m; };
+static constexpr int EPI_DEPTH = 4;
 
-__device__ __forceinline__ void epi_load(EpiOps& o, const ConvArgs& a, long pix, int co, bool valid) {
+__device__ __forceinline__ void epi_load(EpiItem& it, const ConvArgs& a, long pix, int co, bool valid) {
+  it.m = 0xffu;
   if (!valid) return;
-#pragma unroll
-  for (int g = 0; g < 2; ++g) {
-    const int c = co + g * 4;
-    if (a.res) o.res[g] = __ldg(reinterpret_cast<const float4*>(a.res + pix * a.pr + c));
-    if (a.omask) o.om[g] = __ldg(reinterpret_cast<const float4*>(a.omask + pix * a.pom + c));
-    if (a.add) o.ad[g] = __ldg(reinterpret_cast<const float4*>(a.add + pix * a.pa + c));
-    if (a.addmask) o.am[g] = __ldg(reinterpret_cast<const float4*>(a.addmask + pix * a.pam + c));
-    if (a.accumulate) o.ou[g] = *reinterpret_cast<const float4*>(a.out + pix * a.po + c);
+  const float* ap = a.res ? a.res + pix * a.pr + co : (a.add ? a.add + pix * a.pa + co : nullptr);
+  if (ap) { it.a[0] = __ldg(reinterpret_cast<const float4*>(ap)); it.a[1] = __ldg(reinterpret_cast<const float4*>(ap) + 1); }
+  if (a.accumulate) {
+    const float4* op = reinterpret_cast<const float4*>(a.out + pix * a.po + co);
+    it.o[0] = op[0]; it.o[1] = op[1];
+  }
+  if (a.omask) {
+    const float4* mp = reinterpret_cast<const float4*>(a.omask + pix * a.pom + co);
+    const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+    it.m = (m0.x > 0.f ? 1u : 0u) | (m0.y > 0.f ? 2u : 0u) | (m0.z > 0.f ? 4u : 0u) | (m0.w > 0.f ? 8u : 0u) |
+           (m1.x > 0.f ? 16u : 0u) | (m1.y > 0.f ? 32u : 0u) | (m1.z > 0.f ? 64u : 0u) | (m1.w > 0.f ? 128u : 0u);
   }
 }
 
-__device__ __forceinline__ void epi_apply(const EpiOps& o, const ConvArgs& a, long pix, int co, const float* v) {
+// out = mask( relu2( relu(acc + bias) + res ) ) + add + previous
+__device__ __forceinline__ void epi_apply(const EpiItem& it, const ConvArgs& a, long pix, int co, const float* v) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
     const int c = co + g * 4;
-    float4 r4 = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+    float r[4] = {v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]};
     if (a.bias) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(a.bias + c));
-      r4.x += bv.x; r4.y += bv.y; r4.z += bv.z; r4.w += bv.w;
+      r[0] += bv.x; r[1] += bv.y; r[2] += bv.z; r[3] += bv.w;
     }
-    if (a.relu) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
-    if (a.res) { r4.x += o.res[g].x; r4.y += o.res[g].y; r4.z += o.res[g].z; r4.w += o.res[g].w; }
-    if (a.relu2) { r4.x = fmaxf(r4.x, 0.f); r4.y = fmaxf(r4.y, 0.f); r4.z = fmaxf(r4.z, 0.f); r4.w = fmaxf(r4.w, 0.f); }
-    if (a.omask) {
-      r4.x = o.om[g].x > 0.f ? r4.x : 0.f; r4.y = o.om[g].y > 0.f ? r4.y : 0.f;
-      r4.z = o.om[g].z > 0.f ? r4.z : 0.f; r4.w = o.om[g].w > 0.f ? r4.w : 0.f;
+    const float av[4] = {it.a[g].x, it.a[g].y, it.a[g].z, it.a[g].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (a.relu) r[k] = fmaxf(r[k], 0.f);
+      if (a.res) r[k] += av[k];
+      if (a.relu2) r[k] = fmaxf(r[k], 0.f);
+      if (a.omask) r[k] = ((it.m >> (g * 4 + k)) & 1u) ? r[k] : 0.f;
+      if (a.add) r[k] += av[k];
     }
-    if (a.add) {
-      float4 r = o.ad[g];
-      if (a.addmask) {
-        r.x = o.am[g].x > 0.f ? r.x : 0.f; r.y = o.am[g].y > 0.f ? r.y : 0.f;
-        r.z = o.am[g].z > 0.f ? r.z : 0.f; r.w = o.am[g].w > 0.f ? r.w : 0.f;
-      }
-      r4.x += r.x; r4.y += r.y; r4.z += r.z; r4.w += r.w;
-    }
-    if (a.accumulate) { r4.x += o.ou[g].x; r4.y += o.ou[g].y; r4.z += o.ou[g].z; r4.w += o.ou[g].w; }
-    *reinterpret_cast<float4*>(a.out + pix * a.po + c) = r4;
+    if (a.accumulate) { r[0] += it.o[g].x; r[1] += it.o[g].y; r[2] += it.o[g].z; r[3] += it.o[g].w; }
+    *reinterpret_cast<float4*>(a.out + pix * a.po + c) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -220,25 +232,25 @@ static constexpr int PROD_WARPS = 7;     // 7 + 1 + 8 = 16 warps -> 128 register
 static constexpr int PROD_THREADS = PROD_WARPS * 32;
 static constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes every other tile
 static constexpr int TC_THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
-static constexpr int LD_U = 4;        // halo pixels whose global loads are in flight per producer thread
-static constexpr int W_U = 4;         // weight-image uint4s prefetched per producer thread per plane (the rest is copied late)
+static constexpr int W_U = 4;         // weight-image uint4s prefetched per producer thread per plane
 static constexpr int MAX_STAGES = 3;
+static constexpr int RAW_SLOTS = 0;   // (cp.async raw ring experiment: slower than register staging, kept out)
 
 enum { SRC_PLAIN = 0, SRC_RELU = 1, SRC_MASK = 2, SRC_NCHW = 3 };
 
 // One 8-channel plane of the halo tile: fp32 global -> bf16 hi/lo planar image in shared memory.
 // `src` / `mask` already point at (batch b, channel cg); indices stay 32-bit (tensors < 2^31 floats).
-template <int MODE>
+template <int MODE, int LDU>
 __device__ __forceinline__ void produce_plane(const float* __restrict__ src, int pitch, const float* __restrict__ mask, int pm,
                                               int plane_stride, int n_valid, int in_x0, int in_y0, int Hin, int Win,
                                               const TcTile& t, uint8_t* __restrict__ stg, uint32_t plane_bytes, int tid) {
   const int halo_px = t.HH * t.HW;
   int iy_c = tid / t.HW, ix_c = tid - iy_c * t.HW;          // halo coordinates of element e, advanced incrementally
-  for (int e0 = tid; e0 < halo_px; e0 += PROD_THREADS * LD_U) {
-    float v[LD_U][8];
-    float4 mk[LD_U][2];
+  for (int e0 = tid; e0 < halo_px; e0 += PROD_THREADS * LDU) {
+    float v[LDU][8];
+    float4 mk[LDU][2];
 #pragma unroll
-    for (int u = 0; u < LD_U; ++u) {
+    for (int u = 0; u < LDU; ++u) {
       const int e = e0 + u * PROD_THREADS;
       const int gy = in_y0 + iy_c, gx = in_x0 + ix_c;
       iy_c += t.step_q; ix_c += t.step_r;                     // e += PROD_THREADS
@@ -263,7 +275,7 @@ __device__ __forceinline__ void produce_plane(const float* __restrict__ src, int
       }
     }
 #pragma unroll
-    for (int u = 0; u < LD_U; ++u) {
+    for (int u = 0; u < LDU; ++u) {
       const int e = e0 + u * PROD_THREADS;
       if (e >= halo_px) break;
       if (MODE == SRC_MASK) {
@@ -284,7 +296,7 @@ __device__ __forceinline__ void produce_plane(const float* __restrict__ src, int
 }
 
 template <bool GENERAL>
-__device__ __forceinline__ void epi_store(const EpiOps& o, const ConvArgs& a, float* __restrict__ dst, const float* __restrict__ bias8,
+__device__ __forceinline__ void epi_store(const ConvArgs& a, float* __restrict__ dst, const float* __restrict__ bias8,
                                           bool relu, const float* v) {
   // fast path: bias (+ReLU) only -- two 16-byte stores per item
   if (!GENERAL) {
@@ -364,16 +376,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         if (from1) {
           if (SRC_MODE == SRC_NCHW) {
             const int plane_stride = a.Hin * a.Win;
-            produce_plane<SRC_NCHW>(a.src1 + ((long)b * a.c1_logical + cg) * plane_stride, 0, nullptr, 0, plane_stride,
+            produce_plane<SRC_NCHW, 4>(a.src1 + ((long)b * a.c1_logical + cg) * plane_stride, 0, nullptr, 0, plane_stride,
                                     a.c1_logical - cg, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
           } else {
             const long boff = (long)b * a.Hin * a.Win;
-            produce_plane<SRC_MODE>(a.src1 + boff * a.p1 + cg, a.p1, SRC_MODE == SRC_MASK ? a.mask1 + boff * a.pm1 + cg : nullptr,
+            produce_plane<SRC_MODE, 6>(a.src1 + boff * a.p1 + cg, a.p1, SRC_MODE == SRC_MASK ? a.mask1 + boff * a.pm1 + cg : nullptr,
                                     a.pm1, 0, 8, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
           }
         } else {
           const long boff = (long)b * a.Hin * a.Win;
-          produce_plane<SRC_PLAIN>(a.src2 + boff * a.p2 + cg, a.p2, nullptr, 0, 0, 8, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
+          produce_plane<SRC_PLAIN, 6>(a.src2 + boff * a.p2 + cg, a.p2, nullptr, 0, 0, 8, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
         }
         {   // this plane's weight image (already bf16, already in UMMA layout)
           uint4* dst = reinterpret_cast<uint4*>(stg + t.in_bytes);
@@ -455,38 +467,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N) + ((uint32_t)(q * 32) << 16);
       const long rowpix = ((long)b * a.Hout + oy) * a.Wout;
       const bool row_ok = oy < a.Hout;
-      EpiOps cur, nxt;
-      if (EPI_GENERAL && n_items > 0) epi_load(cur, a, rowpix + x0 + sub * 8 + colx, 0, row_ok && (x0 + sub * 8 + colx) < a.Wout);
+      // item k -> (tile, chunk): tile = sub + 2 * (k / chunks), chunk = k % chunks
+      EpiItem items[EPI_DEPTH];
+      if (EPI_GENERAL) {
+#pragma unroll
+        for (int d = 0; d < EPI_DEPTH; ++d) {
+          if (d < n_items) {
+            const int tl = sub + 2 * (d / chunks), chd = d % chunks;
+            epi_load(items[d], a, rowpix + x0 + tl * 8 + colx, chd * 8, row_ok && (x0 + tl * 8 + colx) < a.Wout);
+          }
+        }
+      }
       if (lane == 0) mbar_wait(&bar_acc_full[as], (tcount >> 1) & 1);
       __syncwarp();
       tc_fence_after();
-      int tile = sub, ch = 0;
-      for (int k = 0; k < n_items; ++k) {
-        int ntile = tile, nch = ch + 1;
-        if (nch == chunks) { nch = 0; ntile += 2; }
-        if (EPI_GENERAL && k + 1 < n_items)
-          epi_load(nxt, a, rowpix + x0 + ntile * 8 + colx, nch * 8, row_ok && (x0 + ntile * 8 + colx) < a.Wout);
-        float v[8];
-        tmem_ld8(acc_base + (uint32_t)(tile * t.N + ch * 8), v);        // warp-collective
-        const int ox = x0 + tile * 8 + colx;
-        if (row_ok && ox < a.Wout && !(t.dbg & 4)) {
-          if (EPI_GENERAL) {
-            epi_apply(cur, a, rowpix + ox, ch * 8, v);
-          } else {
-            float b8[8];
-            if (a.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8) + 1);
-              b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
-            } else {
+      for (int k0 = 0; k0 < n_items; k0 += EPI_DEPTH) {
+        if (EPI_GENERAL && k0 > 0) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) b8[i] = 0.f;
+          for (int d = 0; d < EPI_DEPTH; ++d) {
+            if (k0 + d < n_items) {
+              const int tl = sub + 2 * ((k0 + d) / chunks), chd = (k0 + d) % chunks;
+              epi_load(items[d], a, rowpix + x0 + tl * 8 + colx, chd * 8, row_ok && (x0 + tl * 8 + colx) < a.Wout);
             }
-            epi_store<false>(cur, a, a.out + (rowpix + ox) * a.po + ch * 8, b8, a.relu != 0, v);
           }
         }
-        if (EPI_GENERAL) cur = nxt;
-        tile = ntile; ch = nch;
+#pragma unroll
+        for (int d = 0; d < EPI_DEPTH; ++d) {
+          const int k = k0 + d;
+          if (k < n_items) {                                            // warp-uniform
+            const int tile = sub + 2 * (k / chunks), ch = k % chunks;
+            float v[8];
+            tmem_ld8(acc_base + (uint32_t)(tile * t.N + ch * 8), v);    // warp-collective
+            const int ox = x0 + tile * 8 + colx;
+            if (row_ok && ox < a.Wout && !(t.dbg & 4)) {
+              if (EPI_GENERAL) {
+                epi_apply(items[d], a, rowpix + ox, ch * 8, v);
+              } else {
+                float b8[8];
+                if (a.bias) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + ch * 8) + 1);
+                  b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) b8[i] = 0.f;
+                }
+                epi_store<false>(a, a.out + (rowpix + ox) * a.po + ch * 8, b8, a.relu != 0, v);
+              }
+            }
+          }
+        }
       }
       tc_fence_before();
       mbar_arrive(&bar_acc_empty[as]);              // every epilogue thread has finished reading this accumulator set
@@ -499,13 +529,46 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
   }
 }
 
+static bool tc_configure(const ConvArgs& a, TcTile& t) {
+  t.N = a.coutp < 16 ? 16 : round_up(a.coutp, 16);
+  t.T = t.N <= 32 ? 8 : (t.N <= 64 ? 4 : 2);               // 2 accumulator sets x T x N columns <= 512
+  while (t.T > 1 && 8 * (t.T / 2) >= a.Wout) t.T /= 2;     // narrow maps: do not pay for columns that do not exist
+  const int taps = a.kh * a.kw;
+  t.n1 = taps; t.n3 = (taps + 1) / 2;
+  t.P = (a.c1 + a.c2) / 8;
+  t.w_bytes = (uint32_t)(t.n1 + t.n3) * t.N * 32;
+  for (;;) {                                               // shrink the super-tile until >= 2 MMA stages + the raw ring fit
+    t.HH = 16 + (a.kh - 1) * a.dil;
+    t.HW = 8 * t.T + (a.kw - 1) * a.dil;
+    t.in_bytes = (uint32_t)t.HH * t.HW * 32;
+    t.stage_bytes = (t.in_bytes + t.w_bytes + 127) / 128 * 128;
+    t.raw_bytes = t.stage_bytes;                           // raw fp32 plane = 32 B / pixel, same as hi + lo
+    t.stages = MAX_STAGES;
+    while (t.stages > 2 && (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS > 216 * 1024) --t.stages;
+    if ((size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS <= 216 * 1024 || t.T == 1) break;
+    t.T /= 2;
+  }
+  t.step_q = PROD_THREADS / t.HW; t.step_r = PROD_THREADS % t.HW;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
+  t.tiles_x = cdiv(a.Wout, 8 * t.T);
+  t.tiles_y = cdiv(a.Hout, 16);
+  t.n_super = t.tiles_x * t.tiles_y * a.B;
+  const int cols = 2 * t.T * t.N;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
+  const size_t smem = (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS + 1024;
+  return smem <= 220 * 1024 && t.tmem_cols <= 512;
+}
+
 bool conv_tc_supported(const ConvArgs& a) {
+  if ((a.res && a.add) || a.addmask || a.mask1) return false;
   if (a.stride != 1 || a.osy != 1 || a.oy0 != 0 || a.ox0 != 0) return false;
   if (a.Hq != a.Hin || a.Wq != a.Win || a.Hout != a.Hin || a.Wout != a.Win) return false;
   if ((a.c1 & 7) || (a.c2 & 7) || (a.coutp & 7) || a.coutp > 128) return false;
   if (!a.src1_nchw && (a.p1 & 3)) return false;
   if (a.Win < 8) return false;
-  return true;
+  TcTile t;
+  return tc_configure(a, t);
 }
 
 int tc_weight_floats_equiv(int taps, int cin, int coutp) {
@@ -517,32 +580,13 @@ int tc_weight_floats_equiv(int taps, int cin, int coutp) {
 int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   MSAU_CHECK_ARG(conv_tc_supported(a), "conv_tc: unsupported shape");
   TcTile t;
-  t.N = a.coutp < 16 ? 16 : round_up(a.coutp, 16);
-  t.T = t.N <= 32 ? 8 : (t.N <= 64 ? 4 : 2);               // 2 accumulator sets x T x N columns <= 512
-  while (t.T > 1 && 8 * (t.T / 2) >= a.Wout) t.T /= 2;     // narrow maps: do not pay for columns that do not exist
+  MSAU_CHECK_ARG(tc_configure(a, t), "conv_tc: tile does not fit");
   const int taps = a.kh * a.kw;
-  t.n1 = taps; t.n3 = (taps + 1) / 2;
-  t.HH = 16 + (a.kh - 1) * a.dil;
-  t.HW = 8 * t.T + (a.kw - 1) * a.dil;
-  t.step_q = PROD_THREADS / t.HW; t.step_r = PROD_THREADS % t.HW;
-  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
-  t.P = (a.c1 + a.c2) / 8;
-  t.in_bytes = (uint32_t)t.HH * t.HW * 32;
-  t.w_bytes = (uint32_t)(t.n1 + t.n3) * t.N * 32;
-  t.stage_bytes = (t.in_bytes + t.w_bytes + 127) / 128 * 128;
-  t.stages = MAX_STAGES;
-  while (t.stages > 2 && (size_t)t.stage_bytes * t.stages > 200 * 1024) --t.stages;
-  t.tiles_x = cdiv(a.Wout, 8 * t.T);
-  t.tiles_y = cdiv(a.Hout, 16);
-  t.n_super = t.tiles_x * t.tiles_y * a.B;
-  const int cols = 2 * t.T * t.N;
-  t.tmem_cols = 32;
-  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
-  const size_t smem = (size_t)t.stage_bytes * t.stages + 1024;
-  MSAU_CHECK_ARG(smem <= 220 * 1024 && t.tmem_cols <= 512, "conv_tc: tile does not fit (smem %zu B, tmem %u cols)", smem, t.tmem_cols);
+  const size_t smem = (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS + 1024;
   int grid = t.n_super < sm_count() ? t.n_super : sm_count();   // persistent: one CTA per SM
   const int src_mode = a.src1_nchw ? SRC_NCHW : (a.mask1 ? SRC_MASK : (a.relu1 ? SRC_RELU : SRC_PLAIN));
   MSAU_CHECK_ARG(!(a.mask1 && a.relu1), "conv_tc: mask1 and relu1 together are not supported");
+  MSAU_CHECK_ARG(!(a.res && a.add) && !a.addmask, "conv_tc: epilogue supports one of {res, add} and no addmask");
   const bool general = a.res || a.omask || a.add || a.accumulate || a.relu2;
   const double npix = (double)a.B * a.Hin * a.Win;
   double bytes = npix * ((a.src1_nchw ? a.c1_logical : a.c1) + a.c2 + (a.mask1 ? a.c1 : 0)) * 4.0;

@@ -363,22 +363,25 @@ static int res_fwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor&
 // backward of the residual block: G(out) -> G(in) (overwritten: `in` has no other consumer) + weight grads
 static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor& in, const std::vector<Tensor>& a, const Tensor& out) {
   const int R = (int)res.size();
+  // gradient through the block's final ReLU, materialised in place: it feeds the last conv's wgrad and dgrad and
+  // the identity skip path
+  count_launch(1);
+  MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));
   for (int r = R - 1; r >= 0; --r) {
     const bool last = (r == R - 1);
-    // dY of conv r: last conv -> G(out) masked by relu(out); inner convs -> G(a[r]) (already masked when produced)
+    // dY of conv r: last conv -> G(out) (masked above); inner convs -> G(a[r]) (masked when produced)
     const float* dy = last ? p->G(out) : p->G(a[r]);
     const int pdy = last ? out.C : a[r].C;
-    const float* dymask = last ? p->A(out) : nullptr;
     const Tensor& src = r == 0 ? in : a[r - 1];
-    MSAU_TRY(layer_wgrad(p, res[r], 1, p->A(src), src.C, 0, res[r].c1p, r == 0, dy, pdy, dymask, out.C, in.H, in.W));
+    MSAU_TRY(layer_wgrad(p, res[r], 1, p->A(src), src.C, 0, res[r].c1p, r == 0, dy, pdy, nullptr, 0, in.H, in.W));
     ConvOpt o;
     if (r > 0) {
       o.omask = p->A(a[r - 1]); o.pom = a[r - 1].C;          // relu after conv r-1
-      MSAU_TRY(layer_dgrad(p, res[r], 1, dy, pdy, dymask, out.C, a[r - 1], o));
+      MSAU_TRY(layer_dgrad(p, res[r], 1, dy, pdy, nullptr, 0, a[r - 1], o));
     } else {
       o.omask = p->A(in); o.pom = in.C;                       // relu applied to the block input
-      o.add = p->G(out); o.pa = out.C; o.addmask = p->A(out); o.pam = out.C;   // identity skip path
-      MSAU_TRY(layer_dgrad(p, res[r], 1, dy, pdy, dymask, out.C, in, o));
+      o.add = p->G(out); o.pa = out.C;                        // identity skip path (already masked)
+      MSAU_TRY(layer_dgrad(p, res[r], 1, dy, pdy, nullptr, 0, in, o));
     }
   }
   return MSAU_OK;
@@ -386,13 +389,14 @@ static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor&
 
 // coupling 1x1 conv on cat[prev, cur] + ReLU (model/model.py:143-148, 246-252)
 static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const Tensor& cur, const Tensor& out) {
+  count_launch(1);
+  MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));   // 4 consumers below
   const float* dy = p->G(out);
-  const float* mask = p->A(out);
-  MSAU_TRY(layer_wgrad(p, L, 1, p->A(prev), prev.C, 0, L.c1p, false, dy, out.C, mask, out.C, out.H, out.W));
-  MSAU_TRY(layer_wgrad(p, L, 2, p->A(cur), cur.C, 0, L.c2p, false, dy, out.C, mask, out.C, out.H, out.W));
+  MSAU_TRY(layer_wgrad(p, L, 1, p->A(prev), prev.C, 0, L.c1p, false, dy, out.C, nullptr, 0, out.H, out.W));
+  MSAU_TRY(layer_wgrad(p, L, 2, p->A(cur), cur.C, 0, L.c2p, false, dy, out.C, nullptr, 0, out.H, out.W));
   ConvOpt o;
-  MSAU_TRY(layer_dgrad(p, L, 1, dy, out.C, mask, out.C, prev, o));
-  MSAU_TRY(layer_dgrad(p, L, 2, dy, out.C, mask, out.C, cur, o));
+  MSAU_TRY(layer_dgrad(p, L, 1, dy, out.C, nullptr, 0, prev, o));
+  MSAU_TRY(layer_dgrad(p, L, 2, dy, out.C, nullptr, 0, cur, o));
   return MSAU_OK;
 }
 

@@ -227,6 +227,23 @@ __global__ void __launch_bounds__(256) add_kernel(float4* __restrict__ dst, cons
   dst[i] = v;
 }
 
+// g <- g * (y > 0): the gradient through a ReLU, materialised once for all of its consumers
+__global__ void __launch_bounds__(256) relu_mask_kernel(float4* __restrict__ g, const float4* __restrict__ y, long n4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = g[i];
+  const float4 m = __ldg(y + i);
+  v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f; v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+  g[i] = v;
+}
+
+int launch_relu_mask(float* g, const float* y, long n, cudaStream_t st) {
+  ProfScope ps("relu_mask_kernel", 0, (double)n * 4.0 * 3, st);
+  relu_mask_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(g), reinterpret_cast<const float4*>(y), n / 4);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
 int launch_add(float* dst, const float* src, long n, int accumulate, cudaStream_t st) {
   ProfScope ps("add_kernel", 0, (double)n * 4.0 * (accumulate ? 3 : 2), st);
   add_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n / 4, accumulate);

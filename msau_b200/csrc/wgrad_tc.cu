@@ -117,6 +117,7 @@ struct WgTile {
 };
 
 static constexpr int WG_THREADS = 256;
+static constexpr int WU = 4;          // pixels whose global loads are in flight per thread
 
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a, const WgTile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -174,65 +175,92 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
     const int ty = rest % t.tiles_y;
     const int b = rest / t.tiles_y;
     const int qy0 = ty * t.TR, qx0 = tx * t.TC;
-    // ---- X halo tile of this plane: [hi][lo], (HHx x HWx) pixels of 16 B ----
+    // ---- X halo tile of this plane: (HHx x HWx) pixels of 16 B.  WU pixels' loads are in flight per thread ----
     {
       const int in_y0 = qy0 - a.pada_t, in_x0 = qx0 - a.pada_l;
       uint8_t* xh = st;
-      for (int e = tid; e < x_px; e += WG_THREADS) {
-        const int iy = e / t.HWx, ix = e - iy * t.HWx;
-        const int gy = in_y0 + iy, gx = in_x0 + ix;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (gy >= 0 && gy < a.Ha && gx >= 0 && gx < a.Wa) {
+      const int plane_stride = a.Ha * a.Wa;
+      const float* xsrc = a.a_nchw ? a.A + ((long)b * a.ca_logical + ca0) * plane_stride : a.A + (long)b * plane_stride * a.pa + ca0;
+      const int n_valid = a.ca_logical - ca0;
+      for (int e0 = tid; e0 < x_px; e0 += WG_THREADS * WU) {
+        float v[WU][8];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          const int e = e0 + u * WG_THREADS;
+          const int iy = e / t.HWx, ix = e - iy * t.HWx;
+          const int gy = in_y0 + iy, gx = in_x0 + ix;
+          const bool inb = e < x_px && (unsigned)gy < (unsigned)a.Ha && (unsigned)gx < (unsigned)a.Wa;
+          const int lin = gy * a.Wa + gx;
           if (a.a_nchw) {
-            const long pl = (long)a.Ha * a.Wa;
-            const float* sp = a.A + ((long)b * a.ca_logical + ca0) * pl + (long)gy * a.Wa + gx;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-              if (ca0 + k < a.ca_logical) v[k] = __ldg(sp + k * pl);
+            for (int k = 0; k < 8; ++k) v[u][k] = (inb && k < n_valid) ? __ldg(xsrc + lin + k * plane_stride) : 0.f;
           } else {
-            const float* sp = a.A + (((long)b * a.Ha + gy) * a.Wa + gx) * a.pa + ca0;
-            const float4 q0 = __ldg(reinterpret_cast<const float4*>(sp));
-            const float4 q1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-            v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-          }
-          if (a.reluA) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* sp = reinterpret_cast<const float4*>(xsrc + lin * a.pa);
+            const float4 q0 = inb ? __ldg(sp) : z4;
+            const float4 q1 = inb ? __ldg(sp + 1) : z4;
+            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
           }
         }
-        *reinterpret_cast<uint4*>(xh + (size_t)e * 16) = wpack8(v);
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          const int e = e0 + u * WG_THREADS;
+          if (e >= x_px) break;
+          if (a.reluA) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
+          }
+          *reinterpret_cast<uint4*>(xh + e * 16) = wpack8(v[u]);
+        }
       }
     }
     // ---- dY tile: [planes], each plane TR x TC pixels of 16 B ----
     {
       uint8_t* yh = st + t.x_plane_bytes;
       const int total = y_px * t.ny_planes;
-      for (int e = tid; e < total; e += WG_THREADS) {
-        const int pl = e % t.ny_planes;          // constant per thread (256 % ny_planes == 0)
-        const int px = e / t.ny_planes;
-        const int r = px / t.TC, c = px - r * t.TC;
-        const int gy = qy0 + r, gx = qx0 + c;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (gy < a.Hb && gx < a.Wb) {
-          const long pix = ((long)b * a.Hb + gy) * a.Wb + gx;
-          const float* sp = a.Bm + pix * a.pb + (pl << 3);
-          const float4 q0 = __ldg(reinterpret_cast<const float4*>(sp));
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(sp) + 1);
-          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
-          if (a.maskB) {
-            const float* mp = a.maskB + pix * a.pmb + (pl << 3);
-            const float4 m0 = __ldg(reinterpret_cast<const float4*>(mp));
-            const float4 m1 = __ldg(reinterpret_cast<const float4*>(mp) + 1);
-            const float m[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const int pl = tid % t.ny_planes;            // constant per thread (256 % ny_planes == 0)
+      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (pl << 3);
+      const float* msrc = a.maskB ? a.maskB + (long)b * a.Hb * a.Wb * a.pmb + (pl << 3) : nullptr;
+      uint8_t* ydst = yh + (size_t)pl * t.y_plane_bytes;
+      for (int e0 = tid; e0 < total; e0 += WG_THREADS * WU) {
+        float v[WU][8];
+        float4 mk[WU][2];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = m[k] > 0.f ? v[k] : 0.f;
+        for (int u = 0; u < WU; ++u) {
+          const int e = e0 + u * WG_THREADS;
+          const int px = e / t.ny_planes;
+          const int r = px / t.TC, c = px - r * t.TC;
+          const int gy = qy0 + r, gx = qx0 + c;
+          const bool inb = e < total && gy < a.Hb && gx < a.Wb;
+          const int lin = gy * a.Wb + gx;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* sp = reinterpret_cast<const float4*>(ysrc + lin * a.pb);
+          const float4 q0 = inb ? __ldg(sp) : z4;
+          const float4 q1 = inb ? __ldg(sp + 1) : z4;
+          v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+          v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+          if (msrc) {
+            const float4* mp = reinterpret_cast<const float4*>(msrc + lin * a.pmb);
+            mk[u][0] = inb ? __ldg(mp) : z4;
+            mk[u][1] = inb ? __ldg(mp + 1) : z4;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          const int e = e0 + u * WG_THREADS;
+          if (e >= total) break;
+          if (msrc) {
+            const float m[8] = {mk[u][0].x, mk[u][0].y, mk[u][0].z, mk[u][0].w, mk[u][1].x, mk[u][1].y, mk[u][1].z, mk[u][1].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = m[k] > 0.f ? v[u][k] : 0.f;
           }
           if (do_bias) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) bacc[k] += v[k];
+            for (int k = 0; k < 8; ++k) bacc[k] += v[u][k];
           }
+          *reinterpret_cast<uint4*>(ydst + (e / t.ny_planes) * 16) = wpack8(v[u]);
         }
-        *reinterpret_cast<uint4*>(yh + (size_t)pl * t.y_plane_bytes + (size_t)px * 16) = wpack8(v);
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -114,9 +114,12 @@ def test_every_activation_and_gradient_matches_oracle(golden_dir, name, tc):
         if not err <= 2e-4 * scale:
             bad.append(("act", nm, err))
         if t.grad is not None:
-            # inner residual activations a_r = relu(conv_r): the engine stores the gradient w.r.t. the conv
-            # output (already multiplied by the ReLU mask), the oracle w.r.t. the ReLU output
-            want = t.grad * (t.detach() > 0) if nm.rsplit(".", 1)[-1].startswith("a") and nm.rsplit(".", 1)[-1] != "att" else t.grad
+            # tensors that are the output of a ReLU (inner residual activations a_r, residual-block outputs rr,
+            # coupling outputs cc / uc): the engine keeps the gradient w.r.t. the pre-activation (multiplied by
+            # the ReLU mask, materialised once for all consumers), the oracle w.r.t. the ReLU output
+            leaf = nm.rsplit(".", 1)[-1]
+            post_relu = (leaf.startswith("a") and leaf != "att") or leaf in ("rr", "cc", "uc")
+            want = t.grad * (t.detach() > 0) if post_relu else t.grad
             gs = max(want.abs().max().item(), 1e-12)
             diff = (g[:, :c] - want).abs()
             if tc:
