@@ -1,0 +1,81 @@
+"""Reference-shaped drivers on the GPU: KVModel inference path and the train()/evaluate() loop."""
+import json
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import msau_b200
+from msau_b200 import kv_model, train as mtrain
+from oracle import model as om
+from oracle import morph as omo
+from oracle import raster as orr
+
+pytestmark = pytest.mark.gpu
+CHARSET = "".join(chr(c) for c in range(33, 127) if chr(c) != "$") + chr(161)
+
+
+def make_kv(seed=2):
+    cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    sd = om.init_state_dict(cfg, seed)
+    net = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))
+    net.load_state_dict(sd)
+    kv = kv_model.KVModel()
+    kv.net = net
+    kv.load(model_weight=None, charset=None, n_class=5)
+    kv.set_charset(CHARSET)
+    assert kv.n_token == 96
+    return kv, cfg, sd
+
+
+def test_kv_model_inference_path(tmp_path):
+    kv, cfg, sd = make_kv()
+    words, _ = orr.synth_page(5, 40, 44, 25)
+    texts = ["".join(CHARSET[c - 2] for c in ch) for ch in words["chars"]]
+    lines = [dict(box=[int(words["x"][i]), int(words["y"][i]), int(words["x"][i] + words["w"][i]), int(words["y"][i] + words["h"][i])],
+                  text=texts[i], type=0, value=0) for i in range(len(texts))]
+    p = tmp_path / "page.json"
+    p.write_text(json.dumps(dict(lines=lines)))
+    im, lm, cm, label_lines, scale, bg_pad, bbox = kv._generate_masks_from_label(str(p))
+    boxes = np.array([l["box"] for l in lines], np.float64)
+    ids = [np.array([kv.tok_to_id.get(c, 1) for c in "".join(ch if not ch.isdigit() else "0" for ch in t)], np.int32) for t in texts]
+    want = orr.raster_kv_chargrid(boxes, ids)
+    assert np.array_equal(im, want["input_mask"]) and np.array_equal(lm, want["line_id_mask"]) and np.array_equal(cm, want["character_id_mask"])
+    assert scale == want["scale"] and bg_pad == want["bg_pad"]
+    # network on the one-hot grid: class map vs the oracle model
+    ids_dev = torch.from_numpy(im.view(np.int16)).cuda()[None]
+    pred = kv.predict_maps(ids_dev)
+    x = torch.from_numpy(orr.one_hot_nchw(im, kv.n_token))
+    logits, _ = om.msau_forward(sd, cfg, x)
+    ref = logits.argmax(1).numpy().astype(np.uint8)
+    assert (pred.cpu().numpy() == ref).mean() >= 0.999
+    # post-process of the engine's own class map: bit-exact vs the oracle on the same map
+    comps = kv.components(pred, 5)
+    pm = pred[0].cpu().numpy()
+    res = omo.postprocess_page(pm, 5)
+    for c in range(2, 5):
+        closed, labels, n_lab, bboxes = comps[c]
+        assert np.array_equal(closed[0].cpu().numpy().astype(bool), res[c][0])
+        assert np.array_equal(labels[0].cpu().numpy(), res[c][1])
+        assert np.array_equal(bboxes[0, :int(n_lab[0])].cpu().numpy(), res[c][2])
+    kv_results, dbg = kv.predict((str(p), None))
+    assert isinstance(kv_results, dict) and dbg is None
+
+
+def test_train_and_evaluate_loop():
+    cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    model = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))
+    model.load_state_dict(om.init_state_dict(cfg, 4))
+    dataset = []
+    for s in range(3):
+        words, lines = orr.synth_page(20 + s, 32, 40, 16)
+        grid, label = orr.raster_word_chargrid(words, lines, np.eye(96))
+        dataset.append(dict(mask=torch.Tensor(grid).unsqueeze(0), label=torch.Tensor(label).unsqueeze(0)))
+    args = types.SimpleNamespace(num_epochs=2, clip=True, batch_size=1)
+    before = model.flat_params.clone()
+    model, val_accs = mtrain.train(dataset, model, args, val_dataset=dataset)
+    assert len(val_accs) == 2 and all(0.0 <= a <= 1.0 for a in val_accs)
+    assert not torch.equal(before.cuda(), model.flat_params)
+    r = mtrain.evaluate(dataset, model, args, name="Train", max_num_examples=100)
+    assert set(r) == {"prec", "recall", "acc"}
