@@ -162,7 +162,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     K, Wm, P = args.steps, max(args.warmup, 3), args.pages
 
     def barrier():
@@ -256,13 +257,14 @@ def main():
 
     # ---- per-kernel pass (CUDA events around every launch) -> roofline of the dominant kernel
     roof, breakdown = None, None
-    if rank == 0 or world == 1:
+    # every rank runs the pass (the step contains the all-reduce); rank 0 reports its own kernels
+    _lib.profile_enable(True)
+    for _ in range(K):
+        step_resident()
+    rep = _lib.profile_report()
+    _lib.profile_enable(False)
+    if rank == 0:
         pk = peaks()
-        _lib.profile_enable(True)
-        for _ in range(K):
-            step_resident()
-        rep = _lib.profile_report()
-        _lib.profile_enable(False)
         tot = sum(v["ms"] for v in rep.values())
         breakdown = {k: dict(share=round(v["ms"] / tot, 4), ms_per_step=round(v["ms"] / K, 4), launches_per_step=v["launches"] // K,
                              gbs=round(v["bytes"] / v["ms"] / 1e6, 1), tflops=round(v["flops"] / v["ms"] / 1e9, 2))
