@@ -159,6 +159,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # keep stdout clean for the single JSON line: library chatter (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -297,7 +301,7 @@ def main():
                                step="fwd + masked CE (main+aux) + bwd + NCCL all-reduce (N>1) + clip_grad_norm(1.0) + Adam(1e-4)"),
                    e2e=e2e, e2e_dense=e2e_dense, gpu_launches=int(launches), roofline=roof, kernel_breakdown=breakdown,
                    cpu_baseline=cpu, clocks=clocks)
-        print(json.dumps(out))
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
