@@ -91,6 +91,23 @@ int msau_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_
                         int step, float lr, float beta1, float beta2, float eps, float max_norm,
                         float* scratch, float* total_norm, void* stream);
 
+/* SelfAttentionBlock.forward (model/layers/attention.py:138-162) as a stand-alone operator on
+ * channels-last tensors (the fused tcgen05 kernels the plan uses; the N x N map is never materialised).
+ *   fg   [B, N, 2d]  f | g projections (d = channels / 8)      attention.py:152-153
+ *   hh   [B, N, C]   h projection                               attention.py:154
+ *   x    [B, N, C]   block input;  out = x + o                  attention.py:156-161
+ *   lse  [B, N]      log2-domain log-sum-exp of every soft-max row, kept for the backward
+ *   scratch          >= msau_attention_scratch_bytes, 128-byte aligned, contents need not survive
+ * backward: d_out [B,N,C] -> d_fg [B,N,2d], d_hh [B,N,C] (the residual path d_x += d_out is the caller's).
+ * channels must be 32 or 64. */
+size_t msau_attention_scratch_bytes(int batch, int n_pos, int channels);
+int msau_attention_forward(const float* fg, const float* hh, const float* x, int batch, int n_pos,
+                           int channels, float* lse, float* out, void* scratch, size_t scratch_bytes,
+                           void* stream);
+int msau_attention_backward(const float* fg, const float* hh, const float* d_out, const float* lse,
+                            int batch, int n_pos, int channels, float* d_fg, float* d_hh, void* scratch,
+                            size_t scratch_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Rasterisers (CSR batches of pages; all coordinates fp64, arithmetic bit-exact with the reference)
  * ------------------------------------------------------------------------------------------------ */

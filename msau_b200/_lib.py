@@ -20,6 +20,7 @@ SYMBOLS = [
     "msau_rect_filter", "msau_class_equals", "msau_ccl4",
     "msau_debug_layout", "msau_debug_tensor", "msau_profile_enable", "msau_profile_report",
     "msau_set_option",
+    "msau_attention_scratch_bytes", "msau_attention_forward", "msau_attention_backward",
 ]
 
 
@@ -71,6 +72,10 @@ def lib() -> C.CDLL:
     L.msau_debug_layout.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.msau_debug_tensor.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.msau_set_option.argtypes = [C.c_char_p, i32]
+    L.msau_attention_scratch_bytes.argtypes = [i32, i32, i32]
+    L.msau_attention_scratch_bytes.restype = sz
+    L.msau_attention_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
+    L.msau_attention_backward.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
     L.msau_profile_enable.argtypes = [i32]
     L.msau_profile_report.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:

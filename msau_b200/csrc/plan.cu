@@ -118,6 +118,7 @@ struct MsauPlan {
   PackDesc* d_descs = nullptr;
   long pack_blocks = 0;
   long misc_floats = 0;
+  long attn_scratch_off = 0;   // floats, inside misc: operand images of the tensor-core attention
   std::vector<TcPackDesc> tc_descs;
   TcPackDesc* d_tc_descs = nullptr;
   long tc_blocks = 0;
@@ -584,6 +585,9 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   }
   p->written.assign(p->n_tensors, 0);
   p->misc_floats = round_up(loss_partial_count(batch, (long)height * width) + 2 * batch + 2048, 64);
+  p->attn_scratch_off = p->misc_floats;
+  if (attn_tc_supported(fa, da))
+    p->misc_floats += (long)((attn_tc_scratch_bytes(batch, p->Hl[S - 1] * p->Wl[S - 1], fa) + 255) / 256 * 64);
   // descriptor table: the only device memory the plan owns
   cudaError_t e = cudaMalloc(&p->d_descs, sizeof(PackDesc) * p->descs.size());
   if (e == cudaSuccess) e = cudaMemcpy(p->d_descs, p->descs.data(), sizeof(PackDesc) * p->descs.size(), cudaMemcpyHostToDevice);
@@ -668,9 +672,15 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
           ConvOpt oa;
           MSAU_TRY(layer_fwd(p, blk.attn.fg, L.cc, nullptr, blk.fg, oa));
           MSAU_TRY(layer_fwd(p, blk.attn.h, L.cc, nullptr, blk.hh, oa));
-          count_launch(2);
-          MSAU_TRY(launch_attn_fwd(p->A(blk.fg), p->A(blk.hh), p->A(L.cc), p->B, L.cc.H * L.cc.W, blk.attn.C, blk.attn.d,
-                                   p->A(blk.mrow), p->A(blk.zinv), p->A(blk.att), p->st));
+          if (g_use_tc && attn_tc_supported(blk.attn.C, blk.attn.d)) {
+            count_launch(3);
+            MSAU_TRY(launch_attn_tc_fwd(p->A(blk.fg), p->A(blk.hh), p->A(L.cc), p->B, L.cc.H * L.cc.W, blk.attn.C, blk.attn.d,
+                                        p->A(blk.mrow), p->A(blk.att), p->misc + p->attn_scratch_off, p->st));
+          } else {
+            count_launch(2);
+            MSAU_TRY(launch_attn_fwd(p->A(blk.fg), p->A(blk.hh), p->A(L.cc), p->B, L.cc.H * L.cc.W, blk.attn.C, blk.attn.d,
+                                     p->A(blk.mrow), p->A(blk.zinv), p->A(blk.att), p->st));
+          }
         }
       } else {
         count_launch(1);
@@ -758,9 +768,15 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
         if (p->written[blk.att.id]) {   // only the next block's coupling reads the attention output
           const AttnLayer& at = blk.attn;
           const int N = L.cc.H * L.cc.W;
-          count_launch(3);
-          MSAU_TRY(launch_attn_bwd(p->A(blk.fg), p->A(blk.hh), p->G(blk.att), p->A(blk.mrow), p->A(blk.zinv), p->B, N, at.C, at.d,
-                                   p->A(blk.dvec), p->G(blk.fg), p->G(blk.hh), p->st));
+          if (g_use_tc && attn_tc_supported(at.C, at.d)) {
+            count_launch(3);
+            MSAU_TRY(launch_attn_tc_bwd(p->A(blk.fg), p->A(blk.hh), p->G(blk.att), p->A(blk.mrow), p->B, N, at.C, at.d, p->G(blk.fg),
+                                        p->G(blk.hh), p->misc + p->attn_scratch_off, p->st));
+          } else {
+            count_launch(3);
+            MSAU_TRY(launch_attn_bwd(p->A(blk.fg), p->A(blk.hh), p->G(blk.att), p->A(blk.mrow), p->A(blk.zinv), p->B, N, at.C, at.d,
+                                     p->A(blk.dvec), p->G(blk.fg), p->G(blk.hh), p->st));
+          }
           // residual path out = x + o
           count_launch(1);
           MSAU_TRY(launch_add(p->G(L.cc), p->G(blk.att), p->npix(L.cc) * L.cc.C, p->touch(L.cc), p->st));
@@ -808,6 +824,38 @@ extern "C" int msau_clip_adam_step(float* params, float* grads, float* exp_avg, 
   count_launch(2);
   return launch_clip_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, max_norm, scratch, total_norm,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+// SelfAttentionBlock as a stand-alone operator (model/layers/attention.py:152-162), tensor-core path
+extern "C" size_t msau_attention_scratch_bytes(int batch, int n_pos, int channels) {
+  return attn_tc_scratch_bytes(batch, n_pos, channels);
+}
+
+extern "C" int msau_attention_forward(const float* fg, const float* hh, const float* x, int batch, int n_pos, int channels, float* lse,
+                                      float* out, void* scratch, size_t scratch_bytes, void* stream) {
+  MSAU_CHECK_ARG(fg && hh && x && lse && out && scratch, "attention_forward: null argument");
+  MSAU_CHECK_ARG(batch >= 1 && n_pos >= 1, "attention_forward: bad shape");
+  MSAU_CHECK_ARG(attn_tc_supported(channels, channels / 8), "attention_forward: channels must be 32 or 64");
+  if (scratch_bytes < attn_tc_scratch_bytes(batch, n_pos, channels)) {
+    set_error("attention_forward: scratch too small");
+    return MSAU_ERR_WORKSPACE;
+  }
+  count_launch(3);
+  return launch_attn_tc_fwd(fg, hh, x, batch, n_pos, channels, channels / 8, lse, out, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msau_attention_backward(const float* fg, const float* hh, const float* d_out, const float* lse, int batch, int n_pos,
+                                       int channels, float* d_fg, float* d_hh, void* scratch, size_t scratch_bytes, void* stream) {
+  MSAU_CHECK_ARG(fg && hh && d_out && lse && d_fg && d_hh && scratch, "attention_backward: null argument");
+  MSAU_CHECK_ARG(batch >= 1 && n_pos >= 1, "attention_backward: bad shape");
+  MSAU_CHECK_ARG(attn_tc_supported(channels, channels / 8), "attention_backward: channels must be 32 or 64");
+  if (scratch_bytes < attn_tc_scratch_bytes(batch, n_pos, channels)) {
+    set_error("attention_backward: scratch too small");
+    return MSAU_ERR_WORKSPACE;
+  }
+  count_launch(3);
+  return launch_attn_tc_bwd(fg, hh, d_out, lse, batch, n_pos, channels, channels / 8, d_fg, d_hh, scratch,
+                            reinterpret_cast<cudaStream_t>(stream));
 }
 
 // ---- debugging aids (tests/test_model_gpu.py compares every internal activation / activation gradient
