@@ -66,6 +66,12 @@ struct ConvArgs {
   const float* omask; int pom;     // * (omask > 0)
   const float* add; int pa; const float* addmask; int pam;   // + add * (addmask > 0 if addmask)
   int accumulate;                  // out += value
+  // transposed-conv views (tensor-core path only; model/layers/layers.py:207-260):
+  //  s2d: src1 is the space-to-depth view of a physical [B, Hs, Ws, cph] tensor: virtual channel (py, px, c) of
+  //       virtual pixel (y, x) = physical pixel (2y+py, 2x+px), channel c;  c1 = 4*cph, (Hin, Win) = virtual extent
+  //  d2s: the output is the depth-to-space view of [B, Hout, Wout, cph]: virtual output channel (py, px, c) of
+  //       virtual pixel (y, x) is stored at physical pixel (2y+py, 2x+px), channel c;  coutp = 4*cph
+  int s2d, d2s, cph, Hs, Ws;
 };
 
 struct WgradArgs {
@@ -77,6 +83,9 @@ struct WgradArgs {
   int B, Hq, Wq, kh, kw;
   float* dW; long s_ca, s_cb; int ca_lim, cb_lim;   // dW index = ca*s_ca + cb*s_cb + (ty*kw+tx)
   float* dbias;                                     // += sum_q Bm (tap-independent B only) or nullptr
+  // b_s2d (tensor-core path): Bm is the space-to-depth view of a physical [B, Hb, Wb, cph] tensor (cb = 4*cph) and the
+  // result is the weight gradient of a ConvTranspose2d(k3, s2, p1): virtual tap (ty, tx) x phase (py, px) -> (ky, kx)
+  int b_s2d, cph;
 };
 
 int launch_conv(const ConvArgs& a, cudaStream_t st);

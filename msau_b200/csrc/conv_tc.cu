@@ -236,14 +236,16 @@ static constexpr int W_U = 4;         // weight-image uint4s prefetched per prod
 static constexpr int MAX_STAGES = 3;
 static constexpr int RAW_SLOTS = 0;   // (cp.async raw ring experiment: slower than register staging, kept out)
 
-enum { SRC_PLAIN = 0, SRC_RELU = 1, SRC_MASK = 2, SRC_NCHW = 3 };
+enum { SRC_PLAIN = 0, SRC_RELU = 1, SRC_MASK = 2, SRC_NCHW = 3, SRC_S2D = 4 };
 
 // One 8-channel plane of the halo tile: fp32 global -> bf16 hi/lo planar image in shared memory.
 // `src` / `mask` already point at (batch b, channel cg); indices stay 32-bit (tensors < 2^31 floats).
 template <int MODE, int LDU>
 __device__ __forceinline__ void produce_plane(const float* __restrict__ src, int pitch, const float* __restrict__ mask, int pm,
                                               int plane_stride, int n_valid, int in_x0, int in_y0, int Hin, int Win,
-                                              const TcTile& t, uint8_t* __restrict__ stg, uint32_t plane_bytes, int tid) {
+                                              const TcTile& t, uint8_t* __restrict__ stg, uint32_t plane_bytes, int tid,
+                                              int py = 0, int px = 0, int Hs = 0, int Ws = 0) {
+  // SRC_S2D: (Hin, Win) is the virtual extent; virtual pixel (y, x) of this plane = physical (2y+py, 2x+px) of [Hs, Ws]
   const int halo_px = t.HH * t.HW;
   int iy_c = tid / t.HW, ix_c = tid - iy_c * t.HW;          // halo coordinates of element e, advanced incrementally
   for (int e0 = tid; e0 < halo_px; e0 += PROD_THREADS * LDU) {
@@ -255,8 +257,13 @@ __device__ __forceinline__ void produce_plane(const float* __restrict__ src, int
       const int gy = in_y0 + iy_c, gx = in_x0 + ix_c;
       iy_c += t.step_q; ix_c += t.step_r;                     // e += PROD_THREADS
       if (ix_c >= t.HW) { ix_c -= t.HW; ++iy_c; }
-      const bool inb = e < halo_px && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win && !(t.dbg & 2);
-      const int lin = gy * Win + gx;
+      bool inb = e < halo_px && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win && !(t.dbg & 2);
+      int lin = gy * Win + gx;
+      if (MODE == SRC_S2D) {
+        const int sy = 2 * gy + py, sx = 2 * gx + px;
+        inb = inb && sy < Hs && sx < Ws;
+        lin = sy * Ws + sx;
+      }
       if (MODE == SRC_NCHW) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[u][k] = (inb && k < n_valid) ? __ldg(src + lin + k * plane_stride) : 0.f;
@@ -374,7 +381,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         for (int u = 0; u < W_U; ++u)
           if (tid + u * PROD_THREADS < w16) wreg[u] = __ldg(wsrc + tid + u * PROD_THREADS);
         if (from1) {
-          if (SRC_MODE == SRC_NCHW) {
+          if (SRC_MODE == SRC_S2D) {
+            const int ph = cg / a.cph, c0 = cg - ph * a.cph;
+            const long boff = (long)b * a.Hs * a.Ws;
+            produce_plane<SRC_S2D, 6>(a.src1 + boff * a.p1 + c0, a.p1, nullptr, 0, 0, 8, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes,
+                                      tid, ph >> 1, ph & 1, a.Hs, a.Ws);
+          } else if (SRC_MODE == SRC_NCHW) {
             const int plane_stride = a.Hin * a.Win;
             produce_plane<SRC_NCHW, 4>(a.src1 + ((long)b * a.c1_logical + cg) * plane_stride, 0, nullptr, 0, plane_stride,
                                     a.c1_logical - cg, in_x0, in_y0, a.Hin, a.Win, t, stg, plane_bytes, tid);
@@ -499,7 +511,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
             float v[8];
             tmem_ld8(acc_base + (uint32_t)(tile * t.N + ch * 8), v);    // warp-collective
             const int ox = x0 + tile * 8 + colx;
-            if (row_ok && ox < a.Wout && !(t.dbg & 4)) {
+            if (!EPI_GENERAL && a.d2s) {
+              // depth-to-space store (all four sub-pixel phases of a transposed conv in one accumulator)
+              const int ph = (ch * 8) / a.cph, c = ch * 8 - ph * a.cph;
+              const int oyp = 2 * oy + (ph >> 1), oxp = 2 * ox + (ph & 1);
+              if (oy < a.Hq && ox < a.Wq && oyp < a.Hout && oxp < a.Wout && !(t.dbg & 4)) {
+                float b8[8];
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + c));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + c) + 1);
+                b8[0] = b0.x; b8[1] = b0.y; b8[2] = b0.z; b8[3] = b0.w; b8[4] = b1.x; b8[5] = b1.y; b8[6] = b1.z; b8[7] = b1.w;
+                epi_store<false>(a, a.out + (((long)b * a.Hout + oyp) * a.Wout + oxp) * a.po + c, b8, a.relu != 0, v);
+              }
+            } else if (row_ok && ox < a.Wout && !(t.dbg & 4)) {
               if (EPI_GENERAL) {
                 epi_apply(items[d], a, rowpix + ox, ch * 8, v);
               } else {
@@ -532,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
 static bool tc_configure(const ConvArgs& a, TcTile& t) {
   t.N = a.coutp < 16 ? 16 : round_up(a.coutp, 16);
   t.T = t.N <= 32 ? 8 : (t.N <= 64 ? 4 : 2);               // 2 accumulator sets x T x N columns <= 512
-  while (t.T > 1 && 8 * (t.T / 2) >= a.Wout) t.T /= 2;     // narrow maps: do not pay for columns that do not exist
+  while (t.T > 1 && 8 * (t.T / 2) >= a.Wq) t.T /= 2;     // narrow maps: do not pay for columns that do not exist
   const int taps = a.kh * a.kw;
   t.n1 = taps; t.n3 = (taps + 1) / 2;
   t.P = (a.c1 + a.c2) / 8;
@@ -550,8 +573,8 @@ static bool tc_configure(const ConvArgs& a, TcTile& t) {
   }
   t.step_q = PROD_THREADS / t.HW; t.step_r = PROD_THREADS % t.HW;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
-  t.tiles_x = cdiv(a.Wout, 8 * t.T);
-  t.tiles_y = cdiv(a.Hout, 16);
+  t.tiles_x = cdiv(a.Wq, 8 * t.T);
+  t.tiles_y = cdiv(a.Hq, 16);
   t.n_super = t.tiles_x * t.tiles_y * a.B;
   const int cols = 2 * t.T * t.N;
   t.tmem_cols = 32;
@@ -563,7 +586,15 @@ static bool tc_configure(const ConvArgs& a, TcTile& t) {
 bool conv_tc_supported(const ConvArgs& a) {
   if ((a.res && a.add) || a.addmask || a.mask1) return false;
   if (a.stride != 1 || a.osy != 1 || a.oy0 != 0 || a.ox0 != 0) return false;
-  if (a.Hq != a.Hin || a.Wq != a.Win || a.Hout != a.Hin || a.Wout != a.Win) return false;
+  if (a.Hq != a.Hin || a.Wq != a.Win) return false;
+  if (a.d2s) {
+    if (a.coutp != 4 * a.cph || (a.cph & 7) || !a.bias || a.res || a.omask || a.add || a.accumulate || a.relu2) return false;
+    if (a.Hout > 2 * a.Hq || a.Hout < 2 * a.Hq - 1 || a.Wout > 2 * a.Wq || a.Wout < 2 * a.Wq - 1) return false;
+  } else if (a.Hout != a.Hin || a.Wout != a.Win) return false;
+  if (a.s2d) {
+    if (a.c1 != 4 * a.cph || (a.cph & 7) || a.c2 || a.src1_nchw || a.relu1 || (a.p1 & 3)) return false;
+    if (a.Hs > 2 * a.Hin || a.Hs < 2 * a.Hin - 1 || a.Ws > 2 * a.Win || a.Ws < 2 * a.Win - 1) return false;
+  }
   if ((a.c1 & 7) || (a.c2 & 7) || (a.coutp & 7) || a.coutp > 128) return false;
   if (!a.src1_nchw && (a.p1 & 3)) return false;
   if (a.Win < 8) return false;
@@ -584,7 +615,7 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   const int taps = a.kh * a.kw;
   const size_t smem = (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS + 1024;
   int grid = t.n_super < sm_count() ? t.n_super : sm_count();   // persistent: one CTA per SM
-  const int src_mode = a.src1_nchw ? SRC_NCHW : (a.mask1 ? SRC_MASK : (a.relu1 ? SRC_RELU : SRC_PLAIN));
+  const int src_mode = a.s2d ? SRC_S2D : a.src1_nchw ? SRC_NCHW : (a.mask1 ? SRC_MASK : (a.relu1 ? SRC_RELU : SRC_PLAIN));
   MSAU_CHECK_ARG(!(a.mask1 && a.relu1), "conv_tc: mask1 and relu1 together are not supported");
   MSAU_CHECK_ARG(!(a.res && a.add) && !a.addmask, "conv_tc: epilogue supports one of {res, add} and no addmask");
   const bool general = a.res || a.omask || a.add || a.accumulate || a.relu2;
@@ -603,6 +634,7 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
       case SRC_PLAIN: MSAU_TC_LAUNCH(SRC_PLAIN, true) break;
       case SRC_RELU: MSAU_TC_LAUNCH(SRC_RELU, true) break;
       case SRC_MASK: MSAU_TC_LAUNCH(SRC_MASK, true) break;
+      case SRC_S2D: MSAU_TC_LAUNCH(SRC_S2D, true) break;
       default: MSAU_TC_LAUNCH(SRC_NCHW, true) break;
     }
   } else {
@@ -610,6 +642,7 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
       case SRC_PLAIN: MSAU_TC_LAUNCH(SRC_PLAIN, false) break;
       case SRC_RELU: MSAU_TC_LAUNCH(SRC_RELU, false) break;
       case SRC_MASK: MSAU_TC_LAUNCH(SRC_MASK, false) break;
+      case SRC_S2D: MSAU_TC_LAUNCH(SRC_S2D, false) break;
       default: MSAU_TC_LAUNCH(SRC_NCHW, false) break;
     }
   }

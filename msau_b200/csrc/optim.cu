@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
   const int ty = (int)(r / d.TW);
   const int ky = d.ky0 + d.kys * ty, kx = d.kx0 + d.kxs * tx;
   const float v = params[d.src_off + (long)(i + d.i_off) * d.s_i + (long)(o + d.o_off) * d.s_o + ky * d.KW + kx];
-  packed[d.dst_off + ((long)(ty * d.TW + tx) * d.I + d.i_dst0 + i) * d.O + d.o_dst0 + o] = v;
+  packed[d.dst_off + ((long)((ty + d.ty_d0) * d.TWd + tx + d.tx_d0) * d.I + d.i_dst0 + i) * d.O + d.o_dst0 + o] = v;
 }
 
 int launch_pack(const float* params, float* packed, const PackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st) {

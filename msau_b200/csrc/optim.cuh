@@ -10,6 +10,7 @@ struct PackDesc {
   int TH, TW, I, O, i_dst0, o_dst0, I_log, O_log, i_off, o_off;
   long s_i, s_o;
   int ky0, kys, kx0, kxs, KW;
+  int TWd, ty_d0, tx_d0;   // destination tap grid: width and origin of this descriptor's taps inside it
   long blk0;
 };
 int launch_pack(const float* params, float* packed, const PackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st);

@@ -66,6 +66,9 @@ struct DeconvLayer {
   long w_off = 0, b_off = 0;
   int cin = 0, cout = 0, cinp = 0, coutp = 0;
   long pk_phase[4] = {-1, -1, -1, -1}, pk_b = -1, pk_d = -1;
+  // tensor-core path: all four sub-pixel phases as ONE 2x2-tap conv with 4*coutp output channels (depth-to-space
+  // store), and its data gradient as ONE 2x2-tap conv over the space-to-depth view of dOut
+  long pk_m = -1, pk_dm = -1, tc_m = -1, tc_dm = -1;
 };
 
 struct AttnLayer {
@@ -171,8 +174,10 @@ static int pad8(int c) { return round_up(c, 8); }
 
 // ------------------------------------------------------------------ pack descriptors
 static void add_desc(MsauPlan* p, long dst, int TH, int TW, int I, int O, int i_dst0, int o_dst0, int I_log, int O_log, long src,
-                     int i_off, int o_off, long s_i, long s_o, int ky0, int kys, int kx0, int kxs, int KW) {
+                     int i_off, int o_off, long s_i, long s_o, int ky0, int kys, int kx0, int kxs, int KW, int TWd = 0, int ty_d0 = 0,
+                     int tx_d0 = 0) {
   PackDesc d;
+  d.TWd = TWd ? TWd : TW; d.ty_d0 = ty_d0; d.tx_d0 = tx_d0;
   d.dst_off = dst; d.src_off = src; d.TH = TH; d.TW = TW; d.I = I; d.O = O; d.i_dst0 = i_dst0; d.o_dst0 = o_dst0;
   d.I_log = I_log; d.O_log = O_log; d.i_off = i_off; d.o_off = o_off; d.s_i = s_i; d.s_o = s_o;
   d.ky0 = ky0; d.kys = kys; d.kx0 = kx0; d.kxs = kxs; d.KW = KW;
@@ -244,6 +249,23 @@ static void setup_deconv(MsauPlan* p, DeconvLayer& L, int cin, int cout) {
   // dgrad: d_in[iy] = sum_ky dOut[2 iy - 1 + ky] W[ci][co][ky]: stride-2 conv over dOut (rows = co, cols = ci)
   L.pk_d = p->alloc_packed(9L * L.coutp * L.cinp);
   add_desc(p, L.pk_d, 3, 3, L.coutp, L.cinp, 0, 0, cout, cin, L.w_off, 0, 0, 9, (long)cout * 9, 0, 1, 0, 1, 3);
+  if (L.cinp % 8 == 0 && L.coutp % 8 == 0 && 4 * L.coutp <= 128 && L.cinp <= 128) {
+    // forward: Wm[ty][tx][ci][(py,px,co)], tap (ty,tx) reads input pixel (q+ty, q'+tx)
+    L.pk_m = p->alloc_packed(4L * L.cinp * 4 * L.coutp);
+    // dgrad: Wdm[ty][tx][(py,px,co)][ci], tap (ty,tx) reads virtual dOut pixel (q-1+ty, q'-1+tx):
+    //   (ty=0,py=1) -> ky=0   (ty=1,py=0) -> ky=1   (ty=1,py=1) -> ky=2   (ty=0,py=0) -> no contribution
+    L.pk_dm = p->alloc_packed(4L * 4 * L.coutp * L.cinp);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int ph = py * 2 + px, th = py ? 2 : 1, tw = px ? 2 : 1;
+        add_desc(p, L.pk_m, th, tw, L.cinp, 4 * L.coutp, 0, ph * L.coutp, cin, cout, L.w_off, 0, 0, (long)cout * 9, 9,
+                 py ? 2 : 1, py ? -2 : 0, px ? 2 : 1, px ? -2 : 0, 3, 2, 0, 0);
+        add_desc(p, L.pk_dm, th, tw, 4 * L.coutp, L.cinp, ph * L.coutp, 0, cout, cin, L.w_off, 0, 0, 9, (long)cout * 9,
+                 py ? 0 : 1, py ? 2 : 0, px ? 0 : 1, px ? 2 : 0, 3, 2, py ? 0 : 1, px ? 0 : 1);
+      }
+    L.tc_m = add_tc(p, L.pk_m, 4, L.cinp, 4 * L.coutp);
+    L.tc_dm = add_tc(p, L.pk_dm, 4, 4 * L.coutp, L.cinp);
+  }
 }
 
 static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
@@ -402,6 +424,21 @@ static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const 
 }
 
 static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out) {
+  if (g_use_tc && L.tc_m >= 0) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src1 = p->A(in); a.c1 = L.cinp; a.p1 = in.C; a.c1_logical = L.cinp;
+    a.w = p->pk + L.pk_m; a.bias = p->pk + L.pk_b;
+    a.out = p->A(out); a.po = out.C; a.coutp = 4 * L.coutp;
+    a.B = p->B; a.Hin = in.H; a.Win = in.W; a.Hq = in.H; a.Wq = in.W;
+    a.kh = 2; a.kw = 2; a.dil = 1; a.stride = 1; a.pad_t = 0; a.pad_l = 0;
+    a.Hout = out.H; a.Wout = out.W; a.osy = 1;
+    a.d2s = 1; a.cph = L.coutp;
+    if (conv_tc_supported(a)) {
+      count_launch(1);
+      return launch_conv_tc(a, p->pktc + L.tc_m, p->st);
+    }
+  }
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       ConvArgs a;
@@ -422,7 +459,27 @@ static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
 
 static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out) {
   // weights: dW[ci][co][ky][kx] = sum_q x[q][ci] * dOut[2q - 1 + (ky,kx)][co]
-  for (int pass = 0; pass < 1; ++pass) {
+  bool w_done = false;
+  if (g_use_tc && L.tc_m >= 0) {
+    // = weight gradient of the merged 2x2-tap forward conv: A = x (taps (ty,tx) read x[q + (ty,tx)]), B = space-to-depth
+    // view of dOut; the kernel maps (tap, phase) back to (ky, kx) and folds the bias gradient into the dOut loader
+    WgradArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = p->A(in); a.ca = L.cinp; a.pa = in.C; a.ca_logical = L.cinp;
+    a.Ha = in.H; a.Wa = in.W; a.sa = 1; a.dila = 1; a.pada_t = 0; a.pada_l = 0;
+    a.Bm = p->G(out); a.cb = 4 * L.coutp; a.pb = out.C;
+    a.Hb = out.H; a.Wb = out.W; a.sb = 1; a.dilb = 0; a.padb_t = 0; a.padb_l = 0;
+    a.b_s2d = 1; a.cph = L.coutp;
+    a.B = p->B; a.Hq = in.H; a.Wq = in.W; a.kh = 2; a.kw = 2;
+    a.dW = p->gparams + L.w_off; a.s_ca = (long)L.cout * 9; a.s_cb = 9; a.ca_lim = L.cin; a.cb_lim = L.cout;
+    a.dbias = p->gparams + L.b_off;
+    if (wgrad_tc_supported(a)) {
+      count_launch(1);
+      MSAU_TRY(launch_wgrad_tc(a, p->st));
+      w_done = true;
+    }
+  }
+  for (int pass = 0; pass < 1 && !w_done; ++pass) {
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.A = p->A(in); a.ca = L.cinp; a.pa = in.C; a.ca_logical = L.cinp;
@@ -435,8 +492,26 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
     count_launch(1);
     MSAU_TRY(launch_wgrad(a, p->st));
   }
-  count_launch(1);
-  MSAU_TRY(launch_colsum(p->G(out), p->npix(out), out.C, L.cout, p->gparams + L.b_off, p->st));
+  if (!w_done) {
+    count_launch(1);
+    MSAU_TRY(launch_colsum(p->G(out), p->npix(out), out.C, L.cout, p->gparams + L.b_off, p->st));
+  }
+  if (g_use_tc && L.tc_dm >= 0) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src1 = p->G(out); a.c1 = 4 * L.coutp; a.p1 = out.C; a.c1_logical = a.c1;
+    a.s2d = 1; a.cph = L.coutp; a.Hs = out.H; a.Ws = out.W;
+    a.w = p->pk + L.pk_dm; a.bias = nullptr;
+    a.out = p->G(in); a.po = in.C; a.coutp = L.cinp;
+    a.B = p->B; a.Hin = in.H; a.Win = in.W; a.Hq = in.H; a.Wq = in.W;
+    a.kh = 2; a.kw = 2; a.dil = 1; a.stride = 1; a.pad_t = 1; a.pad_l = 1;
+    a.Hout = in.H; a.Wout = in.W; a.osy = 1;
+    if (conv_tc_supported(a)) {
+      a.accumulate = p->touch(in);
+      count_launch(1);
+      return launch_conv_tc(a, p->pktc + L.tc_dm, p->st);
+    }
+  }
   // data: stride-2 gather over dOut
   ConvArgs a;
   memset(&a, 0, sizeof(a));

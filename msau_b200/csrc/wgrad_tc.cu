@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       uint8_t* yh = st + t.x_plane_bytes;
       const int total = y_px * t.ny_planes;
       const int pl = tid % t.ny_planes;            // constant per thread (256 % ny_planes == 0)
-      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (pl << 3);
+      // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
+      const int sph = a.b_s2d ? (pl << 3) / a.cph : 0;
+      const int spy = sph >> 1, spx = sph & 1, smul = a.b_s2d ? 2 : 1;
+      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? (pl << 3) - sph * a.cph : (pl << 3));
       const float* msrc = a.maskB ? a.maskB + (long)b * a.Hb * a.Wb * a.pmb + (pl << 3) : nullptr;
       uint8_t* ydst = yh + (size_t)pl * t.y_plane_bytes;
       for (int e0 = tid; e0 < total; e0 += WG_THREADS * WU) {
@@ -231,8 +234,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
           const int e = e0 + u * WG_THREADS;
           const int px = e / t.ny_planes;
           const int r = px / t.TC, c = px - r * t.TC;
-          const int gy = qy0 + r, gx = qx0 + c;
-          const bool inb = e < total && gy < a.Hb && gx < a.Wb;
+          const int vy = qy0 + r, vx = qx0 + c;
+          const int gy = vy * smul + spy, gx = vx * smul + spx;
+          const bool inb = e < total && vy < a.Hq && vx < a.Wq && gy < a.Hb && gx < a.Wb;
           const int lin = gy * a.Wb + gx;
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
           const float4* sp = reinterpret_cast<const float4*>(ysrc + lin * a.pb);
@@ -327,14 +331,26 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int co = c0 + j;
-            if (co < a.cb_lim) atomicAdd(a.dW + (long)ci * a.s_ca + (long)co * a.s_cb + (ky * a.kw + kx), v[j]);
+            if (a.b_s2d) {
+              // transposed conv: virtual tap (ty, tx) x phase (py, px) -> real tap: (0,0)->1, (0,1)->2, (1,1)->0, (1,0)->none
+              const int ph = co / a.cph, c = co - ph * a.cph;
+              const int py = ph >> 1, px = ph & 1;
+              const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
+              const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
+              if (ph < 4 && c < a.cb_lim && rky >= 0 && rkx >= 0)
+                atomicAdd(a.dW + (long)ci * a.s_ca + (long)c * a.s_cb + (rky * 3 + rkx), v[j]);
+            } else if (co < a.cb_lim) atomicAdd(a.dW + (long)ci * a.s_ca + (long)co * a.s_cb + (ky * a.kw + kx), v[j]);
           }
         }
       }
     }
   }
   __syncthreads();
-  if (do_bias && tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
+  if (do_bias) {
+    if (a.b_s2d) {
+      if (tid < a.cb && (tid % a.cph) < a.cb_lim) atomicAdd(a.dbias + (tid % a.cph), sbias[tid]);
+    } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
@@ -342,7 +358,11 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
 
 bool wgrad_tc_supported(const WgradArgs& a) {
   if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
-  if (a.Ha != a.Hq || a.Wa != a.Wq || a.Hb != a.Hq || a.Wb != a.Wq) return false;
+  if (a.Ha != a.Hq || a.Wa != a.Wq) return false;
+  if (a.b_s2d) {
+    if (a.cb != 4 * a.cph || (a.cph & 7) || a.maskB || a.kh != 2 || a.kw != 2) return false;
+    if (a.Hb > 2 * a.Hq || a.Hb < 2 * a.Hq - 1 || a.Wb > 2 * a.Wq || a.Wb < 2 * a.Wq - 1) return false;
+  } else if (a.Hb != a.Hq || a.Wb != a.Wq) return false;
   if ((a.ca & 7) || (a.cb & 7) || a.cb > 128 || a.kw > 4 || a.kh > 4) return false;
   const int nyp = a.cb >> 3;
   if (256 % nyp) return false;
