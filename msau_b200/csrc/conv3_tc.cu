@@ -1,0 +1,495 @@
+// 3x3 (dilation 1, stride 1, SAME) convolution on tcgen05 with the kx taps folded into the N dimension.
+//
+// The implicit-GEMM kernel of conv_tc.cu issues one instruction per (tap, 8 input channels, term of the bf16 split):
+// 14 per 128-pixel tile and channel plane.  With 8..32 output channels those instructions are bound by the 4 KB
+// A-operand read from shared memory (~39 cycles each, scripts/mma_bench.cu), not by the math, so the tensor pipe --
+// not HBM -- limits the 8/16-channel levels of MSAU.  Here the three kx taps ride along as extra N columns:
+//     D[pixel, (kx, cout)] = sum_{ky, cin} X[pixel + ky rows, cin] * W[ky, kx, cin, cout]        (5 instructions)
+//     out[pixel x, cout]   = D[x-1, (0, cout)] + D[x, (1, cout)] + D[x+1, (2, cout)]             (epilogue)
+// A tile is 4 image rows x 32 columns of the halo image (M = 128: TMEM lane = 32 * row + column, so every warp of
+// the epilogue owns one row segment and the horizontal shift is a warp shuffle); columns 1..30 produce outputs.
+// The halo image is planar bf16 [hi | lo][row][32 cols][8 ch] with a 512-byte row pitch, so the 128 rows of the
+// A operand are one contiguous 2 KB block per K chunk (SBO = 128 B) and a ky tap is a 512-byte start offset.
+//
+// fp32 accuracy from bf16 tensor cores as in conv_tc.cu: x*w ~= hi*whi + lo*whi + hi*wlo:
+//     ky = 0,1,2 : A = [hi(ky) | lo(ky)]        B = [Whi(ky) ; Whi(ky)]
+//     pair (0,1) : A = [hi(0)  | hi(1)]         B = [Wlo(0)  ; Wlo(1)]
+//     pair (2,-) : A = [hi(2)  | lo(2)]         B = [Wlo(2)  ; 0]
+//
+// Persistent CTA per SM: 6 producer warps (fp32 NHWC -> planar bf16 hi/lo), 2 MMA-issuing warps (every other tile
+// each: one instruction stream cannot keep the pipe busy), 8 epilogue warps.  The epilogue's extra operands (residual,
+// ReLU mask source, skip-path add, previous output) are prefetched one super-tile ahead with cp.async into
+// thread-private shared-memory slots, so no HBM latency is exposed between accumulator sets.
+//
+// Reference semantics: model/layers/layers.py:10-102 (conv), model/model.py:37-50 (residual epilogue).
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "prof.cuh"
+#include "tc_ptx.cuh"
+
+namespace msau {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int C3_PROD_WARPS = 6;
+constexpr int C3_PROD_THREADS = C3_PROD_WARPS * 32;
+constexpr int C3_MMA_WARPS = 2;
+constexpr int C3_EPI_WARPS = 8;
+constexpr int C3_THREADS = (C3_PROD_WARPS + C3_MMA_WARPS + C3_EPI_WARPS) * 32;
+constexpr int C3_MAX_STAGES = 3;
+constexpr int C3_SLOTS = 4;          // epilogue work items per thread and super-tile
+constexpr int C3_W_U = 2;            // weight-image uint4s prefetched per producer thread per plane
+
+struct C3Tile {
+  int T, N, CP, RI, P, stages;        // tiles per super-tile, MMA N, padded cout, halo rows, input planes, ring depth
+  int blocks_x, blocks_y, n_super;
+  int n_ops, ia, io, im;              // extra epilogue operands and their slot index (-1 = absent)
+  int dbg;
+  uint32_t plane_bytes, in_bytes, w_bytes, stage_bytes, epi_bytes, tmem_cols;
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+  split_pair(x[0], x[1], hi.x, lo.x);
+  split_pair(x[2], x[3], hi.y, lo.y);
+  split_pair(x[4], x[5], hi.z, lo.z);
+  split_pair(x[6], x[7], hi.w, lo.w);
+}
+
+// one 8-channel plane of the halo image: RI rows x 32 columns, fp32 global -> bf16 hi/lo planar image
+template <bool RELU>
+__device__ __forceinline__ void produce_plane(const float* __restrict__ src, int pitch, int in_x0, int in_y0, int Hin, int Win,
+                                              const C3Tile& t, uint8_t* __restrict__ stg, int tid) {
+  constexpr int LDU = 6;
+  const int halo_px = t.RI * 32;
+  for (int e0 = tid; e0 < halo_px; e0 += C3_PROD_THREADS * LDU) {
+    float v[LDU][8];
+#pragma unroll
+    for (int u = 0; u < LDU; ++u) {
+      const int e = e0 + u * C3_PROD_THREADS;
+      const int gy = in_y0 + (e >> 5), gx = in_x0 + (e & 31);
+      const bool inb = e < halo_px && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win && !(t.dbg & 2);
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* sp = reinterpret_cast<const float4*>(src + (gy * Win + gx) * pitch);
+      const float4 q0 = inb ? __ldg(sp) : z4;
+      const float4 q1 = inb ? __ldg(sp + 1) : z4;
+      v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+      v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+    }
+#pragma unroll
+    for (int u = 0; u < LDU; ++u) {
+      const int e = e0 + u * C3_PROD_THREADS;
+      if (e >= halo_px) break;
+      if (RELU) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
+      }
+      uint4 hi, lo;
+      split8(v[u], hi, lo);
+      *reinterpret_cast<uint4*>(stg + e * 16) = hi;
+      *reinterpret_cast<uint4*>(stg + t.plane_bytes + e * 16) = lo;
+    }
+  }
+}
+
+template <bool RELU1>
+__global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
+  __shared__ uint64_t bar_empty[C3_MAX_STAGES];   // MMA -> producers : the MMAs reading the stage have retired
+  __shared__ uint64_t bar_acc_full[2];            // MMA -> epilogue  : accumulator set complete
+  __shared__ uint64_t bar_acc_empty[2];           // epilogue -> MMA  : accumulator set drained
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[64];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, t.tmem_cols);
+  if (tid >= 64 && tid < 128) bias_s[tid - 64] = (a.bias && tid - 64 < t.CP) ? a.bias[tid - 64] : 0.f;
+  if (tid == 32) {
+    for (int i = 0; i < C3_MAX_STAGES; ++i) { mbar_init(&bar_full[i], C3_PROD_THREADS); mbar_init(&bar_empty[i], C3_MMA_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS * 32); }
+    mbar_init_fence();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int S = t.stages;
+  const int RO = 4 * t.T;                                     // output rows per super-tile
+
+  if (warp < C3_PROD_WARPS) {
+    // =============================================================== producers
+    const int planes1 = a.c1 >> 3;
+    uint32_t c = 0;
+    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
+      const int bx = st_i % t.blocks_x;
+      const int rest = st_i / t.blocks_x;
+      const int by = rest % t.blocks_y;
+      const int b = rest / t.blocks_y;
+      const int in_x0 = bx * 30 - 1, in_y0 = by * RO - 1;
+      const long boff = (long)b * a.Hin * a.Win;
+      for (int p = 0; p < t.P; ++p, ++c) {
+        const int s = c % S;
+        uint8_t* stg = smem + (size_t)s * t.stage_bytes;
+        if (c >= (uint32_t)S) {
+          if (lane == 0) mbar_wait(&bar_empty[s], ((c / S) - 1) & 1);
+          __syncwarp();
+        }
+        uint4 wreg[C3_W_U];
+        const uint4* wsrc = reinterpret_cast<const uint4*>(wtc) + (size_t)p * (t.w_bytes >> 4);
+        const int w16 = (int)(t.w_bytes >> 4);
+#pragma unroll
+        for (int u = 0; u < C3_W_U; ++u)
+          if (tid + u * C3_PROD_THREADS < w16) wreg[u] = __ldg(wsrc + tid + u * C3_PROD_THREADS);
+        if (p < planes1) {
+          produce_plane<RELU1>(a.src1 + boff * a.p1 + (p << 3), a.p1, in_x0, in_y0, a.Hin, a.Win, t, stg, tid);
+        } else {
+          produce_plane<false>(a.src2 + boff * a.p2 + ((p - planes1) << 3), a.p2, in_x0, in_y0, a.Hin, a.Win, t, stg, tid);
+        }
+        {
+          uint4* dst = reinterpret_cast<uint4*>(stg + t.in_bytes);
+#pragma unroll
+          for (int u = 0; u < C3_W_U; ++u)
+            if (tid + u * C3_PROD_THREADS < w16) dst[tid + u * C3_PROD_THREADS] = wreg[u];
+          for (int e = tid + C3_W_U * C3_PROD_THREADS; e < w16; e += C3_PROD_THREADS) dst[e] = __ldg(wsrc + e);
+        }
+        fence_async_smem();
+        mbar_arrive(&bar_full[s]);
+      }
+    }
+  } else if (warp < C3_PROD_WARPS + C3_MMA_WARPS) {
+    // =============================================================== MMA issuers (tiles mw, mw + 2, ...)
+    const int mw = warp - C3_PROD_WARPS;
+    const uint32_t idesc = make_idesc(128, t.N, false, false);
+    const uint32_t N = (uint32_t)t.N;
+    const uint32_t a_hi = (128u >> 4) | (1u << 14);                       // SBO = 128 B, descriptor version 1
+    const uint32_t b_hi = (128u >> 4) | (1u << 14);
+    const uint32_t lbo_plane = ((t.plane_bytes >> 4) & 0x3FFF) << 16;     // hi image -> lo image
+    const uint32_t lbo_row = (512u >> 4) << 16;                           // next image row (next ky)
+    const uint32_t b_lbo = ((N * 16 >> 4) & 0x3FFF) << 16;
+    uint32_t c = 0, tcount = 0;
+    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
+      const uint32_t as = tcount & 1;
+      if (tcount >= 2) mbar_wait(&bar_acc_empty[as], ((tcount >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N);
+      for (int p = 0; p < t.P; ++p, ++c) {
+        const int s = c % S;
+        mbar_wait(&bar_full[s], (c / S) & 1);
+        tc_fence_after();
+        const uint32_t in_addr = smem_u32(smem + (size_t)s * t.stage_bytes);
+        const uint32_t in16 = in_addr >> 4, w16a = (in_addr + t.in_bytes) >> 4;
+        if (elect_one()) {
+          if (!(t.dbg & 1)) {
+            // instruction-major / tile-minor: consecutive instructions hit different accumulators
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+              const uint32_t ky = i < 3 ? (uint32_t)i : (i == 3 ? 0u : 2u);
+              const uint32_t lbo = i == 3 ? lbo_row : lbo_plane;
+              const uint32_t b_lo = ((w16a + (uint32_t)i * 2u * N) & 0x3FFF) | b_lbo;
+              const uint32_t acc = (p > 0 || i > 0) ? 1u : 0u;
+              for (int tile = mw; tile < t.T; tile += C3_MMA_WARPS) {
+                const uint32_t a_lo = ((in16 + ((uint32_t)(4 * tile) + ky) * 32u) & 0x3FFF) | lbo;
+                mma2(acc_base + (uint32_t)tile * N, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+              }
+            }
+          }
+          tc_commit(&bar_empty[s]);
+          if (p == t.P - 1) tc_commit(&bar_acc_full[as]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =============================================================== epilogue
+    // Kept lean on purpose: with 8 x 32 threads x 4 items per super-tile this role is bound by instruction issue, so the
+    // super-tile position is decoded once (for the tile being drained and for the one being prefetched), item -> (tile,
+    // channel chunk) is shifts and masks, and the bias comes from shared memory.
+    const int ew = warp - (C3_PROD_WARPS + C3_MMA_WARPS);   // 0..7
+    const int q = warp & 3;                                  // TMEM lane quarter = tile row
+    const int sub = ew >> 2;
+    const int chunks = t.CP >> 3;                            // 1, 2, 4 or 8
+    const int lc = 31 - __clz(chunks);
+    const int total_items = t.T << lc;                       // <= 8: item kg -> (tile kg >> lc, channel chunk kg & (chunks-1))
+    const int et = ew * 32 + lane;                           // epilogue thread index 0..255
+    uint8_t* epi = smem + (size_t)S * t.stage_bytes;
+    const uint32_t epi_u32 = smem_u32(epi);
+    const uint32_t slot_stride = (uint32_t)t.n_ops * 8192u;  // bytes between consecutive items' slots
+    const uint32_t my_slot = (uint32_t)et * 16u;
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const long tile_pix = 4L * a.Wout;                       // pixel distance between consecutive tiles (4 rows)
+    // position of a super-tile for this thread: pixel index of its tile-0 output, first output row, column validity
+    struct Pos { long pix; int row; bool ok; };
+    auto decode = [&](int st_i) -> Pos {
+      Pos ps;
+      if (st_i >= t.n_super) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; return ps; }
+      const int bx = st_i % t.blocks_x;
+      const int rest = st_i / t.blocks_x;
+      const int by = rest % t.blocks_y;
+      const int b = rest / t.blocks_y;
+      const int ox = bx * 30 - 1 + lane;
+      ps.row = by * RO + q;
+      ps.ok = lane_ok && ox < a.Wout;
+      ps.pix = ((long)b * a.Hout + ps.row) * a.Wout + ox;
+      return ps;
+    };
+    const float* pa = a.res ? a.res : a.add;
+    const int ppa = a.res ? a.pr : a.pa;
+    auto prefetch = [&](const Pos& ps, int k) {
+      // extras of work item k of that super-tile -> this thread's slots (one cp.async group per item, possibly empty)
+      const int kg = sub + 2 * k;
+      const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
+      if (t.n_ops > 0 && ps.ok && kg < total_items && ps.row + 4 * tile < a.Hout && !(t.dbg & 8)) {
+        const long pix = ps.pix + tile * tile_pix;
+        const uint32_t dst = epi_u32 + (uint32_t)k * slot_stride + my_slot;
+        if (t.ia >= 0) {
+          const float* ap = pa + pix * ppa + ch8;
+          cp_async16(dst + (uint32_t)t.ia * 8192u, ap);
+          cp_async16(dst + (uint32_t)t.ia * 8192u + 4096u, ap + 4);
+        }
+        if (t.io >= 0) {
+          const float* op = a.out + pix * a.po + ch8;
+          cp_async16(dst + (uint32_t)t.io * 8192u, op);
+          cp_async16(dst + (uint32_t)t.io * 8192u + 4096u, op + 4);
+        }
+        if (t.im >= 0) {
+          const float* mp = a.omask + pix * a.pom + ch8;
+          cp_async16(dst + (uint32_t)t.im * 8192u, mp);
+          cp_async16(dst + (uint32_t)t.im * 8192u + 4096u, mp + 4);
+        }
+      }
+      cp_async_commit();
+    };
+    Pos cur = decode(blockIdx.x);
+#pragma unroll
+    for (int k = 0; k < C3_SLOTS; ++k) prefetch(cur, k);
+
+    uint32_t tcount = 0;
+    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
+      const Pos nxt = decode(st_i + (int)gridDim.x);
+      const uint32_t as = tcount & 1;
+      const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N) + ((uint32_t)(q * 32) << 16);
+      if (lane == 0) mbar_wait(&bar_acc_full[as], (tcount >> 1) & 1);
+      __syncwarp();
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < C3_SLOTS; ++k) {
+        const int kg = sub + 2 * k;
+        cp_async_wait<C3_SLOTS - 1>();                         // this item's extras have landed
+        if (kg < total_items) {                                // warp-uniform
+          const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
+          float v0[8], v1[8], v2[8];
+          const uint32_t col = (uint32_t)(tile * t.N + ch8);
+          tmem_ld8(acc_base + col, v0);
+          tmem_ld8(acc_base + col + (uint32_t)t.CP, v1);
+          tmem_ld8(acc_base + col + (uint32_t)(2 * t.CP), v2);
+          tmem_ld_wait();
+          float r[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            r[i] = __shfl_up_sync(0xffffffffu, v0[i], 1) + v1[i] + __shfl_down_sync(0xffffffffu, v2[i], 1);
+          if (cur.ok && cur.row + 4 * tile < a.Hout && !(t.dbg & 4)) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch8 + 4);
+            r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w; r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
+            if (a.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
+            }
+            // out = mask( relu2( relu(acc + bias) + res ) ) + add + previous
+            const uint8_t* slot = epi + (uint32_t)k * slot_stride + my_slot;
+            float ev[8];
+            if (t.ia >= 0) {
+              const float4 e0 = *reinterpret_cast<const float4*>(slot + t.ia * 8192);
+              const float4 e1 = *reinterpret_cast<const float4*>(slot + t.ia * 8192 + 4096);
+              ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w; ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
+              if (a.res) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] += ev[i];
+              }
+            }
+            if (a.relu2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
+            }
+            if (t.im >= 0) {
+              const float4 m0 = *reinterpret_cast<const float4*>(slot + t.im * 8192);
+              const float4 m1 = *reinterpret_cast<const float4*>(slot + t.im * 8192 + 4096);
+              const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] = mv[i] > 0.f ? r[i] : 0.f;
+            }
+            if (t.ia >= 0 && !a.res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) r[i] += ev[i];
+            }
+            if (t.io >= 0) {
+              const float4 p0 = *reinterpret_cast<const float4*>(slot + t.io * 8192);
+              const float4 p1 = *reinterpret_cast<const float4*>(slot + t.io * 8192 + 4096);
+              r[0] += p0.x; r[1] += p0.y; r[2] += p0.z; r[3] += p0.w; r[4] += p1.x; r[5] += p1.y; r[6] += p1.z; r[7] += p1.w;
+            }
+            float4* dst = reinterpret_cast<float4*>(a.out + (cur.pix + tile * tile_pix) * a.po + ch8);
+            dst[0] = make_float4(r[0], r[1], r[2], r[3]);
+            dst[1] = make_float4(r[4], r[5], r[6], r[7]);
+          }
+        }
+        prefetch(nxt, k);                                      // this slot is free again: next super-tile's item k
+      }
+      tc_fence_before();
+      mbar_arrive(&bar_acc_empty[as]);
+      cur = nxt;
+    }
+    cp_async_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, t.tmem_cols);
+}
+
+bool c3_configure(const ConvArgs& a, C3Tile& t) {
+  t.CP = a.coutp;
+  if (!(t.CP == 8 || t.CP == 16 || t.CP == 32 || t.CP == 64)) return false;
+  t.N = round_up(3 * t.CP, 16);
+  t.T = 8 / (t.CP >> 3);
+  while (t.T > 1 && 4 * (t.T / 2) >= a.Hout) t.T /= 2;       // short maps: do not pay for rows that do not exist
+  t.RI = 4 * t.T + 2;
+  t.P = (a.c1 + a.c2) / 8;
+  t.plane_bytes = (uint32_t)t.RI * 512;
+  t.in_bytes = 2 * t.plane_bytes;
+  t.w_bytes = 5u * (uint32_t)t.N * 32;
+  t.stage_bytes = (t.in_bytes + t.w_bytes + 127) / 128 * 128;
+  t.n_ops = 0; t.ia = t.io = t.im = -1;
+  if (a.res || a.add) t.ia = t.n_ops++;
+  if (a.accumulate) t.io = t.n_ops++;
+  if (a.omask) t.im = t.n_ops++;
+  t.epi_bytes = (uint32_t)(C3_SLOTS * t.n_ops * 2 * 4096);
+  t.stages = C3_MAX_STAGES;
+  while (t.stages > 2 && (size_t)t.stage_bytes * t.stages + t.epi_bytes > 216 * 1024) --t.stages;
+  if ((size_t)t.stage_bytes * t.stages + t.epi_bytes > 216 * 1024) return false;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
+  t.blocks_x = cdiv(a.Wout, 30);
+  t.blocks_y = cdiv(a.Hout, 4 * t.T);
+  t.n_super = t.blocks_x * t.blocks_y * a.B;
+  const int cols = 2 * t.T * t.N;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
+  return t.tmem_cols <= 512;
+}
+
+}  // namespace
+
+bool conv3_tc_supported(const ConvArgs& a) {
+  if (a.kh != 3 || a.kw != 3 || a.dil != 1 || a.stride != 1 || a.pad_t != 1 || a.pad_l != 1) return false;
+  if ((a.res && a.add) || a.addmask || a.mask1 || a.src1_nchw || a.s2d || a.d2s) return false;
+  if (a.osy != 1 || a.oy0 != 0 || a.ox0 != 0) return false;
+  if (a.Hq != a.Hin || a.Wq != a.Win || a.Hout != a.Hin || a.Wout != a.Win) return false;
+  if ((a.c1 & 7) || (a.c2 & 7) || (a.p1 & 3) || (a.c2 && (a.p2 & 3)) || (a.po & 3)) return false;
+  if ((a.res && (a.pr & 3)) || (a.add && (a.pa & 3)) || (a.omask && (a.pom & 3))) return false;
+  if (a.Win < 8 || a.Hin < 2) return false;
+  C3Tile t;
+  return c3_configure(a, t);
+}
+
+int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
+  MSAU_CHECK_ARG(conv3_tc_supported(a), "conv3_tc: unsupported shape");
+  C3Tile t;
+  MSAU_CHECK_ARG(c3_configure(a, t), "conv3_tc: tile does not fit");
+  const size_t smem = (size_t)t.stage_bytes * t.stages + t.epi_bytes + 1024;
+  const int grid = t.n_super < sm_count() ? t.n_super : sm_count();
+  const bool general = a.res || a.omask || a.add || a.accumulate || a.relu2;
+  const double npix = (double)a.B * a.Hin * a.Win;
+  double bytes = npix * (a.c1 + a.c2) * 4.0;
+  bytes += npix * a.coutp * 4.0 * (1 + (a.res ? 1 : 0) + (a.omask ? 1 : 0) + (a.add ? 1 : 0) + (a.accumulate ? 1 : 0));
+  ProfScope ps("conv3_tc_kernel", a.c1 + a.c2, a.coutp, 3, 1, a.Wout, (a.relu1 ? 2 : 0) + (general ? 1 : 0),
+               2.0 * npix * 9 * (a.c1 + a.c2) * a.coutp, bytes, st);
+  static bool attr = false;
+  if (!attr) {
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  if (a.relu1) conv3_tc_kernel<true><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);
+  else conv3_tc_kernel<false><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+// ------------------------------------------------------------------ weight images
+// src: fp32 packed [tap = ky*3+kx][cin][coutp].  dst (bf16) per 8-channel plane p: 5 images of [chunk0: N x 8][chunk1: N x 8],
+// row n = kx * coutp + co:  images 0..2 = {Whi(ky), Whi(ky)},  image 3 = {Wlo(0), Wlo(1)},  image 4 = {Wlo(2), 0}
+__global__ void __launch_bounds__(256) pack_tc3_kernel(const float* __restrict__ pk, uint16_t* __restrict__ pktc,
+                                                        const TcPackDesc* __restrict__ descs, int n_desc) {
+  const long blk = blockIdx.x;
+  int lo = 0, hi = n_desc - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].blk0 <= blk) lo = mid; else hi = mid - 1;
+  }
+  const TcPackDesc d = descs[lo];
+  const int N = d.N;
+  const long per_plane = 5L * N * 16;
+  const long total = (long)(d.cin / 8) * per_plane;
+  const long e = (blk - d.blk0) * 256 + threadIdx.x;
+  if (e >= total) return;
+  const int p = (int)(e / per_plane);
+  long r = e - (long)p * per_plane;
+  const int img = (int)(r / (N * 16)); r -= (long)img * N * 16;
+  const int chunk = (int)(r / (N * 8)); r -= (long)chunk * N * 8;
+  const int n = (int)(r / 8), k = (int)(r - (long)n * 8);
+  const int kx = n / d.coutp, co = n - kx * d.coutp;
+  int ky = -1;
+  bool want_lo = false;
+  if (img < 3) ky = img;
+  else {
+    want_lo = true;
+    ky = img == 3 ? chunk : (chunk == 0 ? 2 : -1);
+  }
+  float w = 0.f;
+  if (ky >= 0 && kx < 3) w = pk[d.src_off + ((long)(ky * 3 + kx) * d.cin + 8 * p + k) * d.coutp + co];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w - __bfloat162float(h)) : h;
+  pktc[d.dst_off + e] = __bfloat16_as_ushort(out);
+}
+
+int launch_pack_tc3(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st) {
+  if (n_desc == 0) return MSAU_OK;
+  ProfScope ps("pack_tc_kernel", 0, (double)total_blocks * 256 * 6.0, st);
+  pack_tc3_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(pk, pktc, d_descs, n_desc);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+}  // namespace msau

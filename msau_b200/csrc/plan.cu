@@ -59,6 +59,7 @@ struct ConvLayer {
   int coutp = 0, c1p = 0, c2p = 0;                      // padded dims
   long pk_w = -1, pk_b = -1, pk_d1 = -1, pk_d2 = -1;    // packed: fwd weights, bias, dgrad wrt src1 / src2
   long tc_w = -1, tc_d1 = -1, tc_d2 = -1;               // bf16 tensor-core weight images (bf16 element offsets)
+  long t3_w = -1, t3_d1 = -1, t3_d2 = -1;               // same for the kx-folded 3x3 kernel (conv3_tc.cu)
   int pad() const { return ((k - 1) * dil) / 2; }       // SAME "before" padding, model/layers/utils.py:13-18
 };
 
@@ -122,9 +123,10 @@ struct MsauPlan {
   long pack_blocks = 0;
   long misc_floats = 0;
   long attn_scratch_off = 0;   // floats, inside misc: operand images of the tensor-core attention
-  std::vector<TcPackDesc> tc_descs;
+  std::vector<TcPackDesc> tc_descs, t3_descs;
   TcPackDesc* d_tc_descs = nullptr;
-  long tc_blocks = 0;
+  TcPackDesc* d_t3_descs = nullptr;
+  long tc_blocks = 0, t3_blocks = 0;
   long tc_elems = 0;      // bf16 elements
   uint16_t* pktc = nullptr;
   // runtime state (set per call)
@@ -199,6 +201,19 @@ static long add_tc(MsauPlan* p, long src_off, int taps, int cin, int coutp) {
   return d.dst_off;
 }
 
+static long add_tc3(MsauPlan* p, long src_off, int cin, int coutp) {
+  if (cin % 8 != 0 || !(coutp == 8 || coutp == 16 || coutp == 32 || coutp == 64)) return -1;
+  TcPackDesc d;
+  d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = 9; d.cin = cin; d.coutp = coutp;
+  d.N = round_up(3 * coutp, 16);
+  const long elems = (long)(cin / 8) * 5 * d.N * 16;
+  d.blk0 = p->t3_blocks;
+  p->t3_blocks += cdiv(elems, 256);
+  p->tc_elems += (elems + 127) / 128 * 128;
+  p->t3_descs.push_back(d);
+  return d.dst_off;
+}
+
 // torch Conv2d weight [cout][cin1+cin2][k][k]:
 //   fwd   [tap][c1p + c2p][coutp]                     rows = input channels of [src1 | src2]
 //   dgrad [flipped tap][coutp][c_s p] per source s     rows = output channels, cols = that source's channels
@@ -229,6 +244,11 @@ static void setup_conv(MsauPlan* p, ConvLayer& L, int cout, int cin1, int cin2, 
   L.tc_w = add_tc(p, L.pk_w, k * k, cinp, L.coutp);
   if (L.pk_d1 >= 0) L.tc_d1 = add_tc(p, L.pk_d1, k * k, L.coutp, L.c1p);
   if (L.pk_d2 >= 0) L.tc_d2 = add_tc(p, L.pk_d2, k * k, L.coutp, L.c2p);
+  if (k == 3 && dil == 1) {
+    L.t3_w = add_tc3(p, L.pk_w, cinp, L.coutp);
+    if (L.pk_d1 >= 0) L.t3_d1 = add_tc3(p, L.pk_d1, L.coutp, L.c1p);
+    if (L.pk_d2 >= 0) L.t3_d2 = add_tc3(p, L.pk_d2, L.coutp, L.c2p);
+  }
 }
 
 // torch ConvTranspose2d(cin, cout, 3, stride 2, padding 1) weight [cin][cout][3][3]; out[2 iy - 1 + ky] += x[iy] W[ky]
@@ -291,6 +311,8 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 
 // ------------------------------------------------------------------ launch helpers
 static bool g_use_tc = true;
+static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
+static int g_c3_max = 32;        // ... for at most this many output channels
 
 struct ConvOpt {
   bool relu1 = false, relu = false, relu2 = false;
@@ -305,7 +327,7 @@ struct ConvOpt {
 // same-size stride-1 convolution (forward of a layer, or a dgrad with flipped packed weights)
 static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, int c1_logical, const float* src2, int c2, int p2,
                      const float* w, const float* bias, float* out, int po, int coutp, int H, int W, int k, int dil, int pad,
-                     const ConvOpt& o, long tc_off = -1) {
+                     const ConvOpt& o, long tc_off = -1, long t3_off = -1) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.src1 = src1; a.c1 = c1; a.p1 = p1; a.src1_nchw = nchw; a.c1_logical = c1_logical;
@@ -319,13 +341,14 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.omask = o.omask; a.pom = o.pom; a.add = o.add; a.pa = o.pa; a.addmask = o.addmask; a.pam = o.pam;
   a.accumulate = o.accumulate;
   count_launch(1);
+  if (g_use_tc && g_use_c3 && t3_off >= 0 && coutp <= g_c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
   if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
   return launch_conv(a, p->st);
 }
 
 static int layer_fwd(MsauPlan* p, const ConvLayer& L, const Tensor& s1, const Tensor* s2, const Tensor& out, const ConvOpt& o) {
   return conv_same(p, p->A(s1), L.c1p, s1.C, 0, L.c1p, s2 ? p->A(*s2) : nullptr, s2 ? L.c2p : 0, s2 ? s2->C : 0, p->pk + L.pk_w,
-                   p->pk + L.pk_b, p->A(out), out.C, L.coutp, out.H, out.W, L.k, L.dil, L.pad(), o, L.tc_w);
+                   p->pk + L.pk_b, p->A(out), out.C, L.coutp, out.H, out.W, L.k, L.dil, L.pad(), o, L.tc_w, L.t3_w);
 }
 
 // data gradient of a conv layer wrt source `which` (1 or 2): dY (channels coutp) -> dX
@@ -338,7 +361,7 @@ static int layer_dgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   o.accumulate = p->touch(dst);
   const int padd = (L.k - 1) * L.dil - L.pad();
   return conv_same(p, dy, L.coutp, pdy, 0, L.coutp, nullptr, 0, 0, p->pk + pkd, nullptr, p->G(dst), dst.C, cs, dst.H, dst.W, L.k,
-                   L.dil, padd, o, which == 1 ? L.tc_d1 : L.tc_d2);
+                   L.dil, padd, o, which == 1 ? L.tc_d1 : L.tc_d2, which == 1 ? L.t3_d1 : L.t3_d2);
 }
 
 // weight (+bias) gradient of a conv layer wrt source `which`
@@ -671,10 +694,16 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
     if (e == cudaSuccess)
       e = cudaMemcpy(p->d_tc_descs, p->tc_descs.data(), sizeof(TcPackDesc) * p->tc_descs.size(), cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess && !p->t3_descs.empty()) {
+    e = cudaMalloc(&p->d_t3_descs, sizeof(TcPackDesc) * p->t3_descs.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(p->d_t3_descs, p->t3_descs.data(), sizeof(TcPackDesc) * p->t3_descs.size(), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
     set_error("plan_create: descriptor upload failed: %s", cudaGetErrorString(e));
     if (p->d_descs) cudaFree(p->d_descs);
     if (p->d_tc_descs) cudaFree(p->d_tc_descs);
+    if (p->d_t3_descs) cudaFree(p->d_t3_descs);
     delete p;
     return MSAU_ERR_CUDA;
   }
@@ -686,6 +715,7 @@ extern "C" void msau_plan_destroy(MsauPlan* p) {
   if (!p) return;
   if (p->d_descs) cudaFree(p->d_descs);
   if (p->d_tc_descs) cudaFree(p->d_tc_descs);
+  if (p->d_t3_descs) cudaFree(p->d_t3_descs);
   delete p;
 }
 
@@ -717,6 +747,10 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
   if (g_use_tc) {
     count_launch(1);
     MSAU_TRY(launch_pack_tc(p->pk, p->pktc, p->d_tc_descs, (int)p->tc_descs.size(), p->tc_blocks, p->st));
+    if (!p->t3_descs.empty()) {
+      count_launch(1);
+      MSAU_TRY(launch_pack_tc3(p->pk, p->pktc, p->d_t3_descs, (int)p->t3_descs.size(), p->t3_blocks, p->st));
+    }
   }
 
   for (int b = 0; b < NB; ++b) {
@@ -956,6 +990,8 @@ extern "C" int msau_debug_tensor(const MsauPlan* p, int id, long long* off, int*
 extern "C" int msau_set_option(const char* name, int value) {
   MSAU_CHECK_ARG(name, "set_option: null name");
   if (!strcmp(name, "tensor_core_conv")) { g_use_tc = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "conv3_fold")) { g_use_c3 = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return MSAU_ERR_ARG;
 }

@@ -16,6 +16,7 @@
 // split that the forward convolutions need would triple the operand traffic for nothing here.
 // grid = (pixel-tile ranges, input-channel planes).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "conv_tc.cuh"
@@ -356,6 +357,312 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
 }
 
+
+// =====================================================================================================
+// dil = 1 variant: ONE instruction per 16 pixels covers all kh x kw taps.
+//     dW[ky][kx][ci][co] = sum_q X[q_row][q_col + kx - pad_l][ci] * dY[q_row + pad_t - ky][q_col][co]
+// (the sum re-indexed over the X pixel q instead of the output pixel).  The kx taps stay the M row-groups of
+// the X operand (shift by one pixel per group); the ky taps become N column-groups of the dY operand: dY is
+// staged as [row][channel plane][col][8 ch] with (kh-1) halo rows, so column-group j = (kyi, plane) sits exactly
+// j * TC * 16 B after group 0 -> a plain MN-major descriptor with SBO = one staged row of one plane.
+//   M = 64 (kx, ci)   N = kh * cout   K = 16 pixels   -> kh x fewer tcgen05.mma than the per-ky kernel above.
+// Several warps issue concurrently (one instruction stream keeps the tensor pipe ~45 cycles/instruction busy, two or
+// more reach its ~25 cycle floor for M = 64), each into its own accumulator; the copies are summed in the final reduce.
+struct Wg2Tile {
+  int TR, TC, HWx, N, ny_planes, TRy, n_issue;
+  int tiles_x, tiles_y, n_tiles, tiles_per_cta;
+  uint32_t x_bytes, stage_bytes, tmem_cols;
+  int dbg;                                  // MSAU_WG_DEBUG experiments: 1 = no MMAs, 2 = no global loads
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArgs a, const Wg2Tile t) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_free[2];
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int plane = blockIdx.y;
+  const int tile0 = blockIdx.x * t.tiles_per_cta;
+  const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
+  const bool do_bias = a.dbias != nullptr && plane == 0;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    wmbar_init(&bar_free[0], t.n_issue);
+    wmbar_init(&bar_free[1], t.n_issue);
+    wmbar_init(&bar_done, t.n_issue);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 128) sbias[tid] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  if (tile0 >= tile1) {
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+    return;
+  }
+
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(t.N >> 3) << 17) |
+                         ((uint32_t)(64 >> 4) << 24);
+    const int ca0 = plane << 3;
+
+  int it = 0;
+  for (int tile = tile0; tile < tile1; ++tile, ++it) {
+    const int s = it & 1;
+    uint8_t* st = smem + (size_t)s * t.stage_bytes;
+    if (it >= 2) {
+      if (tid == 0) wmbar_wait(&bar_free[s], ((it >> 1) - 1) & 1);
+      __syncthreads();
+    }
+    const int tx = tile % t.tiles_x;
+    const int rest = tile / t.tiles_x;
+    const int ty = rest % t.tiles_y;
+    const int b = rest / t.tiles_y;
+    const int qy0 = ty * t.TR, qx0 = tx * t.TC;
+    // ---- X tile of this plane: TR rows x HWx columns (kw-1 halo columns), 16 B per pixel.  A warp takes rows
+    //      warp, warp+8, ... and 32-column groups; WU pixels' loads are in flight per thread; no integer divisions ----
+    {
+      const int in_x0 = qx0 - a.pada_l;
+      const int plane_stride = a.Ha * a.Wa;
+      const float* xsrc = a.a_nchw ? a.A + ((long)b * a.ca_logical + ca0) * plane_stride : a.A + (long)b * plane_stride * a.pa + ca0;
+      const int n_valid = a.ca_logical - ca0;
+      const int ncg = (t.HWx + 31) >> 5;
+      int r = warp, cg = 0;
+      while (r < t.TR) {
+        float v[WU][8];
+        int so[WU];
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          const int c = (cg << 5) + lane;
+          const int gy = qy0 + r, gx = in_x0 + c;
+          so[u] = (r < t.TR && c < t.HWx) ? r * t.HWx + c : -1;
+          const bool inb = so[u] >= 0 && gy < a.Ha && (unsigned)gx < (unsigned)a.Wa && !(t.dbg & 2);
+          const int lin = gy * a.Wa + gx;
+          if (a.a_nchw) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = (inb && k < n_valid) ? __ldg(xsrc + lin + k * plane_stride) : 0.f;
+          } else {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* sp = reinterpret_cast<const float4*>(xsrc + lin * a.pa);
+            const float4 q0 = inb ? __ldg(sp) : z4;
+            const float4 q1 = inb ? __ldg(sp + 1) : z4;
+            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+          }
+          if (++cg == ncg) { cg = 0; r += 8; }
+        }
+#pragma unroll
+        for (int u = 0; u < WU; ++u) {
+          if (so[u] < 0) continue;
+          if (a.reluA) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
+          }
+          *reinterpret_cast<uint4*>(st + so[u] * 16) = wpack8(v[u]);
+        }
+      }
+    }
+    // ---- dY tile: [TRy rows][planes][TC cols], rows qy0 + pad_t - (kh-1) .. qy0 + pad_t + TR - 1.
+    //      A warp owns one channel plane (two when there are 16) and every (8 / planes)-th row of it ----
+    {
+      uint8_t* yh = st + t.x_bytes;
+      const int nyp = t.ny_planes;
+      const int pgrp = nyp < 8 ? nyp : 8;
+      const int pl0 = warp % pgrp, rstart = warp / pgrp, rstep = 8 / pgrp;
+      const int ncg = (t.TC + 31) >> 5;
+      const int vy0 = qy0 + a.pada_t - (a.kh - 1);
+      const int smul = a.b_s2d ? 2 : 1;
+      for (int pl = pl0; pl < nyp; pl += 8) {
+        // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
+        const int sph = a.b_s2d ? (pl << 3) / a.cph : 0;
+        const int spy = sph >> 1, spx = sph & 1;
+        const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? (pl << 3) - sph * a.cph : (pl << 3));
+        float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int r = rstart, cg = 0;
+        while (r < t.TRy) {
+          float v[WU][8];
+          int so[WU];
+          bool center[WU];
+#pragma unroll
+          for (int u = 0; u < WU; ++u) {
+            const int c = (cg << 5) + lane;
+            const int vy = vy0 + r, vx = qx0 + c;
+            const int gy = vy * smul + spy, gx = vx * smul + spx;
+            so[u] = (r < t.TRy && c < t.TC) ? (r * nyp + pl) * t.TC + c : -1;
+            const bool inb = so[u] >= 0 && (unsigned)vy < (unsigned)a.Hq && vx < a.Wq && gy < a.Hb && gx < a.Wb && !(t.dbg & 2);
+            center[u] = vy >= qy0 && vy < qy0 + t.TR;       // halo rows belong to the neighbouring tiles
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* sp = reinterpret_cast<const float4*>(ysrc + (gy * a.Wb + gx) * a.pb);
+            const float4 q0 = inb ? __ldg(sp) : z4;
+            const float4 q1 = inb ? __ldg(sp + 1) : z4;
+            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+            if (++cg == ncg) { cg = 0; r += rstep; }
+          }
+#pragma unroll
+          for (int u = 0; u < WU; ++u) {
+            if (so[u] < 0) continue;
+            if (do_bias && center[u]) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) bacc[k] += v[u][k];
+            }
+            *reinterpret_cast<uint4*>(yh + (size_t)so[u] * 16) = wpack8(v[u]);
+          }
+        }
+        if (do_bias) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float sum = bacc[k];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) atomicAdd(&sbias[pl * 8 + k], sum);
+          }
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // issuing warps 0..n_issue-1 take the X rows r = warp, warp + n_issue, ... ; each accumulates into its own copy
+    if (warp < t.n_issue) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (welect_one()) {
+        const uint32_t xh = wsmem_u32(st);
+        const uint32_t yh = xh + t.x_bytes;
+        const int chunks = t.TC >> 4;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(warp * t.N);
+        const uint32_t lbo = (128u >> 4) << 16;
+        const uint32_t a_hi = 1u | (1u << 14);                                   // SBO = one pixel per kx group
+        const uint32_t b_hi = (((uint32_t)t.TC * 16 >> 4) & 0x3FFF) | (1u << 14);  // SBO = one staged row of one plane
+        const uint32_t yrow16 = (uint32_t)(t.ny_planes * t.TC);                  // staged dY row pitch, 16-B units
+        uint32_t first = (it == 0) ? 0u : 1u;
+        for (int r = warp; r < t.TR; r += t.n_issue) {
+          uint32_t a_lo = (((xh >> 4) + (uint32_t)(r * t.HWx)) & 0x3FFF) | lbo;
+          uint32_t b_lo = (((yh >> 4) + (uint32_t)r * yrow16) & 0x3FFF) | lbo;
+          for (int cc = 0; cc < chunks; ++cc) {
+            if (!(t.dbg & 1) || first == 0u) wtc_mma2(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+            first = 1u;
+            a_lo += 16; b_lo += 16;
+          }
+        }
+        wtc_commit(&bar_free[s]);
+        if (tile == tile1 - 1) wtc_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+  }
+  // ---- reduce the resident accumulators into dW ----
+  if (tid == 0) wmbar_wait(&bar_done, 0);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (warp < 2) {
+    // M = 64 accumulator: row m = kx * 8 + ci lives in TMEM lane (m % 16) + 32 * (m / 16)
+    const int kx = warp * 2 + (lane >> 3), ci = ca0 + (lane & 7);
+    const bool mine = lane < 16 && kx < a.kw && ci < a.ca_lim;
+    const int n_iss = min(t.n_issue, t.TR);       // warps that issued at least one instruction (their accumulators are defined)
+    for (int c0 = 0; c0 < t.N; c0 += 8) {
+      float v[8];
+      wtmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      for (int i = 1; i < n_iss; ++i) {
+        float w[8];
+        wtmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * t.N + c0), w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w[j];
+      }
+      if (mine) {
+        const int kyi = c0 / a.cb, cb0 = c0 - kyi * a.cb;     // column group = (kyi, 8-channel plane); ky = kh-1-kyi
+        const int ky = a.kh - 1 - kyi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int co = cb0 + j;
+          if (a.b_s2d) {
+            const int ph = co / a.cph, c = co - ph * a.cph;
+            const int py = ph >> 1, px = ph & 1;
+            const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
+            const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
+            if (ph < 4 && c < a.cb_lim && rky >= 0 && rkx >= 0)
+              atomicAdd(a.dW + (long)ci * a.s_ca + (long)c * a.s_cb + (rky * 3 + rkx), v[j]);
+          } else if (co < a.cb_lim) atomicAdd(a.dW + (long)ci * a.s_ca + (long)co * a.s_cb + (ky * a.kw + kx), v[j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (do_bias) {
+    if (a.b_s2d) {
+      if (tid < a.cb && (tid % a.cph) < a.cb_lim) atomicAdd(a.dbias + (tid % a.cph), sbias[tid]);
+    } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+}
+
+static bool wgrad_tc2_config(const WgradArgs& a, Wg2Tile& t) {
+  if (a.dila != 1 || a.kh * a.cb > 256 || a.maskB) return false;
+  t.N = a.kh * a.cb;
+  t.ny_planes = a.cb >> 3;
+  t.TC = round_up(a.Wq, 16);
+  if (t.TC > 64) t.TC = 64;
+  const int row_bytes = t.TC * a.cb * 2;                  // one staged dY row, all planes
+  t.TR = 48 * 1024 / row_bytes - (a.kh - 1);
+  if (t.TR > 16) t.TR = 16;
+  if (t.TR > a.Hq) t.TR = a.Hq;
+  if (t.TR < 1) return false;
+  t.TRy = t.TR + a.kh - 1;
+  t.HWx = t.TC + (a.kw - 1);
+  const int slack_px = 7 + 16;                            // M groups kw..7 read past the useful columns
+  t.x_bytes = (uint32_t)((t.TR * t.HWx + slack_px) * 16 + 127) / 128 * 128;
+  const uint32_t y_bytes = (uint32_t)t.TRy * row_bytes;
+  t.stage_bytes = (t.x_bytes + y_bytes + 1023) / 1024 * 1024;
+  t.n_issue = 128 / t.N;
+  if (t.n_issue > 4) t.n_issue = 4;
+  if (t.n_issue < 1) t.n_issue = 1;
+  if (t.n_issue > t.TR) t.n_issue = t.TR;
+  const int cols = t.n_issue * t.N;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_WG_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
+  t.tiles_x = cdiv(a.Wq, t.TC);
+  t.tiles_y = cdiv(a.Hq, t.TR);
+  t.n_tiles = t.tiles_x * t.tiles_y * a.B;
+  return (size_t)t.stage_bytes * 2 + 1024 <= 200 * 1024 && t.tmem_cols <= 512;
+}
+
+static int launch_wgrad_tc2(const WgradArgs& a, const Wg2Tile& t0, cudaStream_t st) {
+  Wg2Tile t = t0;
+  const int planes = a.ca >> 3;
+  const size_t smem = (size_t)t.stage_bytes * 2 + 1024;
+  int per_sm = (int)((220 * 1024) / (smem + 1024));       // resident CTAs per SM by shared memory ...
+  if (per_sm > 512 / (int)t.tmem_cols) per_sm = 512 / (int)t.tmem_cols;   // ... and by TMEM columns
+  if (per_sm > 3) per_sm = 3;                              // 80 registers x 256 threads
+  if (per_sm < 1) per_sm = 1;
+  int ctas = (per_sm * sm_count() + planes - 1) / planes;
+  if (ctas > t.n_tiles) ctas = t.n_tiles;
+  if (ctas < 1) ctas = 1;
+  t.tiles_per_cta = cdiv(t.n_tiles, ctas);
+  ctas = cdiv(t.n_tiles, t.tiles_per_cta);
+  static bool attr = false;
+  if (!attr) {
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  dim3 grid(ctas, planes);
+  const double npq = (double)a.B * a.Hq * a.Wq;
+  const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb) * (a.maskB ? 2 : 1)) * 4.0;
+  ProfScope ps("wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  wgrad_tc2_kernel<<<grid, WG_THREADS, smem, st>>>(a, t);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
 bool wgrad_tc_supported(const WgradArgs& a) {
   if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
   if (a.Ha != a.Hq || a.Wa != a.Wq) return false;
@@ -374,6 +681,10 @@ bool wgrad_tc_supported(const WgradArgs& a) {
 
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   MSAU_CHECK_ARG(wgrad_tc_supported(a), "wgrad_tc: unsupported shape");
+  {
+    Wg2Tile t2;
+    if (wgrad_tc2_config(a, t2)) return launch_wgrad_tc2(a, t2, st);
+  }
   WgTile t;
   t.N = a.cb;                           // M = 64 allows any multiple of 8
   t.ny_planes = a.cb >> 3;
