@@ -16,10 +16,12 @@
 //     pair (0,1) : A = [hi(0)  | hi(1)]         B = [Wlo(0)  ; Wlo(1)]
 //     pair (2,-) : A = [hi(2)  | lo(2)]         B = [Wlo(2)  ; 0]
 //
-// Persistent CTA per SM: 6 producer warps (fp32 NHWC -> planar bf16 hi/lo), 2 MMA-issuing warps (every other tile
-// each: one instruction stream cannot keep the pipe busy), 8 epilogue warps.  The epilogue's extra operands (residual,
-// ReLU mask source, skip-path add, previous output) are prefetched one super-tile ahead with cp.async into
-// thread-private shared-memory slots, so no HBM latency is exposed between accumulator sets.
+// Persistent CTA per SM: 6 producer warps, 2 MMA-issuing warps (every other tile each: one instruction stream cannot
+// keep the pipe busy), 8 epilogue warps.  Nothing waits on HBM with registers: the producers keep a D-deep ring of raw
+// fp32 halo planes in flight with cp.async (zero-fill = SAME padding) into thread-private shared-memory slots and
+// convert the oldest one to the planar bf16 hi/lo image; the epilogue's extra operands (residual, ReLU mask source,
+// skip-path add, previous output) are prefetched one super-tile ahead the same way.  The weight images of all input
+// planes stay resident in shared memory for the life of the CTA.
 //
 // Reference semantics: model/layers/layers.py:10-102 (conv), model/model.py:37-50 (residual epilogue).
 #include <cuda_bf16.h>
@@ -43,14 +45,32 @@ constexpr int C3_EPI_WARPS = 8;
 constexpr int C3_THREADS = (C3_PROD_WARPS + C3_MMA_WARPS + C3_EPI_WARPS) * 32;
 constexpr int C3_MAX_STAGES = 3;
 constexpr int C3_SLOTS = 4;          // epilogue work items per thread and super-tile
-constexpr int C3_W_U = 2;            // weight-image uint4s prefetched per producer thread per plane
 
 struct C3Tile {
-  int T, N, CP, RI, P, stages;        // tiles per super-tile, MMA N, padded cout, halo rows, input planes, ring depth
+  int T, N, CP, RI, P, stages, D, A;  // tiles per super-tile, MMA N, padded cout, halo rows, input planes, image / raw / accumulator ring depth
   int blocks_x, blocks_y, n_super;
+  int dgx, dgy, dgb;                  // gridDim.x decomposed in (block column, block row, page) steps
   int n_ops, ia, io, im;              // extra epilogue operands and their slot index (-1 = absent)
   int dbg;
-  uint32_t plane_bytes, in_bytes, w_bytes, stage_bytes, epi_bytes, tmem_cols;
+  uint32_t plane_bytes, in_bytes, w_bytes, w_total, raw_bytes, epi_bytes, tmem_cols;
+};
+
+// position of a super-tile, advanced by gridDim.x super-tiles at a time without integer division
+struct TilePos {
+  int bx, by, b;
+  __device__ __forceinline__ void init(int st_i, const C3Tile& t) {
+    bx = st_i % t.blocks_x;
+    const int rest = st_i / t.blocks_x;
+    by = rest % t.blocks_y;
+    b = rest / t.blocks_y;
+  }
+  __device__ __forceinline__ void advance(const C3Tile& t) {
+    bx += t.dgx;
+    if (bx >= t.blocks_x) { bx -= t.blocks_x; ++by; }
+    by += t.dgy;
+    if (by >= t.blocks_y) { by -= t.blocks_y; ++b; }
+    b += t.dgb;
+  }
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -65,9 +85,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// src_bytes = 0 -> the 16 destination bytes are zero-filled (out-of-image halo pixels: SAME padding)
+__device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// polling wait for the few single lanes that wait on behalf of their warp: no suspend hint, so the wake-up is immediate
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
 
 __device__ __forceinline__ void mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
                                      uint32_t accumulate) {
@@ -88,49 +129,13 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   split_pair(x[6], x[7], hi.w, lo.w);
 }
 
-// one 8-channel plane of the halo image: RI rows x 32 columns, fp32 global -> bf16 hi/lo planar image
-template <bool RELU>
-__device__ __forceinline__ void produce_plane(const float* __restrict__ src, int pitch, int in_x0, int in_y0, int Hin, int Win,
-                                              const C3Tile& t, uint8_t* __restrict__ stg, int tid) {
-  constexpr int LDU = 6;
-  const int halo_px = t.RI * 32;
-  for (int e0 = tid; e0 < halo_px; e0 += C3_PROD_THREADS * LDU) {
-    float v[LDU][8];
-#pragma unroll
-    for (int u = 0; u < LDU; ++u) {
-      const int e = e0 + u * C3_PROD_THREADS;
-      const int gy = in_y0 + (e >> 5), gx = in_x0 + (e & 31);
-      const bool inb = e < halo_px && (unsigned)gy < (unsigned)Hin && (unsigned)gx < (unsigned)Win && !(t.dbg & 2);
-      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* sp = reinterpret_cast<const float4*>(src + (gy * Win + gx) * pitch);
-      const float4 q0 = inb ? __ldg(sp) : z4;
-      const float4 q1 = inb ? __ldg(sp + 1) : z4;
-      v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
-      v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
-    }
-#pragma unroll
-    for (int u = 0; u < LDU; ++u) {
-      const int e = e0 + u * C3_PROD_THREADS;
-      if (e >= halo_px) break;
-      if (RELU) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
-      }
-      uint4 hi, lo;
-      split8(v[u], hi, lo);
-      *reinterpret_cast<uint4*>(stg + e * 16) = hi;
-      *reinterpret_cast<uint4*>(stg + t.plane_bytes + e * 16) = lo;
-    }
-  }
-}
-
 template <bool RELU1>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
   __shared__ uint64_t bar_empty[C3_MAX_STAGES];   // MMA -> producers : the MMAs reading the stage have retired
-  __shared__ uint64_t bar_acc_full[2];            // MMA -> epilogue  : accumulator set complete
-  __shared__ uint64_t bar_acc_empty[2];           // epilogue -> MMA  : accumulator set drained
+  __shared__ uint64_t bar_acc_full[4];            // MMA -> epilogue  : accumulator set complete
+  __shared__ uint64_t bar_acc_empty[4];           // epilogue -> MMA  : accumulator set drained
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[64];
 
@@ -138,9 +143,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
 
   if (warp == 0) tmem_alloc(&tmem_base_s, t.tmem_cols);
   if (tid >= 64 && tid < 128) bias_s[tid - 64] = (a.bias && tid - 64 < t.CP) ? a.bias[tid - 64] : 0.f;
+  // shared memory: [weight images of all planes][image ring: S x (hi | lo)][raw ring: D x fp32 plane][epilogue slots]
+  uint8_t* const w_s = smem;
+  uint8_t* const img_s = smem + t.w_total;
+  uint8_t* const raw_s = img_s + (size_t)t.stages * t.in_bytes;
+  uint8_t* const epi = raw_s + (size_t)t.D * t.raw_bytes;
+  for (int e = tid; e < (int)(t.w_total >> 4); e += C3_THREADS)
+    reinterpret_cast<uint4*>(w_s)[e] = __ldg(reinterpret_cast<const uint4*>(wtc) + e);
+  fence_async_smem();
   if (tid == 32) {
     for (int i = 0; i < C3_MAX_STAGES; ++i) { mbar_init(&bar_full[i], C3_PROD_THREADS); mbar_init(&bar_empty[i], C3_MMA_WARPS); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS * 32); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS * 32); }
     mbar_init_fence();
   }
   tc_fence_before();
@@ -148,48 +161,92 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int S = t.stages;
+  const bool spin = !(t.dbg & 16);
+  auto wait = [&](uint64_t* bar, uint32_t parity) { if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); };
   const int RO = 4 * t.T;                                     // output rows per super-tile
 
   if (warp < C3_PROD_WARPS) {
     // =============================================================== producers
+    // chunk = (super-tile, input plane).  Copies of chunk c + D - 1 are issued before chunk c is converted, so D - 1
+    // planes (RI x 32 pixels x 32 B each) are always in flight per CTA; every thread copies and converts its own pixels
+    // e = tid + u * 192, which makes the raw ring thread-private (cp.async.wait_group is the only synchronisation).
+    constexpr int LDU = 3;                                       // RI * 32 <= 576 = 3 * 192
     const int planes1 = a.c1 >> 3;
+    const int halo_px = t.RI * 32;
+    const uint32_t raw_u32 = smem_u32(raw_s);
+    auto issue = [&](const TilePos& tp, int p, int slot) {
+      if (tp.b < a.B && !(t.dbg & 2)) {
+        const int in_x0 = tp.bx * 30 - 1, in_y0 = tp.by * RO - 1;
+        const bool from1 = p < planes1;
+        const float* src = from1 ? a.src1 + (p << 3) : a.src2 + ((p - planes1) << 3);
+        const int pitch = from1 ? a.p1 : a.p2;
+        src += (long)tp.b * a.Hin * a.Win * pitch;
+        const uint32_t dst0 = raw_u32 + (uint32_t)slot * t.raw_bytes + (uint32_t)tid * 16u;
+#pragma unroll
+        for (int u = 0; u < LDU; ++u) {
+          const int e = tid + u * C3_PROD_THREADS;
+          if (e < halo_px) {
+            const int gy = in_y0 + (e >> 5), gx = in_x0 + (e & 31);
+            const bool inb = (unsigned)gy < (unsigned)a.Hin && (unsigned)gx < (unsigned)a.Win;
+            const float* sp = inb ? src + (gy * a.Win + gx) * pitch : src;
+            const uint32_t dst = dst0 + (uint32_t)u * (2u * C3_PROD_THREADS * 16u);
+            cp_async16z(dst, sp, inb ? 16u : 0u);
+            cp_async16z(dst + C3_PROD_THREADS * 16u, sp + 4, inb ? 16u : 0u);
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    TilePos ahead, cur;
+    ahead.init(blockIdx.x, t);
+    cur = ahead;
+    int p_ahead = 0;
+    // (every thread keeps D - 1 groups outstanding: empty groups stand in for chunks that do not exist)
+    for (int d = 0; d < t.D - 1; ++d) {
+      issue(ahead, p_ahead, d);
+      if (++p_ahead == t.P) { p_ahead = 0; ahead.advance(t); }
+    }
     uint32_t c = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
-      const int bx = st_i % t.blocks_x;
-      const int rest = st_i / t.blocks_x;
-      const int by = rest % t.blocks_y;
-      const int b = rest / t.blocks_y;
-      const int in_x0 = bx * 30 - 1, in_y0 = by * RO - 1;
-      const long boff = (long)b * a.Hin * a.Win;
       for (int p = 0; p < t.P; ++p, ++c) {
+        issue(ahead, p_ahead, (int)((c + t.D - 1) % t.D));
+        if (++p_ahead == t.P) { p_ahead = 0; ahead.advance(t); }
         const int s = c % S;
-        uint8_t* stg = smem + (size_t)s * t.stage_bytes;
+        uint8_t* stg = img_s + (size_t)s * t.in_bytes;
         if (c >= (uint32_t)S) {
-          if (lane == 0) mbar_wait(&bar_empty[s], ((c / S) - 1) & 1);
+          if (lane == 0) wait(&bar_empty[s], ((c / S) - 1) & 1);
           __syncwarp();
         }
-        uint4 wreg[C3_W_U];
-        const uint4* wsrc = reinterpret_cast<const uint4*>(wtc) + (size_t)p * (t.w_bytes >> 4);
-        const int w16 = (int)(t.w_bytes >> 4);
+        // chunk c has landed once at most D - 1 newer groups are pending (D is 2..4)
+        if (t.D == 4) cp_async_wait<3>(); else if (t.D == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+        const uint8_t* rsrc = raw_s + (size_t)(c % t.D) * t.raw_bytes + tid * 16;
+        const bool relu = RELU1 && p < planes1;
 #pragma unroll
-        for (int u = 0; u < C3_W_U; ++u)
-          if (tid + u * C3_PROD_THREADS < w16) wreg[u] = __ldg(wsrc + tid + u * C3_PROD_THREADS);
-        if (p < planes1) {
-          produce_plane<RELU1>(a.src1 + boff * a.p1 + (p << 3), a.p1, in_x0, in_y0, a.Hin, a.Win, t, stg, tid);
-        } else {
-          produce_plane<false>(a.src2 + boff * a.p2 + ((p - planes1) << 3), a.p2, in_x0, in_y0, a.Hin, a.Win, t, stg, tid);
-        }
-        {
-          uint4* dst = reinterpret_cast<uint4*>(stg + t.in_bytes);
+        for (int u = 0; u < LDU; ++u) {
+          const int e = tid + u * C3_PROD_THREADS;
+          if (e < halo_px) {
+            const float4 q0 = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16));
+            const float4 q1 = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16) + C3_PROD_THREADS * 16);
+            float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            if (t.dbg & 2) {
 #pragma unroll
-          for (int u = 0; u < C3_W_U; ++u)
-            if (tid + u * C3_PROD_THREADS < w16) dst[tid + u * C3_PROD_THREADS] = wreg[u];
-          for (int e = tid + C3_W_U * C3_PROD_THREADS; e < w16; e += C3_PROD_THREADS) dst[e] = __ldg(wsrc + e);
+              for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            }
+            if (relu) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+            }
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            *reinterpret_cast<uint4*>(stg + e * 16) = hi;
+            *reinterpret_cast<uint4*>(stg + t.plane_bytes + e * 16) = lo;
+          }
         }
         fence_async_smem();
         mbar_arrive(&bar_full[s]);
       }
     }
+    cp_async_wait<0>();
   } else if (warp < C3_PROD_WARPS + C3_MMA_WARPS) {
     // =============================================================== MMA issuers (tiles mw, mw + 2, ...)
     const int mw = warp - C3_PROD_WARPS;
@@ -202,16 +259,20 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const uint32_t b_lbo = ((N * 16 >> 4) & 0x3FFF) << 16;
     uint32_t c = 0, tcount = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
-      const uint32_t as = tcount & 1;
-      if (tcount >= 2) mbar_wait(&bar_acc_empty[as], ((tcount >> 1) - 1) & 1);
+      const uint32_t as = tcount % (uint32_t)t.A;
+      if (tcount >= (uint32_t)t.A) {
+        if (lane == 0) wait(&bar_acc_empty[as], ((tcount / (uint32_t)t.A) - 1) & 1);
+        __syncwarp();
+      }
       tc_fence_after();
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N);
       for (int p = 0; p < t.P; ++p, ++c) {
         const int s = c % S;
-        mbar_wait(&bar_full[s], (c / S) & 1);
+        if (lane == 0) wait(&bar_full[s], (c / S) & 1);
+        __syncwarp();
         tc_fence_after();
-        const uint32_t in_addr = smem_u32(smem + (size_t)s * t.stage_bytes);
-        const uint32_t in16 = in_addr >> 4, w16a = (in_addr + t.in_bytes) >> 4;
+        const uint32_t in16 = smem_u32(img_s + (size_t)s * t.in_bytes) >> 4;
+        const uint32_t w16a = smem_u32(w_s + (size_t)p * t.w_bytes) >> 4;
         if (elect_one()) {
           if (!(t.dbg & 1)) {
             // instruction-major / tile-minor: consecutive instructions hit different accumulators
@@ -245,7 +306,6 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const int lc = 31 - __clz(chunks);
     const int total_items = t.T << lc;                       // <= 8: item kg -> (tile kg >> lc, channel chunk kg & (chunks-1))
     const int et = ew * 32 + lane;                           // epilogue thread index 0..255
-    uint8_t* epi = smem + (size_t)S * t.stage_bytes;
     const uint32_t epi_u32 = smem_u32(epi);
     const uint32_t slot_stride = (uint32_t)t.n_ops * 8192u;  // bytes between consecutive items' slots
     const uint32_t my_slot = (uint32_t)et * 16u;
@@ -253,19 +313,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const long tile_pix = 4L * a.Wout;                       // pixel distance between consecutive tiles (4 rows)
     // position of a super-tile for this thread: pixel index of its tile-0 output, first output row, column validity
     struct Pos { long pix; int row; bool ok; };
-    auto decode = [&](int st_i) -> Pos {
+    auto decode = [&](const TilePos& tp) -> Pos {
       Pos ps;
-      if (st_i >= t.n_super) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; return ps; }
-      const int bx = st_i % t.blocks_x;
-      const int rest = st_i / t.blocks_x;
-      const int by = rest % t.blocks_y;
-      const int b = rest / t.blocks_y;
-      const int ox = bx * 30 - 1 + lane;
-      ps.row = by * RO + q;
+      if (tp.b >= a.B) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; return ps; }
+      const int ox = tp.bx * 30 - 1 + lane;
+      ps.row = tp.by * RO + q;
       ps.ok = lane_ok && ox < a.Wout;
-      ps.pix = ((long)b * a.Hout + ps.row) * a.Wout + ox;
+      ps.pix = ((long)tp.b * a.Hout + ps.row) * a.Wout + ox;
       return ps;
     };
+    TilePos tp;
+    tp.init(blockIdx.x, t);
     const float* pa = a.res ? a.res : a.add;
     const int ppa = a.res ? a.pr : a.pa;
     auto prefetch = [&](const Pos& ps, int k) {
@@ -293,16 +351,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
       }
       cp_async_commit();
     };
-    Pos cur = decode(blockIdx.x);
+    Pos cur = decode(tp);
 #pragma unroll
     for (int k = 0; k < C3_SLOTS; ++k) prefetch(cur, k);
 
     uint32_t tcount = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
-      const Pos nxt = decode(st_i + (int)gridDim.x);
-      const uint32_t as = tcount & 1;
+      tp.advance(t);
+      const Pos nxt = decode(tp);
+      const uint32_t as = tcount % (uint32_t)t.A;
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N) + ((uint32_t)(q * 32) << 16);
-      if (lane == 0) mbar_wait(&bar_acc_full[as], (tcount >> 1) & 1);
+      if (lane == 0) wait(&bar_acc_full[as], (tcount / (uint32_t)t.A) & 1);
       __syncwarp();
       tc_fence_after();
 #pragma unroll
@@ -384,26 +443,35 @@ bool c3_configure(const ConvArgs& a, C3Tile& t) {
   if (!(t.CP == 8 || t.CP == 16 || t.CP == 32 || t.CP == 64)) return false;
   t.N = round_up(3 * t.CP, 16);
   t.T = 8 / (t.CP >> 3);
+  if (t.T > 4) t.T = 4;                                       // one raw plane = RI * 32 <= 576 pixels = 3 per producer thread
   while (t.T > 1 && 4 * (t.T / 2) >= a.Hout) t.T /= 2;       // short maps: do not pay for rows that do not exist
   t.RI = 4 * t.T + 2;
   t.P = (a.c1 + a.c2) / 8;
   t.plane_bytes = (uint32_t)t.RI * 512;
   t.in_bytes = 2 * t.plane_bytes;
+  t.raw_bytes = (uint32_t)(3 * 2 * C3_PROD_THREADS * 16);    // [u][half][thread] x 16 B
   t.w_bytes = 5u * (uint32_t)t.N * 32;
-  t.stage_bytes = (t.in_bytes + t.w_bytes + 127) / 128 * 128;
+  t.w_total = (uint32_t)t.P * t.w_bytes;
   t.n_ops = 0; t.ia = t.io = t.im = -1;
   if (a.res || a.add) t.ia = t.n_ops++;
   if (a.accumulate) t.io = t.n_ops++;
   if (a.omask) t.im = t.n_ops++;
-  t.epi_bytes = (uint32_t)(C3_SLOTS * t.n_ops * 2 * 4096);
-  t.stages = C3_MAX_STAGES;
-  while (t.stages > 2 && (size_t)t.stage_bytes * t.stages + t.epi_bytes > 216 * 1024) --t.stages;
-  if ((size_t)t.stage_bytes * t.stages + t.epi_bytes > 216 * 1024) return false;
+  const int items = (t.T * (t.CP >> 3) + 1) / 2;              // epilogue work items per thread and super-tile
+  t.epi_bytes = (uint32_t)(items * t.n_ops * 2 * 4096);
+  t.stages = C3_MAX_STAGES; t.D = 4;
+  auto total = [&]() { return (size_t)t.w_total + (size_t)t.stages * t.in_bytes + (size_t)t.D * t.raw_bytes + t.epi_bytes; };
+  while (total() > 216 * 1024 && (t.D > 2 || t.stages > 2)) {
+    if (t.D > 2 && t.D >= t.stages) --t.D; else --t.stages;
+  }
+  if (total() > 216 * 1024) return false;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
   t.blocks_x = cdiv(a.Wout, 30);
   t.blocks_y = cdiv(a.Hout, 4 * t.T);
   t.n_super = t.blocks_x * t.blocks_y * a.B;
-  const int cols = 2 * t.T * t.N;
+  t.A = 512 / (t.T * t.N);
+  if (t.A > 4) t.A = 4;
+  if (t.A < 2) return false;
+  const int cols = t.A * t.T * t.N;
   t.tmem_cols = 32;
   while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
   return t.tmem_cols <= 512;
@@ -427,8 +495,11 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   MSAU_CHECK_ARG(conv3_tc_supported(a), "conv3_tc: unsupported shape");
   C3Tile t;
   MSAU_CHECK_ARG(c3_configure(a, t), "conv3_tc: tile does not fit");
-  const size_t smem = (size_t)t.stage_bytes * t.stages + t.epi_bytes + 1024;
+  const size_t smem = (size_t)t.w_total + (size_t)t.stages * t.in_bytes + (size_t)t.D * t.raw_bytes + t.epi_bytes + 1024;
   const int grid = t.n_super < sm_count() ? t.n_super : sm_count();
+  t.dgx = grid % t.blocks_x;
+  t.dgy = (grid / t.blocks_x) % t.blocks_y;
+  t.dgb = (grid / t.blocks_x) / t.blocks_y;
   const bool general = a.res || a.omask || a.add || a.accumulate || a.relu2;
   const double npix = (double)a.B * a.Hin * a.Win;
   double bytes = npix * (a.c1 + a.c2) * 4.0;

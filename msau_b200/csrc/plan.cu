@@ -312,7 +312,7 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 // ------------------------------------------------------------------ launch helpers
 static bool g_use_tc = true;
 static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
-static int g_c3_max = 32;        // ... for at most this many output channels
+static int g_c3_max = 16;        // ... for at most this many output channels
 
 struct ConvOpt {
   bool relu1 = false, relu = false, relu2 = false;

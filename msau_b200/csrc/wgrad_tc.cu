@@ -375,6 +375,7 @@ struct Wg2Tile {
   int dbg;                                  // MSAU_WG_DEBUG experiments: 1 = no MMAs, 2 = no global loads
 };
 
+template <bool NCHW>
 __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArgs a, const Wg2Tile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_free[2];
@@ -427,46 +428,74 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
     const int ty = rest % t.tiles_y;
     const int b = rest / t.tiles_y;
     const int qy0 = ty * t.TR, qx0 = tx * t.TC;
-    // ---- X tile of this plane: TR rows x HWx columns (kw-1 halo columns), 16 B per pixel.  A warp takes rows
-    //      warp, warp+8, ... and 32-column groups; WU pixels' loads are in flight per thread; no integer divisions ----
+    // ---- X tile of this plane: TR rows x HWx columns (kw-1 halo columns), 16 B per pixel.  Kept lean (this kernel is
+    //      bound by instruction issue, not by HBM): a warp takes rows warp, warp+8, ..., a lane the columns lane and
+    //      lane+32; pointers advance by constants; the few halo columns are a separate short pass ----
     {
       const int in_x0 = qx0 - a.pada_l;
-      const int plane_stride = a.Ha * a.Wa;
-      const float* xsrc = a.a_nchw ? a.A + ((long)b * a.ca_logical + ca0) * plane_stride : a.A + (long)b * plane_stride * a.pa + ca0;
-      const int n_valid = a.ca_logical - ca0;
-      const int ncg = (t.HWx + 31) >> 5;
-      int r = warp, cg = 0;
-      while (r < t.TR) {
-        float v[WU][8];
-        int so[WU];
+      if (NCHW) {
+        const int plane_stride = a.Ha * a.Wa;
+        const float* xsrc = a.A + ((long)b * a.ca_logical + ca0) * plane_stride;
+        const int n_valid = a.ca_logical - ca0;
+        for (int r = warp; r < t.TR; r += 8) {
+          const int gy = qy0 + r;
+          for (int c = lane; c < t.HWx; c += 32) {
+            const int gx = in_x0 + c;
+            const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa && !(t.dbg & 2);
+            const float* sp = xsrc + gy * a.Wa + gx;
+            float v[8];
 #pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          const int c = (cg << 5) + lane;
-          const int gy = qy0 + r, gx = in_x0 + c;
-          so[u] = (r < t.TR && c < t.HWx) ? r * t.HWx + c : -1;
-          const bool inb = so[u] >= 0 && gy < a.Ha && (unsigned)gx < (unsigned)a.Wa && !(t.dbg & 2);
-          const int lin = gy * a.Wa + gx;
-          if (a.a_nchw) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[u][k] = (inb && k < n_valid) ? __ldg(xsrc + lin + k * plane_stride) : 0.f;
-          } else {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4* sp = reinterpret_cast<const float4*>(xsrc + lin * a.pa);
-            const float4 q0 = inb ? __ldg(sp) : z4;
-            const float4 q1 = inb ? __ldg(sp + 1) : z4;
-            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
-            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+            for (int k = 0; k < 8; ++k) v[k] = (inb && k < n_valid) ? __ldg(sp + k * plane_stride) : 0.f;
+            *reinterpret_cast<uint4*>(st + (r * t.HWx + c) * 16) = wpack8(v);
           }
-          if (++cg == ncg) { cg = 0; r += 8; }
         }
+      } else {
+        const float* xsrc = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // interior columns [0, TC): 2 rows x 2 column groups = 4 pixels in flight per thread
+        const int gx0 = in_x0 + lane, gx1 = gx0 + 32;
+        const bool okx0 = lane < t.TC && (unsigned)gx0 < (unsigned)a.Wa && !(t.dbg & 2), okx1 = lane + 32 < t.TC && (unsigned)gx1 < (unsigned)a.Wa && !(t.dbg & 2);
+        for (int r = warp; r < t.TR; r += 16) {
+          const int r2 = r + 8;
+          const bool oky0 = qy0 + r < a.Ha, oky1 = r2 < t.TR && qy0 + r2 < a.Ha;
+          const float* p0 = xsrc + ((qy0 + r) * a.Wa + gx0) * a.pa;
+          const float* p1 = p0 + 8 * a.Wa * a.pa;
+          const float4* s00 = reinterpret_cast<const float4*>(p0);
+          const float4* s01 = reinterpret_cast<const float4*>(p0 + 32 * a.pa);
+          const float4* s10 = reinterpret_cast<const float4*>(p1);
+          const float4* s11 = reinterpret_cast<const float4*>(p1 + 32 * a.pa);
+          float4 q[4][2];
+          q[0][0] = (oky0 && okx0) ? __ldg(s00) : z4; q[0][1] = (oky0 && okx0) ? __ldg(s00 + 1) : z4;
+          q[1][0] = (oky0 && okx1) ? __ldg(s01) : z4; q[1][1] = (oky0 && okx1) ? __ldg(s01 + 1) : z4;
+          q[2][0] = (oky1 && okx0) ? __ldg(s10) : z4; q[2][1] = (oky1 && okx0) ? __ldg(s10 + 1) : z4;
+          q[3][0] = (oky1 && okx1) ? __ldg(s11) : z4; q[3][1] = (oky1 && okx1) ? __ldg(s11 + 1) : z4;
+          uint8_t* d0 = st + (r * t.HWx + lane) * 16;
+          uint8_t* d1 = d0 + 8 * t.HWx * 16;
 #pragma unroll
-        for (int u = 0; u < WU; ++u) {
-          if (so[u] < 0) continue;
+          for (int u = 0; u < 4; ++u) {
+            float v[8] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w, q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w};
+            if (a.reluA) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+            }
+            const bool st_ok = (u < 2 || r2 < t.TR) && ((u & 1) ? lane + 32 < t.TC : lane < t.TC);
+            if (st_ok) *reinterpret_cast<uint4*>((u < 2 ? d0 : d1) + (u & 1) * 512) = wpack8(v);
+          }
+        }
+        // halo columns [TC, HWx): at most 3 per row
+        const int nh = t.HWx - t.TC;
+        for (int e = tid; e < t.TR * nh; e += WG_THREADS) {
+          const int r = e / nh, c = t.TC + (e - r * nh);
+          const int gy = qy0 + r, gx = in_x0 + c;
+          const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa && !(t.dbg & 2);
+          const float4* sp = reinterpret_cast<const float4*>(xsrc + (gy * a.Wa + gx) * a.pa);
+          const float4 q0 = inb ? __ldg(sp) : z4, q1 = inb ? __ldg(sp + 1) : z4;
+          float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
           if (a.reluA) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[u][k] = fmaxf(v[u][k], 0.f);
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
           }
-          *reinterpret_cast<uint4*>(st + so[u] * 16) = wpack8(v[u]);
+          *reinterpret_cast<uint4*>(st + (r * t.HWx + c) * 16) = wpack8(v);
         }
       }
     }
@@ -477,44 +506,46 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
       const int nyp = t.ny_planes;
       const int pgrp = nyp < 8 ? nyp : 8;
       const int pl0 = warp % pgrp, rstart = warp / pgrp, rstep = 8 / pgrp;
-      const int ncg = (t.TC + 31) >> 5;
       const int vy0 = qy0 + a.pada_t - (a.kh - 1);
       const int smul = a.b_s2d ? 2 : 1;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool two = lane + 32 < t.TC;
       for (int pl = pl0; pl < nyp; pl += 8) {
         // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
         const int sph = a.b_s2d ? (pl << 3) / a.cph : 0;
         const int spy = sph >> 1, spx = sph & 1;
         const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? (pl << 3) - sph * a.cph : (pl << 3));
+        const int vx0 = qx0 + lane, vx1 = vx0 + 32;
+        const int gx0 = vx0 * smul + spx, gx1 = vx1 * smul + spx;
+        const bool okx0 = lane < t.TC && vx0 < a.Wq && gx0 < a.Wb && !(t.dbg & 2), okx1 = two && vx1 < a.Wq && gx1 < a.Wb && !(t.dbg & 2);
         float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        int r = rstart, cg = 0;
-        while (r < t.TRy) {
-          float v[WU][8];
-          int so[WU];
-          bool center[WU];
+        for (int r = rstart; r < t.TRy; r += 2 * rstep) {
+          const int r2 = r + rstep;
+          const int vya = vy0 + r, vyb = vy0 + r2;
+          const int gya = vya * smul + spy, gyb = vyb * smul + spy;
+          const bool okya = (unsigned)vya < (unsigned)a.Hq && gya < a.Hb, okyb = r2 < t.TRy && (unsigned)vyb < (unsigned)a.Hq && gyb < a.Hb;
+          const float4* s00 = reinterpret_cast<const float4*>(ysrc + (gya * a.Wb + gx0) * a.pb);
+          const float4* s01 = reinterpret_cast<const float4*>(ysrc + (gya * a.Wb + gx1) * a.pb);
+          const float4* s10 = reinterpret_cast<const float4*>(ysrc + (gyb * a.Wb + gx0) * a.pb);
+          const float4* s11 = reinterpret_cast<const float4*>(ysrc + (gyb * a.Wb + gx1) * a.pb);
+          float4 q[4][2];
+          q[0][0] = (okya && okx0) ? __ldg(s00) : z4; q[0][1] = (okya && okx0) ? __ldg(s00 + 1) : z4;
+          q[1][0] = (okya && okx1) ? __ldg(s01) : z4; q[1][1] = (okya && okx1) ? __ldg(s01 + 1) : z4;
+          q[2][0] = (okyb && okx0) ? __ldg(s10) : z4; q[2][1] = (okyb && okx0) ? __ldg(s10 + 1) : z4;
+          q[3][0] = (okyb && okx1) ? __ldg(s11) : z4; q[3][1] = (okyb && okx1) ? __ldg(s11 + 1) : z4;
+          // bias gradient: rows of this tile only (halo rows belong to the neighbours); out-of-image pixels are zero
+          const bool ca = do_bias && vya >= qy0 && vya < qy0 + t.TR, cb2 = do_bias && vyb >= qy0 && vyb < qy0 + t.TR;
+          uint8_t* d0 = yh + (size_t)((r * nyp + pl) * t.TC + lane) * 16;
+          uint8_t* d1 = yh + (size_t)((r2 * nyp + pl) * t.TC + lane) * 16;
 #pragma unroll
-          for (int u = 0; u < WU; ++u) {
-            const int c = (cg << 5) + lane;
-            const int vy = vy0 + r, vx = qx0 + c;
-            const int gy = vy * smul + spy, gx = vx * smul + spx;
-            so[u] = (r < t.TRy && c < t.TC) ? (r * nyp + pl) * t.TC + c : -1;
-            const bool inb = so[u] >= 0 && (unsigned)vy < (unsigned)a.Hq && vx < a.Wq && gy < a.Hb && gx < a.Wb && !(t.dbg & 2);
-            center[u] = vy >= qy0 && vy < qy0 + t.TR;       // halo rows belong to the neighbouring tiles
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4* sp = reinterpret_cast<const float4*>(ysrc + (gy * a.Wb + gx) * a.pb);
-            const float4 q0 = inb ? __ldg(sp) : z4;
-            const float4 q1 = inb ? __ldg(sp + 1) : z4;
-            v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
-            v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
-            if (++cg == ncg) { cg = 0; r += rstep; }
-          }
+          for (int u = 0; u < 4; ++u) {
+            const float v[8] = {q[u][0].x, q[u][0].y, q[u][0].z, q[u][0].w, q[u][1].x, q[u][1].y, q[u][1].z, q[u][1].w};
+            if (u < 2 ? ca : cb2) {
 #pragma unroll
-          for (int u = 0; u < WU; ++u) {
-            if (so[u] < 0) continue;
-            if (do_bias && center[u]) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) bacc[k] += v[u][k];
+              for (int k = 0; k < 8; ++k) bacc[k] += v[k];
             }
-            *reinterpret_cast<uint4*>(yh + (size_t)so[u] * 16) = wpack8(v[u]);
+            const bool st_ok = (u < 2 || r2 < t.TRy) && ((u & 1) ? two : lane < t.TC);
+            if (st_ok) *reinterpret_cast<uint4*>((u < 2 ? d0 : d1) + (u & 1) * 512) = wpack8(v);
           }
         }
         if (do_bias) {
@@ -606,7 +637,9 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
 }
 
 static bool wgrad_tc2_config(const WgradArgs& a, Wg2Tile& t) {
-  if (a.dila != 1 || a.kh * a.cb > 256 || a.maskB) return false;
+  // measured (profiles/): wins for <= 16 output channels (the HBM-streaming levels); with more channels the (kh-1) halo rows
+  // of the staged dY tile cost shared memory (fewer resident CTAs) and the per-ky kernel above is faster
+  if (a.dila != 1 || a.cb > 16 || a.maskB) return false;
   t.N = a.kh * a.cb;
   t.ny_planes = a.cb >> 3;
   t.TC = round_up(a.Wq, 16);
@@ -651,14 +684,16 @@ static int launch_wgrad_tc2(const WgradArgs& a, const Wg2Tile& t0, cudaStream_t 
   ctas = cdiv(t.n_tiles, t.tiles_per_cta);
   static bool attr = false;
   if (!attr) {
-    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid(ctas, planes);
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb) * (a.maskB ? 2 : 1)) * 4.0;
   ProfScope ps("wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
-  wgrad_tc2_kernel<<<grid, WG_THREADS, smem, st>>>(a, t);
+  if (a.a_nchw) wgrad_tc2_kernel<true><<<grid, WG_THREADS, smem, st>>>(a, t);
+  else wgrad_tc2_kernel<false><<<grid, WG_THREADS, smem, st>>>(a, t);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

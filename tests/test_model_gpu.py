@@ -179,7 +179,10 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
     torch.cuda.synchronize()
     live = torch.tensor(m2._live_mask())
     for (k, p2), p1 in zip(m2.named_parameters(), m.parameters()):
-        assert (p2.detach() - p1.detach()).abs().max().item() <= 2e-6, k
+        # attention f.conv.bias: analytically zero gradient, so its Adam update (+-lr) follows the sign of rounding noise,
+        # which depends on the order of the weight-gradient atomics
+        tol = 2.5e-4 if k.endswith("attention_block.f.conv.bias") else 2e-6
+        assert (p2.detach() - p1.detach()).abs().max().item() <= tol, k
     assert abs(float(m2._adam[4]) - float(z["total_norm"])) <= (2e-2 if tc else 2e-3) * float(z["total_norm"])
     # dead attention params untouched
     dead = [k for k, lv in zip(keys, m2._live_mask()) if not lv]
