@@ -87,7 +87,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 // src_bytes = 0 -> the 16 destination bytes are zero-filled (out-of-image halo pixels: SAME padding)
 __device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -129,7 +129,9 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   split_pair(x[6], x[7], hi.w, lo.w);
 }
 
-template <bool RELU1>
+// EPI: 0 = epilogue driven by run-time flags; 1 = bias; 2 = bias + ReLU; 3 = bias + residual + ReLU; 4 = ReLU mask; 5 = ReLU mask + add
+// LDU: raw pixels per producer thread and plane (3: T <= 4 tiles, 6: T = 8)
+template <int EPI, int LDU>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
@@ -152,8 +154,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     reinterpret_cast<uint4*>(w_s)[e] = __ldg(reinterpret_cast<const uint4*>(wtc) + e);
   fence_async_smem();
   if (tid == 32) {
-    for (int i = 0; i < C3_MAX_STAGES; ++i) { mbar_init(&bar_full[i], C3_PROD_THREADS); mbar_init(&bar_empty[i], C3_MMA_WARPS); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS * 32); }
+    for (int i = 0; i < C3_MAX_STAGES; ++i) { mbar_init(&bar_full[i], C3_PROD_WARPS); mbar_init(&bar_empty[i], C3_MMA_WARPS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS); }
     mbar_init_fence();
   }
   tc_fence_before();
@@ -170,9 +172,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     // chunk = (super-tile, input plane).  Copies of chunk c + D - 1 are issued before chunk c is converted, so D - 1
     // planes (RI x 32 pixels x 32 B each) are always in flight per CTA; every thread copies and converts its own pixels
     // e = tid + u * 192, which makes the raw ring thread-private (cp.async.wait_group is the only synchronisation).
-    constexpr int LDU = 3;                                       // RI * 32 <= 576 = 3 * 192
     const int planes1 = a.c1 >> 3;
-    const int halo_px = t.RI * 32;
     const uint32_t raw_u32 = smem_u32(raw_s);
     auto issue = [&](const TilePos& tp, int p, int slot) {
       if (tp.b < a.B && !(t.dbg & 2)) {
@@ -182,13 +182,18 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         const int pitch = from1 ? a.p1 : a.p2;
         src += (long)tp.b * a.Hin * a.Win * pitch;
         const uint32_t dst0 = raw_u32 + (uint32_t)slot * t.raw_bytes + (uint32_t)tid * 16u;
+        // pixel e = tid + 192 u of the halo plane = (row warp + 6 u, column lane)
+        const int gx = in_x0 + lane;
+        const bool okx = (unsigned)gx < (unsigned)a.Win;
+        const float* col = src + gx * pitch;
+        const int rpitch = a.Win * pitch;
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
-          const int e = tid + u * C3_PROD_THREADS;
-          if (e < halo_px) {
-            const int gy = in_y0 + (e >> 5), gx = in_x0 + (e & 31);
-            const bool inb = (unsigned)gy < (unsigned)a.Hin && (unsigned)gx < (unsigned)a.Win;
-            const float* sp = inb ? src + (gy * a.Win + gx) * pitch : src;
+          const int row = warp + u * C3_PROD_WARPS;
+          if (row < t.RI) {
+            const int gy = in_y0 + row;
+            const bool inb = okx && (unsigned)gy < (unsigned)a.Hin;
+            const float* sp = inb ? col + gy * rpitch : src;
             const uint32_t dst = dst0 + (uint32_t)u * (2u * C3_PROD_THREADS * 16u);
             cp_async16z(dst, sp, inb ? 16u : 0u);
             cp_async16z(dst + C3_PROD_THREADS * 16u, sp + 4, inb ? 16u : 0u);
@@ -220,11 +225,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         // chunk c has landed once at most D - 1 newer groups are pending (D is 2..4)
         if (t.D == 4) cp_async_wait<3>(); else if (t.D == 3) cp_async_wait<2>(); else cp_async_wait<1>();
         const uint8_t* rsrc = raw_s + (size_t)(c % t.D) * t.raw_bytes + tid * 16;
-        const bool relu = RELU1 && p < planes1;
+        const bool relu = a.relu1 && p < planes1;
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
           const int e = tid + u * C3_PROD_THREADS;
-          if (e < halo_px) {
+          if (warp + u * C3_PROD_WARPS < t.RI) {
             const float4 q0 = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16));
             const float4 q1 = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16) + C3_PROD_THREADS * 16);
             float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
@@ -242,8 +247,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
             *reinterpret_cast<uint4*>(stg + t.plane_bytes + e * 16) = lo;
           }
         }
+        // one arrival per warp: 192 per-thread arrivals on one mbarrier serialise in shared memory
         fence_async_smem();
-        mbar_arrive(&bar_full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[s]);
       }
     }
     cp_async_wait<0>();
@@ -299,6 +306,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     // Kept lean on purpose: with 8 x 32 threads x 4 items per super-tile this role is bound by instruction issue, so the
     // super-tile position is decoded once (for the tile being drained and for the one being prefetched), item -> (tile,
     // channel chunk) is shifts and masks, and the bias comes from shared memory.
+    constexpr bool G = EPI == 0;
     const int ew = warp - (C3_PROD_WARPS + C3_MMA_WARPS);   // 0..7
     const int q = warp & 3;                                  // TMEM lane quarter = tile row
     const int sub = ew >> 2;
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const int total_items = t.T << lc;                       // <= 8: item kg -> (tile kg >> lc, channel chunk kg & (chunks-1))
     const int et = ew * 32 + lane;                           // epilogue thread index 0..255
     const uint32_t epi_u32 = smem_u32(epi);
-    const uint32_t slot_stride = (uint32_t)t.n_ops * 8192u;  // bytes between consecutive items' slots
+    const uint32_t slot_stride = (uint32_t)(G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0))) * 8192u;  // bytes between consecutive items' slots
     const uint32_t my_slot = (uint32_t)et * 16u;
     const bool lane_ok = lane >= 1 && lane <= 30;
     const long tile_pix = 4L * a.Wout;                       // pixel distance between consecutive tiles (4 rows)
@@ -324,29 +332,37 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     };
     TilePos tp;
     tp.init(blockIdx.x, t);
-    const float* pa = a.res ? a.res : a.add;
-    const int ppa = a.res ? a.pr : a.pa;
+    const bool f_relu = G ? a.relu != 0 : EPI == 2;
+    const bool f_res = G ? a.res != nullptr : EPI == 3;
+    const bool f_relu2 = G ? a.relu2 != 0 : EPI == 3;
+    const bool f_add = G ? a.add != nullptr : EPI == 5;
+    const int ia = G ? t.ia : ((EPI == 3 || EPI == 5) ? 0 : -1);
+    const int io = G ? t.io : -1;
+    const int im = G ? t.im : (EPI == 4 ? 0 : (EPI == 5 ? 1 : -1));
+    const int n_ops = G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0));
+    const float* pa = f_res ? a.res : a.add;
+    const int ppa = f_res ? a.pr : a.pa;
     auto prefetch = [&](const Pos& ps, int k) {
       // extras of work item k of that super-tile -> this thread's slots (one cp.async group per item, possibly empty)
       const int kg = sub + 2 * k;
       const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
-      if (t.n_ops > 0 && ps.ok && kg < total_items && ps.row + 4 * tile < a.Hout && !(t.dbg & 8)) {
+      if (n_ops > 0 && ps.ok && kg < total_items && ps.row + 4 * tile < a.Hout && !(t.dbg & 8)) {
         const long pix = ps.pix + tile * tile_pix;
         const uint32_t dst = epi_u32 + (uint32_t)k * slot_stride + my_slot;
-        if (t.ia >= 0) {
+        if (ia >= 0) {
           const float* ap = pa + pix * ppa + ch8;
-          cp_async16(dst + (uint32_t)t.ia * 8192u, ap);
-          cp_async16(dst + (uint32_t)t.ia * 8192u + 4096u, ap + 4);
+          cp_async16(dst + (uint32_t)ia * 8192u, ap);
+          cp_async16(dst + (uint32_t)ia * 8192u + 4096u, ap + 4);
         }
-        if (t.io >= 0) {
+        if (io >= 0) {
           const float* op = a.out + pix * a.po + ch8;
-          cp_async16(dst + (uint32_t)t.io * 8192u, op);
-          cp_async16(dst + (uint32_t)t.io * 8192u + 4096u, op + 4);
+          cp_async16(dst + (uint32_t)io * 8192u, op);
+          cp_async16(dst + (uint32_t)io * 8192u + 4096u, op + 4);
         }
-        if (t.im >= 0) {
+        if (im >= 0) {
           const float* mp = a.omask + pix * a.pom + ch8;
-          cp_async16(dst + (uint32_t)t.im * 8192u, mp);
-          cp_async16(dst + (uint32_t)t.im * 8192u + 4096u, mp + 4);
+          cp_async16(dst + (uint32_t)im * 8192u, mp);
+          cp_async16(dst + (uint32_t)im * 8192u + 4096u, mp + 4);
         }
       }
       cp_async_commit();
@@ -381,43 +397,45 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
           for (int i = 0; i < 8; ++i)
             r[i] = __shfl_up_sync(0xffffffffu, v0[i], 1) + v1[i] + __shfl_down_sync(0xffffffffu, v2[i], 1);
           if (cur.ok && cur.row + 4 * tile < a.Hout && !(t.dbg & 4)) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch8 + 4);
-            r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w; r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
-            if (a.relu) {
+            if (G || EPI <= 3) {
+              const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch8);
+              const float4 b1 = *reinterpret_cast<const float4*>(bias_s + ch8 + 4);
+              r[0] += b0.x; r[1] += b0.y; r[2] += b0.z; r[3] += b0.w; r[4] += b1.x; r[5] += b1.y; r[6] += b1.z; r[7] += b1.w;
+            }
+            if (f_relu) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
             }
             // out = mask( relu2( relu(acc + bias) + res ) ) + add + previous
             const uint8_t* slot = epi + (uint32_t)k * slot_stride + my_slot;
             float ev[8];
-            if (t.ia >= 0) {
-              const float4 e0 = *reinterpret_cast<const float4*>(slot + t.ia * 8192);
-              const float4 e1 = *reinterpret_cast<const float4*>(slot + t.ia * 8192 + 4096);
+            if (ia >= 0) {
+              const float4 e0 = *reinterpret_cast<const float4*>(slot + ia * 8192);
+              const float4 e1 = *reinterpret_cast<const float4*>(slot + ia * 8192 + 4096);
               ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w; ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
-              if (a.res) {
+              if (f_res) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] += ev[i];
               }
             }
-            if (a.relu2) {
+            if (f_relu2) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
             }
-            if (t.im >= 0) {
-              const float4 m0 = *reinterpret_cast<const float4*>(slot + t.im * 8192);
-              const float4 m1 = *reinterpret_cast<const float4*>(slot + t.im * 8192 + 4096);
+            if (im >= 0) {
+              const float4 m0 = *reinterpret_cast<const float4*>(slot + im * 8192);
+              const float4 m1 = *reinterpret_cast<const float4*>(slot + im * 8192 + 4096);
               const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[i] = mv[i] > 0.f ? r[i] : 0.f;
             }
-            if (t.ia >= 0 && !a.res) {
+            if (ia >= 0 && f_add) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[i] += ev[i];
             }
-            if (t.io >= 0) {
-              const float4 p0 = *reinterpret_cast<const float4*>(slot + t.io * 8192);
-              const float4 p1 = *reinterpret_cast<const float4*>(slot + t.io * 8192 + 4096);
+            if (io >= 0) {
+              const float4 p0 = *reinterpret_cast<const float4*>(slot + io * 8192);
+              const float4 p1 = *reinterpret_cast<const float4*>(slot + io * 8192 + 4096);
               r[0] += p0.x; r[1] += p0.y; r[2] += p0.z; r[3] += p0.w; r[4] += p1.x; r[5] += p1.y; r[6] += p1.z; r[7] += p1.w;
             }
             float4* dst = reinterpret_cast<float4*>(a.out + (cur.pix + tile * tile_pix) * a.po + ch8);
@@ -428,7 +446,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         prefetch(nxt, k);                                      // this slot is free again: next super-tile's item k
       }
       tc_fence_before();
-      mbar_arrive(&bar_acc_empty[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
       cur = nxt;
     }
     cp_async_wait<0>();
@@ -443,13 +462,12 @@ bool c3_configure(const ConvArgs& a, C3Tile& t) {
   if (!(t.CP == 8 || t.CP == 16 || t.CP == 32 || t.CP == 64)) return false;
   t.N = round_up(3 * t.CP, 16);
   t.T = 8 / (t.CP >> 3);
-  if (t.T > 4) t.T = 4;                                       // one raw plane = RI * 32 <= 576 pixels = 3 per producer thread
   while (t.T > 1 && 4 * (t.T / 2) >= a.Hout) t.T /= 2;       // short maps: do not pay for rows that do not exist
   t.RI = 4 * t.T + 2;
   t.P = (a.c1 + a.c2) / 8;
   t.plane_bytes = (uint32_t)t.RI * 512;
   t.in_bytes = 2 * t.plane_bytes;
-  t.raw_bytes = (uint32_t)(3 * 2 * C3_PROD_THREADS * 16);    // [u][half][thread] x 16 B
+  t.raw_bytes = (uint32_t)((t.T > 4 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);    // [u][half][thread] x 16 B
   t.w_bytes = 5u * (uint32_t)t.N * 32;
   t.w_total = (uint32_t)t.P * t.w_bytes;
   t.n_ops = 0; t.ia = t.io = t.im = -1;
@@ -506,14 +524,33 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   bytes += npix * a.coutp * 4.0 * (1 + (a.res ? 1 : 0) + (a.omask ? 1 : 0) + (a.add ? 1 : 0) + (a.accumulate ? 1 : 0));
   ProfScope ps("conv3_tc_kernel", a.c1 + a.c2, a.coutp, 3, 1, a.Wout, (a.relu1 ? 2 : 0) + (general ? 1 : 0),
                2.0 * npix * 9 * (a.c1 + a.c2) * a.coutp, bytes, st);
-  static bool attr = false;
-  if (!attr) {
-    MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr = true;
+  // epilogue specialisation (the flag-driven variant covers everything else, e.g. accumulation into a touched gradient)
+  int epi = 0;
+  const bool bias = a.bias != nullptr;
+  if (!a.accumulate) {
+    if (bias && !a.res && !a.add && !a.omask && !a.relu2) epi = a.relu ? 2 : 1;
+    else if (bias && a.res && a.relu2 && !a.relu && !a.omask && !a.add) epi = 3;
+    else if (!bias && a.omask && !a.res && !a.relu && !a.relu2) epi = a.add ? 5 : 4;
   }
-  if (a.relu1) conv3_tc_kernel<true><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);
-  else conv3_tc_kernel<false><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);
+  { static int gen = -1; if (gen < 0) { const char* e = getenv("MSAU_C3_GENERIC"); gen = e ? atoi(e) : 0; } if (gen) epi = 0; }
+  const int ldu = t.T > 4 ? 6 : 3;
+#define MSAU_C3_LAUNCH(E, L)                                                                                                   \
+  {                                                                                                                            \
+    static bool attr = false;                                                                                                  \
+    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    conv3_tc_kernel<E, L><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);                                                          \
+  }
+#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6) else MSAU_C3_LAUNCH(E, 3) }
+  switch (epi) {
+    case 1: MSAU_C3_LDU(1) break;
+    case 2: MSAU_C3_LDU(2) break;
+    case 3: MSAU_C3_LDU(3) break;
+    case 4: MSAU_C3_LDU(4) break;
+    case 5: MSAU_C3_LDU(5) break;
+    default: MSAU_C3_LDU(0) break;
+  }
+#undef MSAU_C3_LDU
+#undef MSAU_C3_LAUNCH
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

@@ -343,8 +343,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
     tap_off16[tid] = (uint32_t)(ky * a.dil * t.HW + kx * a.dil);
   }
   if (tid == 32) {
-    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bar_full[i], PROD_THREADS); mbar_init(&bar_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS * 32); }
+    for (int i = 0; i < MAX_STAGES; ++i) { mbar_init(&bar_full[i], PROD_WARPS); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
           for (int e = tid + W_U * PROD_THREADS; e < w16; e += PROD_THREADS) dst[e] = __ldg(wsrc + e);
         }
         fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&bar_full[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_full[s]);   // one arrival per warp: per-thread arrivals serialise in shared memory
       }
     }
   } else if (warp == PROD_WARPS) {
@@ -542,7 +543,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         }
       }
       tc_fence_before();
-      mbar_arrive(&bar_acc_empty[as]);              // every epilogue thread has finished reading this accumulator set
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[as]);   // every thread of this warp has finished reading this accumulator set
     }
   }
   tc_fence_before();

@@ -698,6 +698,340 @@ static int launch_wgrad_tc2(const WgradArgs& a, const Wg2Tile& t0, cudaStream_t 
   return MSAU_OK;
 }
 
+
+// =====================================================================================================
+// Pipelined variant of the kernel above for the HBM-streaming levels (<= 16 output channels, NHWC operands):
+// one persistent CTA per SM; 8 converter warps keep D-1 tiles of raw fp32 operands in flight with cp.async
+// (thread-private shared-memory slots, zero-fill for out-of-image pixels) and turn the oldest one into the bf16
+// operand images; 4 MMA warps issue the instructions (one per 16 pixels, all taps) into their own accumulators.
+// Tile = TR x 64 pixels of X (+ kw-1 halo columns) and 8 staged rows of dY per channel plane (TR = 8 / planes - (kh-1)),
+// so every converter warp owns exactly one staged dY (row, plane) pair and at most one X row.
+struct Wg3Tile {
+  int TR, HWx, N, nyp, TRy, n_issue, D, items;   // X rows, X row pitch (px), MMA N, dY planes, staged dY rows, issuers, raw depth, slots/thread
+  int ix_halo, iy0;                              // slot index of the X halo item (-1: none) and of the first dY item
+  int tiles_x, tiles_y, n_tiles, tiles_per_cta;
+  uint32_t x_bytes, stage_bytes, raw_bytes, tmem_cols;
+};
+static constexpr int WG3_CONV_WARPS = 8;
+static constexpr int WG3_MMA_WARPS = 4;
+static constexpr int WG3_THREADS = (WG3_CONV_WARPS + WG3_MMA_WARPS) * 32;
+static constexpr int WG3_TC = 64;
+
+__device__ __forceinline__ void wcp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void wcp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void wcp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void wmbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wsmem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradArgs a, const Wg3Tile t) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[2];      // converters -> MMA : bf16 stage ready
+  __shared__ uint64_t bar_free[2];      // MMA -> converters : the instructions reading the stage have retired
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[32];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int plane = blockIdx.y;
+  const int tile0 = blockIdx.x * t.tiles_per_cta;
+  const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
+  const int n_my = tile1 - tile0;
+  const bool do_bias = a.dbias != nullptr && plane == 0;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < 2; ++i) { wmbar_init(&bar_full[i], WG3_CONV_WARPS); wmbar_init(&bar_free[i], t.n_issue); }
+    wmbar_init(&bar_done, t.n_issue);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 32) sbias[tid] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  uint8_t* const stage_s = smem;                               // 2 x [X image | dY image] (bf16)
+  uint8_t* const raw_s = smem + 2 * (size_t)t.stage_bytes;     // D x raw fp32 slots
+  const int ca0 = plane << 3;
+
+  if (n_my > 0 && warp < WG3_CONV_WARPS) {
+    // =============================================================== converters
+    // items of this thread (the same for every tile): X interior (row = warp, columns lane / lane + 32), one X halo
+    // pixel for the first TR * (kw-1) threads, dY (row, plane) pair = warp (columns lane / lane + 32)
+    const uint32_t raw_u32 = wsmem_u32(raw_s) + (uint32_t)tid * 16u;
+    const int nh = t.HWx - WG3_TC;
+    const bool has_x = warp < t.TR;
+    const bool has_h = t.ix_halo >= 0 && tid < t.TR * nh;
+    const int hr = has_h ? tid / nh : 0, hc = has_h ? WG3_TC + (tid - hr * nh) : 0;
+    const int yr = warp;                                         // staged dY row of this warp
+    auto slot = [&](int d, int item, int half) -> uint32_t { return (uint32_t)d * t.raw_bytes + (uint32_t)((item * 2 + half) * (WG3_CONV_WARPS * 32 * 16)); };
+    auto issue = [&](int tile, int d) {
+      if (tile < tile1) {
+        const int tx = tile % t.tiles_x;
+        const int rest = tile / t.tiles_x;
+        const int ty = rest % t.tiles_y;
+        const int b = rest / t.tiles_y;
+        const int qy0 = ty * t.TR, qx0 = tx * WG3_TC;
+        const float* xb = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0;
+        if (has_x) {
+          const int gy = qy0 + warp;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int gx = qx0 - a.pada_l + lane + 32 * j;
+            const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa;
+            const float* sp = inb ? xb + (gy * a.Wa + gx) * a.pa : xb;
+            wcp_async16z(raw_u32 + slot(d, j, 0), sp, inb ? 16u : 0u);
+            wcp_async16z(raw_u32 + slot(d, j, 1), sp + 4, inb ? 16u : 0u);
+          }
+        }
+        if (has_h) {
+          const int gy = qy0 + hr, gx = qx0 - a.pada_l + hc;
+          const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa;
+          const float* sp = inb ? xb + (gy * a.Wa + gx) * a.pa : xb;
+          wcp_async16z(raw_u32 + slot(d, t.ix_halo, 0), sp, inb ? 16u : 0u);
+          wcp_async16z(raw_u32 + slot(d, t.ix_halo, 1), sp + 4, inb ? 16u : 0u);
+        }
+        {
+          const float* yb = a.Bm + (long)b * a.Hb * a.Wb * a.pb;
+          const int vy = qy0 + a.pada_t - (a.kh - 1) + yr;
+          const bool oky = (unsigned)vy < (unsigned)a.Hq;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int vx = qx0 + lane + 32 * j;
+            const bool inb = oky && vx < a.Wq;
+            const float* sp = inb ? yb + (vy * a.Wb + vx) * a.pb : yb;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+              if (pl < t.nyp) {
+                wcp_async16z(raw_u32 + slot(d, t.iy0 + pl * 2 + j, 0), sp + pl * 8, inb ? 16u : 0u);
+                wcp_async16z(raw_u32 + slot(d, t.iy0 + pl * 2 + j, 1), sp + pl * 8 + 4, inb ? 16u : 0u);
+              }
+            }
+          }
+        }
+      }
+      wcp_commit();
+    };
+    auto load_px = [&](int d, int item, float* v) {
+      const float4 q0 = *reinterpret_cast<const float4*>(raw_s + tid * 16 + slot(d, item, 0));
+      const float4 q1 = *reinterpret_cast<const float4*>(raw_s + tid * 16 + slot(d, item, 1));
+      v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    };
+    for (int d = 0; d < t.D - 1; ++d) issue(tile0 + d, d);
+    float bacc[2][8] = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+    for (int it = 0; it < n_my; ++it) {
+      issue(tile0 + it + t.D - 1, (it + t.D - 1) % t.D);
+      if (t.D == 4) wcp_wait<3>(); else if (t.D == 3) wcp_wait<2>(); else wcp_wait<1>();
+      const int s = it & 1, d = it % t.D;
+      if (it >= 2) {
+        if (lane == 0) wmbar_wait(&bar_free[s], ((it >> 1) - 1) & 1);
+        __syncwarp();
+      }
+      uint8_t* xh = stage_s + (size_t)s * t.stage_bytes;
+      uint8_t* yh = xh + t.x_bytes;
+      float v[8];
+      if (has_x) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          load_px(d, j, v);
+          if (a.reluA) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+          }
+          *reinterpret_cast<uint4*>(xh + (warp * t.HWx + lane + 32 * j) * 16) = wpack8(v);
+        }
+      }
+      if (has_h) {
+        load_px(d, t.ix_halo, v);
+        if (a.reluA) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+        }
+        *reinterpret_cast<uint4*>(xh + (hr * t.HWx + hc) * 16) = wpack8(v);
+      }
+      {
+        // bias gradient: the TR centre rows of the staged dY tile (the halo rows belong to the neighbouring tiles)
+        const int tile = tile0 + it;
+        const int ty = (tile / t.tiles_x) % t.tiles_y;
+        const int vy = ty * t.TR + a.pada_t - (a.kh - 1) + yr;
+        const bool centre = do_bias && vy >= ty * t.TR && vy < ty * t.TR + t.TR;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          if (pl < t.nyp) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              load_px(d, t.iy0 + pl * 2 + j, v);
+              if (centre) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bacc[pl][k] += v[k];
+              }
+              *reinterpret_cast<uint4*>(yh + (size_t)((yr * t.nyp + pl) * WG3_TC + lane + 32 * j) * 16) = wpack8(v);
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) wmbar_arrive(&bar_full[s]);      // one arrival per warp (per-thread arrivals serialise)
+    }
+    wcp_wait<0>();
+    if (do_bias) {
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float sum = bacc[pl][k];
+#pragma unroll
+          for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          if (lane == 0 && pl < t.nyp) atomicAdd(&sbias[pl * 8 + k], sum);
+        }
+      }
+    }
+  } else if (n_my > 0 && warp - WG3_CONV_WARPS < t.n_issue) {
+    // =============================================================== MMA issuers (X rows mw, mw + n_issue, ...)
+    const int mw = warp - WG3_CONV_WARPS;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(t.N >> 3) << 17) |
+                           ((uint32_t)(64 >> 4) << 24);
+    const uint32_t d_tmem = tmem_base + (uint32_t)(mw * t.N);
+    const uint32_t lbo = (128u >> 4) << 16;
+    const uint32_t a_hi = 1u | (1u << 14);                                       // SBO = one pixel per kx group
+    const uint32_t b_hi = (((uint32_t)WG3_TC * 16 >> 4) & 0x3FFF) | (1u << 14);  // SBO = one staged (row, plane) pair
+    const uint32_t yrow16 = (uint32_t)(t.nyp * WG3_TC);                          // staged dY row pitch, 16-B units
+    uint32_t first = 0u;
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it & 1;
+      if (lane == 0) wmbar_wait(&bar_full[s], (it >> 1) & 1);
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (welect_one()) {
+        const uint32_t xh = wsmem_u32(stage_s + (size_t)s * t.stage_bytes);
+        const uint32_t yh = xh + t.x_bytes;
+        for (int r = mw; r < t.TR; r += t.n_issue) {
+          uint32_t a_lo = (((xh >> 4) + (uint32_t)(r * t.HWx)) & 0x3FFF) | lbo;
+          uint32_t b_lo = (((yh >> 4) + (uint32_t)r * yrow16) & 0x3FFF) | lbo;
+#pragma unroll
+          for (int cc = 0; cc < WG3_TC / 16; ++cc) {
+            wtc_mma2(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+            first = 1u;
+            a_lo += 16; b_lo += 16;
+          }
+        }
+        wtc_commit(&bar_free[s]);
+        if (it == n_my - 1) wtc_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+  }
+  // ---- reduce the resident accumulators into dW ----
+  if (n_my > 0 && tid == 0) wmbar_wait(&bar_done, 0);
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (n_my > 0 && warp < 2) {
+    // M = 64 accumulator: row m = kx * 8 + ci lives in TMEM lane (m % 16) + 32 * (m / 16)
+    const int kx = warp * 2 + (lane >> 3), ci = ca0 + (lane & 7);
+    const bool mine = lane < 16 && kx < a.kw && ci < a.ca_lim;
+    const int n_iss = min(t.n_issue, t.TR);
+    for (int c0 = 0; c0 < t.N; c0 += 8) {
+      float v[8];
+      wtmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      for (int i = 1; i < n_iss; ++i) {
+        float w[8];
+        wtmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(i * t.N + c0), w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w[j];
+      }
+      if (mine) {
+        const int kyi = c0 / a.cb, cb0 = c0 - kyi * a.cb;     // column group = (kyi, 8-channel plane); ky = kh-1-kyi
+        const int ky = a.kh - 1 - kyi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int co = cb0 + j;
+          if (a.b_s2d) {
+            const int ph = co / a.cph, c = co - ph * a.cph;
+            const int py = ph >> 1, px = ph & 1;
+            const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
+            const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
+            if (ph < 4 && c < a.cb_lim && rky >= 0 && rkx >= 0)
+              atomicAdd(a.dW + (long)ci * a.s_ca + (long)c * a.s_cb + (rky * 3 + rkx), v[j]);
+          } else if (co < a.cb_lim) atomicAdd(a.dW + (long)ci * a.s_ca + (long)co * a.s_cb + (ky * a.kw + kx), v[j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (do_bias && n_my > 0) {
+    if (a.b_s2d) {
+      if (tid < a.cb && (tid % a.cph) < a.cb_lim) atomicAdd(a.dbias + (tid % a.cph), sbias[tid]);
+    } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+}
+
+static bool wgrad_tc3_config(const WgradArgs& a, Wg3Tile& t) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("MSAU_WG3_OFF"); off = e ? atoi(e) : 0; }
+  if (off || a.dila != 1 || a.cb > 16 || a.maskB || a.a_nchw || a.b_s2d || a.Wq < 16) return false;
+  t.nyp = a.cb >> 3;
+  t.TRy = WG3_CONV_WARPS;
+  t.TR = t.TRy - (a.kh - 1);
+  if (t.TR < 2) return false;
+  t.N = a.kh * a.cb;
+  t.HWx = WG3_TC + (a.kw - 1);
+  t.items = 2; t.ix_halo = -1;
+  if (a.kw > 1) t.ix_halo = t.items++;
+  t.iy0 = t.items; t.items += 2 * t.nyp;
+  const int slack_px = 7 + 16;
+  t.x_bytes = (uint32_t)((t.TR * t.HWx + slack_px) * 16 + 127) / 128 * 128;
+  const uint32_t y_bytes = (uint32_t)(WG3_CONV_WARPS * t.nyp * WG3_TC * 16);
+  t.stage_bytes = (t.x_bytes + y_bytes + 1023) / 1024 * 1024;
+  t.raw_bytes = (uint32_t)(t.items * 2 * WG3_CONV_WARPS * 32 * 16);
+  t.D = 4;
+  while (t.D > 2 && 2 * (size_t)t.stage_bytes + (size_t)t.D * t.raw_bytes > 218 * 1024) --t.D;
+  t.n_issue = 128 / t.N;
+  if (t.n_issue > WG3_MMA_WARPS) t.n_issue = WG3_MMA_WARPS;
+  if (t.n_issue < 1) t.n_issue = 1;
+  if (t.n_issue > t.TR) t.n_issue = t.TR;
+  const int cols = t.n_issue * t.N;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
+  t.tiles_x = cdiv(a.Wq, WG3_TC);
+  t.tiles_y = cdiv(a.Hq, t.TR);
+  t.n_tiles = t.tiles_x * t.tiles_y * a.B;
+  return t.tmem_cols <= 512;
+}
+
+static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t st) {
+  Wg3Tile t = t0;
+  const int planes = a.ca >> 3;
+  const size_t smem = 2 * (size_t)t.stage_bytes + (size_t)t.D * t.raw_bytes + 1024;
+  int ctas = (sm_count() + planes - 1) / planes;
+  if (ctas > t.n_tiles) ctas = t.n_tiles;
+  if (ctas < 1) ctas = 1;
+  t.tiles_per_cta = cdiv(t.n_tiles, ctas);
+  ctas = cdiv(t.n_tiles, t.tiles_per_cta);
+  static bool attr = false;
+  if (!attr) {
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  dim3 grid(ctas, planes);
+  const double npq = (double)a.B * a.Hq * a.Wq;
+  const double wbytes = (npq * a.ca + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb)) * 4.0;
+  ProfScope ps("wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, 2, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  wgrad_tc3_kernel<<<grid, WG3_THREADS, smem, st>>>(a, t);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
 bool wgrad_tc_supported(const WgradArgs& a) {
   if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
   if (a.Ha != a.Hq || a.Wa != a.Wq) return false;
@@ -717,6 +1051,8 @@ bool wgrad_tc_supported(const WgradArgs& a) {
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   MSAU_CHECK_ARG(wgrad_tc_supported(a), "wgrad_tc: unsupported shape");
   {
+    Wg3Tile t3;
+    if (wgrad_tc3_config(a, t3)) return launch_wgrad_tc3(a, t3, st);
     Wg2Tile t2;
     if (wgrad_tc2_config(a, t2)) return launch_wgrad_tc2(a, t2, st);
   }
