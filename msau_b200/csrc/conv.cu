@@ -23,6 +23,7 @@ struct ConvTile {
 template <int CO_T, int PIX_T>
 __global__ void __launch_bounds__(256) conv_kernel(const ConvArgs a, const ConvTile t) {
   extern __shared__ float4 smem4[];
+  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this output
   const int tid = threadIdx.x;
   const int lane = tid & 31, wy = tid >> 5;
   const int cog = wy % t.NG, rip = wy / t.NG;
@@ -238,6 +239,7 @@ struct WgradTile {
 template <int KW, bool BTAP>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradArgs a, const WgradTile t) {
   extern __shared__ float red[];   // [KW][MB][NB] + [NB]
+  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
   const int tid = threadIdx.x;
   const int tile = tid % t.TT, ks = tid / t.TT;
   const bool active = ks < t.KS;

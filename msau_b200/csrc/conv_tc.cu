@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
   __shared__ uint32_t tap_off16[16];           // smem offset of every tap, in 16-B units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this output
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(t.tmem_cols)

@@ -18,6 +18,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "first_layer.cuh"
 #include "optim.cuh"
 #include "pointwise.cuh"
 
@@ -123,6 +124,7 @@ struct MsauPlan {
   long pack_blocks = 0;
   long misc_floats = 0;
   long attn_scratch_off = 0;   // floats, inside misc: operand images of the tensor-core attention
+  long ids_off = -1;           // floats, inside misc: int16 id map of a one-hot input + the is-one-hot flag (first_layer.cu)
   std::vector<TcPackDesc> tc_descs, t3_descs;
   TcPackDesc* d_tc_descs = nullptr;
   TcPackDesc* d_t3_descs = nullptr;
@@ -138,6 +140,7 @@ struct MsauPlan {
   std::vector<char> written;
   std::vector<Tensor> all_tensors;
   cudaStream_t st = nullptr;
+  const int* first_skip = nullptr;   // set by msau_forward when the structured first layer ran (device flag)
 
   Tensor alloc(int C, int Hh, int Ww) {
     Tensor t;
@@ -311,6 +314,7 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 
 // ------------------------------------------------------------------ launch helpers
 static bool g_use_tc = true;
+static bool g_structured = true;   // one-hot inputs: id-gather first layer (first_layer.cu)
 static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
 static int g_c3_max = 16;        // ... for at most this many output channels
 
@@ -327,7 +331,7 @@ struct ConvOpt {
 // same-size stride-1 convolution (forward of a layer, or a dgrad with flipped packed weights)
 static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, int c1_logical, const float* src2, int c2, int p2,
                      const float* w, const float* bias, float* out, int po, int coutp, int H, int W, int k, int dil, int pad,
-                     const ConvOpt& o, long tc_off = -1, long t3_off = -1) {
+                     const ConvOpt& o, long tc_off = -1, long t3_off = -1, const int* skip_flag = nullptr) {
   ConvArgs a;
   memset(&a, 0, sizeof(a));
   a.src1 = src1; a.c1 = c1; a.p1 = p1; a.src1_nchw = nchw; a.c1_logical = c1_logical;
@@ -340,6 +344,7 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.relu = o.relu; a.res = o.res; a.pr = o.pr; a.relu2 = o.relu2;
   a.omask = o.omask; a.pom = o.pom; a.add = o.add; a.pa = o.pa; a.addmask = o.addmask; a.pam = o.pam;
   a.accumulate = o.accumulate;
+  a.skip_flag = skip_flag;
   count_launch(1);
   if (g_use_tc && g_use_c3 && t3_off >= 0 && coutp <= g_c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
   if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
@@ -367,7 +372,7 @@ static int layer_dgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
 // weight (+bias) gradient of a conv layer wrt source `which`
 static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* src, int psrc, int nchw, int c_logical, bool reluA,
                        const float* dy, int pdy, const float* dymask, int pm, int H, int W, long w_off_override = -1,
-                       long b_off_override = -1, int cb_off = 0, int cb = -1, int cb_lim = -1) {
+                       long b_off_override = -1, int cb_off = 0, int cb = -1, int cb_lim = -1, const int* skip_flag = nullptr) {
   WgradArgs a;
   memset(&a, 0, sizeof(a));
   const int cin = L.cin1 + L.cin2;
@@ -383,6 +388,7 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.ca_lim = which == 1 ? L.cin1 : L.cin2;
   a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
+  a.skip_flag = skip_flag;
   count_launch(1);
   if (g_use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->st);
   return launch_wgrad(a, p->st);
@@ -686,6 +692,13 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   p->attn_scratch_off = p->misc_floats;
   if (attn_tc_supported(fa, da))
     p->misc_floats += (long)((attn_tc_scratch_bytes(batch, p->Hl[S - 1] * p->Wl[S - 1], fa) + 255) / 256 * 64);
+  {
+    const ConvLayer& c0 = p->blocks[0].down[0].conv1;
+    if (c0.coutp == 8 && c0.cout <= 8 && ((long)height * width) % 4 == 0 && 9L * cfg->channels * 32 <= 200 * 1024 && cfg->channels < 32768) {
+      p->ids_off = p->misc_floats;
+      p->misc_floats += round_up((int)(((long)batch * height * width + 1) / 2) + 64, 64);
+    }
+  }
   // descriptor table: the only device memory the plan owns
   cudaError_t e = cudaMalloc(&p->d_descs, sizeof(PackDesc) * p->descs.size());
   if (e == cudaSuccess) e = cudaMemcpy(p->d_descs, p->descs.data(), sizeof(PackDesc) * p->descs.size(), cudaMemcpyHostToDevice);
@@ -762,8 +775,20 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
       ConvOpt o;
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
+        const int* skip = nullptr;
+        if (g_use_tc && g_structured && p->ids_off >= 0) {
+          // chargrid input: scan for one-hot structure, then the id-gather conv; the dense kernel below skips itself
+          short* ids = reinterpret_cast<short*>(p->misc + p->ids_off);
+          int* flag = reinterpret_cast<int*>(p->misc + p->ids_off) + (((long)p->B * p->H * p->W + 1) / 2 + 8);
+          count_launch(2);
+          MSAU_TRY(launch_onehot_scan(x, x_layout == 0, cfg.channels, c1, p->B, p->H, p->W, ids, flag, p->st));
+          MSAU_TRY(launch_first_fwd(ids, flag, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b, cfg.channels, c1, p->B, p->H, p->W, p->A(L.z1),
+                                    L.z1.C, p->st));
+          skip = flag;
+        }
+        p->first_skip = skip;
         MSAU_TRY(conv_same(p, x, c1, c1, x_layout == 0, cfg.channels, nullptr, 0, 0, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b,
-                           p->A(L.z1), L.z1.C, L.conv1.coutp, p->H, p->W, 3, 1, 1, o, L.conv1.tc_w));
+                           p->A(L.z1), L.z1.C, L.conv1.coutp, p->H, p->W, 3, 1, 1, o, L.conv1.tc_w, -1, skip));
       } else {
         const Tensor& src = l == 0 ? prev->logits : blk.down[l - 1].pooled;
         MSAU_TRY(layer_fwd(p, L.conv1, src, nullptr, L.z1, o));
@@ -914,7 +939,14 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       MSAU_TRY(launch_lrn_bwd(p->A(L.z1), p->G(L.y1), p->G(L.z1), p->npix(L.z1), L.z1.C, p->st));
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
-        MSAU_TRY(layer_wgrad(p, L.conv1, 1, x, c1, x_layout == 0, cfg.channels, false, p->G(L.z1), L.z1.C, nullptr, 0, p->H, p->W));
+        if (p->first_skip) {
+          const short* ids = reinterpret_cast<const short*>(p->misc + p->ids_off);
+          count_launch(1);
+          MSAU_TRY(launch_first_wgrad(ids, p->first_skip, p->G(L.z1), L.z1.C, cfg.channels, L.conv1.cout, p->B, p->H, p->W,
+                                      p->gparams + L.conv1.w_off, p->gparams + L.conv1.b_off, p->st));
+        }
+        MSAU_TRY(layer_wgrad(p, L.conv1, 1, x, c1, x_layout == 0, cfg.channels, false, p->G(L.z1), L.z1.C, nullptr, 0, p->H, p->W, -1, -1,
+                             0, -1, -1, p->first_skip));
       } else {
         const Tensor& src = l == 0 ? prev->logits : blk.down[l - 1].pooled;
         MSAU_TRY(layer_wgrad(p, L.conv1, 1, p->A(src), src.C, 0, L.conv1.c1p, false, p->G(L.z1), L.z1.C, nullptr, 0, L.z1.H, L.z1.W));
@@ -991,6 +1023,7 @@ extern "C" int msau_set_option(const char* name, int value) {
   MSAU_CHECK_ARG(name, "set_option: null name");
   if (!strcmp(name, "tensor_core_conv")) { g_use_tc = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_fold")) { g_use_c3 = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "structured_first_layer")) { g_structured = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return MSAU_ERR_ARG;

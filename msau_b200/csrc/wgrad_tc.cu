@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   const int tile0 = blockIdx.x * t.tiles_per_cta;
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const bool do_bias = a.dbias != nullptr && plane == 0;
+  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
   const int tile0 = blockIdx.x * t.tiles_per_cta;
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const bool do_bias = a.dbias != nullptr && plane == 0;
+  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -741,6 +743,7 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const int n_my = tile1 - tile0;
   const bool do_bias = a.dbias != nullptr && plane == 0;
+  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)

@@ -190,6 +190,40 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
         assert torch.equal(dict(m2.named_parameters())[k].detach().cpu(), sd[k])
 
 
+@pytest.mark.parametrize("option", ["conv3_fold", "structured_first_layer"])
+def test_alternative_kernel_paths_match_oracle(golden_dir, option):
+    """The default tensor-core path uses the kx-folded 3x3 kernel (conv3_tc.cu) and, for one-hot inputs, the id-gather first
+    layer (first_layer.cu).  With either switched off the generic implicit-GEMM kernels do the same work; with a dense
+    (not one-hot) input the structured first layer must step aside on its own (device flag)."""
+    z, meta, cfg = load(golden_dir, "model_s4r2_c96")
+    sd = om.init_state_dict(cfg, meta["seed"])
+    x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
+    _lib.set_option(option, 0)
+    try:
+        m = build(cfg, sd).train()
+        _, logits, aux = m(x.cuda())
+        assert (logits.cpu() - torch.from_numpy(z["logits"])).abs().max().item() <= LOGIT_ATOL
+        loss = m.loss(logits, aux, labels.cuda())
+        loss.backward()
+        keys = [k for k, _ in om.param_schema(cfg)]
+        named = dict(m.named_parameters())
+        norms = np.array([0.0 if named[k].grad is None else float(named[k].grad.double().norm()) for k in keys])
+        np.testing.assert_allclose(norms, z["grad_norms"], rtol=3e-2, atol=2e-5)
+    finally:
+        _lib.set_option(option, 1)
+    # dense input (0.5 * one-hot is not one-hot): same network, generic first-layer kernels, checked against the oracle
+    xd = 0.5 * x
+    m = build(cfg, sd).train()
+    _, logits, aux = m(xd.cuda())
+    ref_loss, ref_logits, _, ref_grads = om.loss_and_grads(sd, cfg, xd, labels)
+    assert (logits.cpu() - ref_logits).abs().max().item() <= LOGIT_ATOL
+    loss = m.loss(logits, aux, labels.cuda())
+    loss.backward()
+    k = "msau_net.blocks.0.downsamplingblock.conv1s.0.conv.weight"
+    g = dict(m.named_parameters())[k].grad.cpu()
+    assert (g - ref_grads[k]).double().norm().item() <= 3e-2 * ref_grads[k].double().norm().item()
+
+
 def test_full_size_page_properties():
     """512x512 chargrid page at the train-script config: finite outputs, soft-max rows sum to 1, loss decreases
     over a few fused steps (size-independent sanity at BASELINE.json's full page size)."""
