@@ -87,7 +87,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 // src_bytes = 0 -> the 16 destination bytes are zero-filled (out-of-image halo pixels: SAME padding)
 __device__ __forceinline__ void cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -182,21 +182,23 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         const int pitch = from1 ? a.p1 : a.p2;
         src += (long)tp.b * a.Hin * a.Win * pitch;
         const uint32_t dst0 = raw_u32 + (uint32_t)slot * t.raw_bytes + (uint32_t)tid * 16u;
-        // pixel e = tid + 192 u of the halo plane = (row warp + 6 u, column lane)
-        const int gx = in_x0 + lane;
-        const bool okx = (unsigned)gx < (unsigned)a.Win;
-        const float* col = src + gx * pitch;
+        // a halo row (32 pixels x 32 B) is 64 chunks of 16 B: lane l copies chunks l and l + 32 of the rows warp + 6 u, i.e.
+        // half (l & 1) of the pixels l / 2 and l / 2 + 16 -- each warp instruction moves 512 contiguous bytes and every
+        // 32-byte sector is requested exactly once (cp.async.cg goes straight to L2)
+        const int gx0 = in_x0 + (lane >> 1), gx1 = gx0 + 16;
+        const bool okx0 = (unsigned)gx0 < (unsigned)a.Win, okx1 = (unsigned)gx1 < (unsigned)a.Win;
+        const float* col = src + gx0 * pitch + (lane & 1) * 4;
         const int rpitch = a.Win * pitch;
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
           const int row = warp + u * C3_PROD_WARPS;
           if (row < t.RI) {
             const int gy = in_y0 + row;
-            const bool inb = okx && (unsigned)gy < (unsigned)a.Hin;
-            const float* sp = inb ? col + gy * rpitch : src;
+            const bool oky = (unsigned)gy < (unsigned)a.Hin;
+            const float* sp = col + gy * rpitch;
             const uint32_t dst = dst0 + (uint32_t)u * (2u * C3_PROD_THREADS * 16u);
-            cp_async16z(dst, sp, inb ? 16u : 0u);
-            cp_async16z(dst + C3_PROD_THREADS * 16u, sp + 4, inb ? 16u : 0u);
+            cp_async16z(dst, (oky && okx0) ? sp : src, (oky && okx0) ? 16u : 0u);
+            cp_async16z(dst + C3_PROD_THREADS * 16u, (oky && okx1) ? sp + 16 * pitch : src, (oky && okx1) ? 16u : 0u);
           }
         }
       }
@@ -226,25 +228,27 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         if (t.D == 4) cp_async_wait<3>(); else if (t.D == 3) cp_async_wait<2>(); else cp_async_wait<1>();
         const uint8_t* rsrc = raw_s + (size_t)(c % t.D) * t.raw_bytes + tid * 16;
         const bool relu = a.relu1 && p < planes1;
+        // this thread's two half-pixels of every row: 4 channels each -> 8 bytes of the hi image + 8 bytes of the lo image
+        uint8_t* dimg = stg + (lane >> 1) * 16 + (lane & 1) * 8;
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
-          const int e = tid + u * C3_PROD_THREADS;
-          if (warp + u * C3_PROD_WARPS < t.RI) {
-            const float4 q0 = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16));
-            const float4 q1 = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16) + C3_PROD_THREADS * 16);
-            float v[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            if (t.dbg & 2) {
+          const int row = warp + u * C3_PROD_WARPS;
+          if (row < t.RI) {
+            float4 q[2];
+            q[0] = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16));
+            q[1] = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16) + C3_PROD_THREADS * 16);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            for (int j = 0; j < 2; ++j) {
+              float4 v = q[j];
+              if (t.dbg & 2) v = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              uint2 hi, lo;
+              split_pair(v.x, v.y, hi.x, lo.x);
+              split_pair(v.z, v.w, hi.y, lo.y);
+              uint8_t* d = dimg + (row * 32 + 16 * j) * 16;
+              *reinterpret_cast<uint2*>(d) = hi;
+              *reinterpret_cast<uint2*>(d + t.plane_bytes) = lo;
             }
-            if (relu) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-            }
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            *reinterpret_cast<uint4*>(stg + e * 16) = hi;
-            *reinterpret_cast<uint4*>(stg + t.plane_bytes + e * 16) = lo;
           }
         }
         // one arrival per warp: 192 per-thread arrivals on one mbarrier serialise in shared memory

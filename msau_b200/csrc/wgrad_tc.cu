@@ -709,18 +709,19 @@ static int launch_wgrad_tc2(const WgradArgs& a, const Wg2Tile& t0, cudaStream_t 
 // Tile = TR x 64 pixels of X (+ kw-1 halo columns) and 8 staged rows of dY per channel plane (TR = 8 / planes - (kh-1)),
 // so every converter warp owns exactly one staged dY (row, plane) pair and at most one X row.
 struct Wg3Tile {
-  int TR, HWx, N, nyp, TRy, n_issue, D, items;   // X rows, X row pitch (px), MMA N, dY planes, staged dY rows, issuers, raw depth, slots/thread
+  int TR, HWx, N, nyp, TRy, n_issue, D, S, items;   // X rows, X row pitch (px), MMA N, dY planes, staged dY rows, issuers, raw / bf16 ring depth, slots/thread
   int ix_halo, iy0;                              // slot index of the X halo item (-1: none) and of the first dY item
   int tiles_x, tiles_y, n_tiles, tiles_per_cta;
   uint32_t x_bytes, stage_bytes, raw_bytes, tmem_cols;
 };
-static constexpr int WG3_CONV_WARPS = 8;
+static constexpr int WG3_CONV_WARPS = 16;  // two per tile row (32 pixels each): a warp's ~200-instruction serial chain per tile is the pace
+static constexpr int WG3_ROWS = 8;          // staged dY rows per tile
 static constexpr int WG3_MMA_WARPS = 4;
 static constexpr int WG3_THREADS = (WG3_CONV_WARPS + WG3_MMA_WARPS) * 32;
 static constexpr int WG3_TC = 64;
 
 __device__ __forceinline__ void wcp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void wcp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -729,10 +730,27 @@ __device__ __forceinline__ void wmbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(wsmem_u32(bar)) : "memory");
 }
 
+// polling wait for the single lanes that wait on behalf of their warp (no suspend hint: immediate wake-up)
+__device__ __forceinline__ void wmbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = wsmem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+
 __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradArgs a, const Wg3Tile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_full[2];      // converters -> MMA : bf16 stage ready
-  __shared__ uint64_t bar_free[2];      // MMA -> converters : the instructions reading the stage have retired
+  __shared__ uint64_t bar_full[4];      // converters -> MMA : bf16 stage ready
+  __shared__ uint64_t bar_free[4];      // MMA -> converters : the instructions reading the stage have retired
   __shared__ uint64_t bar_done;
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[32];
@@ -751,7 +769,7 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 32) {
-    for (int i = 0; i < 2; ++i) { wmbar_init(&bar_full[i], WG3_CONV_WARPS); wmbar_init(&bar_free[i], t.n_issue); }
+    for (int i = 0; i < 4; ++i) { wmbar_init(&bar_full[i], WG3_CONV_WARPS); wmbar_init(&bar_free[i], t.n_issue); }
     wmbar_init(&bar_done, t.n_issue);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -761,121 +779,114 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   uint8_t* const stage_s = smem;                               // 2 x [X image | dY image] (bf16)
-  uint8_t* const raw_s = smem + 2 * (size_t)t.stage_bytes;     // D x raw fp32 slots
+  uint8_t* const raw_s = smem + (size_t)t.S * t.stage_bytes;     // D x raw fp32 slots
   const int ca0 = plane << 3;
 
   if (n_my > 0 && warp < WG3_CONV_WARPS) {
     // =============================================================== converters
-    // items of this thread (the same for every tile): X interior (row = warp, columns lane / lane + 32), one X halo
-    // pixel for the first TR * (kw-1) threads, dY (row, plane) pair = warp (columns lane / lane + 32)
+    // Work of this thread, the same for every tile.  Half a row (32 pixels x 32 B) is 64 chunks of 16 B; lane l copies the
+    // chunks l and l+32 (pixel = chunk / 2, half = chunk & 1), so every cp.async warp instruction moves 512 contiguous
+    // bytes and every 32-byte sector is requested once (cp.async.cg bypasses L1, which is a few KB next to 200 KB of
+    // shared memory).  Warp w: row w / 2, columns 32 (w & 1) .. +31 of X (if row < TR) and of the staged dY row (all
+    // channel planes); X halo: the first 2 * TR * (kw-1) threads take half a pixel each.
+    // Items are 16 B: [X 0..1][halo][dY plane 0: 0..1][dY plane 1: 0..1].
     const uint32_t raw_u32 = wsmem_u32(raw_s) + (uint32_t)tid * 16u;
     const int nh = t.HWx - WG3_TC;
-    const bool has_x = warp < t.TR;
-    const bool has_h = t.ix_halo >= 0 && tid < t.TR * nh;
-    const int hr = has_h ? tid / nh : 0, hc = has_h ? WG3_TC + (tid - hr * nh) : 0;
-    const int yr = warp;                                         // staged dY row of this warp
-    auto slot = [&](int d, int item, int half) -> uint32_t { return (uint32_t)d * t.raw_bytes + (uint32_t)((item * 2 + half) * (WG3_CONV_WARPS * 32 * 16)); };
+    const int wr = warp >> 1, wc = (warp & 1) * 32;              // row / first column of this warp
+    const bool has_x = wr < t.TR;
+    const bool has_h = t.ix_halo >= 0 && tid < 2 * t.TR * nh;
+    const int hr = has_h ? (tid >> 1) / nh : 0, hc = has_h ? WG3_TC + ((tid >> 1) - hr * nh) : 0, hhalf = tid & 1;
+    const int yr = wr;                                           // staged dY row of this warp
+    const int half = lane & 1, px0 = wc + (lane >> 1);           // chunk l + 32 j -> pixel px0 + 16 j, same half
+    auto slot = [&](int d, int item) -> uint32_t { return (uint32_t)d * t.raw_bytes + (uint32_t)(item * (WG3_CONV_WARPS * 32 * 16)); };
+    struct Cur { int tx, ty, b; };
+    auto next = [&](Cur& c) { if (++c.tx == t.tiles_x) { c.tx = 0; if (++c.ty == t.tiles_y) { c.ty = 0; ++c.b; } } };
+    Cur ahead;
+    ahead.tx = tile0 % t.tiles_x; ahead.ty = (tile0 / t.tiles_x) % t.tiles_y; ahead.b = (tile0 / t.tiles_x) / t.tiles_y;
+
     auto issue = [&](int tile, int d) {
       if (tile < tile1) {
-        const int tx = tile % t.tiles_x;
-        const int rest = tile / t.tiles_x;
-        const int ty = rest % t.tiles_y;
-        const int b = rest / t.tiles_y;
-        const int qy0 = ty * t.TR, qx0 = tx * WG3_TC;
-        const float* xb = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0;
+        const int b = ahead.b;
+        const int qy0 = ahead.ty * t.TR, qx0 = ahead.tx * WG3_TC;
+        const float* xb = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0 + half * 4;
         if (has_x) {
-          const int gy = qy0 + warp;
+          const int gy = qy0 + wr;
+          const float* rowp = xb + (long)gy * a.Wa * a.pa;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int gx = qx0 - a.pada_l + lane + 32 * j;
+            const int gx = qx0 - a.pada_l + px0 + 16 * j;
             const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa;
-            const float* sp = inb ? xb + (gy * a.Wa + gx) * a.pa : xb;
-            wcp_async16z(raw_u32 + slot(d, j, 0), sp, inb ? 16u : 0u);
-            wcp_async16z(raw_u32 + slot(d, j, 1), sp + 4, inb ? 16u : 0u);
+            wcp_async16z(raw_u32 + slot(d, j), inb ? rowp + gx * a.pa : xb, inb ? 16u : 0u);
           }
         }
         if (has_h) {
           const int gy = qy0 + hr, gx = qx0 - a.pada_l + hc;
           const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa;
-          const float* sp = inb ? xb + (gy * a.Wa + gx) * a.pa : xb;
-          wcp_async16z(raw_u32 + slot(d, t.ix_halo, 0), sp, inb ? 16u : 0u);
-          wcp_async16z(raw_u32 + slot(d, t.ix_halo, 1), sp + 4, inb ? 16u : 0u);
+          const float* hb = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0 + hhalf * 4;
+          wcp_async16z(raw_u32 + slot(d, t.ix_halo), inb ? hb + ((long)gy * a.Wa + gx) * a.pa : hb, inb ? 16u : 0u);
         }
         {
-          const float* yb = a.Bm + (long)b * a.Hb * a.Wb * a.pb;
+          const float* yb = a.Bm + (long)b * a.Hb * a.Wb * a.pb + half * 4;
           const int vy = qy0 + a.pada_t - (a.kh - 1) + yr;
           const bool oky = (unsigned)vy < (unsigned)a.Hq;
+          const float* rowp = yb + (long)vy * a.Wb * a.pb;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const int vx = qx0 + lane + 32 * j;
+            const int vx = qx0 + px0 + 16 * j;
             const bool inb = oky && vx < a.Wq;
-            const float* sp = inb ? yb + (vy * a.Wb + vx) * a.pb : yb;
+            const float* sp = inb ? rowp + vx * a.pb : yb;
 #pragma unroll
-            for (int pl = 0; pl < 2; ++pl) {
-              if (pl < t.nyp) {
-                wcp_async16z(raw_u32 + slot(d, t.iy0 + pl * 2 + j, 0), sp + pl * 8, inb ? 16u : 0u);
-                wcp_async16z(raw_u32 + slot(d, t.iy0 + pl * 2 + j, 1), sp + pl * 8 + 4, inb ? 16u : 0u);
-              }
-            }
+            for (int pl = 0; pl < 2; ++pl)
+              if (pl < t.nyp) wcp_async16z(raw_u32 + slot(d, t.iy0 + pl * 2 + j), sp + pl * 8, inb ? 16u : 0u);
           }
         }
       }
+      next(ahead);
       wcp_commit();
     };
-    auto load_px = [&](int d, int item, float* v) {
-      const float4 q0 = *reinterpret_cast<const float4*>(raw_s + tid * 16 + slot(d, item, 0));
-      const float4 q1 = *reinterpret_cast<const float4*>(raw_s + tid * 16 + slot(d, item, 1));
-      v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    // 4 fp32 -> 4 bf16 (8 bytes)
+    auto pack4 = [](const float4& q, bool relu) -> uint2 {
+      float4 v = q;
+      if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+      return make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     };
     for (int d = 0; d < t.D - 1; ++d) issue(tile0 + d, d);
-    float bacc[2][8] = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+    float bacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     for (int it = 0; it < n_my; ++it) {
       issue(tile0 + it + t.D - 1, (it + t.D - 1) % t.D);
       if (t.D == 4) wcp_wait<3>(); else if (t.D == 3) wcp_wait<2>(); else wcp_wait<1>();
-      const int s = it & 1, d = it % t.D;
-      if (it >= 2) {
-        if (lane == 0) wmbar_wait(&bar_free[s], ((it >> 1) - 1) & 1);
+      const int s = it % t.S, d = it % t.D;
+      if (it >= t.S) {
+        if (lane == 0) wmbar_wait(&bar_free[s], ((it / t.S) - 1) & 1);
         __syncwarp();
       }
       uint8_t* xh = stage_s + (size_t)s * t.stage_bytes;
       uint8_t* yh = xh + t.x_bytes;
-      float v[8];
+      const uint8_t* rsrc = raw_s + tid * 16;
       if (has_x) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          load_px(d, j, v);
-          if (a.reluA) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-          }
-          *reinterpret_cast<uint4*>(xh + (warp * t.HWx + lane + 32 * j) * 16) = wpack8(v);
+          const float4 q = *reinterpret_cast<const float4*>(rsrc + slot(d, j));
+          *reinterpret_cast<uint2*>(xh + (wr * t.HWx + px0 + 16 * j) * 16 + half * 8) = pack4(q, a.reluA != 0);
         }
       }
       if (has_h) {
-        load_px(d, t.ix_halo, v);
-        if (a.reluA) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-        }
-        *reinterpret_cast<uint4*>(xh + (hr * t.HWx + hc) * 16) = wpack8(v);
+        const float4 q = *reinterpret_cast<const float4*>(rsrc + slot(d, t.ix_halo));
+        *reinterpret_cast<uint2*>(xh + (hr * t.HWx + hc) * 16 + hhalf * 8) = pack4(q, a.reluA != 0);
       }
       {
         // bias gradient: the TR centre rows of the staged dY tile (the halo rows belong to the neighbouring tiles)
-        const int tile = tile0 + it;
-        const int ty = (tile / t.tiles_x) % t.tiles_y;
-        const int vy = ty * t.TR + a.pada_t - (a.kh - 1) + yr;
-        const bool centre = do_bias && vy >= ty * t.TR && vy < ty * t.TR + t.TR;
+        const int vrel = a.pada_t - (a.kh - 1) + yr;             // staged row relative to the tile's first X row
+        const bool centre = do_bias && vrel >= 0 && vrel < t.TR;
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
           if (pl < t.nyp) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              load_px(d, t.iy0 + pl * 2 + j, v);
-              if (centre) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) bacc[pl][k] += v[k];
-              }
-              *reinterpret_cast<uint4*>(yh + (size_t)((yr * t.nyp + pl) * WG3_TC + lane + 32 * j) * 16) = wpack8(v);
+              const float4 q = *reinterpret_cast<const float4*>(rsrc + slot(d, t.iy0 + pl * 2 + j));
+              if (centre) { bacc[pl][0] += q.x; bacc[pl][1] += q.y; bacc[pl][2] += q.z; bacc[pl][3] += q.w; }
+              *reinterpret_cast<uint2*>(yh + (size_t)((yr * t.nyp + pl) * WG3_TC + px0 + 16 * j) * 16 + half * 8) = pack4(q, false);
             }
           }
         }
@@ -889,11 +900,11 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
 #pragma unroll
       for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 4; ++k) {
           float sum = bacc[pl][k];
 #pragma unroll
-          for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-          if (lane == 0 && pl < t.nyp) atomicAdd(&sbias[pl * 8 + k], sum);
+          for (int o = 16; o > 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);   // lanes of equal parity (same half)
+          if (lane < 2 && pl < t.nyp) atomicAdd(&sbias[pl * 8 + half * 4 + k], sum);
         }
       }
     }
@@ -909,8 +920,8 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
     const uint32_t yrow16 = (uint32_t)(t.nyp * WG3_TC);                          // staged dY row pitch, 16-B units
     uint32_t first = 0u;
     for (int it = 0; it < n_my; ++it) {
-      const int s = it & 1;
-      if (lane == 0) wmbar_wait(&bar_full[s], (it >> 1) & 1);
+      const int s = it % t.S;
+      if (lane == 0) wmbar_wait(&bar_full[s], (it / t.S) & 1);
       __syncwarp();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (welect_one()) {
@@ -984,21 +995,24 @@ static bool wgrad_tc3_config(const WgradArgs& a, Wg3Tile& t) {
   if (off < 0) { const char* e = getenv("MSAU_WG3_OFF"); off = e ? atoi(e) : 0; }
   if (off || a.dila != 1 || a.cb > 16 || a.maskB || a.a_nchw || a.b_s2d || a.Wq < 16) return false;
   t.nyp = a.cb >> 3;
-  t.TRy = WG3_CONV_WARPS;
+  t.TRy = WG3_ROWS;
   t.TR = t.TRy - (a.kh - 1);
   if (t.TR < 2) return false;
   t.N = a.kh * a.cb;
   t.HWx = WG3_TC + (a.kw - 1);
-  t.items = 2; t.ix_halo = -1;
+  t.items = 2; t.ix_halo = -1;            // 16-byte items
   if (a.kw > 1) t.ix_halo = t.items++;
   t.iy0 = t.items; t.items += 2 * t.nyp;
   const int slack_px = 7 + 16;
   t.x_bytes = (uint32_t)((t.TR * t.HWx + slack_px) * 16 + 127) / 128 * 128;
-  const uint32_t y_bytes = (uint32_t)(WG3_CONV_WARPS * t.nyp * WG3_TC * 16);
+  const uint32_t y_bytes = (uint32_t)(WG3_ROWS * t.nyp * WG3_TC * 16);
   t.stage_bytes = (t.x_bytes + y_bytes + 1023) / 1024 * 1024;
-  t.raw_bytes = (uint32_t)(t.items * 2 * WG3_CONV_WARPS * 32 * 16);
+  t.raw_bytes = (uint32_t)(t.items * WG3_CONV_WARPS * 32 * 16);
   t.D = 4;
-  while (t.D > 2 && 2 * (size_t)t.stage_bytes + (size_t)t.D * t.raw_bytes > 218 * 1024) --t.D;
+  t.S = 4;
+  while ((t.D > 2 || t.S > 2) && (size_t)t.S * t.stage_bytes + (size_t)t.D * t.raw_bytes > 218 * 1024) {
+    if (t.S > 2 && t.S >= t.D) --t.S; else --t.D;
+  }
   t.n_issue = 128 / t.N;
   if (t.n_issue > WG3_MMA_WARPS) t.n_issue = WG3_MMA_WARPS;
   if (t.n_issue < 1) t.n_issue = 1;
@@ -1015,7 +1029,7 @@ static bool wgrad_tc3_config(const WgradArgs& a, Wg3Tile& t) {
 static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t st) {
   Wg3Tile t = t0;
   const int planes = a.ca >> 3;
-  const size_t smem = 2 * (size_t)t.stage_bytes + (size_t)t.D * t.raw_bytes + 1024;
+  const size_t smem = (size_t)t.S * t.stage_bytes + (size_t)t.D * t.raw_bytes + 1024;
   int ctas = (sm_count() + planes - 1) / planes;
   if (ctas > t.n_tiles) ctas = t.n_tiles;
   if (ctas < 1) ctas = 1;
