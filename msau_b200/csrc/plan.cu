@@ -9,6 +9,7 @@
 // Concats are never materialised (two-source convs), F.pad never runs (bounds-checked tiles), ReLU /
 // residual add / ReLU-backward masks live in conv epilogues and operand loaders.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -346,6 +347,7 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.accumulate = o.accumulate;
   a.skip_flag = skip_flag;
   count_launch(1);
+  { static bool init = false; if (!init) { const char* e = getenv("MSAU_C3_MAX"); if (e) g_c3_max = atoi(e); init = true; } }
   if (g_use_tc && g_use_c3 && t3_off >= 0 && coutp <= g_c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
   if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
   return launch_conv(a, p->st);

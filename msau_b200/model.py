@@ -322,11 +322,29 @@ class MSAUWrapper(torch.nn.Module):
         self._last = (pl, x, 0, logits.data_ptr(), aux.data_ptr()) if track else None
         return (probs if want_probs else logits), logits, aux
 
-    def predict_classes(self, inp, layout: int = 0):
+    def _eval_workspace_bytes(self, B: int, H: int, W: int) -> int:
+        n = C.c_size_t()
+        _lib.check(_lib.lib().msau_workspace_bytes(self._plan(B, H, W).handle, 0, C.byref(n)))
+        return n.value
+
+    def predict_classes(self, inp, layout: int = 0, pages_per_call: Optional[int] = None):
         """argmax over classes, uint8 [B,H,W] (train_chargrid_funsd_msau.py:133-136, kv_model.py:162) without
-        materialising logits on the host."""
-        _, _, _, _, _, amax = self._run_forward(inp, layout, False, False, want_argmax=True, want_logits=False)
-        return amax
+        materialising logits on the host.  Large batches (BASELINE.json config 5: 64 pages of 1024x768 per GPU) run in
+        chunks of ``pages_per_call`` pages; by default the largest power-of-two chunk whose activation workspace fits in
+        80 % of the free device memory."""
+        B, H, W = self._check_input(inp, layout)
+        if pages_per_call is None:
+            free = torch.cuda.mem_get_info(inp.device)[0]
+            pages_per_call = B
+            while pages_per_call > 1 and self._eval_workspace_bytes(pages_per_call, H, W) > 0.8 * free:
+                pages_per_call = (pages_per_call + 1) // 2
+        if pages_per_call >= B:
+            return self._run_forward(inp, layout, False, False, want_argmax=True, want_logits=False)[5]
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=inp.device)
+        for b0 in range(0, B, pages_per_call):
+            chunk = inp[b0:b0 + pages_per_call]
+            out[b0:b0 + chunk.shape[0]] = self._run_forward(chunk, layout, False, False, want_argmax=True, want_logits=False)[5]
+        return out
 
     def _backward_from_last(self, labels: torch.Tensor, loss_scale: float = 1.0) -> torch.Tensor:
         if self._last is None:

@@ -239,3 +239,56 @@ def test_full_size_page_properties():
         probs, logits, aux = m(xc)
     assert torch.isfinite(logits).all() and torch.isfinite(aux).all()
     assert (probs.sum(1) - 1).abs().max().item() < 1e-5
+
+
+def test_bert_grid_config():
+    """BASELINE.json config 3: 768-channel BERT-grid input (dense, not one-hot): parity with the oracle on a small page,
+    then one full-size batch (8 x 768 x 512 x 512) through two fused train steps."""
+    cfg = om.MsauConfig(channels=768)
+    sd = om.init_state_dict(cfg, 3)
+    g = torch.Generator().manual_seed(4)
+    x = 0.3 * torch.randn(1, 768, 16, 24, generator=g)
+    x = x * (torch.rand(1, 1, 16, 24, generator=g) < 0.4)          # boxes cover part of the page
+    labels = torch.randint(0, cfg.n_class, (1, 16, 24), generator=g)
+    labels[:, 0, 0] = 1
+    m = build(cfg, sd).train()
+    _, logits, aux = m(x.cuda())
+    ref_loss, ref_logits, _, ref_grads = om.loss_and_grads(sd, cfg, x, labels)
+    assert (logits.cpu() - ref_logits).abs().max().item() <= LOGIT_ATOL
+    loss = m.loss(logits, aux, labels.cuda())
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-4 * max(1.0, float(ref_loss))
+    loss.backward()
+    k = "msau_net.blocks.0.downsamplingblock.conv1s.0.conv.weight"
+    gk = dict(m.named_parameters())[k].grad.cpu()
+    assert (gk - ref_grads[k]).double().norm().item() <= 3e-2 * ref_grads[k].double().norm().item()
+    del m
+    # full size
+    m = build(cfg, sd).train()
+    xg = 0.3 * torch.randn(8, 768, 512, 512, device="cuda")
+    xg *= (torch.rand(8, 1, 512, 512, device="cuda") < 0.3)
+    lg = torch.randint(0, cfg.n_class, (8, 512, 512), device="cuda")
+    losses = [float(m.train_step(xg, lg, lr=1e-3)) for _ in range(3)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_high_resolution_inference():
+    """BASELINE.json config 5: 1024 x 768 chargrid pages, inference only.  The class map of a batch equals the class maps of
+    its chunks, agrees with the arg-max of the full forward, and (one page) with the oracle on >= 99.9 % of the pixels."""
+    cfg = om.MsauConfig()
+    sd = om.init_state_dict(cfg, 0)
+    m = build(cfg, sd).eval()
+    B, H, W = 6, 1024, 768
+    g = torch.Generator(device="cuda").manual_seed(9)
+    ids = torch.randint(0, cfg.channels, (B, 1, H, W), device="cuda", generator=g)
+    occ = (torch.rand((B, 1, H, W), device="cuda", generator=g) < 0.1).float()
+    x = torch.zeros(B, cfg.channels, H, W, device="cuda").scatter_(1, ids, occ)
+    with torch.no_grad():
+        cm = m.predict_classes(x)
+        cm2 = m.predict_classes(x, pages_per_call=4)
+        probs, logits, _ = m(x[:2])
+    assert cm.dtype == torch.uint8 and cm.shape == (B, H, W) and int(cm.max()) < cfg.n_class
+    assert torch.equal(cm, cm2)
+    assert torch.equal(cm[:2].long(), logits.argmax(1))
+    out, _ = om.msau_forward(sd, cfg, x[:1].cpu())
+    agree = (out.argmax(1) == cm[:1].cpu().long()).float().mean().item()
+    assert agree >= 0.999, agree
