@@ -798,50 +798,67 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
     const int hr = has_h ? (tid >> 1) / nh : 0, hc = has_h ? WG3_TC + ((tid >> 1) - hr * nh) : 0, hhalf = tid & 1;
     const int yr = wr;                                           // staged dY row of this warp
     const int half = lane & 1, px0 = wc + (lane >> 1);           // chunk l + 32 j -> pixel px0 + 16 j, same half
-    auto slot = [&](int d, int item) -> uint32_t { return (uint32_t)d * t.raw_bytes + (uint32_t)(item * (WG3_CONV_WARPS * 32 * 16)); };
-    struct Cur { int tx, ty, b; };
-    auto next = [&](Cur& c) { if (++c.tx == t.tiles_x) { c.tx = 0; if (++c.ty == t.tiles_y) { c.ty = 0; ++c.b; } } };
+    constexpr uint32_t ITEM = WG3_CONV_WARPS * 32 * 16;          // bytes between this thread's consecutive raw items
+    // Everything that does not depend on the tile is computed once: element offsets of this thread's items relative to the
+    // tile origin (32-bit: every tensor here has < 2^31 elements), and the tile origin itself advances incrementally.
+    const int xo = (wr * a.Wa + px0 - a.pada_l) * a.pa + ca0 + half * 4;        // X item 0 (item 1: + 16 pa)
+    const int ho = (hr * a.Wa + hc - a.pada_l) * a.pa + ca0 + hhalf * 4;        // X halo item
+    const int vrel = a.pada_t - (a.kh - 1) + yr;                                  // staged dY row relative to the tile's first row
+    const int yo = (vrel * a.Wb + px0) * a.pb + half * 4;                         // dY item 0 (item 1: + 16 pb; plane 1: + 8)
+    struct Cur { int tx, ty, b, xt, yt; };
+    auto origin = [&](Cur& c) {
+      c.xt = ((c.b * a.Ha + c.ty * t.TR) * a.Wa + c.tx * WG3_TC) * a.pa;
+      c.yt = ((c.b * a.Hb + c.ty * t.TR) * a.Wb + c.tx * WG3_TC) * a.pb;
+    };
+    auto next = [&](Cur& c) {
+      if (++c.tx == t.tiles_x) {
+        c.tx = 0;
+        if (++c.ty == t.tiles_y) { c.ty = 0; ++c.b; }
+        origin(c);
+      } else {
+        c.xt += WG3_TC * a.pa;
+        c.yt += WG3_TC * a.pb;
+      }
+    };
     Cur ahead;
     ahead.tx = tile0 % t.tiles_x; ahead.ty = (tile0 / t.tiles_x) % t.tiles_y; ahead.b = (tile0 / t.tiles_x) / t.tiles_y;
-
-    auto issue = [&](int tile, int d) {
-      if (tile < tile1) {
-        const int b = ahead.b;
+    origin(ahead);
+    int n_ahead = 0;                                              // tiles issued so far
+    uint32_t d_issue = 0;                                         // raw slot of the next issue, bytes
+    auto issue = [&]() {
+      if (n_ahead < n_my) {
         const int qy0 = ahead.ty * t.TR, qx0 = ahead.tx * WG3_TC;
-        const float* xb = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0 + half * 4;
+        const uint32_t dst = raw_u32 + d_issue;
         if (has_x) {
-          const int gy = qy0 + wr;
-          const float* rowp = xb + (long)gy * a.Wa * a.pa;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int gx = qx0 - a.pada_l + px0 + 16 * j;
-            const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa;
-            wcp_async16z(raw_u32 + slot(d, j), inb ? rowp + gx * a.pa : xb, inb ? 16u : 0u);
-          }
+          const bool oky = qy0 + wr < a.Ha;
+          const int gx = qx0 - a.pada_l + px0;
+          const bool in0 = oky && (unsigned)gx < (unsigned)a.Wa, in1 = oky && (unsigned)(gx + 16) < (unsigned)a.Wa;
+          const float* sp = a.A + (long)(ahead.xt + xo);      // may point left of the row (halo): only dereferenced where in-bounds
+          wcp_async16z(dst, in0 ? sp : a.A, in0 ? 16u : 0u);
+          wcp_async16z(dst + ITEM, in1 ? sp + 16 * a.pa : a.A, in1 ? 16u : 0u);
         }
         if (has_h) {
-          const int gy = qy0 + hr, gx = qx0 - a.pada_l + hc;
-          const bool inb = gy < a.Ha && (unsigned)gx < (unsigned)a.Wa;
-          const float* hb = a.A + (long)b * a.Ha * a.Wa * a.pa + ca0 + hhalf * 4;
-          wcp_async16z(raw_u32 + slot(d, t.ix_halo), inb ? hb + ((long)gy * a.Wa + gx) * a.pa : hb, inb ? 16u : 0u);
+          const bool inb = qy0 + hr < a.Ha && (unsigned)(qx0 - a.pada_l + hc) < (unsigned)a.Wa;
+          wcp_async16z(dst + (uint32_t)t.ix_halo * ITEM, inb ? a.A + (long)(ahead.xt + ho) : a.A, inb ? 16u : 0u);
         }
         {
-          const float* yb = a.Bm + (long)b * a.Hb * a.Wb * a.pb + half * 4;
-          const int vy = qy0 + a.pada_t - (a.kh - 1) + yr;
-          const bool oky = (unsigned)vy < (unsigned)a.Hq;
-          const float* rowp = yb + (long)vy * a.Wb * a.pb;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int vx = qx0 + px0 + 16 * j;
-            const bool inb = oky && vx < a.Wq;
-            const float* sp = inb ? rowp + vx * a.pb : yb;
-#pragma unroll
-            for (int pl = 0; pl < 2; ++pl)
-              if (pl < t.nyp) wcp_async16z(raw_u32 + slot(d, t.iy0 + pl * 2 + j), sp + pl * 8, inb ? 16u : 0u);
+          const bool oky = (unsigned)(qy0 + vrel) < (unsigned)a.Hq;
+          const int vx = qx0 + px0;
+          const bool in0 = oky && vx < a.Wq, in1 = oky && vx + 16 < a.Wq;
+          const float* sp = a.Bm + (long)(ahead.yt + yo);
+          const uint32_t dy = dst + (uint32_t)t.iy0 * ITEM;
+          wcp_async16z(dy, in0 ? sp : a.Bm, in0 ? 16u : 0u);
+          wcp_async16z(dy + ITEM, in1 ? sp + 16 * a.pb : a.Bm, in1 ? 16u : 0u);
+          if (t.nyp > 1) {
+            wcp_async16z(dy + 2 * ITEM, in0 ? sp + 8 : a.Bm, in0 ? 16u : 0u);
+            wcp_async16z(dy + 3 * ITEM, in1 ? sp + 16 * a.pb + 8 : a.Bm, in1 ? 16u : 0u);
           }
         }
+        next(ahead);
       }
-      next(ahead);
+      ++n_ahead;
+      d_issue += t.raw_bytes;
+      if (d_issue == (uint32_t)t.D * t.raw_bytes) d_issue = 0;
       wcp_commit();
     };
     // 4 fp32 -> 4 bf16 (8 bytes)
@@ -851,49 +868,60 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
       const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
       return make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     };
-    for (int d = 0; d < t.D - 1; ++d) issue(tile0 + d, d);
+    for (int d = 0; d < t.D - 1; ++d) issue();
     float bacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    const bool centre = do_bias && vrel >= 0 && vrel < t.TR;     // the halo rows belong to the neighbouring tiles
+    const bool relu = a.reluA != 0;
+    // destinations inside a bf16 stage (constant per thread)
+    const uint32_t xd = (uint32_t)((wr * t.HWx + px0) * 16 + half * 8);
+    const uint32_t hd = (uint32_t)((hr * t.HWx + hc) * 16 + hhalf * 8);
+    const uint32_t yd = t.x_bytes + (uint32_t)((yr * t.nyp * WG3_TC + px0) * 16 + half * 8);
+    int s = 0;
+    uint32_t sphase = 0, d_cur = 0;
     for (int it = 0; it < n_my; ++it) {
-      issue(tile0 + it + t.D - 1, (it + t.D - 1) % t.D);
+      issue();
       if (t.D == 4) wcp_wait<3>(); else if (t.D == 3) wcp_wait<2>(); else wcp_wait<1>();
-      const int s = it % t.S, d = it % t.D;
       if (it >= t.S) {
-        if (lane == 0) wmbar_wait(&bar_free[s], ((it / t.S) - 1) & 1);
+        if (lane == 0) wmbar_wait(&bar_free[s], sphase ^ 1u);
         __syncwarp();
       }
-      uint8_t* xh = stage_s + (size_t)s * t.stage_bytes;
-      uint8_t* yh = xh + t.x_bytes;
-      const uint8_t* rsrc = raw_s + tid * 16;
+      uint8_t* st = stage_s + (size_t)s * t.stage_bytes;
+      const uint8_t* rsrc = raw_s + tid * 16 + d_cur;
       if (has_x) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const float4 q = *reinterpret_cast<const float4*>(rsrc + slot(d, j));
-          *reinterpret_cast<uint2*>(xh + (wr * t.HWx + px0 + 16 * j) * 16 + half * 8) = pack4(q, a.reluA != 0);
-        }
+        const float4 q0 = *reinterpret_cast<const float4*>(rsrc);
+        const float4 q1 = *reinterpret_cast<const float4*>(rsrc + ITEM);
+        *reinterpret_cast<uint2*>(st + xd) = pack4(q0, relu);
+        *reinterpret_cast<uint2*>(st + xd + 256) = pack4(q1, relu);
       }
       if (has_h) {
-        const float4 q = *reinterpret_cast<const float4*>(rsrc + slot(d, t.ix_halo));
-        *reinterpret_cast<uint2*>(xh + (hr * t.HWx + hc) * 16 + hhalf * 8) = pack4(q, a.reluA != 0);
+        const float4 q = *reinterpret_cast<const float4*>(rsrc + t.ix_halo * ITEM);
+        *reinterpret_cast<uint2*>(st + hd) = pack4(q, relu);
       }
       {
-        // bias gradient: the TR centre rows of the staged dY tile (the halo rows belong to the neighbouring tiles)
-        const int vrel = a.pada_t - (a.kh - 1) + yr;             // staged row relative to the tile's first X row
-        const bool centre = do_bias && vrel >= 0 && vrel < t.TR;
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
-          if (pl < t.nyp) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const float4 q = *reinterpret_cast<const float4*>(rsrc + slot(d, t.iy0 + pl * 2 + j));
-              if (centre) { bacc[pl][0] += q.x; bacc[pl][1] += q.y; bacc[pl][2] += q.z; bacc[pl][3] += q.w; }
-              *reinterpret_cast<uint2*>(yh + (size_t)((yr * t.nyp + pl) * WG3_TC + px0 + 16 * j) * 16 + half * 8) = pack4(q, false);
-            }
+        const uint8_t* ry = rsrc + t.iy0 * ITEM;
+        const float4 q0 = *reinterpret_cast<const float4*>(ry);
+        const float4 q1 = *reinterpret_cast<const float4*>(ry + ITEM);
+        if (centre) {
+          bacc[0][0] += q0.x + q1.x; bacc[0][1] += q0.y + q1.y; bacc[0][2] += q0.z + q1.z; bacc[0][3] += q0.w + q1.w;
+        }
+        *reinterpret_cast<uint2*>(st + yd) = pack4(q0, false);
+        *reinterpret_cast<uint2*>(st + yd + 256) = pack4(q1, false);
+        if (t.nyp > 1) {
+          const float4 p0 = *reinterpret_cast<const float4*>(ry + 2 * ITEM);
+          const float4 p1 = *reinterpret_cast<const float4*>(ry + 3 * ITEM);
+          if (centre) {
+            bacc[1][0] += p0.x + p1.x; bacc[1][1] += p0.y + p1.y; bacc[1][2] += p0.z + p1.z; bacc[1][3] += p0.w + p1.w;
           }
+          *reinterpret_cast<uint2*>(st + yd + WG3_TC * 16) = pack4(p0, false);
+          *reinterpret_cast<uint2*>(st + yd + WG3_TC * 16 + 256) = pack4(p1, false);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) wmbar_arrive(&bar_full[s]);      // one arrival per warp (per-thread arrivals serialise)
+      if (++s == t.S) { s = 0; sphase ^= 1u; }
+      d_cur += t.raw_bytes;
+      if (d_cur == (uint32_t)t.D * t.raw_bytes) d_cur = 0;
     }
     wcp_wait<0>();
     if (do_bias) {
