@@ -174,66 +174,69 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     // e = tid + u * 192, which makes the raw ring thread-private (cp.async.wait_group is the only synchronisation).
     const int planes1 = a.c1 >> 3;
     const uint32_t raw_u32 = smem_u32(raw_s);
-    auto issue = [&](const TilePos& tp, int p, int slot) {
+    // Lean on purpose (the role is paced by its serial instruction chain): ring positions are counters, addresses are
+    // 32-bit element offsets (every tensor here has < 2^31 elements) built from per-thread constants.
+    const int lpx = lane >> 1, lhalf = (lane & 1) * 4;
+    uint32_t d_issue = 0;                                          // raw slot of the next issue (bytes)
+    auto issue = [&](const TilePos& tp, int p) {
       if (tp.b < a.B && !(t.dbg & 2)) {
         const int in_x0 = tp.bx * 30 - 1, in_y0 = tp.by * RO - 1;
         const bool from1 = p < planes1;
-        const float* src = from1 ? a.src1 + (p << 3) : a.src2 + ((p - planes1) << 3);
+        const float* base = from1 ? a.src1 : a.src2;
         const int pitch = from1 ? a.p1 : a.p2;
-        src += (long)tp.b * a.Hin * a.Win * pitch;
-        const uint32_t dst0 = raw_u32 + (uint32_t)slot * t.raw_bytes + (uint32_t)tid * 16u;
+        const int ch = ((from1 ? p : p - planes1) << 3) + lhalf;
         // a halo row (32 pixels x 32 B) is 64 chunks of 16 B: lane l copies chunks l and l + 32 of the rows warp + 6 u, i.e.
         // half (l & 1) of the pixels l / 2 and l / 2 + 16 -- each warp instruction moves 512 contiguous bytes and every
         // 32-byte sector is requested exactly once (cp.async.cg goes straight to L2)
-        const int gx0 = in_x0 + (lane >> 1), gx1 = gx0 + 16;
-        const bool okx0 = (unsigned)gx0 < (unsigned)a.Win, okx1 = (unsigned)gx1 < (unsigned)a.Win;
-        const float* col = src + gx0 * pitch + (lane & 1) * 4;
-        const int rpitch = a.Win * pitch;
+        const int gx0 = in_x0 + lpx;
+        const bool okx0 = (unsigned)gx0 < (unsigned)a.Win, okx1 = (unsigned)(gx0 + 16) < (unsigned)a.Win;
+        int gy = in_y0 + warp;
+        int off = ((tp.b * a.Hin + gy) * a.Win + gx0) * pitch + ch;
+        const int roff = C3_PROD_WARPS * a.Win * pitch;
+        uint32_t dst = raw_u32 + d_issue + (uint32_t)tid * 16u;
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
-          const int row = warp + u * C3_PROD_WARPS;
-          if (row < t.RI) {
-            const int gy = in_y0 + row;
+          if (warp + u * C3_PROD_WARPS < t.RI) {
             const bool oky = (unsigned)gy < (unsigned)a.Hin;
-            const float* sp = col + gy * rpitch;
-            const uint32_t dst = dst0 + (uint32_t)u * (2u * C3_PROD_THREADS * 16u);
-            cp_async16z(dst, (oky && okx0) ? sp : src, (oky && okx0) ? 16u : 0u);
-            cp_async16z(dst + C3_PROD_THREADS * 16u, (oky && okx1) ? sp + 16 * pitch : src, (oky && okx1) ? 16u : 0u);
+            const float* sp = base + (long)off;
+            cp_async16z(dst, (oky && okx0) ? sp : base, (oky && okx0) ? 16u : 0u);
+            cp_async16z(dst + C3_PROD_THREADS * 16u, (oky && okx1) ? sp + 16 * pitch : base, (oky && okx1) ? 16u : 0u);
           }
+          gy += C3_PROD_WARPS; off += roff; dst += 2u * C3_PROD_THREADS * 16u;
         }
       }
+      d_issue += t.raw_bytes;
+      if (d_issue == (uint32_t)t.D * t.raw_bytes) d_issue = 0;
       cp_async_commit();
     };
-    TilePos ahead, cur;
+    TilePos ahead;
     ahead.init(blockIdx.x, t);
-    cur = ahead;
     int p_ahead = 0;
     // (every thread keeps D - 1 groups outstanding: empty groups stand in for chunks that do not exist)
     for (int d = 0; d < t.D - 1; ++d) {
-      issue(ahead, p_ahead, d);
+      issue(ahead, p_ahead);
       if (++p_ahead == t.P) { p_ahead = 0; ahead.advance(t); }
     }
-    uint32_t c = 0;
+    int s = 0;
+    uint32_t sphase = 0, d_cur = 0, c = 0;
+    const uint32_t dimg = (uint32_t)(lpx * 16 + (lane & 1) * 8 + warp * 512);   // this thread's first half-pixel in an image
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
       for (int p = 0; p < t.P; ++p, ++c) {
-        issue(ahead, p_ahead, (int)((c + t.D - 1) % t.D));
+        issue(ahead, p_ahead);
         if (++p_ahead == t.P) { p_ahead = 0; ahead.advance(t); }
-        const int s = c % S;
-        uint8_t* stg = img_s + (size_t)s * t.in_bytes;
+        uint8_t* stg = img_s + (size_t)s * t.in_bytes + dimg;
         if (c >= (uint32_t)S) {
-          if (lane == 0) wait(&bar_empty[s], ((c / S) - 1) & 1);
+          if (lane == 0) wait(&bar_empty[s], sphase ^ 1u);
           __syncwarp();
         }
         // chunk c has landed once at most D - 1 newer groups are pending (D is 2..4)
         if (t.D == 4) cp_async_wait<3>(); else if (t.D == 3) cp_async_wait<2>(); else cp_async_wait<1>();
-        const uint8_t* rsrc = raw_s + (size_t)(c % t.D) * t.raw_bytes + tid * 16;
+        const uint8_t* rsrc = raw_s + d_cur + tid * 16;
         const bool relu = a.relu1 && p < planes1;
         // this thread's two half-pixels of every row: 4 channels each -> 8 bytes of the hi image + 8 bytes of the lo image
-        uint8_t* dimg = stg + (lane >> 1) * 16 + (lane & 1) * 8;
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
-          const int row = warp + u * C3_PROD_WARPS;
-          if (row < t.RI) {
+          if (warp + u * C3_PROD_WARPS < t.RI) {
             float4 q[2];
             q[0] = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16));
             q[1] = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16) + C3_PROD_THREADS * 16);
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               uint2 hi, lo;
               split_pair(v.x, v.y, hi.x, lo.x);
               split_pair(v.z, v.w, hi.y, lo.y);
-              uint8_t* d = dimg + (row * 32 + 16 * j) * 16;
+              uint8_t* d = stg + u * (C3_PROD_WARPS * 512) + j * 256;
               *reinterpret_cast<uint2*>(d) = hi;
               *reinterpret_cast<uint2*>(d + t.plane_bytes) = lo;
             }
@@ -255,6 +258,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full[s]);
+        if (++s == S) { s = 0; sphase ^= 1u; }
+        d_cur += t.raw_bytes;
+        if (d_cur == (uint32_t)t.D * t.raw_bytes) d_cur = 0;
       }
     }
     cp_async_wait<0>();
@@ -268,18 +274,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const uint32_t lbo_plane = ((t.plane_bytes >> 4) & 0x3FFF) << 16;     // hi image -> lo image
     const uint32_t lbo_row = (512u >> 4) << 16;                           // next image row (next ky)
     const uint32_t b_lbo = ((N * 16 >> 4) & 0x3FFF) << 16;
-    uint32_t c = 0, tcount = 0;
+    uint32_t tcount = 0, as = 0, aphase = 0, sphase = 0;
+    int s = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
-      const uint32_t as = tcount % (uint32_t)t.A;
       if (tcount >= (uint32_t)t.A) {
-        if (lane == 0) wait(&bar_acc_empty[as], ((tcount / (uint32_t)t.A) - 1) & 1);
+        if (lane == 0) wait(&bar_acc_empty[as], aphase ^ 1u);
         __syncwarp();
       }
       tc_fence_after();
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N);
-      for (int p = 0; p < t.P; ++p, ++c) {
-        const int s = c % S;
-        if (lane == 0) wait(&bar_full[s], (c / S) & 1);
+      for (int p = 0; p < t.P; ++p) {
+        if (lane == 0) wait(&bar_full[s], sphase);
         __syncwarp();
         tc_fence_after();
         const uint32_t in16 = smem_u32(img_s + (size_t)s * t.in_bytes) >> 4;
@@ -303,7 +308,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
           if (p == t.P - 1) tc_commit(&bar_acc_full[as]);
         }
         __syncwarp();
+        if (++s == S) { s = 0; sphase ^= 1u; }
       }
+      if (++as == (uint32_t)t.A) { as = 0; aphase ^= 1u; }
     }
   } else {
     // =============================================================== epilogue
@@ -322,16 +329,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const uint32_t slot_stride = (uint32_t)(G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0))) * 8192u;  // bytes between consecutive items' slots
     const uint32_t my_slot = (uint32_t)et * 16u;
     const bool lane_ok = lane >= 1 && lane <= 30;
-    const long tile_pix = 4L * a.Wout;                       // pixel distance between consecutive tiles (4 rows)
+    const int tile_pix = 4 * a.Wout;                         // pixel distance between consecutive tiles (4 rows)
     // position of a super-tile for this thread: pixel index of its tile-0 output, first output row, column validity
-    struct Pos { long pix; int row; bool ok; };
+    struct Pos { int pix; int row; bool ok; };                // (32-bit: every tensor here has < 2^31 elements)
     auto decode = [&](const TilePos& tp) -> Pos {
       Pos ps;
       if (tp.b >= a.B) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; return ps; }
       const int ox = tp.bx * 30 - 1 + lane;
       ps.row = tp.by * RO + q;
       ps.ok = lane_ok && ox < a.Wout;
-      ps.pix = ((long)tp.b * a.Hout + ps.row) * a.Wout + ox;
+      ps.pix = (tp.b * a.Hout + ps.row) * a.Wout + ox;
       return ps;
     };
     TilePos tp;
@@ -351,20 +358,20 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
       const int kg = sub + 2 * k;
       const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
       if (n_ops > 0 && ps.ok && kg < total_items && ps.row + 4 * tile < a.Hout && !(t.dbg & 8)) {
-        const long pix = ps.pix + tile * tile_pix;
+        const int pix = ps.pix + tile * tile_pix;
         const uint32_t dst = epi_u32 + (uint32_t)k * slot_stride + my_slot;
         if (ia >= 0) {
-          const float* ap = pa + pix * ppa + ch8;
+          const float* ap = pa + (long)(pix * ppa + ch8);
           cp_async16(dst + (uint32_t)ia * 8192u, ap);
           cp_async16(dst + (uint32_t)ia * 8192u + 4096u, ap + 4);
         }
         if (io >= 0) {
-          const float* op = a.out + pix * a.po + ch8;
+          const float* op = a.out + (long)(pix * a.po + ch8);
           cp_async16(dst + (uint32_t)io * 8192u, op);
           cp_async16(dst + (uint32_t)io * 8192u + 4096u, op + 4);
         }
         if (im >= 0) {
-          const float* mp = a.omask + pix * a.pom + ch8;
+          const float* mp = a.omask + (long)(pix * a.pom + ch8);
           cp_async16(dst + (uint32_t)im * 8192u, mp);
           cp_async16(dst + (uint32_t)im * 8192u + 4096u, mp + 4);
         }
@@ -375,13 +382,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
 #pragma unroll
     for (int k = 0; k < C3_SLOTS; ++k) prefetch(cur, k);
 
-    uint32_t tcount = 0;
-    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
+    uint32_t as = 0, aphase = 0;
+    for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
       tp.advance(t);
       const Pos nxt = decode(tp);
-      const uint32_t as = tcount % (uint32_t)t.A;
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N) + ((uint32_t)(q * 32) << 16);
-      if (lane == 0) wait(&bar_acc_full[as], (tcount / (uint32_t)t.A) & 1);
+      if (lane == 0) wait(&bar_acc_full[as], aphase);
       __syncwarp();
       tc_fence_after();
 #pragma unroll
@@ -442,7 +448,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               const float4 p1 = *reinterpret_cast<const float4*>(slot + io * 8192 + 4096);
               r[0] += p0.x; r[1] += p0.y; r[2] += p0.z; r[3] += p0.w; r[4] += p1.x; r[5] += p1.y; r[6] += p1.z; r[7] += p1.w;
             }
-            float4* dst = reinterpret_cast<float4*>(a.out + (cur.pix + tile * tile_pix) * a.po + ch8);
+            float4* dst = reinterpret_cast<float4*>(a.out + (long)((cur.pix + tile * tile_pix) * a.po + ch8));
             dst[0] = make_float4(r[0], r[1], r[2], r[3]);
             dst[1] = make_float4(r[4], r[5], r[6], r[7]);
           }
@@ -452,6 +458,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
+      if (++as == (uint32_t)t.A) { as = 0; aphase ^= 1u; }
       cur = nxt;
     }
     cp_async_wait<0>();
