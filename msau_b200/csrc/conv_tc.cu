@@ -359,6 +359,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
     // =============================================================== producers
     const int planes1 = a.c1 >> 3;
     uint32_t c = 0;                                               // (super-tile, plane) chunk counter
+    int s = 0;                                                    // ring position / phase as counters (no divisions)
+    uint32_t sphase = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
       const int sx = st_i % t.tiles_x;
       const int rest = st_i / t.tiles_x;
@@ -366,10 +368,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
       const int b = rest / t.tiles_y;
       const int in_x0 = sx * (8 * t.T) - a.pad_l, in_y0 = sy * 16 - a.pad_t;
       for (int p = 0; p < t.P; ++p, ++c) {
-        const int s = c % S;
         uint8_t* stg = smem + (size_t)s * t.stage_bytes;
         if (c >= (uint32_t)S) {
-          if (lane == 0) mbar_wait(&bar_empty[s], ((c / S) - 1) & 1);
+          if (lane == 0) mbar_wait(&bar_empty[s], sphase ^ 1u);
           __syncwarp();
         }
         const bool from1 = p < planes1;
@@ -410,6 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         fence_async_smem();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_full[s]);   // one arrival per warp: per-thread arrivals serialise in shared memory
+        if (++s == S) { s = 0; sphase ^= 1u; }
       }
     }
   } else if (warp == PROD_WARPS) {
@@ -423,15 +425,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
       const uint32_t b_hi = (128u >> 4) | (1u << 14);
       const uint32_t a1_lbo = ((plane_bytes >> 4) & 0x3FFF) << 16;
       const uint32_t b_lbo = (((uint32_t)t.N * 16 >> 4) & 0x3FFF) << 16;
-      uint32_t c = 0, tcount = 0;
+      uint32_t tcount = 0, sphase = 0;
+      int s = 0;
       for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
         const uint32_t as = tcount & 1;
         if (tcount >= 2) mbar_wait(&bar_acc_empty[as], ((tcount >> 1) - 1) & 1);
         tc_fence_after();
         const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N);
-        for (int p = 0; p < t.P; ++p, ++c) {
-          const int s = c % S;
-          mbar_wait(&bar_full[s], (c / S) & 1);
+        for (int p = 0; p < t.P; ++p) {
+          mbar_wait(&bar_full[s], sphase);
           tc_fence_after();
           const uint32_t in_addr = smem_u32(smem + (size_t)s * t.stage_bytes);
           const uint32_t in16 = in_addr >> 4, w16a = (in_addr + t.in_bytes) >> 4;
@@ -454,6 +456,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
             if (p == t.P - 1) tc_commit(&bar_acc_full[as]);   // accumulator set complete
           }
           __syncwarp();
+          if (++s == S) { s = 0; sphase ^= 1u; }
         }
       }
     }
@@ -467,7 +470,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
     const int sub = ew >> 2;                        // 0/1: which half of the tiles
     const int row = q * 4 + (lane >> 3);            // lane i of the accumulator = pixel (i / 8, i % 8) of the tile
     const int colx = lane & 7;
-    const int chunks = a.coutp >> 3;                // 8-channel chunks per pixel
+    const int chunks = a.coutp >> 3;                // 8-channel chunks per pixel (a power of two: coutp is 8 .. 128)
+    const int lc = 31 - __clz(chunks);
     const int tiles_mine = (t.T - sub + 1) >> 1;    // tiles sub, sub+2, ...
     const int n_items = tiles_mine * chunks;
     uint32_t tcount = 0;
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
 #pragma unroll
         for (int d = 0; d < EPI_DEPTH; ++d) {
           if (d < n_items) {
-            const int tl = sub + 2 * (d / chunks), chd = d % chunks;
+            const int tl = sub + 2 * (d >> lc), chd = d & (chunks - 1);
             epi_load(items[d], a, rowpix + x0 + tl * 8 + colx, chd * 8, row_ok && (x0 + tl * 8 + colx) < a.Wout);
           }
         }
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
 #pragma unroll
           for (int d = 0; d < EPI_DEPTH; ++d) {
             if (k0 + d < n_items) {
-              const int tl = sub + 2 * ((k0 + d) / chunks), chd = (k0 + d) % chunks;
+              const int tl = sub + 2 * ((k0 + d) >> lc), chd = (k0 + d) & (chunks - 1);
               epi_load(items[d], a, rowpix + x0 + tl * 8 + colx, chd * 8, row_ok && (x0 + tl * 8 + colx) < a.Wout);
             }
           }
@@ -509,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
         for (int d = 0; d < EPI_DEPTH; ++d) {
           const int k = k0 + d;
           if (k < n_items) {                                            // warp-uniform
-            const int tile = sub + 2 * (k / chunks), ch = k % chunks;
+            const int tile = sub + 2 * (k >> lc), ch = k & (chunks - 1);
             float v[8];
             tmem_ld8(acc_base + (uint32_t)(tile * t.N + ch * 8), v);    // warp-collective
             const int ox = x0 + tile * 8 + colx;
@@ -599,6 +603,7 @@ bool conv_tc_supported(const ConvArgs& a) {
     if (a.Hs > 2 * a.Hin || a.Hs < 2 * a.Hin - 1 || a.Ws > 2 * a.Win || a.Ws < 2 * a.Win - 1) return false;
   }
   if ((a.c1 & 7) || (a.c2 & 7) || (a.coutp & 7) || a.coutp > 128) return false;
+  if (a.coutp & (a.coutp - 1)) return false;      // the epilogue decodes (tile, channel chunk) with shifts
   if (!a.src1_nchw && (a.p1 & 3)) return false;
   if (a.Win < 8) return false;
   TcTile t;

@@ -113,6 +113,7 @@ __device__ __forceinline__ uint4 wpack8(const float* x) {
 
 struct WgTile {
   int TR, TC, HHx, HWx, N, ny_planes;       // tile rows/cols, X halo extent, MMA N, dY channel planes
+  int xq, xr, yq, yr;                       // 256 elements ahead = (xq rows, xr cols) of the X tile / (yq, yr) of the dY tile
   int tiles_x, tiles_y, n_tiles, tiles_per_cta;
   uint32_t x_plane_bytes, y_plane_bytes, stage_bytes, tmem_cols;
 };
@@ -184,13 +185,15 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       const int plane_stride = a.Ha * a.Wa;
       const float* xsrc = a.a_nchw ? a.A + ((long)b * a.ca_logical + ca0) * plane_stride : a.A + (long)b * plane_stride * a.pa + ca0;
       const int n_valid = a.ca_logical - ca0;
+      int iy = tid / t.HWx, ix = tid - iy * t.HWx;        // element tid + k * 256 of the halo tile, advanced without divisions
       for (int e0 = tid; e0 < x_px; e0 += WG_THREADS * WU) {
         float v[WU][8];
 #pragma unroll
         for (int u = 0; u < WU; ++u) {
           const int e = e0 + u * WG_THREADS;
-          const int iy = e / t.HWx, ix = e - iy * t.HWx;
           const int gy = in_y0 + iy, gx = in_x0 + ix;
+          iy += t.xq; ix += t.xr;
+          if (ix >= t.HWx) { ix -= t.HWx; ++iy; }
           const bool inb = e < x_px && (unsigned)gy < (unsigned)a.Ha && (unsigned)gx < (unsigned)a.Wa;
           const int lin = gy * a.Wa + gx;
           if (a.a_nchw) {
@@ -228,14 +231,18 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? (pl << 3) - sph * a.cph : (pl << 3));
       const float* msrc = a.maskB ? a.maskB + (long)b * a.Hb * a.Wb * a.pmb + (pl << 3) : nullptr;
       uint8_t* ydst = yh + (size_t)pl * t.y_plane_bytes;
+      int yr_ = (tid / t.ny_planes) / t.TC, yc_ = (tid / t.ny_planes) - yr_ * t.TC;   // pixel of element tid + k * 256
       for (int e0 = tid; e0 < total; e0 += WG_THREADS * WU) {
         float v[WU][8];
         float4 mk[WU][2];
+        int so[WU];
 #pragma unroll
         for (int u = 0; u < WU; ++u) {
           const int e = e0 + u * WG_THREADS;
-          const int px = e / t.ny_planes;
-          const int r = px / t.TC, c = px - r * t.TC;
+          const int r = yr_, c = yc_;
+          so[u] = r * t.TC + c;
+          yr_ += t.yq; yc_ += t.yr;
+          if (yc_ >= t.TC) { yc_ -= t.TC; ++yr_; }
           const int vy = qy0 + r, vx = qx0 + c;
           const int gy = vy * smul + spy, gx = vx * smul + spx;
           const bool inb = e < total && vy < a.Hq && vx < a.Wq && gy < a.Hb && gx < a.Wb;
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
 #pragma unroll
             for (int k = 0; k < 8; ++k) bacc[k] += v[u][k];
           }
-          *reinterpret_cast<uint4*>(ydst + (e / t.ny_planes) * 16) = wpack8(v[u]);
+          *reinterpret_cast<uint4*>(ydst + so[u] * 16) = wpack8(v[u]);
         }
       }
     }
@@ -1120,6 +1127,8 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   t.y_plane_bytes = (uint32_t)(t.TR * t.TC * 16);
   const uint32_t y_bytes = (uint32_t)t.ny_planes * t.y_plane_bytes;
   t.stage_bytes = (t.x_plane_bytes + y_bytes + 1023) / 1024 * 1024;
+  t.xq = WG_THREADS / t.HWx; t.xr = WG_THREADS % t.HWx;
+  { const int dpx = WG_THREADS / t.ny_planes; t.yq = dpx / t.TC; t.yr = dpx % t.TC; }
   t.tiles_x = cdiv(a.Wq, t.TC);
   t.tiles_y = cdiv(a.Hq, t.TR);
   t.n_tiles = t.tiles_x * t.tiles_y * a.B;
