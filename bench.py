@@ -282,6 +282,14 @@ def main():
         else:
             ach = tv["flops"] / (tv["ms"] * 1e-3) / 1e12
             roof = dict(bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=None)
+        try:   # DRAM bytes per launch of this kernel family, from the committed ncu launch list of the same step
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json"))).get(top)
+            if tr:
+                roof["traffic"] = tr["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/traffic_r1.json: " + tr["source"]
+                roof["algorithmic_bytes_per_launch"] = tv["bytes"] / tv["launches"]
+        except Exception:
+            pass
         roof.update(kernel=top, peak_source=pk["src"], launches=tv["launches"], avg_launch_ms=tv["ms"] / tv["launches"],
                     share_of_step=tv["ms"] / tot, pass_="separate K-step pass with CUDA events around every launch")
     barrier()
