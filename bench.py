@@ -227,17 +227,18 @@ def main():
         wb = raster.BoxBatch(words, dev, with_chars=True)
         lb = raster.BoxBatch(lines, dev, with_chars=False, with_labels=True)
         geom = wb.geometry()
-        g = raster.raster_features(wb, geom, table, (H, W), True, "nhwc")
+        # the chargrid as the int16 channel-id map (feature table = identity): the structured first layer consumes it directly
+        g = raster.raster_features(wb, geom, table, (H, W), True, "ids")
         lab = raster.raster_labels(lb, geom, (H, W))
         h2d[0] = wb.h_bytes + lb.h_bytes
-        loss = model.train_step(g, lab, layout=1, process_group=pg, world_size=world)
+        loss = model.train_step(g, lab, layout=2, process_group=pg, world_size=world)
         return float(loss)            # D2H read of the step's result
 
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, K) / K
     e2e = dict(value=world * P / (ms_e2e * 1e-3), unit="pages/s", h2d_bytes_per_step=h2d[0], d2h_bytes_per_step=4,
-               input="host page records (CSR boxes + char ids, pinned) rasterised on the device (R1) every step")
+               input="host page records (CSR boxes + char ids, pinned) rasterised on the device (R1 -> int16 id map) every step")
 
     # ---- e2e with the reference's literal input format: dense fp32 NCHW page tensor in pinned host memory
     e2e_dense = None

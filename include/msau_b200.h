@@ -63,7 +63,9 @@ int msau_param_info(const MsauPlan* plan, int idx, long long* offset, long long*
 int msau_workspace_bytes(const MsauPlan* plan, int training, size_t* bytes);
 
 /* MSAUWrapper.forward (model/model.py:435-437) = MSAUNet.forward (:378-396) + Softmax(dim=1).
- *   x            [B, channels, H, W] fp32 (x_layout 0, NCHW) or [B, H, W, round_up(channels,4)] (1, NHWC)
+ *   x            [B, channels, H, W] fp32 (x_layout 0, NCHW) or [B, H, W, round_up(channels,4)] (1, NHWC), or the int16 id map
+ *                [B, H, W] of a one-hot chargrid (2: channel index per pixel, -1 = all-zero pixel; what
+ *                msau_raster_features writes with layout 2)
  *   params       flat fp32 parameter buffer (msau_param_count floats)
  *   logits, aux  [B, n_class, H, W] fp32 NCHW, either may be NULL
  *   probs        [B, n_class, H, W] softmax over classes, or NULL

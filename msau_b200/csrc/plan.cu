@@ -142,6 +142,7 @@ struct MsauPlan {
   std::vector<Tensor> all_tensors;
   cudaStream_t st = nullptr;
   const int* first_skip = nullptr;   // set by msau_forward when the structured first layer ran (device flag)
+  const short* first_ids = nullptr;  // ... and the id map it used (plan workspace, or the caller's with x_layout 2)
 
   Tensor alloc(int C, int Hh, int Ww) {
     Tensor t;
@@ -778,6 +779,18 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
         const int* skip = nullptr;
+        p->first_ids = nullptr;
+        if (x_layout == 2) {
+          // the caller already holds the id map (e.g. from the rasteriser, layout 2): no dense tensor exists at all
+          if (p->ids_off < 0) { set_error("forward: x_layout 2 (id map) needs a first layer with 8 output channels"); return MSAU_ERR_UNSUPPORTED; }
+          int* flag = reinterpret_cast<int*>(p->misc + p->ids_off) + (((long)p->B * p->H * p->W + 1) / 2 + 8);
+          MSAU_CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), p->st));
+          count_launch(1);
+          MSAU_TRY(launch_first_fwd(reinterpret_cast<const short*>(x), flag, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b, cfg.channels, c1,
+                                    p->B, p->H, p->W, p->A(L.z1), L.z1.C, p->st));
+          p->first_skip = flag;
+          p->first_ids = reinterpret_cast<const short*>(x);
+        } else {
         if (g_use_tc && g_structured && p->ids_off >= 0) {
           // chargrid input: scan for one-hot structure, then the id-gather conv; the dense kernel below skips itself
           short* ids = reinterpret_cast<short*>(p->misc + p->ids_off);
@@ -787,10 +800,12 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
           MSAU_TRY(launch_first_fwd(ids, flag, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b, cfg.channels, c1, p->B, p->H, p->W, p->A(L.z1),
                                     L.z1.C, p->st));
           skip = flag;
+          p->first_ids = ids;
         }
         p->first_skip = skip;
         MSAU_TRY(conv_same(p, x, c1, c1, x_layout == 0, cfg.channels, nullptr, 0, 0, p->pk + L.conv1.pk_w, p->pk + L.conv1.pk_b,
                            p->A(L.z1), L.z1.C, L.conv1.coutp, p->H, p->W, 3, 1, 1, o, L.conv1.tc_w, -1, skip));
+        }
       } else {
         const Tensor& src = l == 0 ? prev->logits : blk.down[l - 1].pooled;
         MSAU_TRY(layer_fwd(p, L.conv1, src, nullptr, L.z1, o));
@@ -942,11 +957,11 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
         if (p->first_skip) {
-          const short* ids = reinterpret_cast<const short*>(p->misc + p->ids_off);
           count_launch(1);
-          MSAU_TRY(launch_first_wgrad(ids, p->first_skip, p->G(L.z1), L.z1.C, cfg.channels, L.conv1.cout, p->B, p->H, p->W,
+          MSAU_TRY(launch_first_wgrad(p->first_ids, p->first_skip, p->G(L.z1), L.z1.C, cfg.channels, L.conv1.cout, p->B, p->H, p->W,
                                       p->gparams + L.conv1.w_off, p->gparams + L.conv1.b_off, p->st));
         }
+        if (x_layout != 2)
         MSAU_TRY(layer_wgrad(p, L.conv1, 1, x, c1, x_layout == 0, cfg.channels, false, p->G(L.z1), L.z1.C, nullptr, 0, p->H, p->W, -1, -1,
                              0, -1, -1, p->first_skip));
       } else {

@@ -164,6 +164,17 @@ __global__ void __launch_bounds__(256) feature_fill_nhwc_kernel(const int32_t* _
   reinterpret_cast<float4*>(grid)[idx] = v;
 }
 
+// layout 2: the feature-table ROW of the owning box / character per pixel (-1 = background) instead of the row's values.
+// With a one-hot table whose row r is e_r (np.eye: the chargrid case) this is the id map the structured first layer of the
+// network consumes directly (x_layout = 2 of msau_forward), so the dense [D, H, W] grid is never written.
+__global__ void __launch_bounds__(256) feature_ids_kernel(const int32_t* __restrict__ owner, const int32_t* __restrict__ row_of,
+                                                           long total, int16_t* __restrict__ ids) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int o = owner[idx];
+  ids[idx] = o > 0 ? (int16_t)row_of[o - 1] : (int16_t)-1;
+}
+
 __global__ void __launch_bounds__(256) label_fill_kernel(const int32_t* __restrict__ owner, const int32_t* __restrict__ labels,
                                                           long total, uint8_t* __restrict__ out) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -350,7 +361,9 @@ extern "C" int msau_raster_features(const double* x, const double* y, const doub
     feature_owner_kernel<<<cdiv(n_boxes, 8), 256, 0, st>>>(x, y, w, h, page_ptr, n_pages, n_boxes, char_ptr, geom, use_min_scale,
                                                            out_h, out_w, owner_scratch);
   const int32_t* row_of = char_ptr ? char_feat : feat_row;
-  if (layout == 0) {
+  if (layout == 2) {
+    feature_ids_kernel<<<cdiv(total, 256), 256, 0, st>>>(owner_scratch, row_of, total, reinterpret_cast<int16_t*>(grid));
+  } else if (layout == 0) {
     feature_fill_nchw_kernel<<<cdiv(total, 256), 256, 0, st>>>(owner_scratch, row_of, feat_table, feat_dim, npix, total, grid);
   } else {
     const int Dp = round_up(feat_dim, 4);

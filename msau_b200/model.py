@@ -284,6 +284,10 @@ class MSAUWrapper(torch.nn.Module):
     def _check_input(self, x: torch.Tensor, layout: int):
         if not x.is_cuda or x.device != self._flat.device:
             raise _lib.MsauError("input must be a CUDA tensor on the model's device (no CPU fallback)")
+        if layout == 2:
+            if x.dtype != torch.int16 or x.dim() != 3:
+                raise TypeError("layout 2 expects an int16 [B, H, W] channel-id map (-1 = empty pixel)")
+            return tuple(x.shape)
         if x.dtype != torch.float32:
             raise TypeError("input must be float32")
         if layout == 0:

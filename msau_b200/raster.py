@@ -99,13 +99,19 @@ class BoxBatch:
 
 def raster_features(boxes: BoxBatch, geom: torch.Tensor, feat_table: torch.Tensor, out_hw: Tuple[int, int], use_chars: bool,
                     layout: str = "nchw", feat_row: Optional[torch.Tensor] = None, owner: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """R1 (use_chars) / R2 feature grid.  feat_table: fp64 CUDA [rows, D].  Returns fp32 [n,D,H,W] or [n,H,W,Dp]."""
+    """R1 (use_chars) / R2 feature grid.  feat_table: fp64 CUDA [rows, D].  Returns fp32 [n,D,H,W] ("nchw") or [n,H,W,Dp]
+    ("nhwc"), or -- layout "ids" -- the int16 [n,H,W] map of feature-table ROW indices (-1 = background): for a one-hot
+    table with row r = e_r (``np.eye``, the chargrid) that is the channel id map ``MSAUWrapper.train_step(..., layout=2)``
+    consumes without the dense grid ever being written."""
     H, W = out_hw
     D = feat_table.shape[1]
     dev = boxes.device
     n = boxes.n_pages
-    lay = 0 if layout == "nchw" else 1
-    grid = torch.empty((n, D, H, W) if lay == 0 else (n, H, W, (D + 3) // 4 * 4), dtype=torch.float32, device=dev)
+    lay = {"nchw": 0, "nhwc": 1, "ids": 2}[layout]
+    if lay == 2:
+        grid = torch.empty((n, H, W), dtype=torch.int16, device=dev)
+    else:
+        grid = torch.empty((n, D, H, W) if lay == 0 else (n, H, W, (D + 3) // 4 * 4), dtype=torch.float32, device=dev)
     if owner is None:
         owner = torch.empty((n * H * W,), dtype=torch.int32, device=dev)
     if not use_chars and feat_row is None:

@@ -107,6 +107,37 @@ def test_raster_batch_matches_oracle():
             assert got[h3:].sum() == 0 and got[:, w3:].sum() == 0
 
 
+def test_id_map_path_equals_dense_path():
+    """The rasteriser's id map (layout "ids") is the arg-max of its dense one-hot grid, and a train step fed with the id map
+    (x_layout 2: structured first layer, no dense tensor) gives the same loss and parameters as the dense-grid step."""
+    import msau_b200
+    from oracle import model as om
+    wp, lp = [], []
+    for seed, n in ((3, 60), (9, 45)):
+        w, l = orr.synth_page(seed, 64, 64, n)
+        wp.append(w); lp.append(l)
+    table = torch.eye(96, dtype=torch.float64, device="cuda")
+    words = raster.BoxBatch(wp, "cuda", with_chars=True)
+    lines = raster.BoxBatch(lp, "cuda", with_chars=False, with_labels=True)
+    geom = words.geometry()
+    dense = raster.raster_features(words, geom, table, (64, 64), True, "nchw")
+    ids = raster.raster_features(words, geom, table, (64, 64), True, "ids")
+    label = raster.raster_labels(lines, geom, (64, 64))
+    want = torch.where(dense.sum(1) > 0, dense.argmax(1), torch.full_like(dense.argmax(1), -1))
+    assert ids.dtype == torch.int16 and torch.equal(ids.long(), want)
+    cfg = om.MsauConfig()
+    sd = om.init_state_dict(cfg, 2)
+    kw = dict(final_act="softmax", featRoot=8, scale_space_num=4, res_depth=2)
+    ma = msau_b200.MSAUWrapper(96, 5, kw); ma.load_state_dict(sd); ma = ma.cuda().train()
+    mb = msau_b200.MSAUWrapper(96, 5, kw); mb.load_state_dict(sd); mb = mb.cuda().train()
+    la = float(ma.train_step(dense, label.long()))
+    lb_ = float(mb.train_step(ids, label.long(), layout=2))
+    assert abs(la - lb_) <= 1e-6 * max(1.0, abs(la))
+    for (k, pa), pb in zip(ma.named_parameters(), mb.parameters()):
+        tol = 2.5e-4 if k.endswith("attention_block.f.conv.bias") else 2e-6
+        assert (pa.detach() - pb.detach()).abs().max().item() <= tol, k
+
+
 @pytest.fixture(scope="module")
 def mgold(golden_dir):
     z = np.load(os.path.join(golden_dir, "morph.npz"))
