@@ -18,6 +18,7 @@
 #include "../../include/msau_b200.h"
 #include "attention.cuh"
 #include "common.cuh"
+#include "conv1x1.cuh"
 #include "conv_tc.cuh"
 #include "first_layer.cuh"
 #include "optim.cuh"
@@ -317,6 +318,7 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 // ------------------------------------------------------------------ launch helpers
 static bool g_use_tc = true;
 static bool g_structured = true;   // one-hot inputs: id-gather first layer (first_layer.cu)
+static bool g_use_pw = true;       // 1x1 convs on the fp32 streaming kernel (conv1x1.cu)
 static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
 static int g_c3_max = 16;        // ... for at most this many output channels
 
@@ -349,6 +351,7 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.skip_flag = skip_flag;
   count_launch(1);
   { static bool init = false; if (!init) { const char* e = getenv("MSAU_C3_MAX"); if (e) g_c3_max = atoi(e); init = true; } }
+  if (g_use_tc && g_use_pw && k == 1 && conv1x1_supported(a)) return launch_conv1x1(a, p->st);
   if (g_use_tc && g_use_c3 && t3_off >= 0 && coutp <= g_c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
   if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
   return launch_conv(a, p->st);
@@ -1040,6 +1043,7 @@ extern "C" int msau_set_option(const char* name, int value) {
   MSAU_CHECK_ARG(name, "set_option: null name");
   if (!strcmp(name, "tensor_core_conv")) { g_use_tc = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_fold")) { g_use_c3 = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "pointwise_conv")) { g_use_pw = value != 0; return MSAU_OK; }
   if (!strcmp(name, "structured_first_layer")) { g_structured = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
