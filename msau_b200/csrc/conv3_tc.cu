@@ -47,6 +47,7 @@ constexpr int C3_MAX_STAGES = 3;
 constexpr int C3_SLOTS = 4;          // epilogue work items per thread and super-tile
 
 struct C3Tile {
+  int KS, pad, OW, NI;                // kernel size (3 or 4), SAME padding before, output columns per block (32 - KS + 1), MMAs per tile-plane
   int T, N, CP, RI, P, stages, D, A;  // tiles per super-tile, MMA N, padded cout, halo rows, input planes, image / raw / accumulator ring depth
   int blocks_x, blocks_y, n_super;
   int dgx, dgy, dgb;                  // gridDim.x decomposed in (block column, block row, page) steps
@@ -131,7 +132,7 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 
 // EPI: 0 = epilogue driven by run-time flags; 1 = bias; 2 = bias + ReLU; 3 = bias + residual + ReLU; 4 = ReLU mask; 5 = ReLU mask + add
 // LDU: raw pixels per producer thread and plane (3: T <= 4 tiles, 6: T = 8)
-template <int EPI, int LDU>
+template <int EPI, int LDU, int KS>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     uint32_t d_issue = 0;                                          // raw slot of the next issue (bytes)
     auto issue = [&](const TilePos& tp, int p) {
       if (tp.b < a.B && !(t.dbg & 2)) {
-        const int in_x0 = tp.bx * 30 - 1, in_y0 = tp.by * RO - 1;
+        const int in_x0 = tp.bx * t.OW - t.pad, in_y0 = tp.by * RO - t.pad;
         const bool from1 = p < planes1;
         const float* base = from1 ? a.src1 : a.src2;
         const int pitch = from1 ? a.p1 : a.p2;
@@ -293,9 +294,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
           if (!(t.dbg & 1)) {
             // instruction-major / tile-minor: consecutive instructions hit different accumulators
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const uint32_t ky = i < 3 ? (uint32_t)i : (i == 3 ? 0u : 2u);
-              const uint32_t lbo = i == 3 ? lbo_row : lbo_plane;
+            for (int i = 0; i < KS + (KS + 1) / 2; ++i) {
+              // i < KS: A = [hi(ky) | lo(ky)];  then pairs: A = [hi(2j) | hi(2j+1)] (next image row), the odd one out: [hi | lo] x [Wlo ; 0]
+              const uint32_t ky = i < KS ? (uint32_t)i : (uint32_t)(2 * (i - KS));
+              const uint32_t lbo = (i >= KS && 2 * (i - KS) + 1 < KS) ? lbo_row : lbo_plane;
               const uint32_t b_lo = ((w16a + (uint32_t)i * 2u * N) & 0x3FFF) | b_lbo;
               const uint32_t acc = (p > 0 || i > 0) ? 1u : 0u;
               for (int tile = mw; tile < t.T; tile += C3_MMA_WARPS) {
@@ -328,14 +330,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const uint32_t epi_u32 = smem_u32(epi);
     const uint32_t slot_stride = (uint32_t)(G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0))) * 8192u;  // bytes between consecutive items' slots
     const uint32_t my_slot = (uint32_t)et * 16u;
-    const bool lane_ok = lane >= 1 && lane <= 30;
+    const bool lane_ok = lane >= t.pad && lane < t.pad + t.OW;
     const int tile_pix = 4 * a.Wout;                         // pixel distance between consecutive tiles (4 rows)
     // position of a super-tile for this thread: pixel index of its tile-0 output, first output row, column validity
     struct Pos { int pix; int row; bool ok; };                // (32-bit: every tensor here has < 2^31 elements)
     auto decode = [&](const TilePos& tp) -> Pos {
       Pos ps;
       if (tp.b >= a.B) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; return ps; }
-      const int ox = tp.bx * 30 - 1 + lane;
+      const int ox = tp.bx * t.OW - t.pad + lane;
       ps.row = tp.by * RO + q;
       ps.ok = lane_ok && ox < a.Wout;
       ps.pix = (tp.b * a.Hout + ps.row) * a.Wout + ox;
@@ -396,16 +398,32 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         cp_async_wait<C3_SLOTS - 1>();                         // this item's extras have landed
         if (kg < total_items) {                                // warp-uniform
           const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
-          float v0[8], v1[8], v2[8];
+          float vk[KS][8];
           const uint32_t col = (uint32_t)(tile * t.N + ch8);
-          tmem_ld8(acc_base + col, v0);
-          tmem_ld8(acc_base + col + (uint32_t)t.CP, v1);
-          tmem_ld8(acc_base + col + (uint32_t)(2 * t.CP), v2);
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) tmem_ld8(acc_base + col + (uint32_t)(kx * t.CP), vk[kx]);
           tmem_ld_wait();
           float r[8];
+          if (KS == 3) {
+            // out[x] = D[x-1][kx=0] + D[x][kx=1] + D[x+1][kx=2]
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            r[i] = __shfl_up_sync(0xffffffffu, v0[i], 1) + v1[i] + __shfl_down_sync(0xffffffffu, v2[i], 1);
+            for (int i = 0; i < 8; ++i)
+              r[i] = __shfl_up_sync(0xffffffffu, vk[0][i], 1) + vk[1][i] + __shfl_down_sync(0xffffffffu, vk[KS - 1][i], 1);
+          } else {
+            // out[x] = sum_kx D[x + kx - pad][kx], pad = 1 (forward of the 4x4 SAME conv) or 2 (its data gradient)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float acc = 0.f;
+#pragma unroll
+              for (int kx = 0; kx < KS; ++kx) {
+                const int sh = kx - t.pad;                      // warp-uniform
+                const float up = __shfl_up_sync(0xffffffffu, vk[kx][i], (unsigned)(sh < 0 ? -sh : 0));
+                const float dn = __shfl_down_sync(0xffffffffu, vk[kx][i], (unsigned)(sh > 0 ? sh : 0));
+                acc += sh < 0 ? up : (sh > 0 ? dn : vk[kx][i]);
+              }
+              r[i] = acc;
+            }
+          }
           if (cur.ok && cur.row + 4 * tile < a.Hout && !(t.dbg & 4)) {
             if (G || EPI <= 3) {
               const float4 b0 = *reinterpret_cast<const float4*>(bias_s + ch8);
@@ -471,15 +489,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
 bool c3_configure(const ConvArgs& a, C3Tile& t) {
   t.CP = a.coutp;
   if (!(t.CP == 8 || t.CP == 16 || t.CP == 32 || t.CP == 64)) return false;
-  t.N = round_up(3 * t.CP, 16);
+  t.KS = a.kh; t.pad = a.pad_l; t.OW = 32 - (t.KS - 1); t.NI = t.KS + (t.KS + 1) / 2;
+  t.N = round_up(t.KS * t.CP, 16);
   t.T = 8 / (t.CP >> 3);
   while (t.T > 1 && 4 * (t.T / 2) >= a.Hout) t.T /= 2;       // short maps: do not pay for rows that do not exist
-  t.RI = 4 * t.T + 2;
+  t.RI = 4 * t.T + t.KS - 1;
   t.P = (a.c1 + a.c2) / 8;
   t.plane_bytes = (uint32_t)t.RI * 512;
   t.in_bytes = 2 * t.plane_bytes;
-  t.raw_bytes = (uint32_t)((t.T > 4 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);    // [u][half][thread] x 16 B
-  t.w_bytes = 5u * (uint32_t)t.N * 32;
+  t.raw_bytes = (uint32_t)((t.RI > 18 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);    // [u][half][thread] x 16 B, rows warp + 6 u
+  t.w_bytes = (uint32_t)t.NI * (uint32_t)t.N * 32;
   t.w_total = (uint32_t)t.P * t.w_bytes;
   t.n_ops = 0; t.ia = t.io = t.im = -1;
   if (a.res || a.add) t.ia = t.n_ops++;
@@ -494,7 +513,7 @@ bool c3_configure(const ConvArgs& a, C3Tile& t) {
   }
   if (total() > 216 * 1024) return false;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_TC_DEBUG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
-  t.blocks_x = cdiv(a.Wout, 30);
+  t.blocks_x = cdiv(a.Wout, t.OW);
   t.blocks_y = cdiv(a.Hout, 4 * t.T);
   t.n_super = t.blocks_x * t.blocks_y * a.B;
   t.A = 512 / (t.T * t.N);
@@ -509,7 +528,9 @@ bool c3_configure(const ConvArgs& a, C3Tile& t) {
 }  // namespace
 
 bool conv3_tc_supported(const ConvArgs& a) {
-  if (a.kh != 3 || a.kw != 3 || a.dil != 1 || a.stride != 1 || a.pad_t != 1 || a.pad_l != 1) return false;
+  if (a.kh != a.kw || (a.kh != 3 && a.kh != 4) || a.dil != 1 || a.stride != 1 || a.pad_t != a.pad_l) return false;
+  if (a.kh == 3 ? a.pad_l != 1 : (a.pad_l != 1 && a.pad_l != 2)) return false;
+  if (a.kh == 4 && a.coutp != 8) return false;     // the 4x4 heads (8 -> n_class) and their data gradient
   if ((a.res && a.add) || a.addmask || a.mask1 || a.src1_nchw || a.s2d || a.d2s) return false;
   if (a.osy != 1 || a.oy0 != 0 || a.ox0 != 0) return false;
   if (a.Hq != a.Hin || a.Wq != a.Win || a.Hout != a.Hin || a.Wout != a.Win) return false;
@@ -533,8 +554,8 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   const double npix = (double)a.B * a.Hin * a.Win;
   double bytes = npix * (a.c1 + a.c2) * 4.0;
   bytes += npix * a.coutp * 4.0 * (1 + (a.res ? 1 : 0) + (a.omask ? 1 : 0) + (a.add ? 1 : 0) + (a.accumulate ? 1 : 0));
-  ProfScope ps("conv3_tc_kernel", a.c1 + a.c2, a.coutp, 3, 1, a.Wout, (a.relu1 ? 2 : 0) + (general ? 1 : 0),
-               2.0 * npix * 9 * (a.c1 + a.c2) * a.coutp, bytes, st);
+  ProfScope ps("conv3_tc_kernel", a.c1 + a.c2, a.coutp, a.kh, 1, a.Wout, (a.relu1 ? 2 : 0) + (general ? 1 : 0),
+               2.0 * npix * a.kh * a.kw * (a.c1 + a.c2) * a.coutp, bytes, st);
   // epilogue specialisation (the flag-driven variant covers everything else, e.g. accumulation into a touched gradient)
   int epi = 0;
   const bool bias = a.bias != nullptr;
@@ -544,14 +565,18 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
     else if (!bias && a.omask && !a.res && !a.relu && !a.relu2) epi = a.add ? 5 : 4;
   }
   { static int gen = -1; if (gen < 0) { const char* e = getenv("MSAU_C3_GENERIC"); gen = e ? atoi(e) : 0; } if (gen) epi = 0; }
-  const int ldu = t.T > 4 ? 6 : 3;
-#define MSAU_C3_LAUNCH(E, L)                                                                                                   \
+  const int ldu = t.RI > 18 ? 6 : 3;
+#define MSAU_C3_LAUNCH(E, L, K)                                                                                                   \
   {                                                                                                                            \
     static bool attr = false;                                                                                                  \
-    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
-    conv3_tc_kernel<E, L><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);                                                          \
+    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    conv3_tc_kernel<E, L, K><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);                                                          \
   }
-#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6) else MSAU_C3_LAUNCH(E, 3) }
+#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3) else MSAU_C3_LAUNCH(E, 3, 3) }
+#define MSAU_C3_K4(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 4) else MSAU_C3_LAUNCH(E, 3, 4) }
+  if (t.KS == 4) {
+    if (epi == 1) MSAU_C3_K4(1) else MSAU_C3_K4(0)
+  } else
   switch (epi) {
     case 1: MSAU_C3_LDU(1) break;
     case 2: MSAU_C3_LDU(2) break;
@@ -561,6 +586,7 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
     default: MSAU_C3_LDU(0) break;
   }
 #undef MSAU_C3_LDU
+#undef MSAU_C3_K4
 #undef MSAU_C3_LAUNCH
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -579,7 +605,8 @@ __global__ void __launch_bounds__(256) pack_tc3_kernel(const float* __restrict__
   }
   const TcPackDesc d = descs[lo];
   const int N = d.N;
-  const long per_plane = 5L * N * 16;
+  const int KS = d.taps == 16 ? 4 : 3, NI = KS + (KS + 1) / 2;
+  const long per_plane = (long)NI * N * 16;
   const long total = (long)(d.cin / 8) * per_plane;
   const long e = (blk - d.blk0) * 256 + threadIdx.x;
   if (e >= total) return;
@@ -591,13 +618,14 @@ __global__ void __launch_bounds__(256) pack_tc3_kernel(const float* __restrict__
   const int kx = n / d.coutp, co = n - kx * d.coutp;
   int ky = -1;
   bool want_lo = false;
-  if (img < 3) ky = img;
+  if (img < KS) ky = img;
   else {
     want_lo = true;
-    ky = img == 3 ? chunk : (chunk == 0 ? 2 : -1);
+    ky = 2 * (img - KS) + chunk;
+    if (ky >= KS) ky = -1;
   }
   float w = 0.f;
-  if (ky >= 0 && kx < 3) w = pk[d.src_off + ((long)(ky * 3 + kx) * d.cin + 8 * p + k) * d.coutp + co];
+  if (ky >= 0 && kx < KS) w = pk[d.src_off + ((long)(ky * KS + kx) * d.cin + 8 * p + k) * d.coutp + co];
   const __nv_bfloat16 h = __float2bfloat16_rn(w);
   const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w - __bfloat162float(h)) : h;
   pktc[d.dst_off + e] = __bfloat16_as_ushort(out);

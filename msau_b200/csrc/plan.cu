@@ -207,12 +207,12 @@ static long add_tc(MsauPlan* p, long src_off, int taps, int cin, int coutp) {
   return d.dst_off;
 }
 
-static long add_tc3(MsauPlan* p, long src_off, int cin, int coutp) {
-  if (cin % 8 != 0 || !(coutp == 8 || coutp == 16 || coutp == 32 || coutp == 64)) return -1;
+static long add_tc3(MsauPlan* p, long src_off, int cin, int coutp, int ks = 3) {
+  if (cin % 8 != 0 || !(coutp == 8 || coutp == 16 || coutp == 32 || coutp == 64) || (ks == 4 && coutp != 8)) return -1;
   TcPackDesc d;
-  d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = 9; d.cin = cin; d.coutp = coutp;
-  d.N = round_up(3 * coutp, 16);
-  const long elems = (long)(cin / 8) * 5 * d.N * 16;
+  d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = ks * ks; d.cin = cin; d.coutp = coutp;
+  d.N = round_up(ks * coutp, 16);
+  const long elems = (long)(cin / 8) * (ks + (ks + 1) / 2) * d.N * 16;
   d.blk0 = p->t3_blocks;
   p->t3_blocks += cdiv(elems, 256);
   p->tc_elems += (elems + 127) / 128 * 128;
@@ -250,10 +250,10 @@ static void setup_conv(MsauPlan* p, ConvLayer& L, int cout, int cin1, int cin2, 
   L.tc_w = add_tc(p, L.pk_w, k * k, cinp, L.coutp);
   if (L.pk_d1 >= 0) L.tc_d1 = add_tc(p, L.pk_d1, k * k, L.coutp, L.c1p);
   if (L.pk_d2 >= 0) L.tc_d2 = add_tc(p, L.pk_d2, k * k, L.coutp, L.c2p);
-  if (k == 3 && dil == 1) {
-    L.t3_w = add_tc3(p, L.pk_w, cinp, L.coutp);
-    if (L.pk_d1 >= 0) L.t3_d1 = add_tc3(p, L.pk_d1, L.coutp, L.c1p);
-    if (L.pk_d2 >= 0) L.t3_d2 = add_tc3(p, L.pk_d2, L.coutp, L.c2p);
+  if ((k == 3 || k == 4) && dil == 1) {
+    L.t3_w = add_tc3(p, L.pk_w, cinp, L.coutp, k);
+    if (L.pk_d1 >= 0) L.t3_d1 = add_tc3(p, L.pk_d1, L.coutp, L.c1p, k);
+    if (L.pk_d2 >= 0) L.t3_d2 = add_tc3(p, L.pk_d2, L.coutp, L.c2p, k);
   }
 }
 
