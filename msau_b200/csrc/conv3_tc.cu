@@ -132,7 +132,7 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 
 // EPI: 0 = epilogue driven by run-time flags; 1 = bias; 2 = bias + ReLU; 3 = bias + residual + ReLU; 4 = ReLU mask; 5 = ReLU mask + add
 // LDU: raw pixels per producer thread and plane (3: T <= 4 tiles, 6: T = 8)
-template <int EPI, int LDU, int KS>
+template <int EPI, int LDU, int KS, int PAD>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
@@ -416,10 +416,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               float acc = 0.f;
 #pragma unroll
               for (int kx = 0; kx < KS; ++kx) {
-                const int sh = kx - t.pad;                      // warp-uniform
-                const float up = __shfl_up_sync(0xffffffffu, vk[kx][i], (unsigned)(sh < 0 ? -sh : 0));
-                const float dn = __shfl_down_sync(0xffffffffu, vk[kx][i], (unsigned)(sh > 0 ? sh : 0));
-                acc += sh < 0 ? up : (sh > 0 ? dn : vk[kx][i]);
+                constexpr int dummy = 0; (void)dummy;
+                const int sh = kx - PAD;                        // compile-time after unrolling
+                if (sh < 0) acc += __shfl_up_sync(0xffffffffu, vk[kx][i], (unsigned)(-sh));
+                else if (sh > 0) acc += __shfl_down_sync(0xffffffffu, vk[kx][i], (unsigned)sh);
+                else acc += vk[kx][i];
               }
               r[i] = acc;
             }
@@ -566,16 +567,17 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   }
   { static int gen = -1; if (gen < 0) { const char* e = getenv("MSAU_C3_GENERIC"); gen = e ? atoi(e) : 0; } if (gen) epi = 0; }
   const int ldu = t.RI > 18 ? 6 : 3;
-#define MSAU_C3_LAUNCH(E, L, K)                                                                                                   \
+#define MSAU_C3_LAUNCH(E, L, K, PD)                                                                                                   \
   {                                                                                                                            \
     static bool attr = false;                                                                                                  \
-    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
-    conv3_tc_kernel<E, L, K><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);                                                          \
+    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L, K, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    conv3_tc_kernel<E, L, K, PD><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);                                                          \
   }
-#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3) else MSAU_C3_LAUNCH(E, 3, 3) }
-#define MSAU_C3_K4(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 4) else MSAU_C3_LAUNCH(E, 3, 4) }
+#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3, 1) else MSAU_C3_LAUNCH(E, 3, 3, 1) }
+#define MSAU_C3_K4(E, PD) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 4, PD) else MSAU_C3_LAUNCH(E, 3, 4, PD) }
   if (t.KS == 4) {
-    if (epi == 1) MSAU_C3_K4(1) else MSAU_C3_K4(0)
+    if (t.pad == 1) { if (epi == 1) MSAU_C3_K4(1, 1) else MSAU_C3_K4(0, 1) }
+    else { if (epi == 1) MSAU_C3_K4(1, 2) else MSAU_C3_K4(0, 2) }
   } else
   switch (epi) {
     case 1: MSAU_C3_LDU(1) break;
