@@ -222,10 +222,13 @@ def main():
 
     # ---- e2e: host page records -> device every step (public API: raster.rasterize_word_chargrid + train_step)
     h2d = [0]
+    # the step's inputs in pinned host memory (what a data loader hands over): CSR page records, ~300 KB per 16 pages
+    host_words = raster.HostBatch(words, with_chars=True)
+    host_lines = raster.HostBatch(lines, with_chars=False, with_labels=True)
 
     def step_e2e():
-        wb = raster.BoxBatch(words, dev, with_chars=True)
-        lb = raster.BoxBatch(lines, dev, with_chars=False, with_labels=True)
+        wb = raster.BoxBatch.from_host(host_words, dev)
+        lb = raster.BoxBatch.from_host(host_lines, dev)
         geom = wb.geometry()
         # the chargrid as the int16 channel-id map (feature table = identity): the structured first layer consumes it directly
         g = raster.raster_features(wb, geom, table, (H, W), True, "ids")

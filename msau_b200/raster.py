@@ -23,7 +23,6 @@ def _dev(device=None) -> torch.device:
     return torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
 
 
-_STAGING: Dict[Tuple[int, int], torch.Tensor] = {}
 
 
 def _h2d(a: np.ndarray, device) -> torch.Tensor:
@@ -31,38 +30,13 @@ def _h2d(a: np.ndarray, device) -> torch.Tensor:
     return t.pin_memory().to(device, non_blocking=True)
 
 
-def _h2d_packed(arrays: List[np.ndarray], device) -> Tuple[List[torch.Tensor], int]:
-    """One pinned staging buffer + ONE async copy for a list of small arrays; returns device views."""
-    offs, total = [], 0
-    for a in arrays:
-        offs.append(total)
-        total += (a.nbytes + 15) // 16 * 16
-    total = max(total, 16)
-    cap = 1 << max(12, (total - 1).bit_length())
-    key = (cap, torch.device(device).index or 0)
-    host = _STAGING.get(key)
-    if host is None:
-        host = torch.empty(cap, dtype=torch.uint8).pin_memory()
-        _STAGING[key] = host
-    else:
-        torch.cuda.current_stream(device).synchronize()   # the previous copy out of this buffer must be done
-    hv = host.numpy()
-    for a, o in zip(arrays, offs):
-        hv[o:o + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-    dev_buf = torch.empty(total, dtype=torch.uint8, device=device)
-    dev_buf.copy_(host[:total], non_blocking=True)
-    out = []
-    for a, o in zip(arrays, offs):
-        out.append(dev_buf[o:o + a.nbytes].view(getattr(torch, str(a.dtype))).reshape(a.shape))
-    return out, total
+class HostBatch:
+    """Page records packed once into ONE pinned host buffer (CSR arrays back to back): what a data loader hands to the
+    training loop.  ``BoxBatch.from_host`` uploads it with a single asynchronous copy."""
 
-
-class BoxBatch:
-    """CSR batch of pages of boxes on the device.  ``chars`` (list of int arrays per box) is optional."""
-
-    def __init__(self, pages: Sequence[Dict], device=None, with_chars: bool = True, with_labels: bool = False):
-        dev = _dev(device)
+    def __init__(self, pages: Sequence[Dict], with_chars: bool = True, with_labels: bool = False):
         self.n_pages = len(pages)
+        self.with_chars, self.with_labels = with_chars, with_labels
         ptr = np.zeros(len(pages) + 1, np.int32)
         ptr[1:] = np.cumsum([len(pg["x"]) for pg in pages])
         self.n_boxes = int(ptr[-1])
@@ -76,14 +50,42 @@ class BoxBatch:
             arrays += [lens, cptr, cfeat]
         if with_labels:
             arrays.append(np.concatenate([np.asarray(pg["label"], np.int32) for pg in pages]))
-        dv, self.h_bytes = _h2d_packed(arrays, dev)
+        self.layout, total = [], 0
+        for a in arrays:
+            self.layout.append((total, a.nbytes, str(a.dtype), a.shape))
+            total += (a.nbytes + 15) // 16 * 16
+        self.nbytes = max(total, 16)
+        self.buf = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+        hv = self.buf.numpy()
+        for a, (o, nb, _, _) in zip(arrays, self.layout):
+            hv[o:o + nb] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
+
+
+class BoxBatch:
+    """CSR batch of pages of boxes on the device.  ``chars`` (list of int arrays per box) is optional."""
+
+    def __init__(self, pages: Sequence[Dict], device=None, with_chars: bool = True, with_labels: bool = False):
+        self._bind(HostBatch(pages, with_chars, with_labels), _dev(device))
+
+    @classmethod
+    def from_host(cls, host: HostBatch, device=None) -> "BoxBatch":
+        self = cls.__new__(cls)
+        self._bind(host, _dev(device))
+        return self
+
+    def _bind(self, host: HostBatch, dev: torch.device):
+        self.n_pages, self.n_boxes, self.h_bytes = host.n_pages, host.n_boxes, host.nbytes
+        dev_buf = torch.empty(host.nbytes, dtype=torch.uint8, device=dev)
+        dev_buf.copy_(host.buf, non_blocking=True)          # one pinned -> device copy
+        self._keep = host                                   # the pinned buffer must outlive the asynchronous copy
+        dv = [dev_buf[o:o + nb].view(getattr(torch, dt)).reshape(shape) for o, nb, dt, shape in host.layout]
         self.x, self.y, self.w, self.h, self.page_ptr = dv[:5]
         k = 5
         self.n_chars = self.char_ptr = self.char_feat = self.labels = None
-        if with_chars:
+        if host.with_chars:
             self.n_chars, self.char_ptr, self.char_feat = dv[5:8]
             k = 8
-        if with_labels:
+        if host.with_labels:
             self.labels = dv[k]
         self.device = dev
 
