@@ -16,7 +16,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROF = os.path.join(ROOT, "profiles")
 
-FAMILY = [("wgrad_tc", "wgrad_tc_kernel"), ("conv3_tc", "conv3_tc_kernel"), ("conv_tc", "conv_tc_kernel"), ("attn_tc", "attn_kernels")]
+FAMILY = [("wgrad_tc3", "wgrad_tc3_kernel"), ("wgrad_tc2", "wgrad_tc2_kernel"), ("wgrad_tc", "wgrad_tc_kernel"), ("conv3_tc", "conv3_tc_kernel"),
+          ("conv_tc", "conv_tc_kernel"), ("conv1x1", "conv1x1_kernel"), ("relu_mask", "relu_mask_kernel"), ("attn_tc", "attn_kernels")]
 
 
 def launches(path):
