@@ -142,6 +142,10 @@ struct MsauPlan {
   std::vector<char> written;
   std::vector<Tensor> all_tensors;
   cudaStream_t st = nullptr;
+  // weight gradients run on a side stream (they only feed the optimiser): fork after dY is final, join at the end of backward
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t wst = nullptr;        // stream the weight-gradient kernels of the current call go to
   const int* first_skip = nullptr;   // set by msau_forward when the structured first layer ran (device flag)
   const short* first_ids = nullptr;  // ... and the id map it used (plan workspace, or the caller's with x_layout 2)
 
@@ -318,6 +322,7 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 // ------------------------------------------------------------------ launch helpers
 static bool g_use_tc = true;
 static bool g_structured = true;   // one-hot inputs: id-gather first layer (first_layer.cu)
+static bool g_side_stream = true;  // weight-gradient kernels on a side stream, overlapping the data-gradient chain
 static bool g_use_pw = true;       // 1x1 convs on the fp32 streaming kernel (conv1x1.cu)
 static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
 static int g_c3_max = 16;        // ... for at most this many output channels
@@ -375,6 +380,14 @@ static int layer_dgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
                    L.dil, padd, o, which == 1 ? L.tc_d1 : L.tc_d2, which == 1 ? L.t3_d1 : L.t3_d2);
 }
 
+// the weight-gradient kernel about to be launched may start once everything enqueued so far on the main stream is done
+static int wgrad_fork(MsauPlan* p) {
+  if (p->wst == p->st) return MSAU_OK;
+  MSAU_CUDA_TRY(cudaEventRecord(p->ev_fork, p->st));
+  MSAU_CUDA_TRY(cudaStreamWaitEvent(p->wst, p->ev_fork, 0));
+  return MSAU_OK;
+}
+
 // weight (+bias) gradient of a conv layer wrt source `which`
 static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* src, int psrc, int nchw, int c_logical, bool reluA,
                        const float* dy, int pdy, const float* dymask, int pm, int H, int W, long w_off_override = -1,
@@ -396,8 +409,9 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
   a.skip_flag = skip_flag;
   count_launch(1);
-  if (g_use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->st);
-  return launch_wgrad(a, p->st);
+  MSAU_TRY(wgrad_fork(p));
+  if (g_use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->wst);
+  return launch_wgrad(a, p->wst);
 }
 
 // MultiConvResidualBlock forward, model/model.py:37-50
@@ -510,7 +524,8 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
     a.dbias = p->gparams + L.b_off;
     if (wgrad_tc_supported(a)) {
       count_launch(1);
-      MSAU_TRY(launch_wgrad_tc(a, p->st));
+      MSAU_TRY(wgrad_fork(p));
+      MSAU_TRY(launch_wgrad_tc(a, p->wst));
       w_done = true;
     }
   }
@@ -525,7 +540,8 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
     a.dW = p->gparams + L.w_off; a.s_ca = (long)L.cout * 9; a.s_cb = 9; a.ca_lim = L.cin; a.cb_lim = L.cout;
     a.dbias = nullptr;
     count_launch(1);
-    MSAU_TRY(launch_wgrad(a, p->st));
+    MSAU_TRY(wgrad_fork(p));
+    MSAU_TRY(launch_wgrad(a, p->wst));
   }
   if (!w_done) {
     count_launch(1);
@@ -735,6 +751,9 @@ extern "C" void msau_plan_destroy(MsauPlan* p) {
   if (p->d_descs) cudaFree(p->d_descs);
   if (p->d_tc_descs) cudaFree(p->d_tc_descs);
   if (p->d_t3_descs) cudaFree(p->d_t3_descs);
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
 }
 
@@ -878,6 +897,15 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
   p->gparams = grads;
   std::fill(p->written.begin(), p->written.end(), 0);
   MSAU_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p->n_params, p->st));
+  p->wst = p->st;
+  if (g_side_stream) {
+    if (!p->side) {
+      MSAU_CUDA_TRY(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+      MSAU_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+      MSAU_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
+    p->wst = p->side;
+  }
   const long npp = (long)p->H * p->W;
   {
     Block& last = p->blocks[NB - 1];
@@ -961,8 +989,9 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
         const int c1 = pad4(cfg.channels);
         if (p->first_skip) {
           count_launch(1);
+          MSAU_TRY(wgrad_fork(p));
           MSAU_TRY(launch_first_wgrad(p->first_ids, p->first_skip, p->G(L.z1), L.z1.C, cfg.channels, L.conv1.cout, p->B, p->H, p->W,
-                                      p->gparams + L.conv1.w_off, p->gparams + L.conv1.b_off, p->st));
+                                      p->gparams + L.conv1.w_off, p->gparams + L.conv1.b_off, p->wst));
         }
         if (x_layout != 2)
         MSAU_TRY(layer_wgrad(p, L.conv1, 1, x, c1, x_layout == 0, cfg.channels, false, p->G(L.z1), L.z1.C, nullptr, 0, p->H, p->W, -1, -1,
@@ -974,6 +1003,10 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
         MSAU_TRY(layer_dgrad(p, L.conv1, 1, p->G(L.z1), L.z1.C, nullptr, 0, src, o));
       }
     }
+  }
+  if (p->wst != p->st) {     // join: the caller's stream continues only after the last weight-gradient kernel
+    MSAU_CUDA_TRY(cudaEventRecord(p->ev_join, p->wst));
+    MSAU_CUDA_TRY(cudaStreamWaitEvent(p->st, p->ev_join, 0));
   }
   return MSAU_OK;
 }
@@ -1044,6 +1077,7 @@ extern "C" int msau_set_option(const char* name, int value) {
   if (!strcmp(name, "tensor_core_conv")) { g_use_tc = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_fold")) { g_use_c3 = value != 0; return MSAU_OK; }
   if (!strcmp(name, "pointwise_conv")) { g_use_pw = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "wgrad_side_stream")) { g_side_stream = value != 0; return MSAU_OK; }
   if (!strcmp(name, "structured_first_layer")) { g_structured = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
