@@ -266,11 +266,15 @@ def main():
     # ---- per-kernel pass (CUDA events around every launch) -> roofline of the dominant kernel
     roof, breakdown = None, None
     # every rank runs the pass (the step contains the all-reduce); rank 0 reports its own kernels
+    # (weight gradients normally overlap the data-gradient chain on a side stream; serialise them here so that every
+    #  kernel's events measure that kernel alone)
+    _lib.set_option("wgrad_side_stream", 0)
     _lib.profile_enable(True)
     for _ in range(K):
         step_resident()
     rep = _lib.profile_report()
     _lib.profile_enable(False)
+    _lib.set_option("wgrad_side_stream", 1)
     if rank == 0:
         pk = peaks()
         tot = sum(v["ms"] for v in rep.values())
@@ -295,7 +299,7 @@ def main():
         except Exception:
             pass
         roof.update(kernel=top, peak_source=pk["src"], launches=tv["launches"], avg_launch_ms=tv["ms"] / tv["launches"],
-                    share_of_step=tv["ms"] / tot, pass_="separate K-step pass with CUDA events around every launch")
+                    share_of_step=tv["ms"] / tot, pass_="separate K-step pass with CUDA events around every launch, single stream")
     barrier()
 
     cpu = None
