@@ -123,12 +123,6 @@ __device__ __forceinline__ void mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_
       : "memory");
 }
 
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-  split_pair(x[0], x[1], hi.x, lo.x);
-  split_pair(x[2], x[3], hi.y, lo.y);
-  split_pair(x[4], x[5], hi.z, lo.z);
-  split_pair(x[6], x[7], hi.w, lo.w);
-}
 
 // EPI: 0 = epilogue driven by run-time flags; 1 = bias; 2 = bias + ReLU; 3 = bias + residual + ReLU; 4 = ReLU mask; 5 = ReLU mask + add
 // LDU: raw pixels per producer thread and plane (3: T <= 4 tiles, 6: T = 8)
@@ -416,7 +410,6 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               float acc = 0.f;
 #pragma unroll
               for (int kx = 0; kx < KS; ++kx) {
-                constexpr int dummy = 0; (void)dummy;
                 const int sh = kx - PAD;                        // compile-time after unrolling
                 if (sh < 0) acc += __shfl_up_sync(0xffffffffu, vk[kx][i], (unsigned)(-sh));
                 else if (sh > 0) acc += __shfl_down_sync(0xffffffffu, vk[kx][i], (unsigned)sh);

@@ -72,16 +72,6 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_
       : "memory");
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 // exactly one lane of a converged warp (the compiler then emits straight-line UTCHMMA without per-lane election loops)
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -164,7 +154,7 @@ struct TcTile {
   int tiles_x, tiles_y, n_super;    // super-tile grid (16 rows x 8T columns each)
   int step_q, step_r;               // PROD_THREADS = step_q * HW + step_r
   int dbg;                          // MSAU_TC_DEBUG experiments: 1 = no MMAs, 2 = no producer loads, 4 = no epilogue stores
-  uint32_t in_bytes, w_bytes, stage_bytes, raw_bytes, tmem_cols;
+  uint32_t in_bytes, w_bytes, stage_bytes, tmem_cols;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
@@ -234,7 +224,6 @@ static constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each t
 static constexpr int TC_THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
 static constexpr int W_U = 4;         // weight-image uint4s prefetched per producer thread per plane
 static constexpr int MAX_STAGES = 3;
-static constexpr int RAW_SLOTS = 0;   // (cp.async raw ring experiment: slower than register staging, kept out)
 
 enum { SRC_PLAIN = 0, SRC_RELU = 1, SRC_MASK = 2, SRC_NCHW = 3, SRC_S2D = 4 };
 
@@ -567,15 +556,14 @@ static bool tc_configure(const ConvArgs& a, TcTile& t) {
   t.n1 = taps; t.n3 = (taps + 1) / 2;
   t.P = (a.c1 + a.c2) / 8;
   t.w_bytes = (uint32_t)(t.n1 + t.n3) * t.N * 32;
-  for (;;) {                                               // shrink the super-tile until >= 2 MMA stages + the raw ring fit
+  for (;;) {                                               // shrink the super-tile until >= 2 MMA stages fit
     t.HH = 16 + (a.kh - 1) * a.dil;
     t.HW = 8 * t.T + (a.kw - 1) * a.dil;
     t.in_bytes = (uint32_t)t.HH * t.HW * 32;
     t.stage_bytes = (t.in_bytes + t.w_bytes + 127) / 128 * 128;
-    t.raw_bytes = t.stage_bytes;                           // raw fp32 plane = 32 B / pixel, same as hi + lo
     t.stages = MAX_STAGES;
-    while (t.stages > 2 && (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS > 216 * 1024) --t.stages;
-    if ((size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS <= 216 * 1024 || t.T == 1) break;
+    while (t.stages > 2 && (size_t)t.stage_bytes * t.stages > 216 * 1024) --t.stages;
+    if ((size_t)t.stage_bytes * t.stages <= 216 * 1024 || t.T == 1) break;
     t.T /= 2;
   }
   t.step_q = PROD_THREADS / t.HW; t.step_r = PROD_THREADS % t.HW;
@@ -586,7 +574,7 @@ static bool tc_configure(const ConvArgs& a, TcTile& t) {
   const int cols = 2 * t.T * t.N;
   t.tmem_cols = 32;
   while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
-  const size_t smem = (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS + 1024;
+  const size_t smem = (size_t)t.stage_bytes * t.stages + 1024;
   return smem <= 220 * 1024 && t.tmem_cols <= 512;
 }
 
@@ -621,7 +609,7 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   TcTile t;
   MSAU_CHECK_ARG(tc_configure(a, t), "conv_tc: tile does not fit");
   const int taps = a.kh * a.kw;
-  const size_t smem = (size_t)t.stage_bytes * t.stages + (size_t)t.raw_bytes * RAW_SLOTS + 1024;
+  const size_t smem = (size_t)t.stage_bytes * t.stages + 1024;
   int grid = t.n_super < sm_count() ? t.n_super : sm_count();   // persistent: one CTA per SM
   const int src_mode = a.s2d ? SRC_S2D : a.src1_nchw ? SRC_NCHW : (a.mask1 ? SRC_MASK : (a.relu1 ? SRC_RELU : SRC_PLAIN));
   MSAU_CHECK_ARG(!(a.mask1 && a.relu1), "conv_tc: mask1 and relu1 together are not supported");

@@ -529,7 +529,7 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
       w_done = true;
     }
   }
-  for (int pass = 0; pass < 1 && !w_done; ++pass) {
+  if (!w_done) {
     WgradArgs a;
     memset(&a, 0, sizeof(a));
     a.A = p->A(in); a.ca = L.cinp; a.pa = in.C; a.ca_logical = L.cinp;
