@@ -60,12 +60,19 @@ void msau_plan_destroy(MsauPlan* plan);
 long long msau_param_count(const MsauPlan* plan);
 /* offset (in floats) and element count of the idx-th state_dict tensor; returns MSAU_ERR_ARG past the end */
 int msau_param_info(const MsauPlan* plan, int idx, long long* offset, long long* numel);
+/* Box-constant (BERT-grid) input, reference data_generator_funsd_bert.py:64-93: every pixel of a box carries that box's
+ * feature vector.  `table` is a device fp32 [rows, channels] array (row r = the vector painted where the id map says r) that
+ * must stay valid while msau_forward / msau_loss_backward run with x_layout 3 (x = int16 [B, H, W] row ids, -1 = background).
+ * The 768 -> 8 first conv then runs as a rows x channels x 72 projection + an id gather; rows <= 32767.  Not a data-path
+ * call: it may (re)allocate two small plan-owned scratch buffers. */
+int msau_plan_set_feature_table(MsauPlan* plan, const float* table, int rows);
 int msau_workspace_bytes(const MsauPlan* plan, int training, size_t* bytes);
 
 /* MSAUWrapper.forward (model/model.py:435-437) = MSAUNet.forward (:378-396) + Softmax(dim=1).
  *   x            [B, channels, H, W] fp32 (x_layout 0, NCHW) or [B, H, W, round_up(channels,4)] (1, NHWC), or the int16 id map
  *                [B, H, W] of a one-hot chargrid (2: channel index per pixel, -1 = all-zero pixel; what
- *                msau_raster_features writes with layout 2)
+ *                msau_raster_features writes with layout 2), or the int16 row-id map of a box-constant grid (3, see
+ *                msau_plan_set_feature_table)
  *   params       flat fp32 parameter buffer (msau_param_count floats)
  *   logits, aux  [B, n_class, H, W] fp32 NCHW, either may be NULL
  *   probs        [B, n_class, H, W] softmax over classes, or NULL

@@ -13,7 +13,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmsau_b200.so")
 
 SYMBOLS = [
     "msau_last_error", "msau_version", "msau_launch_count",
-    "msau_plan_create", "msau_plan_destroy", "msau_param_count", "msau_param_info", "msau_workspace_bytes",
+    "msau_plan_create", "msau_plan_destroy", "msau_param_count", "msau_param_info", "msau_plan_set_feature_table",
+    "msau_workspace_bytes",
     "msau_forward", "msau_loss_backward", "msau_clip_adam_step",
     "msau_raster_geometry", "msau_raster_features", "msau_raster_labels",
     "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
@@ -56,6 +57,7 @@ def lib() -> C.CDLL:
     L.msau_param_count.argtypes = [vp]
     L.msau_param_count.restype = i64
     L.msau_param_info.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.msau_plan_set_feature_table.argtypes = [vp, vp, i32]
     L.msau_workspace_bytes.argtypes = [vp, i32, C.POINTER(sz)]
     L.msau_forward.argtypes = [vp, vp, i32, vp, vp, sz, i32, vp, vp, vp, vp, vp]
     L.msau_loss_backward.argtypes = [vp, vp, i32, vp, i32, f32, vp, sz, vp, vp, vp]

@@ -231,4 +231,145 @@ int launch_first_wgrad(const short* ids, const int* flag, const float* dz, int p
   return MSAU_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------- BERT grid
+// Box-constant input (data_generator_funsd_bert.py:64-93: every pixel of a box carries that box's feature vector):
+// with ids[p] = feature-table row of the owning box,
+//     z[p][co] = bias[co] + sum_tap P[ids[p + off(tap)]][tap][co],     P[r][tap][co] = sum_ci table[r][ci] * W[co][ci][tap]
+// i.e. the 768 -> 8 conv over a 768-channel dense grid becomes a rows x 768 x 72 projection (tiny) + the id-gather above;
+// the weight gradient is the same histogram keyed by row, followed by dW[co][ci][tap] = sum_r table[r][ci] * hist[r][tap][co].
+
+// P[r][tap][co]; w: packed fp32 [tap][cinp][8]; one block per table row, thread = (tap, co)
+__global__ void __launch_bounds__(96) table_project_kernel(const float* __restrict__ table, int cin, int cinp, const float* __restrict__ w,
+                                                            float* __restrict__ P) {
+  const int r = blockIdx.x, t = threadIdx.x;
+  if (t >= 72) return;
+  const int tap = t >> 3, co = t & 7;
+  const float* row = table + (long)r * cin;
+  const float* wp = w + (long)tap * cinp * 8 + co;
+  float acc = 0.f;
+  for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(row + ci), __ldg(wp + ci * 8), acc);
+  P[(long)r * 72 + t] = acc;
+}
+
+__global__ void __launch_bounds__(256) first_fwd_table_kernel(const short* __restrict__ ids, const float* __restrict__ P,
+                                                               const float* __restrict__ bias, int B, int H, int W, float* __restrict__ out,
+                                                               int po) {
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias)), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 1);
+  const long npix = (long)B * H * W;
+  for (long p = (long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long)gridDim.x * 256) {
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    float acc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      if ((unsigned)(y + ky - 1) >= (unsigned)H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if ((unsigned)(x + kx - 1) >= (unsigned)W) continue;
+        const int id = ids[p + (long)(ky - 1) * W + (kx - 1)];
+        if (id >= 0) {
+          const float4* wp = reinterpret_cast<const float4*>(P + (long)id * 72 + (ky * 3 + kx) * 8);
+          const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+          acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+          acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
+        }
+      }
+    }
+    float4* dst = reinterpret_cast<float4*>(out + p * po);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// hist[r][tap][co] += dz[q - off(tap)][co] for the pixels q with ids[q] = r.  A thread walks 16 consecutive pixels of an image
+// row and keeps the 72 partial sums of the current run of equal ids in registers (boxes are wide: few flushes).
+__global__ void __launch_bounds__(128) first_wgrad_table_kernel(const short* __restrict__ ids, const float* __restrict__ dz, int pdz, int B,
+                                                                 int H, int W, float* __restrict__ hist) {
+  const int segs = (W + 15) >> 4;
+  const long n_seg = (long)B * H * segs;
+  for (long sg = (long)blockIdx.x * 128 + threadIdx.x; sg < n_seg; sg += (long)gridDim.x * 128) {
+    const int sx = (int)(sg % segs);
+    const long row = sg / segs;
+    const int y = (int)(row % H);
+    const long rowpix = row * W;
+    float acc[72];
+#pragma unroll
+    for (int i = 0; i < 72; ++i) acc[i] = 0.f;
+    int cur = -1;
+    const int x1 = min(W, sx * 16 + 16);
+    for (int x = sx * 16; x <= x1; ++x) {
+      const int id = x < x1 ? (int)ids[rowpix + x] : -2;
+      if (id != cur) {
+        if (cur >= 0) {
+          float* h = hist + (long)cur * 72;
+#pragma unroll
+          for (int i = 0; i < 72; ++i) {
+            if (acc[i] != 0.f) atomicAdd(h + i, acc[i]);
+            acc[i] = 0.f;
+          }
+        }
+        cur = id;
+      }
+      if (id < 0) continue;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int py = y - (ky - 1);
+        if ((unsigned)py >= (unsigned)H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int px = x - (kx - 1);
+          if ((unsigned)px >= (unsigned)W) continue;
+          const float4* sp = reinterpret_cast<const float4*>(dz + (rowpix + x - (long)(ky - 1) * W - (kx - 1)) * pdz);
+          const float4 s0 = __ldg(sp), s1 = __ldg(sp + 1);
+          float* t = acc + (ky * 3 + kx) * 8;
+          t[0] += s0.x; t[1] += s0.y; t[2] += s0.z; t[3] += s0.w; t[4] += s1.x; t[5] += s1.y; t[6] += s1.z; t[7] += s1.w;
+        }
+      }
+    }
+  }
+}
+
+// dW[co][ci][tap] = sum_r table[r][ci] * hist[r][tap][co]; one block per input channel, thread = (tap, co)
+__global__ void __launch_bounds__(96) table_wgrad_kernel(const float* __restrict__ table, int rows, int cin, const float* __restrict__ hist,
+                                                          int cout, float* __restrict__ dW) {
+  const int ci = blockIdx.x, t = threadIdx.x;
+  if (t >= 72) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc = fmaf(__ldg(table + (long)r * cin + ci), __ldg(hist + (long)r * 72 + t), acc);
+  const int tap = t >> 3, co = t & 7;
+  if (co < cout) dW[((long)co * cin + ci) * 9 + tap] += acc;
+}
+
+int launch_table_first_fwd(const short* ids, const float* table, int rows, int cin, int cinp, const float* w, const float* bias, float* P,
+                           int B, int H, int W, float* out, int po, cudaStream_t st) {
+  const long npix = (long)B * H * W;
+  {
+    ProfScope ps("table_project_kernel", 2.0 * rows * cin * 72, (double)rows * (cin + 72) * 4.0, st);
+    table_project_kernel<<<rows, 96, 0, st>>>(table, cin, cinp, w, P);
+  }
+  int grid = sm_count() * 8;
+  if ((long)grid * 256 > npix) grid = cdiv(npix, 256);
+  ProfScope ps("first_fwd_kernel", 2.0 * npix * 9 * 8, (double)npix * (2.0 + 32.0), st);
+  first_fwd_table_kernel<<<grid, 256, 0, st>>>(ids, P, bias, B, H, W, out, po);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+int launch_table_first_wgrad(const short* ids, const float* table, int rows, int cin, int cout, const float* dz, int pdz, float* hist, int B,
+                             int H, int W, float* dW, cudaStream_t st) {
+  MSAU_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(float) * 72 * rows, st));
+  const long n_seg = (long)B * H * ((W + 15) / 16);
+  int grid = sm_count() * 8;
+  if ((long)grid * 128 > n_seg) grid = cdiv(n_seg, 128);
+  {
+    ProfScope ps("first_wgrad_kernel", 2.0 * B * H * W * 9 * 8, (double)B * H * W * (2.0 + 32.0), st);
+    first_wgrad_table_kernel<<<grid, 128, 0, st>>>(ids, dz, pdz, B, H, W, hist);
+  }
+  ProfScope ps("table_wgrad_kernel", 2.0 * rows * cin * 72, (double)rows * (cin + 72) * 4.0, st);
+  table_wgrad_kernel<<<cin, 96, 0, st>>>(table, rows, cin, hist, cout, dW);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
 }  // namespace msau

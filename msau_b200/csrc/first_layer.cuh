@@ -7,4 +7,10 @@ int launch_first_fwd(const short* ids, const int* flag, const float* w, const fl
                      float* out, int po, cudaStream_t st);
 int launch_first_wgrad(const short* ids, const int* flag, const float* dz, int pdz, int cin, int cout, int B, int H, int W, float* dW,
                        float* dbias, cudaStream_t st);
+// Box-constant (BERT-grid) input given as (row-id map, feature table [rows, cin] fp32): P = table x W projection + id-gather
+// forward; histogram by row + table^T x hist for the weight gradient.  P: rows*72 floats, hist: rows*72 floats (caller scratch).
+int launch_table_first_fwd(const short* ids, const float* table, int rows, int cin, int cinp, const float* w, const float* bias, float* P,
+                           int B, int H, int W, float* out, int po, cudaStream_t st);
+int launch_table_first_wgrad(const short* ids, const float* table, int rows, int cin, int cout, const float* dz, int pdz, float* hist, int B,
+                             int H, int W, float* dW, cudaStream_t st);
 }  // namespace msau

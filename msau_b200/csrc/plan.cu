@@ -147,6 +147,9 @@ struct MsauPlan {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaStream_t wst = nullptr;        // stream the weight-gradient kernels of the current call go to
   const int* first_skip = nullptr;   // set by msau_forward when the structured first layer ran (device flag)
+  // box-constant input as (row-id map, feature table): x_layout 3
+  const float* ftable = nullptr; int ftable_rows = 0;
+  float* tabP = nullptr; float* tabH = nullptr; long tab_cap = 0;   // plan-owned scratch: projected taps / row histogram
   const short* first_ids = nullptr;  // ... and the id map it used (plan workspace, or the caller's with x_layout 2)
 
   Tensor alloc(int C, int Hh, int Ww) {
@@ -619,13 +622,13 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   const int S = cfg->scale_space_num, R = cfg->res_depth, NB = cfg->num_blocks;
   const int fa = cfg->feat_root << (S - 1), da = fa / 8;
   if (!attn_supported(fa, da)) {
-    set_error("plan_create: attention at %d channels (d=%d) is not supported yet (supported: 64/8, 32/4)", fa, da);
+    set_error("plan_create: attention at %d channels (d=%d) is not supported (supported: 32, 64, 128, 256 channels)", fa, da);
     return MSAU_ERR_UNSUPPORTED;
   }
   for (int l = 0; l < S; ++l) {
     const int f = cfg->feat_root << l;
-    if (!(f == 8 || f == 16 || f == 32 || f == 64)) {
-      set_error("plan_create: level %d has %d channels; LRN kernels cover 8/16/32/64", l, f);
+    if (!(f == 8 || f == 16 || f == 32 || f == 64 || f == 128 || f == 256)) {
+      set_error("plan_create: level %d has %d channels; LRN kernels cover 8/16/32/64/128/256", l, f);
       return MSAU_ERR_UNSUPPORTED;
     }
   }
@@ -751,10 +754,28 @@ extern "C" void msau_plan_destroy(MsauPlan* p) {
   if (p->d_descs) cudaFree(p->d_descs);
   if (p->d_tc_descs) cudaFree(p->d_tc_descs);
   if (p->d_t3_descs) cudaFree(p->d_t3_descs);
+  if (p->tabP) cudaFree(p->tabP);
+  if (p->tabH) cudaFree(p->tabH);
   if (p->side) cudaStreamDestroy(p->side);
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
+}
+
+extern "C" int msau_plan_set_feature_table(MsauPlan* p, const float* table, int rows) {
+  MSAU_CHECK_ARG(p && table && rows >= 1 && rows <= 32767, "set_feature_table: need a device table with 1..32767 rows");
+  if (rows > p->tab_cap) {     // setup path, not the data path: grow the plan-owned scratch geometrically
+    long cap = p->tab_cap ? p->tab_cap : 1024;
+    while (cap < rows) cap *= 2;
+    if (p->tabP) cudaFree(p->tabP);
+    if (p->tabH) cudaFree(p->tabH);
+    p->tabP = p->tabH = nullptr;
+    MSAU_CUDA_TRY(cudaMalloc(&p->tabP, sizeof(float) * 72 * cap));
+    MSAU_CUDA_TRY(cudaMalloc(&p->tabH, sizeof(float) * 72 * cap));
+    p->tab_cap = cap;
+  }
+  p->ftable = table; p->ftable_rows = rows;
+  return MSAU_OK;
 }
 
 extern "C" long long msau_param_count(const MsauPlan* p) { return p ? p->n_params : 0; }
@@ -802,7 +823,15 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
         const int c1 = pad4(cfg.channels);
         const int* skip = nullptr;
         p->first_ids = nullptr;
-        if (x_layout == 2) {
+        if (x_layout == 3) {
+          // BERT grid as (row-id map, feature table): projected taps + id-gather instead of the 768-channel dense conv
+          if (!p->ftable || L.conv1.coutp != 8) { set_error("forward: x_layout 3 needs msau_plan_set_feature_table() and an 8-channel first layer"); return MSAU_ERR_ARG; }
+          count_launch(2);
+          MSAU_TRY(launch_table_first_fwd(reinterpret_cast<const short*>(x), p->ftable, p->ftable_rows, cfg.channels, c1, p->pk + L.conv1.pk_w,
+                                          p->pk + L.conv1.pk_b, p->tabP, p->B, p->H, p->W, p->A(L.z1), L.z1.C, p->st));
+          p->first_skip = nullptr;
+          p->first_ids = reinterpret_cast<const short*>(x);
+        } else if (x_layout == 2) {
           // the caller already holds the id map (e.g. from the rasteriser, layout 2): no dense tensor exists at all
           if (p->ids_off < 0) { set_error("forward: x_layout 2 (id map) needs a first layer with 8 output channels"); return MSAU_ERR_UNSUPPORTED; }
           int* flag = reinterpret_cast<int*>(p->misc + p->ids_off) + (((long)p->B * p->H * p->W + 1) / 2 + 8);
@@ -987,13 +1016,19 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       MSAU_TRY(launch_lrn_bwd(p->A(L.z1), p->G(L.y1), p->G(L.z1), p->npix(L.z1), L.z1.C, p->st));
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
-        if (p->first_skip) {
+        if (x_layout == 3) {
+          count_launch(3);
+          MSAU_TRY(wgrad_fork(p));
+          MSAU_TRY(launch_table_first_wgrad(p->first_ids, p->ftable, p->ftable_rows, cfg.channels, L.conv1.cout, p->G(L.z1), L.z1.C, p->tabH,
+                                            p->B, p->H, p->W, p->gparams + L.conv1.w_off, p->wst));
+          MSAU_TRY(launch_colsum(p->G(L.z1), p->npix(L.z1), L.z1.C, L.conv1.cout, p->gparams + L.conv1.b_off, p->wst));
+        } else if (p->first_skip) {
           count_launch(1);
           MSAU_TRY(wgrad_fork(p));
           MSAU_TRY(launch_first_wgrad(p->first_ids, p->first_skip, p->G(L.z1), L.z1.C, cfg.channels, L.conv1.cout, p->B, p->H, p->W,
                                       p->gparams + L.conv1.w_off, p->gparams + L.conv1.b_off, p->wst));
         }
-        if (x_layout != 2)
+        if (x_layout != 2 && x_layout != 3)
         MSAU_TRY(layer_wgrad(p, L.conv1, 1, x, c1, x_layout == 0, cfg.channels, false, p->G(L.z1), L.z1.C, nullptr, 0, p->H, p->W, -1, -1,
                              0, -1, -1, p->first_skip));
       } else {

@@ -105,10 +105,59 @@ __global__ void __launch_bounds__(256) lrn_bwd_kernel(const float* __restrict__ 
   for (int i = 0; i < C / 4; ++i) dst[i] = make_float4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
 }
 
+// Wide levels (128 / 256 channels: the wrapper-default S=6 model, model/model.py:406): one thread per (pixel, channel),
+// 256 / C pixels per block, the two channel windows as differences of an inclusive scan kept in shared memory.  These levels
+// are 1/16 and 1/32 of the page resolution, so the kernels are launch-latency sized; registers would not hold a pixel.
+__device__ __forceinline__ float seg_scan(float v, float* sh, int c, int C) {
+  // inclusive scan of v over the C-thread segment this thread belongs to (Hillis-Steele in shared memory)
+  float* seg = sh + (threadIdx.x - c);
+  seg[c] = v;
+  __syncthreads();
+  for (int off = 1; off < C; off <<= 1) {
+    const float t = c >= off ? seg[c - off] : 0.f;
+    __syncthreads();
+    seg[c] += t;
+    __syncthreads();
+  }
+  return seg[c];
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) lrn_wide_kernel(const float* __restrict__ z, const float* __restrict__ gy, float* __restrict__ out,
+                                                        long npix, int C) {
+  __shared__ float sh[256], sh2[256];
+  const int c = threadIdx.x % C;
+  const long pix = (long)blockIdx.x * (256 / C) + threadIdx.x / C;
+  const bool live = pix < npix;                     // dead threads still take part in the barriers
+  const int LO = C / 2, HI = (C - 1) / 2;
+  const float v = live ? __ldg(z + pix * C + c) : 0.f;
+  seg_scan(v * v, sh, c, C);
+  const float* seg = sh + (threadIdx.x - c);
+  const int hi = min(C - 1, c + HI), lo = c - LO - 1;
+  const float s = seg[hi] - (lo >= 0 ? seg[lo] : 0.f);
+  const float d = fmaf(s, kLrnAlpha / C, 1.f);
+  const float pw = pow_m075(d);
+  if (!BWD) {
+    if (live) out[pix * C + c] = v * pw;
+    return;
+  }
+  const float g = live ? __ldg(gy + pix * C + c) : 0.f;
+  seg_scan(g * v * pw / d, sh2, c, C);
+  const float* seg2 = sh2 + (threadIdx.x - c);
+  const int hi2 = min(C - 1, c + LO), lo2 = c - HI - 1;
+  const float u = seg2[hi2] - (lo2 >= 0 ? seg2[lo2] : 0.f);
+  if (live) out[pix * C + c] = g * pw - (2.f * kLrnAlpha * kLrnBeta / C) * v * u;
+}
+
 template <bool BWD>
 static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, cudaStream_t st) {
   const int grid = cdiv(npix, 256);
   ProfScope ps(BWD ? "lrn_bwd_kernel" : "lrn_fwd_kernel", (double)npix * C * (BWD ? 12 : 6), (double)npix * C * 4.0 * (BWD ? 3 : 2), st);
+  if (C == 128 || C == 256) {
+    lrn_wide_kernel<BWD><<<cdiv(npix, 256 / C), 256, 0, st>>>(z, gy, out, npix, C);
+    MSAU_CUDA_TRY(cudaGetLastError());
+    return MSAU_OK;
+  }
 #define MSAU_LRN(CV)                                                             \
   case CV:                                                                       \
     if (BWD) lrn_bwd_kernel<CV><<<grid, 256, 0, st>>>(z, gy, out, npix);         \
@@ -117,7 +166,7 @@ static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, 
   switch (C) {
     MSAU_LRN(4) MSAU_LRN(8) MSAU_LRN(16) MSAU_LRN(32) MSAU_LRN(64)
     default:
-      set_error("lrn: unsupported channel count %d (supported 4,8,16,32,64)", C);
+      set_error("lrn: unsupported channel count %d (supported 4,8,16,32,64,128,256)", C);
       return MSAU_ERR_UNSUPPORTED;
   }
 #undef MSAU_LRN

@@ -170,6 +170,7 @@ class MSAUWrapper(torch.nn.Module):
         self._loss_value = None
         self._anchor = None
         self._adam = None            # (exp_avg, exp_avg_sq, step, scratch)
+        self._table = None           # fp32 [rows, channels] feature table of a box-constant (BERT-grid) batch, layout 3
 
     # ------------------------------------------------------------------ parameters
     def _build_tree(self):
@@ -235,6 +236,7 @@ class MSAUWrapper(torch.nn.Module):
         self._rebind()
         self._plans = {}
         self._last = None
+        self._table = None
         return self
 
     def load_state_dict(self, state_dict, strict=True, assign=False):
@@ -284,9 +286,11 @@ class MSAUWrapper(torch.nn.Module):
     def _check_input(self, x: torch.Tensor, layout: int):
         if not x.is_cuda or x.device != self._flat.device:
             raise _lib.MsauError("input must be a CUDA tensor on the model's device (no CPU fallback)")
-        if layout == 2:
+        if layout in (2, 3):
             if x.dtype != torch.int16 or x.dim() != 3:
-                raise TypeError("layout 2 expects an int16 [B, H, W] channel-id map (-1 = empty pixel)")
+                raise TypeError(f"layout {layout} expects an int16 [B, H, W] id map (-1 = empty pixel)")
+            if layout == 3 and self._table is None:
+                raise _lib.MsauError("layout 3 (row-id map of a box-constant grid) needs set_feature_table() first")
             return tuple(x.shape)
         if x.dtype != torch.float32:
             raise TypeError("input must be float32")
@@ -307,6 +311,8 @@ class MSAUWrapper(torch.nn.Module):
         pl = self._plan(B, H, W)
         ws, ws_bytes = pl.ws_ptr(training)
         dev = x.device
+        if layout == 3:
+            _lib.check(_lib.lib().msau_plan_set_feature_table(pl.handle, self._table.data_ptr(), self._table.shape[0]))
         logits = torch.empty((B, self.n_class, H, W), dtype=torch.float32, device=dev) if want_logits else None
         aux = torch.empty((B, self.n_class, H, W), dtype=torch.float32, device=dev) if want_logits else None
         probs = torch.empty((B, self.n_class, H, W), dtype=torch.float32, device=dev) if want_probs else None
@@ -316,6 +322,18 @@ class MSAUWrapper(torch.nn.Module):
                                                _lib.ptr(logits), _lib.ptr(aux), _lib.ptr(probs), _lib.ptr(amax),
                                                _lib.current_stream()))
         return pl, x, logits, aux, probs, amax
+
+    def set_feature_table(self, table: torch.Tensor):
+        """Feature vectors of the boxes of the next batch(es) for ``layout=3`` inputs (data_generator_funsd_bert.py:64-93
+        paints ``feats[i]`` over the whole rectangle of cell i, so a BERT-grid page is an int16 map of table rows -- what
+        ``raster.raster_features(..., layout="ids")`` writes -- plus this [rows, channels] table; the dense 768-channel grid is
+        never built).  ``table`` is converted to fp32 exactly like ``torch.Tensor(float64 ndarray)`` (:82-84)."""
+        if not self._flat.is_cuda:
+            raise _lib.MsauError("msau_b200 has no CPU path: move the model to a CUDA device first")
+        t = torch.as_tensor(table).to(device=self._flat.device, dtype=torch.float32).contiguous()
+        if t.dim() != 2 or t.shape[1] != self.channels or not 1 <= t.shape[0] <= 32767:
+            raise ValueError(f"feature table must be [1..32767, {self.channels}], got {tuple(t.shape)}")
+        self._table = t
 
     # ------------------------------------------------------------------ reference API
     def forward(self, inp):

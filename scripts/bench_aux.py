@@ -68,7 +68,30 @@ def main():
     lg = torch.randint(0, 5, (8, 512, 512), device="cuda")
     ms3 = timed(lambda: m3.train_step(xg, lg))
     out["c3_bert_grid_train_b8"] = dict(ms_per_step=ms3, pages_per_s=8 / (ms3 * 1e-3))
-    del m3, xg, lg
+    del xg, lg
+    torch.cuda.empty_cache()
+    # c3 as (row-id map, feature table): R2 page records -> id map on the device -> structured first layer (x_layout 3)
+    cp, fe = [], []
+    for i in range(8):
+        _, l = orr.synth_page(500 + i, 512, 512, 198)
+        cp.append(l)
+        fe.append(0.3 * np.random.RandomState(500 + i).randn(len(l["x"]), 768))
+    host = raster.HostBatch(cp, with_chars=False, with_labels=True)
+    feats = torch.from_numpy(np.concatenate(fe)).pin_memory()
+
+    def bert_step():
+        cells = raster.BoxBatch.from_host(host, "cuda")
+        geom = cells.geometry()
+        table = feats.to("cuda", non_blocking=True)
+        ids = raster.raster_features(cells, geom, table, (512, 512), False, "ids")
+        lab = raster.raster_labels(cells, geom, (512, 512))
+        m3.set_feature_table(table)
+        return m3.train_step(ids, lab, layout=3)
+
+    ms3t = timed(bert_step)
+    out["c3_bert_grid_train_b8_row_ids"] = dict(ms_per_step=ms3t, pages_per_s=8 / (ms3t * 1e-3), h2d_bytes=host.nbytes + feats.numel() * 8,
+                                                note="host R2 page records + fp64 feature table -> H2D -> int16 row-id map -> train step")
+    del m3
     torch.cuda.empty_cache()
     # c4
     wp, lp = [], []

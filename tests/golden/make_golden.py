@@ -225,16 +225,31 @@ def golden_morph():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    golden_raster()
-    golden_morph()
+    only = set(sys.argv[1:])          # e.g. `make_golden.py model_s6r3_c16` regenerates one fixture
+
+    def want(name):
+        return not only or name in only
+
+    if want("raster"):
+        golden_raster()
+    if want("morph"):
+        golden_morph()
     small = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
-    golden_model("model_s3r2_c12", small, B=2, H=37, W=43, seed=11,
-                 full_grads=["msau_net.blocks.0.downsamplingblock.conv1s.0.conv.weight",
-                             "msau_net.blocks.1.downsamplingblock.layer_attentions.attention_block.g.conv.weight",
-                             "msau_net.blocks.1.upsamplingblock.deconvs.0.conv.weight",
-                             "msau_net.end_convs.2.custom_conv.bias"])
+    if want("model_s3r2_c12"):
+        golden_model("model_s3r2_c12", small, B=2, H=37, W=43, seed=11,
+                     full_grads=["msau_net.blocks.0.downsamplingblock.conv1s.0.conv.weight",
+                                 "msau_net.blocks.1.downsamplingblock.layer_attentions.attention_block.g.conv.weight",
+                                 "msau_net.blocks.1.upsamplingblock.deconvs.0.conv.weight",
+                                 "msau_net.end_convs.2.custom_conv.bias"])
     train_cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=4, res_depth=2, feat_root=8)
-    golden_model("model_s4r2_c96", train_cfg, B=1, H=64, W=48, seed=0,
-                 full_grads=["msau_net.blocks.2.upsamplingblock.conv1_1s.0.custom_conv.weight"])
+    if want("model_s4r2_c96"):
+        golden_model("model_s4r2_c96", train_cfg, B=1, H=64, W=48, seed=0,
+                     full_grads=["msau_net.blocks.2.upsamplingblock.conv1_1s.0.custom_conv.weight"])
     deep = om.MsauConfig(channels=8, n_class=3, scale_space_num=2, res_depth=3, feat_root=16)
-    golden_model("model_s2r3_c8", deep, B=3, H=16, W=24, seed=5, full_grads=[])
+    if want("model_s2r3_c8"):
+        golden_model("model_s2r3_c8", deep, B=3, H=16, W=24, seed=5, full_grads=[])
+    # the wrapper's own defaults (model/model.py:406-408): S=6, R=3, featRoot=8 -> levels of 8..256 channels, attention at 256
+    dflt = om.MsauConfig(channels=16, n_class=5, scale_space_num=6, res_depth=3, feat_root=8)
+    if want("model_s6r3_c16"):
+        golden_model("model_s6r3_c16", dflt, B=1, H=64, W=160, seed=21,
+                     full_grads=["msau_net.blocks.0.downsamplingblock.layer_attentions.attention_block.f.conv.weight"])

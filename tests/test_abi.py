@@ -31,7 +31,7 @@ def test_plan_rejects_bad_config_without_gpu_work():
     h = C.c_void_p()
     rc = L.msau_plan_create(C.byref(cfg), 1, 64, 64, C.byref(h))
     assert rc == -1 and b"filter_size" in L.msau_last_error()
-    cfg = _lib.MsauConfig(96, 5, 6, 3, 8, 3, 2, 3)       # S6: attention at 256 channels not built yet
+    cfg = _lib.MsauConfig(96, 5, 6, 3, 16, 3, 2, 3)      # S6 with featRoot 16: 512-channel levels are not covered
     rc = L.msau_plan_create(C.byref(cfg), 1, 64, 64, C.byref(h))
     assert rc == -3
 

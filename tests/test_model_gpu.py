@@ -26,7 +26,7 @@ def tc(request):
     _lib.set_option("tensor_core_conv", request.param)
     yield request.param
     _lib.set_option("tensor_core_conv", 1)
-FIXTURES = ["model_s3r2_c12", "model_s4r2_c96", "model_s2r3_c8"]
+FIXTURES = ["model_s3r2_c12", "model_s4r2_c96", "model_s2r3_c8", "model_s6r3_c16"]
 
 
 def load(golden_dir, name):

@@ -138,6 +138,63 @@ def test_id_map_path_equals_dense_path():
         assert (pa.detach() - pb.detach()).abs().max().item() <= tol, k
 
 
+def test_bert_row_id_path_equals_dense_path():
+    """BERT grid (R2, data_generator_funsd_bert.py:64-93) as (row-id map, feature table), x_layout 3: the id map is the owner
+    map of the dense 768-channel grid, forward / loss / gradients equal the dense-grid run of the fp32 kernels and the oracle,
+    and a fused train step moves the parameters the same way."""
+    import msau_b200
+    from msau_b200 import _lib
+    from oracle import model as om
+    D = 768
+    lp, fe = [], []
+    for seed, n in ((5, 40), (11, 25)):
+        _, l = orr.synth_page(seed, 64, 64, n)
+        lp.append(l)
+        fe.append(0.3 * np.random.RandomState(seed).randn(len(l["x"]), D))
+    cells = raster.BoxBatch(lp, "cuda", with_chars=False, with_labels=True)
+    geom = cells.geometry()
+    table = torch.from_numpy(np.concatenate(fe)).cuda()
+    dense = raster.raster_features(cells, geom, table, (64, 64), False, "nchw")
+    ids = raster.raster_features(cells, geom, table, (64, 64), False, "ids")
+    label = raster.raster_labels(cells, geom, (64, 64)).long()
+    t32 = table.float()
+    want = torch.zeros_like(dense)
+    sel = ids.long().clamp(min=0)
+    want = (t32[sel] * (ids >= 0).unsqueeze(-1)).permute(0, 3, 1, 2)
+    assert ids.dtype == torch.int16 and (ids >= 0).any() and torch.equal(want.contiguous(), dense)
+    cfg = om.MsauConfig(channels=D)
+    sd = om.init_state_dict(cfg, 6)
+    kw = dict(final_act="softmax", featRoot=8, scale_space_num=4, res_depth=2)
+    ref_loss, ref_logits, _, ref_grads = om.loss_and_grads(sd, cfg, dense.cpu(), label.cpu())
+    mb = msau_b200.MSAUWrapper(D, 5, kw); mb.load_state_dict(sd); mb = mb.cuda().train()
+    with pytest.raises(_lib.MsauError):
+        mb.train_step(ids, label, layout=3)            # no table yet
+    mb.set_feature_table(table)
+    pl, xc, logits, aux, _, _ = mb._run_forward(ids, 3, True, False)
+    assert (logits.cpu() - ref_logits).abs().max().item() <= 5e-4
+    mb._last = (pl, xc, 3, 0, 0)
+    loss = mb._backward_from_last(label)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * max(1.0, float(ref_loss))
+    gb = mb.flat_grads.clone()
+    ma = msau_b200.MSAUWrapper(D, 5, kw); ma.load_state_dict(sd); ma = ma.cuda().train()
+    _, la_logits, la_aux = ma(dense)
+    ma.loss(la_logits, la_aux, label).backward()
+    ga = ma.flat_grads
+    assert (la_logits - logits).abs().max().item() <= 5e-4
+    assert (ga - gb).double().norm().item() <= 3e-2 * ga.double().norm().item()
+    off = 0
+    for k, p in mb.named_parameters():
+        n = p.numel()
+        if k.startswith("msau_net.blocks.0.downsamplingblock.conv1s.0.conv."):
+            g = gb[off:off + n].view(p.shape).cpu()
+            assert (g - ref_grads[k]).double().norm().item() <= 3e-2 * ref_grads[k].double().norm().item(), k
+        off += n
+    l0 = float(mb.train_step(ids, label, layout=3, lr=1e-3))
+    l1 = float(mb.train_step(ids, label, layout=3, lr=1e-3))
+    l2 = float(mb.train_step(ids, label, layout=3, lr=1e-3))
+    assert abs(l0 - float(ref_loss)) <= 1e-4 * max(1.0, float(ref_loss)) and l2 < l0 and np.isfinite(l1)
+
+
 @pytest.fixture(scope="module")
 def mgold(golden_dir):
     z = np.load(os.path.join(golden_dir, "morph.npz"))
