@@ -12,7 +12,9 @@
 namespace msau {
 
 // w: packed fp32 [c1 + c2][coutp] (rows = input channels of [src1 | src2]); epilogue: + bias, ReLU, += previous
-template <int CO>
+// PX pixels per thread and iteration (256 pixels apart, so every load / store instruction of a warp is still one contiguous
+// run): PX x more independent 16-byte loads in flight before the FMA chain starts.
+template <int CO, int PX>
 __global__ void __launch_bounds__(256) conv1x1_kernel(const ConvArgs a, long npix) {
   extern __shared__ __align__(16) float wsm[];                 // [cin][CO]
   if (a.skip_flag && *a.skip_flag == 0) return;
@@ -21,55 +23,64 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const ConvArgs a, long npi
   float* bsm = wsm + cin * CO;                                 // [CO] bias row after the weights
   if (threadIdx.x < CO) bsm[threadIdx.x] = a.bias ? __ldg(a.bias + threadIdx.x) : 0.f;
   __syncthreads();
-  for (long p = (long)blockIdx.x * 256 + threadIdx.x; p < npix; p += (long)gridDim.x * 256) {
-    float acc[CO];
+  for (long p0 = (long)blockIdx.x * (256 * PX) + threadIdx.x; p0 < npix; p0 += (long)gridDim.x * (256 * PX)) {
+    float acc[PX][CO];
+    long pp[PX];
 #pragma unroll
-    for (int c4 = 0; c4 < CO / 4; ++c4) {
-      const float4 b = *reinterpret_cast<const float4*>(bsm + c4 * 4);
-      acc[c4 * 4] = b.x; acc[c4 * 4 + 1] = b.y; acc[c4 * 4 + 2] = b.z; acc[c4 * 4 + 3] = b.w;
-    }
-    const float4* s1 = reinterpret_cast<const float4*>(a.src1 + p * a.p1);
-    const float* wr = wsm;
-    for (int q = 0; q < (a.c1 >> 2); ++q, wr += 4 * CO) {
-      const float4 x = __ldg(s1 + q);
-      const float xs[4] = {x.x, x.y, x.z, x.w};
+    for (int u = 0; u < PX; ++u) {
+      pp[u] = p0 + u * 256 < npix ? p0 + u * 256 : p0;         // out-of-range slots recompute pixel p0 and are not stored
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int c4 = 0; c4 < CO / 4; ++c4) {
-          const float4 w = *reinterpret_cast<const float4*>(wr + k * CO + c4 * 4);
-          acc[c4 * 4 + 0] = fmaf(xs[k], w.x, acc[c4 * 4 + 0]);
-          acc[c4 * 4 + 1] = fmaf(xs[k], w.y, acc[c4 * 4 + 1]);
-          acc[c4 * 4 + 2] = fmaf(xs[k], w.z, acc[c4 * 4 + 2]);
-          acc[c4 * 4 + 3] = fmaf(xs[k], w.w, acc[c4 * 4 + 3]);
-        }
+      for (int c4 = 0; c4 < CO / 4; ++c4) {
+        const float4 b = *reinterpret_cast<const float4*>(bsm + c4 * 4);
+        acc[u][c4 * 4] = b.x; acc[u][c4 * 4 + 1] = b.y; acc[u][c4 * 4 + 2] = b.z; acc[u][c4 * 4 + 3] = b.w;
       }
     }
-    if (a.c2) {
-      const float4* s2 = reinterpret_cast<const float4*>(a.src2 + p * a.p2);
-      for (int q = 0; q < (a.c2 >> 2); ++q, wr += 4 * CO) {
-        const float4 x = __ldg(s2 + q);
-        const float xs[4] = {x.x, x.y, x.z, x.w};
+    const float* wr = wsm;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float* src = s == 0 ? a.src1 : a.src2;
+      const int pitch = s == 0 ? a.p1 : a.p2;
+      const int nq = (s == 0 ? a.c1 : a.c2) >> 2;
+#pragma unroll 2
+      for (int q = 0; q < nq; ++q, wr += 4 * CO) {
+        float4 x[PX];
+#pragma unroll
+        for (int u = 0; u < PX; ++u) x[u] = __ldg(reinterpret_cast<const float4*>(src + pp[u] * pitch) + q);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
 #pragma unroll
           for (int c4 = 0; c4 < CO / 4; ++c4) {
             const float4 w = *reinterpret_cast<const float4*>(wr + k * CO + c4 * 4);
-            acc[c4 * 4 + 0] = fmaf(xs[k], w.x, acc[c4 * 4 + 0]);
-            acc[c4 * 4 + 1] = fmaf(xs[k], w.y, acc[c4 * 4 + 1]);
-            acc[c4 * 4 + 2] = fmaf(xs[k], w.z, acc[c4 * 4 + 2]);
-            acc[c4 * 4 + 3] = fmaf(xs[k], w.w, acc[c4 * 4 + 3]);
+#pragma unroll
+            for (int u = 0; u < PX; ++u) {
+              const float xv = k == 0 ? x[u].x : k == 1 ? x[u].y : k == 2 ? x[u].z : x[u].w;
+              acc[u][c4 * 4 + 0] = fmaf(xv, w.x, acc[u][c4 * 4 + 0]);
+              acc[u][c4 * 4 + 1] = fmaf(xv, w.y, acc[u][c4 * 4 + 1]);
+              acc[u][c4 * 4 + 2] = fmaf(xv, w.z, acc[u][c4 * 4 + 2]);
+              acc[u][c4 * 4 + 3] = fmaf(xv, w.w, acc[u][c4 * 4 + 3]);
+            }
           }
         }
       }
     }
-    float4* dst = reinterpret_cast<float4*>(a.out + p * a.po);
+    float4 prev[PX][CO / 4];
+    if (a.accumulate) {
 #pragma unroll
-    for (int c4 = 0; c4 < CO / 4; ++c4) {
-      float4 r = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
-      if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
-      if (a.accumulate) { const float4 o = dst[c4]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
-      dst[c4] = r;
+      for (int u = 0; u < PX; ++u)
+#pragma unroll
+        for (int c4 = 0; c4 < CO / 4; ++c4) prev[u][c4] = reinterpret_cast<const float4*>(a.out + pp[u] * a.po)[c4];
+    }
+#pragma unroll
+    for (int u = 0; u < PX; ++u) {
+      if (p0 + u * 256 >= npix) continue;
+      float4* dst = reinterpret_cast<float4*>(a.out + pp[u] * a.po);
+#pragma unroll
+      for (int c4 = 0; c4 < CO / 4; ++c4) {
+        float4 r = make_float4(acc[u][c4 * 4], acc[u][c4 * 4 + 1], acc[u][c4 * 4 + 2], acc[u][c4 * 4 + 3]);
+        if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+        if (a.accumulate) { const float4 o = prev[u][c4]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+        dst[c4] = r;
+      }
     }
   }
 }
@@ -89,22 +100,23 @@ int launch_conv1x1(const ConvArgs& a, cudaStream_t st) {
   MSAU_CHECK_ARG(conv1x1_supported(a), "conv1x1: unsupported shape");
   const long npix = (long)a.B * a.Hin * a.Win;
   const size_t smem = (size_t)(a.c1 + a.c2 + 1) * a.coutp * 4;
-  long blocks = (npix + 255) / 256;
+  const int px = a.coutp <= 16 ? 2 : 1;
+  long blocks = (npix + 256 * px - 1) / (256 * px);
   const long cap = (long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   double bytes = (double)npix * (a.c1 + a.c2 + a.coutp * (1 + (a.accumulate ? 1 : 0))) * 4.0;
   ProfScope ps("conv1x1_kernel", a.c1 + a.c2, a.coutp, 1, 1, a.Wout, a.accumulate, 2.0 * npix * (a.c1 + a.c2) * a.coutp, bytes, st);
-#define MSAU_PW(CO)                                                                                             \
+#define MSAU_PW(CO, PX)                                                                                         \
   {                                                                                                             \
     static bool attr = false;                                                                                   \
-    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv1x1_kernel<CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; } \
-    conv1x1_kernel<CO><<<(unsigned)blocks, 256, smem, st>>>(a, npix);                                           \
+    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv1x1_kernel<CO, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; } \
+    conv1x1_kernel<CO, PX><<<(unsigned)blocks, 256, smem, st>>>(a, npix);                                       \
   }
   switch (a.coutp) {
-    case 8: MSAU_PW(8) break;
-    case 16: MSAU_PW(16) break;
-    case 32: MSAU_PW(32) break;
-    default: MSAU_PW(64) break;
+    case 8: MSAU_PW(8, 2) break;
+    case 16: MSAU_PW(16, 2) break;
+    case 32: MSAU_PW(32, 1) break;
+    default: MSAU_PW(64, 1) break;
   }
 #undef MSAU_PW
   MSAU_CUDA_TRY(cudaGetLastError());

@@ -1114,6 +1114,7 @@ extern "C" int msau_set_option(const char* name, int value) {
   if (!strcmp(name, "pointwise_conv")) { g_use_pw = value != 0; return MSAU_OK; }
   if (!strcmp(name, "wgrad_side_stream")) { g_side_stream = value != 0; return MSAU_OK; }
   if (!strcmp(name, "structured_first_layer")) { g_structured = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "lrn_coop")) { g_lrn_coop = value; return MSAU_OK; }
   if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return MSAU_ERR_ARG;

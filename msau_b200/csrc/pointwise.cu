@@ -149,10 +149,119 @@ __global__ void __launch_bounds__(256) lrn_wide_kernel(const float* __restrict__
   if (live) out[pix * C + c] = g * pw - (2.f * kLrnAlpha * kLrnBeta / C) * v * u;
 }
 
+// Lane-cooperative LRN for 16..128 channels: C/4 consecutive lanes own one pixel (a float4 of channels each), so a warp reads
+// and writes 512 contiguous bytes per instruction whatever C is and nobody holds a whole pixel in registers (the
+// thread-per-pixel kernels above need 145 / 255 registers at 32 / 64 channels and their 128 / 256-byte lane stride defeats
+// L1).  Both channel windows are half-open prefix differences: with LO = C/2 and HI = C/2 - 1 a channel in the lower half of
+// the pixel only needs a prefix value from the lane C/8 lanes above it and a channel in the upper half only one from the lane
+// C/8 lanes below it (plus the pixel total), i.e. ONE xor-shuffle partner per lane.
+template <int LP>
+__device__ __forceinline__ float seg_inclusive(float v, int j) {
+  constexpr unsigned full = 0xffffffffu;
+#pragma unroll
+  for (int off = 1; off < LP; off <<= 1) {
+    const float t = __shfl_up_sync(full, v, off, LP);
+    if (j >= off) v += t;
+  }
+  return v;
+}
+
+template <int C, bool BWD, int UNR>
+__global__ void __launch_bounds__(256) lrn_coop_kernel(const float4* __restrict__ z, const float4* __restrict__ gy, float4* __restrict__ out,
+                                                        long nquad) {
+  constexpr int LP = C / 4, HALF = LP / 2;
+  constexpr unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int j = lane & (LP - 1);
+  const bool low = j < HALF;
+  const long nwarps = (long)gridDim.x * 8;
+  const long nchunk = (nquad + 32 * UNR - 1) / (32 * UNR);
+  for (long ch = (long)blockIdx.x * 8 + (threadIdx.x >> 5); ch < nchunk; ch += nwarps) {
+    float4 v[UNR], g[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long q = (ch * UNR + u) * 32 + lane;
+      v[u] = q < nquad ? __ldg(z + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (BWD) g[u] = q < nquad ? __ldg(gy + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long q = (ch * UNR + u) * 32 + lane;
+      const float x[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float l[4];
+      l[0] = x[0] * x[0]; l[1] = fmaf(x[1], x[1], l[0]); l[2] = fmaf(x[2], x[2], l[1]); l[3] = fmaf(x[3], x[3], l[2]);
+      const float inc = seg_inclusive<LP>(l[3], j);
+      const float total = __shfl_sync(full, inc, LP - 1, LP);
+      float e = __shfl_up_sync(full, inc, 1, LP);
+      if (j == 0) e = 0.f;
+      // A[k] = prefix of the squares up to channel 4j + k - 1
+      const float A[4] = {e, e + l[0], e + l[1], e + l[2]};
+      float pw[4], d[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float pa = __shfl_xor_sync(full, A[k], HALF, LP);
+        const float sw = low ? pa : total - pa;
+        d[k] = fmaf(sw, kLrnAlpha / C, 1.f);
+        pw[k] = pow_m075(d[k]);
+      }
+      float4 r;
+      if (!BWD) {
+        r = make_float4(x[0] * pw[0], x[1] * pw[1], x[2] * pw[2], x[3] * pw[3]);
+      } else {
+        const float gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+        float m[4];
+        m[0] = gg[0] * x[0] * pw[0] / d[0];
+        m[1] = m[0] + gg[1] * x[1] * pw[1] / d[1];
+        m[2] = m[1] + gg[2] * x[2] * pw[2] / d[2];
+        m[3] = m[2] + gg[3] * x[3] * pw[3] / d[3];
+        const float inc2 = seg_inclusive<LP>(m[3], j);
+        const float total2 = __shfl_sync(full, inc2, LP - 1, LP);
+        float e2 = __shfl_up_sync(full, inc2, 1, LP);
+        if (j == 0) e2 = 0.f;
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float pb = __shfl_xor_sync(full, e2 + m[k], HALF, LP);   // prefix up to channel 4j' + k, inclusive
+          const float uu = low ? pb : total2 - pb;
+          o[k] = gg[k] * pw[k] - (2.f * kLrnAlpha * kLrnBeta / C) * x[k] * uu;
+        }
+        r = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      if (q < nquad) out[q] = r;
+    }
+  }
+}
+
+template <int C, bool BWD>
+static void lrn_coop_launch(const float* z, const float* gy, float* out, long npix, cudaStream_t st) {
+  constexpr int UNR = BWD ? 2 : 4;
+  const long nquad = npix * (C / 4);
+  const long nchunk = (nquad + 32 * UNR - 1) / (32 * UNR);
+  long blocks = (nchunk + 7) / 8;
+  const long cap = (long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  lrn_coop_kernel<C, BWD, UNR><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(gy),
+                                                                 reinterpret_cast<float4*>(out), nquad);
+}
+
+int g_lrn_coop = 1;   // msau_set_option("lrn_coop", v): 0 = thread-per-pixel kernels only, 1 = cooperative from 16 channels up, 2 = from 8
+
 template <bool BWD>
 static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, cudaStream_t st) {
   const int grid = cdiv(npix, 256);
-  ProfScope ps(BWD ? "lrn_bwd_kernel" : "lrn_fwd_kernel", (double)npix * C * (BWD ? 12 : 6), (double)npix * C * 4.0 * (BWD ? 3 : 2), st);
+  ProfScope ps(BWD ? "lrn_bwd_kernel" : "lrn_fwd_kernel", C, C, 0, 0, (int)(npix >> 10), 0, (double)npix * C * (BWD ? 12 : 6),
+               (double)npix * C * 4.0 * (BWD ? 3 : 2), st);
+  if ((g_lrn_coop && (C == 16 || C == 32 || C == 64 || C == 128)) || (g_lrn_coop == 2 && C == 8)) {
+    switch (C) {
+      case 8: lrn_coop_launch<8, BWD>(z, gy, out, npix, st); break;
+      case 16: lrn_coop_launch<16, BWD>(z, gy, out, npix, st); break;
+      case 32: lrn_coop_launch<32, BWD>(z, gy, out, npix, st); break;
+      case 64: lrn_coop_launch<64, BWD>(z, gy, out, npix, st); break;
+      default: lrn_coop_launch<128, BWD>(z, gy, out, npix, st); break;
+    }
+    MSAU_CUDA_TRY(cudaGetLastError());
+    return MSAU_OK;
+  }
   if (C == 128 || C == 256) {
     lrn_wide_kernel<BWD><<<cdiv(npix, 256 / C), 256, 0, st>>>(z, gy, out, npix, C);
     MSAU_CUDA_TRY(cudaGetLastError());
@@ -239,14 +348,21 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
   pool_route(a.z, v01.z, v10.z, v11.z, g.z, g00.z, g01.z, g10.z, g11.z);
   pool_route(a.w, v01.w, v10.w, v11.w, g.w, g00.w, g01.w, g10.w, g11.w);
   float4* dst = reinterpret_cast<float4*>(gx);
-  auto put = [&](long i, float4 v) {
-    if (accumulate) { const float4 o = dst[i]; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-    dst[i] = v;
-  };
-  put(i00, g00);
-  if (hx) put(i01, g01);
-  if (hy) put(i10, g10);
-  if (hx && hy) put(i11, g11);
+  if (accumulate) {
+    // all four previous values first: interleaved load-add-store pairs on the same pointer serialise into four round trips
+    const float4 o00 = dst[i00];
+    const float4 o01 = hx ? dst[i01] : zero;
+    const float4 o10 = hy ? dst[i10] : zero;
+    const float4 o11 = (hx && hy) ? dst[i11] : zero;
+    g00.x += o00.x; g00.y += o00.y; g00.z += o00.z; g00.w += o00.w;
+    g01.x += o01.x; g01.y += o01.y; g01.z += o01.z; g01.w += o01.w;
+    g10.x += o10.x; g10.y += o10.y; g10.z += o10.z; g10.w += o10.w;
+    g11.x += o11.x; g11.y += o11.y; g11.z += o11.z; g11.w += o11.w;
+  }
+  dst[i00] = g00;
+  if (hx) dst[i01] = g01;
+  if (hy) dst[i10] = g10;
+  if (hx && hy) dst[i11] = g11;
 }
 
 int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st) {
@@ -261,7 +377,7 @@ int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaSt
 int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long total = (long)B * Ho * Wo * (C / 4);
-  ProfScope ps("pool_bwd_kernel", 0, ((double)B * H * W * (accumulate ? 3 : 2) + (double)B * Ho * Wo) * C * 4.0, st);
+  ProfScope ps("pool_bwd_kernel", C, C, 0, 0, W, accumulate, 0, ((double)B * H * W * (accumulate ? 3 : 2) + (double)B * Ho * Wo) * C * 4.0, st);
   pool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -287,7 +403,7 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(float4* __restrict__ g, 
 }
 
 int launch_relu_mask(float* g, const float* y, long n, cudaStream_t st) {
-  ProfScope ps("relu_mask_kernel", 0, (double)n * 4.0 * 3, st);
+  ProfScope ps("relu_mask_kernel", 0, 0, 0, 0, (int)(n >> 20), 0, 0, (double)n * 4.0 * 3, st);
   relu_mask_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4*>(g), reinterpret_cast<const float4*>(y), n / 4);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;

@@ -1,6 +1,7 @@
 #pragma once
 #include "common.cuh"
 namespace msau {
+extern int g_lrn_coop;   // engine option "lrn_coop"
 int launch_lrn_fwd(const float* z, float* y, long npix, int C, cudaStream_t st);
 int launch_lrn_bwd(const float* z, const float* gy, float* gz, long npix, int C, cudaStream_t st);
 int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st);

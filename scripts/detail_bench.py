@@ -8,6 +8,9 @@ from msau_b200 import _lib
 from oracle import model as om
 from oracle.synth import synth_input
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+for kv in sys.argv[3:]:                      # engine options, e.g. wgrad_side_stream=0 lrn_coop=0
+    k, v = kv.split("=")
+    _lib.set_option(k, int(v))
 cfg = om.MsauConfig()
 m = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=8, scale_space_num=4, res_depth=2))
 m.load_state_dict(om.init_state_dict(cfg, 0)); m = m.cuda().train()
