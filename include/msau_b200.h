@@ -182,6 +182,22 @@ int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int c
 int msau_ccl4(const uint8_t* binary, int n_maps, int height, int width, int32_t* labels, int32_t* n_labels,
               int32_t* bboxes, int max_labels, int32_t* scratch, void* stream);
 
+/* Tail of KVModel._extract_value (inference/kv_model.py:178-261) on the device, after msau_ccl4 of every foreground class.
+ * msau_kv_select_components: for every pixel whose component k (labels int32 [n_maps, H, W], one map per class) was picked by
+ * the host (slot_of int32 [n_maps, max_labels + 1]: global slot id of component k of map m, or -1):
+ *     presence[slot][line_mask[p]] = 1      -- np.unique(line_mask[labels == k])              kv_model.py:208,212
+ *     new_mask[m][p] = 1 (else 0)           -- new_pred_mask[:, :, c][labels == k] = 1        kv_model.py:213,221
+ * line_mask uint16 [H, W] (R3 line ids, 0 = none); presence uint8 [n_slots, n_lines + 1] (zeroed by the call);
+ * new_mask uint8 [n_maps, H, W] (fully written).
+ * msau_kv_char_range: queries int32 [n_queries, 5] = {map, x1, y1, x2, y2} (already clipped to the image); out int32
+ * [n_queries, 2] = {min, max} of char_mask over the box pixels with new_mask[map] > 0 and char_mask > 0, {INT_MAX, 0} if there
+ * are none                                                                                    kv_model.py:236-241 */
+int msau_kv_select_components(const int32_t* labels, const uint16_t* line_mask, int n_maps, int height, int width,
+                              const int32_t* slot_of, int max_labels, int n_slots, int n_lines, uint8_t* presence,
+                              uint8_t* new_mask, void* stream);
+int msau_kv_char_range(const uint16_t* char_mask, const uint8_t* new_mask, int height, int width, const int32_t* queries,
+                       int n_queries, int32_t* out, void* stream);
+
 /* Engine options.  "tensor_core_conv" (default 1): run the convolutions that fit on the tcgen05 implicit-GEMM
  * kernel; 0 = every convolution on the fp32 CUDA-core kernel (used by the parity tests to cross-check). */
 int msau_set_option(const char* name, int value);

@@ -244,14 +244,18 @@ static void lrn_coop_launch(const float* z, const float* gy, float* out, long np
                                                                  reinterpret_cast<float4*>(out), nquad);
 }
 
-int g_lrn_coop = 1;   // msau_set_option("lrn_coop", v): 0 = thread-per-pixel kernels only, 1 = cooperative from 16 channels up, 2 = from 8
+int g_lrn_coop = 1;   // msau_set_option("lrn_coop", v): 0 = thread-per-pixel kernels only, 1 = cooperative where it wins, 2 = from 8 channels up
 
 template <bool BWD>
 static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, cudaStream_t st) {
   const int grid = cdiv(npix, 256);
   ProfScope ps(BWD ? "lrn_bwd_kernel" : "lrn_fwd_kernel", C, C, 0, 0, (int)(npix >> 10), 0, (double)npix * C * (BWD ? 12 : 6),
                (double)npix * C * 4.0 * (BWD ? 3 : 2), st);
-  if ((g_lrn_coop && (C == 16 || C == 32 || C == 64 || C == 128)) || (g_lrn_coop == 2 && C == 8)) {
+  // measured (B = 16, 512^2 pages, profiles/README.md): the cooperative kernel wins from 16 channels up in the forward pass
+  // (25 vs 29 us at 16, 15 vs 23 us at 32, 12 vs 19 us at 64) and from 32 channels up in the backward pass (35 vs 66 us at
+  // 32, 21 vs 41 us at 64; 58 vs 54 us at 16); at 8 channels the thread-per-pixel kernels already stream at 5-5.9 TB/s
+  const int coop_min = g_lrn_coop == 2 ? 8 : (BWD ? 32 : 16);
+  if (g_lrn_coop && C >= coop_min && (C == 8 || C == 16 || C == 32 || C == 64 || C == 128)) {
     switch (C) {
       case 8: lrn_coop_launch<8, BWD>(z, gy, out, npix, st); break;
       case 16: lrn_coop_launch<16, BWD>(z, gy, out, npix, st); break;

@@ -3,8 +3,9 @@ connected components -> field values.
 
 Mirrors inference/kv_model.py: ``KVModel.load`` (:37-57), ``_generate_masks_from_label`` (:83-148), ``predict``
 (:264-338) and ``_extract_value`` (:151-261) keep their names and argument meaning.  On the hot path the grid
-rasterisation, the one-hot expansion, the network, the argmax, the (1,3) closing and the labelling all run on the device;
-only the small per-class component summaries come back for the text assembly, which stays host-side.
+rasterisation, the one-hot expansion, the network, the argmax, the (1,3) closing, the labelling and the line / character
+look-ups of ``_extract_value`` all run on the device; only the per-class component summaries (bounding boxes, touched line
+ids, character ranges) come back for the text assembly, which stays host-side.
 Visualisation (PIL / cv2 debug images) is out of scope: ``predict`` returns ``(kv_results, None)``.
 """
 from __future__ import annotations
@@ -102,78 +103,186 @@ class KVModel:
             out[c] = (closed, labels, n_labels, bboxes)
         return out
 
+    # ------------------------------------------------------------------ _extract_value (kv_model.py:151-261)
+    multiple_lines_fields = (5, 11)          # kv_model.py:156 (the reference's other two lists are empty)
+
     @staticmethod
-    def _extract_value(line_mask, char_mask, label_lines, pred_mask, num_classes):
-        """kv_model.py:151-261 with the argmax / closing / labelling on the device.  ``pred_mask`` is [H,W,C] probabilities
-        (numpy or CUDA tensor).  Returns (values, new_pred_mask) like the reference."""
-        pm = pred_mask if torch.is_tensor(pred_mask) else torch.from_numpy(np.asarray(pred_mask))
-        pm = pm.cuda()
-        n_class = pm.shape[2]
-        pred_class = pm.argmax(dim=-1).to(torch.uint8)[None].contiguous()
-        comps = KVModel.components(pred_class, n_class)
-        line_mask = np.asarray(line_mask)
-        char_mask = np.asarray(char_mask)
+    def _reading_order(lines):
+        """sort_box_reading_order (inference/generic_util.py:51-91): repeatedly take the top-left-most remaining line."""
+        rest, out = list(lines), []
+        if not rest:
+            return rest
+        while len(rest) > 1:
+            pick = rest[0]
+            for cand in rest[1:]:
+                _, py1, px2, py2 = pick["box"]
+                x1, y1, x2, y2 = cand["box"]
+                cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+                if cy <= (py1 + py2) / 2 - (y2 - y1) / 2 or (cx < px2 and cy < py2):
+                    pick = cand
+            out.append(pick)
+            rest.remove(pick)
+        return out + [rest[0]]
+
+    @staticmethod
+    def _merge_boxes(boxes, outer: bool):
+        """union_boxes / intersect_boxes (inference/morph_util.py:86-104)."""
+        if not boxes:
+            return None
+        lo, hi = (min, max) if outer else (max, min)
+        x1, y1, x2, y2 = boxes[0]
+        for b in boxes[1:]:
+            x1, y1, x2, y2 = lo(x1, b[0]), lo(y1, b[1]), hi(x2, b[2]), hi(y2, b[3])
+        return [x1, y1, x2, y2]
+
+    @classmethod
+    def extract_value_device(cls, line_mask: torch.Tensor, char_mask: torch.Tensor, label_lines, pred_class: torch.Tensor,
+                             n_class: int, num_classes: int, max_labels: int = 4096):
+        """The reference's ``_extract_value`` with every full-size map kept on the device.  ``line_mask`` / ``char_mask``: int16
+        [H,W] CUDA (uint16 values, as ``_generate_masks_from_label(as_numpy=False)`` returns them), ``pred_class``: uint8 [H,W]
+        CUDA arg-max map.  Returns (values, new_mask) with ``new_mask`` uint8 [n_class-2, H, W] on the device = the planes
+        2.. of the reference's ``new_pred_mask``.  Host<->device traffic: the component bounding boxes (16 B each), one slot
+        table per class, one byte per (picked component, line) and 8 B per doubly-claimed line."""
+        from . import _lib
+        L = _lib.lib()
+        dev = pred_class.device
+        H, W = pred_class.shape
+        n_maps = n_class - 2
         num_lines = len(label_lines)
         values = [("", None, None, None)] * n_class
-        new_pred_mask = np.zeros(tuple(pm.shape))
-        new_pred_mask[:, :, 0] = pm[:, :, 0].cpu().numpy()
-        line_used_count = [0] * (num_lines + 1)
+        used = [0] * (num_lines + 1)
         line_ids_for_field = [[] for _ in range(num_classes + 1)]
         boxes_for_field = [[] for _ in range(num_classes + 1)]
-        for idx, l in enumerate(label_lines):
-            l["id"] = idx + 1
+        for i, l in enumerate(label_lines):
+            l["id"] = i + 1
+        new_mask = torch.zeros((max(n_maps, 1), H, W), dtype=torch.uint8, device=dev)
+        if n_maps <= 0:
+            return values, new_mask[:0]
+        # closing + labelling of every class map in one batch (kv_model.py:174-177)
+        maps = torch.stack([morph.class_equals(pred_class[None], c)[0] for c in range(2, n_class)])
+        labels, n_lab, bboxes = morph.ccl_batch(morph.closing_batch(maps, (1, 3)), max_labels)
+        n_lab_h = n_lab.cpu().numpy()
+        if int(n_lab_h.max()) > max_labels:
+            raise _lib.MsauError(f"_extract_value: {int(n_lab_h.max())} components in one class map, max_labels={max_labels}")
+        bb_h = bboxes[:, :max(int(n_lab_h.max()), 1)].cpu().numpy()
+        # ---- pick components per class from the bounding boxes (kv_model.py:181-205)
+        slot_of = np.full((n_maps, max_labels + 1), -1, np.int32)
+        picked = {}                                       # c -> [component ids, best first then alternatives]
+        n_slots = 0
         for c in range(2, n_class):
-            _, labels_d, n_lab, bboxes = comps[c]
-            n = int(n_lab[0])
+            n = int(n_lab_h[c - 2])
             if n == 0:
                 continue
-            objects = morph.objects_from_bboxes(n, bboxes[0].cpu().numpy())
-            areas = [(o[1].stop - o[1].start) * (o[0].stop - o[0].start) for o in objects]
-            best = int(np.argsort(areas)[-1])
-            if areas[best] < 5:
+            objects = morph.objects_from_bboxes(n, bb_h[c - 2])
+            area = [(o[1].stop - o[1].start) * (o[0].stop - o[0].start) for o in objects]
+            multi = c in cls.multiple_lines_fields
+            order = np.argsort([-np.mean([o[0].stop, o[0].start]) for o in objects]) if multi else np.argsort(area)
+            best = int(order[-1])
+            if area[best] < 5:
                 continue
-            labels = labels_d[0].cpu().numpy()
-            box = objects[best]
-            boxes_for_field[c].append([box[1].start, box[0].start, box[1].stop, box[0].stop])
-            line_ids = [int(i) for i in np.unique(line_mask[labels == best + 1]) if i > 0]
-            line_ids_for_field[c] = list(set(line_ids))
-            for i in line_ids:
-                line_used_count[i] += 1
-            new_pred_mask[:, :, c][labels == best + 1] = 1
+            alts = [int(k) for k in order[:-1] if area[int(k)] > 5] if (multi and n > 1) else []
+            for k in alts + [best]:
+                o = objects[k]
+                boxes_for_field[c].append([o[1].start, o[0].start, o[1].stop, o[0].stop])
+            picked[c] = [best] + alts
+            for k in picked[c]:
+                slot_of[c - 2, k + 1] = n_slots
+                n_slots += 1
+        if n_slots:
+            slot_d = torch.from_numpy(slot_of).to(dev)
+            presence = torch.empty((n_slots, num_lines + 1), dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.msau_kv_select_components(labels.data_ptr(), line_mask.data_ptr(), n_maps, H, W, slot_d.data_ptr(),
+                                                       max_labels, n_slots, num_lines, presence.data_ptr(), new_mask.data_ptr(),
+                                                       _lib.current_stream()))
+            pres_h = presence.cpu().numpy()
+            for c, comps in picked.items():
+                line_ids = []
+                for k in comps:                           # np.unique order = ascending ids; 0 (no line) dropped (:208, :212)
+                    line_ids += [int(i) for i in np.nonzero(pres_h[slot_of[c - 2, k + 1]])[0] if i > 0]
+                line_ids_for_field[c] = list(set(line_ids))
+                for i in line_ids:
+                    used[i] += 1
+        # ---- character ranges of the lines claimed by more than one field (kv_model.py:236-241)
+        ordered, queries = {}, []
         for c in range(2, n_class):
-            line_ids = line_ids_for_field[c]
-            if not line_ids:
+            if not line_ids_for_field[c]:
                 continue
-            lines = sorted((label_lines[i - 1] for i in line_ids), key=lambda l: (l["box"][1], l["box"][0]))
+            ordered[c] = cls._reading_order([label_lines[i - 1] for i in line_ids_for_field[c] if i > 0])
+            for line in ordered[c]:
+                if used[line["id"]] > 1:
+                    x1, y1, x2, y2 = line["box"]
+                    ys, ye, _ = slice(y1, y2).indices(H)       # numpy slice semantics (clipping, negative wrap)
+                    xs, xe, _ = slice(x1, x2).indices(W)
+                    queries.append((c - 2, xs, ys, xe, ye))
+        ranges = {}
+        if queries:
+            q_d = torch.tensor(queries, dtype=torch.int32, device=dev)
+            r_d = torch.empty((len(queries), 2), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.msau_kv_char_range(char_mask.data_ptr(), new_mask.data_ptr(), H, W, q_d.data_ptr(), len(queries),
+                                                r_d.data_ptr(), _lib.current_stream()))
+            for q, r in zip(queries, r_d.cpu().numpy()):
+                ranges[q] = (int(r[0]), int(r[1]))
+        # ---- text assembly (kv_model.py:223-255)
+        qi = iter(queries)
+        for c in range(2, n_class):
+            if c not in ordered:
+                continue
             value, line_boxes = "", []
-            for line in lines:
+            for line in ordered[c]:
                 line_boxes.append(line["box"])
-                if line_used_count[line["id"]] <= 1:
+                if used[line["id"]] <= 1:
                     value += line["text"]
-                    continue
-                x1, y1, x2, y2 = line["box"]
-                sel = set(np.unique(char_mask[y1:y2, x1:x2][new_pred_mask[:, :, c][y1:y2, x1:x2] > 0])) - {0}
-                if not sel:
-                    continue
-                lo, hi = min(sel), max(sel)
-                if hi > len(line["text"]) - 3:
-                    hi = len(line["text"]) + 1
-                value += line["text"][lo - 2 if lo >= 2 else 0: hi - 1]
-            xs1, ys1 = min(b[0] for b in line_boxes), min(b[1] for b in line_boxes)
-            xs2, ys2 = max(b[2] for b in line_boxes), max(b[3] for b in line_boxes)
-            values[c] = (value, [boxes_for_field[c][-1]], None, [xs1, ys1, xs2, ys2])
+                else:
+                    lo, hi = ranges[next(qi)]
+                    if hi == 0:                           # no character of this line under the field's mask
+                        continue
+                    if hi > len(line["text"]) - 3:
+                        hi = len(line["text"]) + 1
+                    value += line["text"][lo - 2 if lo >= 2 else 0: hi - 1]
+                if c in cls.multiple_lines_fields:
+                    value += "\n"
+            if value and value[-1] == "\n":
+                value = value[:-1]
+            merged = cls._merge_boxes(line_boxes, True)
+            values[c] = (value, [boxes_for_field[c][-1]], cls._merge_boxes(boxes_for_field[c] + [merged], False),
+                         cls._merge_boxes(boxes_for_field[c] + [merged], True))
+        return values, new_mask
+
+    @staticmethod
+    def _extract_value(line_mask, char_mask, label_lines, pred_mask, num_classes):
+        """kv_model.py:151-261, same arguments and return value: ``pred_mask`` [H,W,C] probabilities (numpy or CUDA tensor),
+        returns ``(values, new_pred_mask)`` with ``values[c] = (text, [box], intersect_box, union_box)`` and ``new_pred_mask``
+        a float64 [H,W,C] numpy array.  Everything between the arg-max and the text assembly runs on the device
+        (``extract_value_device``); only this compatibility wrapper brings the mask planes back to build the reference's
+        return value -- ``predict`` does not."""
+        pm = pred_mask if torch.is_tensor(pred_mask) else torch.from_numpy(np.ascontiguousarray(pred_mask))
+        pm = pm.cuda()
+        n_class = pm.shape[2]
+
+        def dev16(m):
+            if torch.is_tensor(m):
+                return m.cuda().contiguous()
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(m).astype(np.uint16)).view(np.int16)).cuda()
+
+        pred_class = pm.argmax(dim=-1).to(torch.uint8).contiguous()          # first maximum wins, like np.argmax (:162)
+        values, new_mask = KVModel.extract_value_device(dev16(line_mask), dev16(char_mask), label_lines, pred_class, n_class,
+                                                        num_classes)
+        new_pred_mask = np.zeros(tuple(pm.shape))
+        new_pred_mask[:, :, 0] = pm[:, :, 0].cpu().numpy()
+        if n_class > 2:
+            new_pred_mask[:, :, 2:] = new_mask.permute(1, 2, 0).cpu().numpy()
         return values, new_pred_mask
 
     def predict(self, data, debug_info=None, label_path=None, eval_results=None):
         """kv_model.py:264-338 -> (kv_results, debug_im).  ``data`` = (json_path, image); the image is only used by the
-        reference for its debug rendering and is ignored here (debug_im is None)."""
+        reference for its debug rendering and is ignored here (debug_im is None).  The network's arg-max map, the closing,
+        the labelling and the line / character look-ups stay on the device; a few hundred bytes per field come back."""
         json_path, _ = data
         input_im, line_mask, char_mask, label_lines, scale, bg_pad, bbox = self._generate_masks_from_label(json_path, as_numpy=False)
-        x = raster.one_hot(input_im[None], self.n_token, layout="nhwc")
         with torch.no_grad():
-            probs = self.net._run_forward(x, 1, False, True)[4]                   # softmax probabilities [1,C,H,W]
-        a_pred = probs[0].permute(1, 2, 0)                                           # [H,W,C]  (kv_model.py:307)
-        values, _ = self._extract_value(line_mask.cpu().numpy().view(np.uint16), char_mask.cpu().numpy().view(np.uint16),
-                                        label_lines, a_pred, self.n_class)
+            pred_class = self.predict_maps(input_im[None])[0]
+        values, _ = self.extract_value_device(line_mask, char_mask, label_lines, pred_class, self.n_class, self.n_class)
         kv_results = {i: v[0] for i, v in enumerate(values) if v[0]}
         return kv_results, None

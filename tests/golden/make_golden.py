@@ -45,7 +45,7 @@ with contextlib.redirect_stdout(io.StringIO()):
 
 from oracle import model as om                               # noqa: E402
 from oracle import raster as orr                             # noqa: E402
-from oracle.synth import synth_input as _synth_input, class_map  # noqa: E402
+from oracle.synth import synth_input as _synth_input, class_map, kv_pred_mask  # noqa: E402
 
 
 def sha(a: np.ndarray) -> str:
@@ -223,6 +223,43 @@ def golden_morph():
     print("morph ok")
 
 
+# ----------------------------------------------------------------------------- _extract_value
+def _plain(v):
+    """values tuple -> JSON-able (numpy ints from slices / np.unique -> int)."""
+    if v is None:
+        return None
+    if isinstance(v, str):
+        return v
+    if isinstance(v, (list, tuple)):
+        return [_plain(e) for e in v]
+    return int(v)
+
+
+def golden_kv():
+    """KVModel._extract_value (inference/kv_model.py:151-261) of the unmodified reference on the R3 masks of two synthetic
+    pages and a seeded synthetic soft-max map (oracle.synth.kv_pred_mask), with 5 classes and with 7 (class 5 is one of the
+    reference's multiple_lines_fields)."""
+    out, meta = {}, []
+    for tag, (gh, gw, n, seed) in dict(small=(48, 40, 24, 3), odd=(37, 53, 30, 4)).items():
+        words, _ = orr.synth_page(seed, gh, gw, n)
+        boxes = np.stack([words["x"], words["y"], words["x"] + words["w"], words["y"] + words["h"]], 1)
+        texts = texts_for(words)
+        for n_class, noise in ((5, 0.01), (7, 0.01), (7, 0.0)):
+            kv, (im, lm, cm, label_lines, scale, bg_pad, bbox) = _ref_r3(boxes, texts, CHARSET)
+            pm = kv_pred_mask(seed * 10 + n_class, im.shape, [l["box"] for l in label_lines], n_class, noise)
+            values, new_mask = KVModel._extract_value(lm, cm, label_lines, pm, n_class)
+            key = f"{tag}::{n_class}::{noise}"
+            out[key + "::values"] = np.array(json.dumps([_plain(v) for v in values]))
+            out[key + "::new_mask_sha"] = np.array(sha(new_mask))
+            out[key + "::new_mask_fg"] = np.packbits(new_mask[:, :, 1:] > 0)
+            out[key + "::shape"] = np.array(new_mask.shape)
+            meta.append(dict(key=key, gh=gh, gw=gw, n_words=n, seed=seed, n_class=n_class, noise=noise, pred_seed=seed * 10 + n_class))
+            print(key, [v[0] for v in values])
+    out["meta"] = np.array(json.dumps(dict(cases=meta, charset=CHARSET)))
+    np.savez_compressed(os.path.join(HERE, "kv_extract.npz"), **out)
+    print("kv ok")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     only = set(sys.argv[1:])          # e.g. `make_golden.py model_s6r3_c16` regenerates one fixture
@@ -234,6 +271,8 @@ if __name__ == "__main__":
         golden_raster()
     if want("morph"):
         golden_morph()
+    if want("kv"):
+        golden_kv()
     small = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
     if want("model_s3r2_c12"):
         golden_model("model_s3r2_c12", small, B=2, H=37, W=43, seed=11,

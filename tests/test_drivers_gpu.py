@@ -63,6 +63,39 @@ def test_kv_model_inference_path(tmp_path):
     assert isinstance(kv_results, dict) and dbg is None
 
 
+@pytest.mark.parametrize("idx", range(6))
+def test_extract_value_matches_reference(golden_dir, idx):
+    """KVModel._extract_value (device closing / labelling / line and character look-ups + host text assembly) against the
+    outputs of the unmodified reference on the same inputs (tests/golden/kv_extract.npz): field texts, boxes and the
+    float64 new_pred_mask bit for bit."""
+    import hashlib
+    from kv_cases import build_case, load_golden, plain
+    z, cases, charset = load_golden(golden_dir)
+    case = cases[idx]
+    lm, cm, label_lines, pm = build_case(case, charset)
+    values, new_mask = kv_model.KVModel._extract_value(lm, cm, label_lines, pm, case["n_class"])
+    key = case["key"]
+    assert [plain(v) for v in values] == json.loads(str(z[key + "::values"]))
+    assert new_mask.dtype == np.float64 and tuple(new_mask.shape) == tuple(z[key + "::shape"])
+    assert hashlib.sha256(np.ascontiguousarray(new_mask).tobytes()).hexdigest() == str(z[key + "::new_mask_sha"])
+
+
+@pytest.mark.parametrize("seed,n_class,noise", [(21, 5, 0.01), (22, 7, 0.0), (23, 12, 0.0), (24, 6, 0.02)])
+def test_extract_value_matches_oracle(seed, n_class, noise):
+    """Other pages / class counts (12 classes reach the reference's second multi-line field, 11) against the numpy oracle."""
+    from kv_cases import build_case, plain
+    from oracle import kv as okv
+    charset = "".join(chr(c) for c in range(33, 127) if chr(c) != "$") + chr(161)
+    case = dict(seed=seed, gh=56, gw=44, n_words=36, n_class=n_class, noise=noise, pred_seed=seed + 100)
+    lm, cm, lines_a, pm = build_case(case, charset)
+    _, _, lines_b, _ = build_case(case, charset)
+    want, want_mask = okv.extract_value(lm, cm, lines_a, pm, n_class)
+    got, got_mask = kv_model.KVModel._extract_value(lm, cm, lines_b, pm, n_class)
+    assert [plain(v) for v in got] == [plain(v) for v in want]
+    assert np.array_equal(got_mask, want_mask)
+    assert any(v[0] for v in want)
+
+
 def test_train_and_evaluate_loop():
     cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
     model = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))

@@ -206,15 +206,16 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
         assert torch.equal(dict(m2.named_parameters())[k].detach().cpu(), sd[k])
 
 
-@pytest.mark.parametrize("option", ["conv3_fold", "structured_first_layer", "lrn_coop"])
-def test_alternative_kernel_paths_match_oracle(golden_dir, option):
+@pytest.mark.parametrize("option,value", [("conv3_fold", 0), ("structured_first_layer", 0), ("lrn_coop", 0), ("lrn_coop", 2)])
+def test_alternative_kernel_paths_match_oracle(golden_dir, option, value):
     """The default tensor-core path uses the kx-folded 3x3 kernel (conv3_tc.cu) and, for one-hot inputs, the id-gather first
     layer (first_layer.cu).  With either switched off the generic implicit-GEMM kernels do the same work; with a dense
-    (not one-hot) input the structured first layer must step aside on its own (device flag)."""
+    (not one-hot) input the structured first layer must step aside on its own (device flag).  LRN: thread-per-pixel kernels
+    only (0) / lane-cooperative kernels at every width (2) instead of the measured per-width choice."""
     z, meta, cfg = load(golden_dir, "model_s4r2_c96")
     sd = om.init_state_dict(cfg, meta["seed"])
     x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
-    _lib.set_option(option, 0)
+    _lib.set_option(option, value)
     try:
         m = build(cfg, sd).train()
         _, logits, aux = m(x.cuda())
