@@ -11,7 +11,7 @@
 
 namespace msau {
 
-// w: packed fp32 [c1 + c2][coutp] (rows = input channels of [src1 | src2]); epilogue: + bias, ReLU, += previous
+// w: packed fp32 [c1 + c2][coutp] (rows = input channels of [src1 | src2]); epilogue: + bias, ReLU, * (omask > 0), += previous
 // PX pixels per thread and iteration (256 pixels apart, so every load / store instruction of a warp is still one contiguous
 // run): PX x more independent 16-byte loads in flight before the FMA chain starts.
 template <int CO, int PX>
@@ -78,6 +78,10 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const ConvArgs a, long npi
       for (int c4 = 0; c4 < CO / 4; ++c4) {
         float4 r = make_float4(acc[u][c4 * 4], acc[u][c4 * 4 + 1], acc[u][c4 * 4 + 2], acc[u][c4 * 4 + 3]);
         if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+        if (a.omask) {        // gradient through the ReLU that produced this tensor (same epilogue order as conv_kernel)
+          const float4 m = __ldg(reinterpret_cast<const float4*>(a.omask + pp[u] * a.pom) + c4);
+          r.x = m.x > 0.f ? r.x : 0.f; r.y = m.y > 0.f ? r.y : 0.f; r.z = m.z > 0.f ? r.z : 0.f; r.w = m.w > 0.f ? r.w : 0.f;
+        }
         if (a.accumulate) { const float4 o = prev[u][c4]; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
         dst[c4] = r;
       }
@@ -88,8 +92,8 @@ __global__ void __launch_bounds__(256) conv1x1_kernel(const ConvArgs a, long npi
 bool conv1x1_supported(const ConvArgs& a) {
   if (a.kh != 1 || a.kw != 1 || a.stride != 1 || a.pad_t || a.pad_l || a.osy != 1 || a.oy0 || a.ox0) return false;
   if (a.Hq != a.Hin || a.Wq != a.Win || a.Hout != a.Hin || a.Wout != a.Win) return false;
-  if (a.src1_nchw || a.mask1 || a.relu1 || a.res || a.relu2 || a.omask || a.add || a.addmask || a.s2d || a.d2s) return false;
-  if ((a.c1 & 3) || (a.c2 & 3) || (a.p1 & 3) || (a.c2 && (a.p2 & 3)) || (a.po & 3)) return false;
+  if (a.src1_nchw || a.mask1 || a.relu1 || a.res || a.relu2 || a.add || a.addmask || a.s2d || a.d2s) return false;
+  if ((a.c1 & 3) || (a.c2 & 3) || (a.p1 & 3) || (a.c2 && (a.p2 & 3)) || (a.po & 3) || (a.omask && (a.pom & 3))) return false;
   if (!(a.coutp == 8 || a.coutp == 16 || a.coutp == 32 || a.coutp == 64)) return false;
   // measured: wins where the FMA work per pixel is small (the 8/16-channel levels); the wider 1x1 convs (maps <= 128^2, few
   // pixels per SM) stay on the tensor-core kernel
@@ -104,7 +108,7 @@ int launch_conv1x1(const ConvArgs& a, cudaStream_t st) {
   long blocks = (npix + 256 * px - 1) / (256 * px);
   const long cap = (long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  double bytes = (double)npix * (a.c1 + a.c2 + a.coutp * (1 + (a.accumulate ? 1 : 0))) * 4.0;
+  double bytes = (double)npix * (a.c1 + a.c2 + a.coutp * (1 + (a.accumulate ? 1 : 0) + (a.omask ? 1 : 0))) * 4.0;
   ProfScope ps("conv1x1_kernel", a.c1 + a.c2, a.coutp, 1, 1, a.Wout, a.accumulate, 2.0 * npix * (a.c1 + a.c2) * a.coutp, bytes, st);
 #define MSAU_PW(CO, PX)                                                                                         \
   {                                                                                                             \

@@ -326,6 +326,7 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 static bool g_use_tc = true;
 static bool g_structured = true;   // one-hot inputs: id-gather first layer (first_layer.cu)
 static bool g_side_stream = true;  // weight-gradient kernels on a side stream, overlapping the data-gradient chain
+static bool g_fuse_mask = true;    // coupling dgrad applies the ReLU mask of the residual block it feeds (no relu_mask pass)
 static bool g_use_pw = true;       // 1x1 convs on the fp32 streaming kernel (conv1x1.cu)
 static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
 static int g_c3_max = 16;        // ... for at most this many output channels
@@ -436,12 +437,15 @@ static int res_fwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor&
 }
 
 // backward of the residual block: G(out) -> G(in) (overwritten: `in` has no other consumer) + weight grads
-static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor& in, const std::vector<Tensor>& a, const Tensor& out) {
+static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor& in, const std::vector<Tensor>& a, const Tensor& out,
+                   bool premasked = false) {
   const int R = (int)res.size();
   // gradient through the block's final ReLU, materialised in place: it feeds the last conv's wgrad and dgrad and
-  // the identity skip path
-  count_launch(1);
-  MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));
+  // the identity skip path.  premasked: the single kernel that wrote G(out) already applied the mask in its epilogue
+  if (!premasked) {
+    count_launch(1);
+    MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));
+  }
   for (int r = R - 1; r >= 0; --r) {
     const bool last = (r == R - 1);
     // dY of conv r: last conv -> G(out) (masked above); inner convs -> G(a[r]) (masked when produced)
@@ -463,14 +467,21 @@ static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor&
 }
 
 // coupling 1x1 conv on cat[prev, cur] + ReLU (model/model.py:143-148, 246-252)
-static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const Tensor& cur, const Tensor& out) {
-  count_launch(1);
-  MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));   // 4 consumers below
+// `cur` is the output of a residual block whose only reader is this conv: its gradient has this one writer, which therefore
+// also applies the block's final ReLU mask (omask = A(cur)) -- *mask_cur tells res_bwd to skip its relu_mask pass
+static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const Tensor& cur, const Tensor& out, bool* mask_cur,
+                     bool out_premasked = false) {
+  if (!out_premasked) {
+    count_launch(1);
+    MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));   // 4 consumers below
+  }
   const float* dy = p->G(out);
   MSAU_TRY(layer_wgrad(p, L, 1, p->A(prev), prev.C, 0, L.c1p, false, dy, out.C, nullptr, 0, out.H, out.W));
   MSAU_TRY(layer_wgrad(p, L, 2, p->A(cur), cur.C, 0, L.c2p, false, dy, out.C, nullptr, 0, out.H, out.W));
   ConvOpt o;
   MSAU_TRY(layer_dgrad(p, L, 1, dy, out.C, nullptr, 0, prev, o));
+  *mask_cur = g_fuse_mask && !p->written[cur.id];
+  if (*mask_cur) { o.omask = p->A(cur); o.pom = cur.C; }
   MSAU_TRY(layer_dgrad(p, L, 2, dy, out.C, nullptr, 0, cur, o));
   return MSAU_OK;
 }
@@ -960,8 +971,9 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
     for (int l = 0; l <= S - 2; ++l) {
       UpLevel& U = blk.up[l];
       const Tensor& xin = (l == S - 2) ? blk.down[S - 1].cc : blk.up[l + 1].uc;
-      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc));
-      MSAU_TRY(res_bwd(p, U.res, U.u, U.a, U.ur));
+      bool pre = false;
+      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc, &pre));
+      MSAU_TRY(res_bwd(p, U.res, U.u, U.a, U.ur, pre));
       p->touch(U.u);
       // conv1s on cat[dw[l], deconv]
       const Tensor& skip = blk.down[l].cc;
@@ -1003,15 +1015,19 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
           MSAU_TRY(layer_dgrad(p, at.fg, 1, p->G(blk.fg), blk.fg.C, nullptr, 0, L.cc, o));
         }
       }
+      // the pool gradient is the last contribution to G(cc) (the skip connection and the next block's coupling came earlier):
+      // it also applies the mask of the ReLU that produced cc, so the relu_mask pass of coupl_bwd / res_bwd is skipped
+      const bool pool_masks = g_fuse_mask && l < S - 1;
       if (l < S - 1) {
         count_launch(1);
-        MSAU_TRY(launch_pool_bwd(p->A(L.cc), p->G(L.pooled), p->G(L.cc), p->B, L.cc.H, L.cc.W, L.cc.C, p->touch(L.cc), p->st));
+        MSAU_TRY(launch_pool_bwd(p->A(L.cc), p->G(L.pooled), p->G(L.cc), p->B, L.cc.H, L.cc.W, L.cc.C, p->touch(L.cc), pool_masks, p->st));
       }
+      bool pre = (b == 0) && pool_masks;        // block 0 has no coupling conv: cc IS the residual block's output
       if (b > 0) {
         const Tensor& pd = (l == S - 1) ? prev->att : prev->down[l].cc;
-        MSAU_TRY(coupl_bwd(p, L.coupl, pd, L.rr, L.cc));
+        MSAU_TRY(coupl_bwd(p, L.coupl, pd, L.rr, L.cc, &pre, pool_masks));
       }
-      MSAU_TRY(res_bwd(p, L.res, L.y1, L.a, L.rr));
+      MSAU_TRY(res_bwd(p, L.res, L.y1, L.a, L.rr, pre));
       count_launch(1);
       MSAU_TRY(launch_lrn_bwd(p->A(L.z1), p->G(L.y1), p->G(L.z1), p->npix(L.z1), L.z1.C, p->st));
       if (b == 0 && l == 0) {
@@ -1114,6 +1130,7 @@ extern "C" int msau_set_option(const char* name, int value) {
   if (!strcmp(name, "pointwise_conv")) { g_use_pw = value != 0; return MSAU_OK; }
   if (!strcmp(name, "wgrad_side_stream")) { g_side_stream = value != 0; return MSAU_OK; }
   if (!strcmp(name, "structured_first_layer")) { g_structured = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "fuse_relu_mask")) { g_fuse_mask = value != 0; return MSAU_OK; }
   if (!strcmp(name, "lrn_coop")) { g_lrn_coop = value; return MSAU_OK; }
   if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);

@@ -325,8 +325,10 @@ __device__ __forceinline__ void pool_route(float a, float b, float c, float d, f
   ga = k == 0 ? g : 0.f; gb = k == 1 ? g : 0.f; gc = k == 2 ? g : 0.f; gd = k == 3 ? g : 0.f;
 }
 
+// relu_mask: x is the output of a ReLU and this kernel is the last writer of its gradient, so the gradient through that ReLU
+// (g * (x > 0), what relu_mask_kernel would do in a separate pass) is applied here, where x is in registers anyway
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
-                                                        int B, int H, int W, int Ho, int Wo, int C4, int accumulate) {
+                                                        int B, int H, int W, int Ho, int Wo, int C4, int accumulate, int relu_mask) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Ho * Wo * C4;
   if (idx >= total) return;
@@ -363,6 +365,12 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__
     g10.x += o10.x; g10.y += o10.y; g10.z += o10.z; g10.w += o10.w;
     g11.x += o11.x; g11.y += o11.y; g11.z += o11.z; g11.w += o11.w;
   }
+  if (relu_mask) {
+    g00.x = a.x > 0.f ? g00.x : 0.f; g00.y = a.y > 0.f ? g00.y : 0.f; g00.z = a.z > 0.f ? g00.z : 0.f; g00.w = a.w > 0.f ? g00.w : 0.f;
+    g01.x = v01.x > 0.f ? g01.x : 0.f; g01.y = v01.y > 0.f ? g01.y : 0.f; g01.z = v01.z > 0.f ? g01.z : 0.f; g01.w = v01.w > 0.f ? g01.w : 0.f;
+    g10.x = v10.x > 0.f ? g10.x : 0.f; g10.y = v10.y > 0.f ? g10.y : 0.f; g10.z = v10.z > 0.f ? g10.z : 0.f; g10.w = v10.w > 0.f ? g10.w : 0.f;
+    g11.x = v11.x > 0.f ? g11.x : 0.f; g11.y = v11.y > 0.f ? g11.y : 0.f; g11.z = v11.z > 0.f ? g11.z : 0.f; g11.w = v11.w > 0.f ? g11.w : 0.f;
+  }
   dst[i00] = g00;
   if (hx) dst[i01] = g01;
   if (hy) dst[i10] = g10;
@@ -378,11 +386,11 @@ int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaSt
   return MSAU_OK;
 }
 
-int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, cudaStream_t st) {
+int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, int relu_mask, cudaStream_t st) {
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long total = (long)B * Ho * Wo * (C / 4);
   ProfScope ps("pool_bwd_kernel", C, C, 0, 0, W, accumulate, 0, ((double)B * H * W * (accumulate ? 3 : 2) + (double)B * Ho * Wo) * C * 4.0, st);
-  pool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate);
+  pool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate, relu_mask);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

@@ -5,7 +5,7 @@ extern int g_lrn_coop;   // engine option "lrn_coop"
 int launch_lrn_fwd(const float* z, float* y, long npix, int C, cudaStream_t st);
 int launch_lrn_bwd(const float* z, const float* gy, float* gz, long npix, int C, cudaStream_t st);
 int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaStream_t st);
-int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, cudaStream_t st);
+int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, int W, int C, int accumulate, int relu_mask, cudaStream_t st);
 int launch_relu_mask(float* g, const float* y, long n, cudaStream_t st);
 int launch_add(float* dst, const float* src, long n, int accumulate, cudaStream_t st);
 int launch_head(const float* lg, int P, int n_class, int B, long npix_per_page, float* logits_nchw, float* probs_nchw, uint8_t* argmax, cudaStream_t st);

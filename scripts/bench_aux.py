@@ -2,6 +2,7 @@
 
   c1  chargrid inference, 1 page 512x512                      -> ms / page (latency), pages/s at batch 16
   c3  BERT-grid (768-channel dense input) train step, batch 8  -> pages/s
+  s6r3  the wrapper-default model (S=6, R=3: levels of 8..256 channels), chargrid train step, batch 16 -> pages/s
   c4  R1 rasterisation of 256 pages (~200 boxes) + closing(1,3) + 4-connected labelling of 3 class maps per page
       -> pages/s and achieved HBM GB/s of the dense-grid write
   c5  1024x768 chargrid inference, 64 pages (chunked)          -> pages/s
@@ -92,6 +93,17 @@ def main():
     out["c3_bert_grid_train_b8_row_ids"] = dict(ms_per_step=ms3t, pages_per_s=8 / (ms3t * 1e-3), h2d_bytes=host.nbytes + feats.numel() * 8,
                                                 note="host R2 page records + fp64 feature table -> H2D -> int16 row-id map -> train step")
     del m3
+    torch.cuda.empty_cache()
+    # wrapper-default model (model/model.py:406-408: S=6, R=3, featRoot=8; 13 M parameters), chargrid train step, batch 16
+    cfg6 = om.MsauConfig(channels=96, n_class=5, scale_space_num=6, res_depth=3, feat_root=8)
+    m6 = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax"))          # the reference's own defaults
+    m6.load_state_dict(om.init_state_dict(cfg6, 6))
+    m6 = m6.cuda().train()
+    x6 = onehot_pages(16, 96, 512, 512, 7)
+    l6 = torch.randint(0, 5, (16, 512, 512), device="cuda")
+    ms6 = timed(lambda: m6.train_step(x6, l6))
+    out["s6r3_default_model_train_b16"] = dict(ms_per_step=ms6, pages_per_s=16 / (ms6 * 1e-3), params=int(m6.flat_params.numel()))
+    del m6, x6, l6
     torch.cuda.empty_cache()
     # c4
     wp, lp = [], []

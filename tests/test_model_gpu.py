@@ -206,7 +206,7 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
         assert torch.equal(dict(m2.named_parameters())[k].detach().cpu(), sd[k])
 
 
-@pytest.mark.parametrize("option,value", [("conv3_fold", 0), ("structured_first_layer", 0), ("lrn_coop", 0), ("lrn_coop", 2)])
+@pytest.mark.parametrize("option,value", [("conv3_fold", 0), ("structured_first_layer", 0), ("lrn_coop", 0), ("lrn_coop", 2), ("fuse_relu_mask", 0)])
 def test_alternative_kernel_paths_match_oracle(golden_dir, option, value):
     """The default tensor-core path uses the kx-folded 3x3 kernel (conv3_tc.cu) and, for one-hot inputs, the id-gather first
     layer (first_layer.cu).  With either switched off the generic implicit-GEMM kernels do the same work; with a dense
