@@ -469,8 +469,9 @@ static int res_bwd(MsauPlan* p, const std::vector<ConvLayer>& res, const Tensor&
 // coupling 1x1 conv on cat[prev, cur] + ReLU (model/model.py:143-148, 246-252)
 // `cur` is the output of a residual block whose only reader is this conv: its gradient has this one writer, which therefore
 // also applies the block's final ReLU mask (omask = A(cur)) -- *mask_cur tells res_bwd to skip its relu_mask pass
+// mask_prev: `prev` is a post-ReLU tensor all of whose gradient writers mask their own contribution ((a + b) m = a m + b m)
 static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const Tensor& cur, const Tensor& out, bool* mask_cur,
-                     bool out_premasked = false) {
+                     bool out_premasked = false, bool mask_prev = false) {
   if (!out_premasked) {
     count_launch(1);
     MSAU_TRY(launch_relu_mask(p->G(out), p->A(out), p->npix(out) * out.C, p->st));   // 4 consumers below
@@ -479,7 +480,9 @@ static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const 
   MSAU_TRY(layer_wgrad(p, L, 1, p->A(prev), prev.C, 0, L.c1p, false, dy, out.C, nullptr, 0, out.H, out.W));
   MSAU_TRY(layer_wgrad(p, L, 2, p->A(cur), cur.C, 0, L.c2p, false, dy, out.C, nullptr, 0, out.H, out.W));
   ConvOpt o;
+  if (mask_prev) { o.omask = p->A(prev); o.pom = prev.C; }
   MSAU_TRY(layer_dgrad(p, L, 1, dy, out.C, nullptr, 0, prev, o));
+  o.omask = nullptr; o.pom = 0;
   *mask_cur = g_fuse_mask && !p->written[cur.id];
   if (*mask_cur) { o.omask = p->A(cur); o.pom = cur.C; }
   MSAU_TRY(layer_dgrad(p, L, 2, dy, out.C, nullptr, 0, cur, o));
@@ -520,7 +523,7 @@ static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
   return MSAU_OK;
 }
 
-static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out) {
+static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out, bool mask_in = false) {
   // weights: dW[ci][co][ky][kx] = sum_q x[q][ci] * dOut[2q - 1 + (ky,kx)][co]
   bool w_done = false;
   if (g_use_tc && L.tc_m >= 0) {
@@ -571,6 +574,7 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
     a.B = p->B; a.Hin = in.H; a.Win = in.W; a.Hq = in.H; a.Wq = in.W;
     a.kh = 2; a.kw = 2; a.dil = 1; a.stride = 1; a.pad_t = 1; a.pad_l = 1;
     a.Hout = in.H; a.Wout = in.W; a.osy = 1;
+    if (mask_in) { a.omask = p->A(in); a.pom = in.C; }
     if (conv_tc_supported(a)) {
       a.accumulate = p->touch(in);
       count_launch(1);
@@ -586,6 +590,7 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
   a.B = p->B; a.Hin = out.H; a.Win = out.W; a.Hq = in.H; a.Wq = in.W;
   a.kh = 3; a.kw = 3; a.dil = 1; a.stride = 2; a.pad_t = 1; a.pad_l = 1;
   a.Hout = in.H; a.Wout = in.W; a.osy = 1;
+  if (mask_in) { a.omask = p->A(in); a.pom = in.C; }
   a.accumulate = p->touch(in);
   count_launch(1);
   return launch_conv(a, p->st);
@@ -965,14 +970,17 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       const Tensor& src = blk.up[0].uc;
       MSAU_TRY(layer_wgrad(p, blk.end, 1, p->A(src), src.C, 0, blk.end.c1p, false, p->G(blk.logits), 8, nullptr, 0, p->H, p->W));
       ConvOpt o;
+      // up-tower outputs uc (post-ReLU) have two gradient writers, this head / the deconv below and the next block's coupling:
+      // each masks its own contribution, so the relu_mask pass over G(uc) is not needed
+      if (g_fuse_mask) { o.omask = p->A(src); o.pom = src.C; }
       MSAU_TRY(layer_dgrad(p, blk.end, 1, p->G(blk.logits), 8, nullptr, 0, src, o));
     }
     // ---- up tower (forward ran l = S-2..0, so backward runs l = 0..S-2) ----
     for (int l = 0; l <= S - 2; ++l) {
       UpLevel& U = blk.up[l];
       const Tensor& xin = (l == S - 2) ? blk.down[S - 1].cc : blk.up[l + 1].uc;
-      bool pre = false;
-      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc, &pre));
+      bool pre = (b == 0) && g_fuse_mask;       // block 0: uc IS the residual block's output ur
+      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc, &pre, g_fuse_mask, g_fuse_mask));
       MSAU_TRY(res_bwd(p, U.res, U.u, U.a, U.ur, pre));
       p->touch(U.u);
       // conv1s on cat[dw[l], deconv]
@@ -982,7 +990,7 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       ConvOpt o;
       MSAU_TRY(layer_dgrad(p, U.conv1, 1, p->G(U.u), U.u.C, nullptr, 0, skip, o));
       MSAU_TRY(layer_dgrad(p, U.conv1, 2, p->G(U.u), U.u.C, nullptr, 0, U.d, o));
-      MSAU_TRY(deconv_bwd(p, U.deconv, xin, U.d));
+      MSAU_TRY(deconv_bwd(p, U.deconv, xin, U.d, g_fuse_mask && l < S - 2));   // xin = uc of level l+1 (l = S-2: the deepest cc)
     }
     // ---- down tower, deepest level first ----
     for (int l = S - 1; l >= 0; --l) {

@@ -135,17 +135,54 @@ class KVModel:
             x1, y1, x2, y2 = lo(x1, b[0]), lo(y1, b[1]), hi(x2, b[2]), hi(y2, b[3])
         return [x1, y1, x2, y2]
 
+    # The three device steps of ``extract_value_device``; tests/test_kv_host.py swaps in numpy stand-ins to check the host logic
+    # (component choice, reading order, text assembly) without a GPU.
+    @staticmethod
+    def _dev_components(pred_class: torch.Tensor, n_class: int, max_labels: int):
+        """closing + labelling of every foreground class map in one batch (kv_model.py:174-177) ->
+        (labels int32 [n_maps,H,W] on the device, component counts [n_maps] and bounding boxes [n_maps, n, 4] on the host)."""
+        maps = torch.stack([morph.class_equals(pred_class[None], c)[0] for c in range(2, n_class)])
+        labels, n_lab, bboxes = morph.ccl_batch(morph.closing_batch(maps, (1, 3)), max_labels)
+        n_lab_h = n_lab.cpu().numpy()
+        return labels, n_lab_h, bboxes[:, :max(int(n_lab_h.max()), 1)].cpu().numpy()
+
+    @staticmethod
+    def _dev_select(labels, line_mask, slot_of: np.ndarray, n_slots: int, num_lines: int):
+        """-> (presence uint8 [n_slots, num_lines+1] on the host, new_mask uint8 [n_maps,H,W] on the device)."""
+        from . import _lib
+        dev = labels.device
+        n_maps, H, W = labels.shape
+        slot_d = torch.from_numpy(slot_of).to(dev)
+        presence = torch.empty((n_slots, num_lines + 1), dtype=torch.uint8, device=dev)
+        new_mask = torch.empty((n_maps, H, W), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().msau_kv_select_components(labels.data_ptr(), line_mask.data_ptr(), n_maps, H, W, slot_d.data_ptr(),
+                                                            slot_of.shape[1] - 1, n_slots, num_lines, presence.data_ptr(),
+                                                            new_mask.data_ptr(), _lib.current_stream()))
+        return presence.cpu().numpy(), new_mask
+
+    @staticmethod
+    def _dev_char_ranges(char_mask, new_mask, queries):
+        """queries [(map, x1, y1, x2, y2)] -> int array [nq, 2] = (min, max) character index, (INT_MAX, 0) if none."""
+        from . import _lib
+        dev = new_mask.device
+        _, H, W = new_mask.shape
+        q_d = torch.tensor(queries, dtype=torch.int32, device=dev)
+        r_d = torch.empty((len(queries), 2), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().msau_kv_char_range(char_mask.data_ptr(), new_mask.data_ptr(), H, W, q_d.data_ptr(), len(queries),
+                                                     r_d.data_ptr(), _lib.current_stream()))
+        return r_d.cpu().numpy()
+
     @classmethod
-    def extract_value_device(cls, line_mask: torch.Tensor, char_mask: torch.Tensor, label_lines, pred_class: torch.Tensor,
-                             n_class: int, num_classes: int, max_labels: int = 4096):
+    def extract_value_device(cls, line_mask, char_mask, label_lines, pred_class, n_class: int, num_classes: int,
+                             max_labels: int = 4096):
         """The reference's ``_extract_value`` with every full-size map kept on the device.  ``line_mask`` / ``char_mask``: int16
         [H,W] CUDA (uint16 values, as ``_generate_masks_from_label(as_numpy=False)`` returns them), ``pred_class``: uint8 [H,W]
         CUDA arg-max map.  Returns (values, new_mask) with ``new_mask`` uint8 [n_class-2, H, W] on the device = the planes
-        2.. of the reference's ``new_pred_mask``.  Host<->device traffic: the component bounding boxes (16 B each), one slot
-        table per class, one byte per (picked component, line) and 8 B per doubly-claimed line."""
-        from . import _lib
-        L = _lib.lib()
-        dev = pred_class.device
+        2.. of the reference's ``new_pred_mask`` (None when no component was picked: all zeros).  Host<->device traffic: the
+        component bounding boxes (16 B each), one slot table per class, one byte per (picked component, line) and 8 B per
+        doubly-claimed line."""
         H, W = pred_class.shape
         n_maps = n_class - 2
         num_lines = len(label_lines)
@@ -155,16 +192,11 @@ class KVModel:
         boxes_for_field = [[] for _ in range(num_classes + 1)]
         for i, l in enumerate(label_lines):
             l["id"] = i + 1
-        new_mask = torch.zeros((max(n_maps, 1), H, W), dtype=torch.uint8, device=dev)
         if n_maps <= 0:
-            return values, new_mask[:0]
-        # closing + labelling of every class map in one batch (kv_model.py:174-177)
-        maps = torch.stack([morph.class_equals(pred_class[None], c)[0] for c in range(2, n_class)])
-        labels, n_lab, bboxes = morph.ccl_batch(morph.closing_batch(maps, (1, 3)), max_labels)
-        n_lab_h = n_lab.cpu().numpy()
+            return values, None
+        labels, n_lab_h, bb_h = cls._dev_components(pred_class, n_class, max_labels)
         if int(n_lab_h.max()) > max_labels:
-            raise _lib.MsauError(f"_extract_value: {int(n_lab_h.max())} components in one class map, max_labels={max_labels}")
-        bb_h = bboxes[:, :max(int(n_lab_h.max()), 1)].cpu().numpy()
+            raise RuntimeError(f"_extract_value: {int(n_lab_h.max())} components in one class map, max_labels={max_labels}")
         # ---- pick components per class from the bounding boxes (kv_model.py:181-205)
         slot_of = np.full((n_maps, max_labels + 1), -1, np.int32)
         picked = {}                                       # c -> [component ids, best first then alternatives]
@@ -188,14 +220,9 @@ class KVModel:
             for k in picked[c]:
                 slot_of[c - 2, k + 1] = n_slots
                 n_slots += 1
+        new_mask = None
         if n_slots:
-            slot_d = torch.from_numpy(slot_of).to(dev)
-            presence = torch.empty((n_slots, num_lines + 1), dtype=torch.uint8, device=dev)
-            with torch.cuda.device(dev):
-                _lib.check(L.msau_kv_select_components(labels.data_ptr(), line_mask.data_ptr(), n_maps, H, W, slot_d.data_ptr(),
-                                                       max_labels, n_slots, num_lines, presence.data_ptr(), new_mask.data_ptr(),
-                                                       _lib.current_stream()))
-            pres_h = presence.cpu().numpy()
+            pres_h, new_mask = cls._dev_select(labels, line_mask, slot_of, n_slots, num_lines)
             for c, comps in picked.items():
                 line_ids = []
                 for k in comps:                           # np.unique order = ascending ids; 0 (no line) dropped (:208, :212)
@@ -215,17 +242,9 @@ class KVModel:
                     ys, ye, _ = slice(y1, y2).indices(H)       # numpy slice semantics (clipping, negative wrap)
                     xs, xe, _ = slice(x1, x2).indices(W)
                     queries.append((c - 2, xs, ys, xe, ye))
-        ranges = {}
-        if queries:
-            q_d = torch.tensor(queries, dtype=torch.int32, device=dev)
-            r_d = torch.empty((len(queries), 2), dtype=torch.int32, device=dev)
-            with torch.cuda.device(dev):
-                _lib.check(L.msau_kv_char_range(char_mask.data_ptr(), new_mask.data_ptr(), H, W, q_d.data_ptr(), len(queries),
-                                                r_d.data_ptr(), _lib.current_stream()))
-            for q, r in zip(queries, r_d.cpu().numpy()):
-                ranges[q] = (int(r[0]), int(r[1]))
+        ranges = cls._dev_char_ranges(char_mask, new_mask, queries) if queries else []
         # ---- text assembly (kv_model.py:223-255)
-        qi = iter(queries)
+        qi = iter(ranges)
         for c in range(2, n_class):
             if c not in ordered:
                 continue
@@ -235,7 +254,7 @@ class KVModel:
                 if used[line["id"]] <= 1:
                     value += line["text"]
                 else:
-                    lo, hi = ranges[next(qi)]
+                    lo, hi = (int(v) for v in next(qi))
                     if hi == 0:                           # no character of this line under the field's mask
                         continue
                     if hi > len(line["text"]) - 3:
@@ -271,7 +290,7 @@ class KVModel:
                                                         num_classes)
         new_pred_mask = np.zeros(tuple(pm.shape))
         new_pred_mask[:, :, 0] = pm[:, :, 0].cpu().numpy()
-        if n_class > 2:
+        if new_mask is not None:
             new_pred_mask[:, :, 2:] = new_mask.permute(1, 2, 0).cpu().numpy()
         return values, new_pred_mask
 
