@@ -36,6 +36,9 @@ const char* msau_last_error(void);
 int msau_version(void);
 /* number of kernels this library has launched in the calling process so far (bench.py `gpu_launches`) */
 long long msau_launch_count(void);
+/* a caller that replays a captured CUDA graph of these calls adds the graph's kernel count per replay (the library only sees the
+ * launches it enqueues itself, i.e. the capture) */
+void msau_launch_count_add(long long n);
 
 /* ------------------------------------------------------------------------------------------------
  * Model: MSAUWrapper / MSAUNet            model/model.py:347-459 (kwargs :406-419)

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmsau_b200.so")
 
 SYMBOLS = [
-    "msau_last_error", "msau_version", "msau_launch_count",
+    "msau_last_error", "msau_version", "msau_launch_count", "msau_launch_count_add",
     "msau_plan_create", "msau_plan_destroy", "msau_param_count", "msau_param_info", "msau_plan_set_feature_table",
     "msau_workspace_bytes",
     "msau_forward", "msau_loss_backward", "msau_clip_adam_step",
@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
     L.msau_last_error.argtypes = []
     L.msau_version.restype = i32
     L.msau_launch_count.restype = i64
+    L.msau_launch_count_add.argtypes = [i64]
+    L.msau_launch_count_add.restype = None
     L.msau_plan_create.argtypes = [C.POINTER(MsauConfig), i32, i32, i32, C.POINTER(vp)]
     L.msau_plan_destroy.argtypes = [vp]
     L.msau_plan_destroy.restype = None

@@ -625,6 +625,7 @@ static int bind(MsauPlan* p, void* ws, size_t bytes, int training, void* stream)
 extern "C" const char* msau_last_error(void) { return msau::get_error(); }
 extern "C" int msau_version(void) { return 100; }
 extern "C" long long msau_launch_count(void) { return msau::g_launches.load(); }
+extern "C" void msau_launch_count_add(long long n) { msau::g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, int width, MsauPlan** out) {
   MSAU_CHECK_ARG(cfg && out, "plan_create: null argument");

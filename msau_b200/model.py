@@ -171,6 +171,8 @@ class MSAUWrapper(torch.nn.Module):
         self._anchor = None
         self._adam = None            # (exp_avg, exp_avg_sq, step, scratch)
         self._table = None           # fp32 [rows, channels] feature table of a box-constant (BERT-grid) batch, layout 3
+        self._graphs = {}            # (B, H, W, layout, dtype) -> (CUDAGraph, static input, static class map)
+        self._train_graphs = {}      # ... -> (CUDAGraph of forward + loss + backward, static x, static labels, loss, launches)
 
     # ------------------------------------------------------------------ parameters
     def _build_tree(self):
@@ -235,6 +237,8 @@ class MSAUWrapper(torch.nn.Module):
         self._flat = new_flat.contiguous()
         self._rebind()
         self._plans = {}
+        self._graphs = {}
+        self._train_graphs = {}
         self._last = None
         self._table = None
         return self
@@ -368,6 +372,32 @@ class MSAUWrapper(torch.nn.Module):
             out[b0:b0 + chunk.shape[0]] = self._run_forward(chunk, layout, False, False, want_argmax=True, want_logits=False)[5]
         return out
 
+    def predict_classes_graph(self, inp, layout: int = 0):
+        """``predict_classes`` replayed from a CUDA graph: the ~150 kernel launches of one inference forward are captured once
+        per (B, H, W, layout) and replayed with a single launch, which takes the host out of the latency of small batches
+        (BASELINE.json config 1: one 512x512 page).  The input is copied into the graph's static buffer, the class map comes
+        back as a fresh tensor; parameters are read from the flat buffer at every replay, so ``load_state_dict`` / training
+        steps between calls are seen."""
+        B, H, W = self._check_input(inp, layout)
+        key = (B, H, W, layout, inp.dtype)
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = inp.contiguous().clone()
+            side = torch.cuda.Stream(device=inp.device)
+            side.wait_stream(torch.cuda.current_stream(inp.device))
+            with torch.cuda.stream(side):            # warm-up outside capture: plan, workspace, kernel attributes
+                for _ in range(2):
+                    self._run_forward(static_in, layout, False, False, want_argmax=True, want_logits=False)
+            torch.cuda.current_stream(inp.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._run_forward(static_in, layout, False, False, want_argmax=True, want_logits=False)[5]
+            ent = self._graphs[key] = (graph, static_in, static_out)
+        graph, static_in, static_out = ent
+        static_in.copy_(inp)
+        graph.replay()
+        return static_out.clone()
+
     def _backward_from_last(self, labels: torch.Tensor, loss_scale: float = 1.0) -> torch.Tensor:
         if self._last is None:
             raise _lib.MsauError("loss/backward needs a preceding forward() in training mode with grad enabled")
@@ -424,17 +454,72 @@ class MSAUWrapper(torch.nn.Module):
 
     # ------------------------------------------------------------------ fused training step
     def train_step(self, x: torch.Tensor, labels: torch.Tensor, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                   max_norm: float = 1.0, layout: int = 0, process_group=None, world_size: int = 1):
+                   max_norm: float = 1.0, layout: int = 0, process_group=None, world_size: int = 1, use_graph: bool = False):
         """One step of train_chargrid_funsd_msau.py:45-59 on a batch of pages: forward, masked CE (main + aux),
         backward, [NCCL all-reduce of the flat gradient over ``process_group``], clip_grad_norm(max_norm),
-        Adam.  Returns the (local-batch) loss as a 0-d CUDA tensor; nothing synchronises with the host."""
-        pl, xc, _, _, _, _ = self._run_forward(x, layout, True, False, want_logits=False)
-        self._last = (pl, xc, layout, 0, 0)
-        loss = self._backward_from_last(labels, loss_scale=1.0 / world_size)
+        Adam.  Returns the (local-batch) loss as a 0-d CUDA tensor; nothing synchronises with the host.
+        ``use_graph``: forward + loss + backward (~420 kernel launches on two streams) are captured once per input shape into
+        a CUDA graph and replayed with one launch per step, so the step no longer depends on how fast the host can enqueue
+        kernels; the all-reduce and the clip + Adam kernels (which take the step count as an argument) stay eager.
+        ``use_graph="static"``: the caller keeps feeding the same (refilled) input tensors, so the graph reads them in place."""
+        if use_graph and layout != 3:
+            loss = self._fwd_bwd_graph(x, labels, layout, world_size, use_graph == "static")
+        else:
+            pl, xc, _, _, _, _ = self._run_forward(x, layout, True, False, want_logits=False)
+            self._last = (pl, xc, layout, 0, 0)
+            loss = self._backward_from_last(labels, loss_scale=1.0 / world_size)
         if world_size > 1:
             torch.distributed.all_reduce(self.flat_grads, group=process_group)
         self.adam_step(lr, betas, eps, max_norm)
         return loss
+
+    def _fwd_bwd_graph(self, x: torch.Tensor, labels: torch.Tensor, layout: int, world_size: int, static: bool) -> torch.Tensor:
+        """forward(training) + loss + backward as one CUDA-graph launch.  The graph reads private copies of the inputs (every
+        call copies x / labels into them: 12 MB for an id-map batch of 16 pages); with ``static`` it is bound to the caller's
+        own tensors instead, for loops that refill the same buffers in place (no copy; a dense 1.6 GB batch stays put)."""
+        B, H, W = self._check_input(x, layout)
+        if labels.dim() == 2:
+            labels = labels.unsqueeze(0)
+        if labels.dtype != torch.uint8:
+            labels = labels.to(torch.int64)
+        labels = labels.to(x.device)
+        key = (B, H, W, layout, x.dtype, labels.dtype, world_size, static)
+        ent = self._train_graphs.get(key)
+        if ent is None:
+            if static:
+                if not (x.is_contiguous() and labels.is_contiguous()):
+                    raise ValueError("use_graph='static' needs contiguous input tensors")
+                sx, sl = x, labels                        # the caller promises to keep feeding these very tensors
+            else:
+                sx, sl = x.contiguous().clone(), labels.contiguous().clone()
+            dev = x.device
+
+            def fwd_bwd():
+                pl, xc, _, _, _, _ = self._run_forward(sx, layout, True, False, want_logits=False)
+                self._last = (pl, xc, layout, 0, 0)
+                return self._backward_from_last(sl, loss_scale=1.0 / world_size)
+
+            self.flat_grads                               # allocate outside the capture
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                 # warm-up: plan, workspace, side stream / events, kernel attributes
+                fwd_bwd()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            n0 = _lib.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sloss = fwd_bwd()
+            ent = self._train_graphs[key] = (graph, sx, sl, sloss, _lib.launch_count() - n0)
+        graph, sx, sl, sloss, n_launch = ent
+        if static:
+            if x.data_ptr() != sx.data_ptr() or labels.data_ptr() != sl.data_ptr():
+                raise _lib.MsauError("use_graph='static': the step must be fed the tensors the graph was captured with")
+        else:
+            sx.copy_(x)
+            sl.copy_(labels)
+        graph.replay()
+        _lib.lib().msau_launch_count_add(n_launch)
+        return sloss.clone()
 
     def adam_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
         if self._adam is None:

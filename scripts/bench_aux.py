@@ -51,9 +51,10 @@ def main():
     with torch.no_grad():
         x1 = onehot_pages(1, 96, 512, 512, 1)
         ms1 = timed(lambda: m.predict_classes(x1))
+        ms1g = timed(lambda: m.predict_classes_graph(x1), reps=20)
         x16 = onehot_pages(16, 96, 512, 512, 2)
         ms16 = timed(lambda: m.predict_classes(x16))
-        out["c1_inference_512"] = dict(ms_per_page_batch1=ms1, pages_per_s_batch16=16 / (ms16 * 1e-3))
+        out["c1_inference_512"] = dict(ms_per_page_batch1=ms1, ms_per_page_batch1_cuda_graph=ms1g, pages_per_s_batch16=16 / (ms16 * 1e-3))
         x64 = onehot_pages(64, 96, 1024, 768, 3)
         ms64 = timed(lambda: m.predict_classes(x64), reps=3, warm=1)
         out["c5_inference_1024x768_b64"] = dict(ms=ms64, pages_per_s=64 / (ms64 * 1e-3))

@@ -309,3 +309,62 @@ def test_high_resolution_inference():
     out, _ = om.msau_forward(sd, cfg, x[:1].cpu())
     agree = (out.argmax(1) == cm[:1].cpu().long()).float().mean().item()
     assert agree >= 0.999, agree
+
+
+def test_inference_graph_replay_matches_eager(golden_dir):
+    """predict_classes_graph (one CUDA-graph launch per call) returns the eager class map, follows new inputs through its
+    static buffer and sees parameter updates made between replays."""
+    z, meta, cfg = load(golden_dir, "model_s4r2_c96")
+    sd = om.init_state_dict(cfg, meta["seed"])
+    m = build(cfg, sd).eval()
+    xs = [synth_input(cfg.channels, cfg.n_class, 1, 64, 48, s)[0].cuda() for s in (3, 4)]
+    with torch.no_grad():
+        for x in xs + xs[:1]:
+            assert torch.equal(m.predict_classes_graph(x), m.predict_classes(x))
+        assert len(m._graphs) == 1
+        sd2 = om.init_state_dict(cfg, meta["seed"] + 1)
+        m.load_state_dict(sd2)
+        got = m.predict_classes_graph(xs[0])
+        assert torch.equal(got, m.predict_classes(xs[0]))
+        assert torch.equal(got, build(cfg, sd2).eval().predict_classes(xs[0]))
+
+
+def test_graph_train_step_matches_eager(golden_dir):
+    """train_step(use_graph=...) -- forward + loss + backward replayed from a CUDA graph (two streams inside) -- gives the eager
+    step's losses and parameters, with private input copies (True) and bound to the caller's tensors ("static")."""
+    z, meta, cfg = load(golden_dir, "model_s4r2_c96")
+    sd = om.init_state_dict(cfg, meta["seed"])
+    batches = [synth_input(cfg.channels, cfg.n_class, 2, 64, 48, s) for s in (5, 6, 7)]
+    batches = [(x.cuda(), l.cuda()) for x, l in batches]
+    me, mg, ms = (build(cfg, sd).train() for _ in range(3))
+    xs, ls = batches[0][0].clone(), batches[0][1].clone()
+    def compare_params():
+        # atomics make the weight gradient's summation order (and the Adam sign of ~zero gradients) run-dependent: same
+        # bounds as the eager-vs-eager comparison in test_param_grads_and_train_step_match_golden
+        for (k, pe), pg, ps in zip(me.named_parameters(), mg.parameters(), ms.parameters()):
+            tol = 2.5e-4 if k.endswith("attention_block.f.conv.bias") else 2e-6
+            assert (pe.detach() - pg.detach()).abs().max().item() <= tol, k
+            assert (pe.detach() - ps.detach()).abs().max().item() <= tol, k
+
+    le, lg, lst = [], [], []
+    n_eager = n_graph = 0
+    for i, (x, l) in enumerate(batches):
+        n0 = _lib.launch_count()
+        le.append(float(me.train_step(x, l)))
+        n1 = _lib.launch_count()
+        lg.append(float(mg.train_step(x, l, use_graph=True)))
+        n2 = _lib.launch_count()
+        n_eager += n1 - n0
+        n_graph += n2 - n1
+        xs.copy_(x); ls.copy_(l)
+        lst.append(float(ms.train_step(xs, ls, use_graph="static")))
+        if i == 0:
+            compare_params()
+    assert len(mg._train_graphs) == 1 and len(ms._train_graphs) == 1
+    # warm-up + capture enqueue the forward/backward kernels twice more than the eager loop; every replay counts like an eager step
+    assert n_graph == n_eager + 2 * (n_eager - 6) // 3
+    for a, b, c in zip(le, lg, lst):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(a)) and abs(a - c) <= 1e-4 * max(1.0, abs(a))
+    assert le[-1] != le[0]
+    with pytest.raises(_lib.MsauError):
+        ms.train_step(batches[1][0], batches[1][1], use_graph="static")
