@@ -390,7 +390,7 @@ class MSAUWrapper(torch.nn.Module):
                     self._run_forward(static_in, layout, False, False, want_argmax=True, want_logits=False)
             torch.cuda.current_stream(inp.device).wait_stream(side)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                 static_out = self._run_forward(static_in, layout, False, False, want_argmax=True, want_logits=False)[5]
             ent = self._graphs[key] = (graph, static_in, static_out)
         graph, static_in, static_out = ent
@@ -507,7 +507,7 @@ class MSAUWrapper(torch.nn.Module):
             torch.cuda.current_stream(dev).wait_stream(side)
             n0 = _lib.launch_count()
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                 sloss = fwd_bwd()
             ent = self._train_graphs[key] = (graph, sx, sl, sloss, _lib.launch_count() - n0)
         graph, sx, sl, sloss, n_launch = ent
