@@ -598,6 +598,11 @@ bool conv_tc_supported(const ConvArgs& a) {
   return tc_configure(a, t);
 }
 
+long tc_half_elems(int taps, int cin) {
+  const long elems = (long)(cin / 8) * (taps + (taps + 1) / 2) * 128 * 16;
+  return (elems + 127) / 128 * 128;
+}
+
 int tc_weight_floats_equiv(int taps, int cin, int coutp) {
   const int N = coutp < 16 ? 16 : round_up(coutp, 16);
   const long bytes = (long)(cin / 8) * (taps + (taps + 1) / 2) * N * 32;
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
     tap = 2 * (img - taps) + chunk;
     if (tap >= taps) tap = -1;
   }
-  if (tap >= 0 && n < d.coutp) w = pk[d.src_off + ((long)tap * d.cin + 8 * p + k) * d.coutp + n];
+  if (tap >= 0 && n < d.coutp) w = pk[d.src_off + ((long)tap * d.cin + 8 * p + k) * d.src_pitch + d.col0 + n];
   const __nv_bfloat16 h = __float2bfloat16_rn(w);
   const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w - __bfloat162float(h)) : h;
   pktc[d.dst_off + e] = __bfloat16_as_ushort(out);

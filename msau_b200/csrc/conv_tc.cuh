@@ -2,11 +2,14 @@
 #include "common.cuh"
 namespace msau {
 struct TcPackDesc {
-  long src_off;   // floats, into the fp32 packed buffer: [taps][cin][coutp]
+  long src_off;   // floats, into the fp32 packed buffer: [taps][cin][src_pitch]
   long dst_off;   // bf16 elements, into the tensor-core weight buffer
   int taps, cin, coutp, N;
   long blk0;
+  int src_pitch, col0;   // the image covers columns col0 .. col0 + coutp - 1 of the source (256-column layers = two 128-column images)
 };
+// bf16 elements of one 128-column weight image (second half of a 256-column layer sits this far behind the first)
+long tc_half_elems(int taps, int cin);
 bool conv_tc_supported(const ConvArgs& a);
 int tc_weight_floats_equiv(int taps, int cin, int coutp);
 int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st);

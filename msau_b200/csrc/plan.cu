@@ -202,22 +202,31 @@ static void add_desc(MsauPlan* p, long dst, int TH, int TW, int I, int O, int i_
 }
 
 static long add_tc(MsauPlan* p, long src_off, int taps, int cin, int coutp) {
-  if (cin % 8 != 0 || coutp > 128) return -1;
-  TcPackDesc d;
-  d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = taps; d.cin = cin; d.coutp = coutp;
-  d.N = coutp < 16 ? 16 : round_up(coutp, 16);
-  const long elems = (long)(cin / 8) * (taps + (taps + 1) / 2) * d.N * 16;
-  d.blk0 = p->tc_blocks;
-  p->tc_blocks += cdiv(elems, 256);
-  p->tc_elems += (elems + 127) / 128 * 128;
-  p->tc_descs.push_back(d);
-  return d.dst_off;
+  // conv_tc takes up to 128 output columns per launch; a 256-column layer (the S6 model's deepest level) gets two images back
+  // to back (tc_half_elems apart) and runs as two launches on the two halves of the output channels
+  if (cin % 8 != 0 || (coutp > 128 && coutp != 256)) return -1;
+  const int halves = coutp > 128 ? 2 : 1, cw = coutp / halves;
+  long first = -1;
+  for (int h = 0; h < halves; ++h) {
+    TcPackDesc d;
+    d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = taps; d.cin = cin; d.coutp = cw;
+    d.src_pitch = coutp; d.col0 = h * cw;
+    d.N = cw < 16 ? 16 : round_up(cw, 16);
+    const long elems = (long)(cin / 8) * (taps + (taps + 1) / 2) * d.N * 16;
+    d.blk0 = p->tc_blocks;
+    p->tc_blocks += cdiv(elems, 256);
+    p->tc_elems += (elems + 127) / 128 * 128;
+    p->tc_descs.push_back(d);
+    if (h == 0) first = d.dst_off;
+  }
+  return first;
 }
 
 static long add_tc3(MsauPlan* p, long src_off, int cin, int coutp, int ks = 3) {
   if (cin % 8 != 0 || !(coutp == 8 || coutp == 16 || coutp == 32 || coutp == 64) || (ks == 4 && coutp != 8)) return -1;
   TcPackDesc d;
   d.src_off = src_off; d.dst_off = p->tc_elems; d.taps = ks * ks; d.cin = cin; d.coutp = coutp;
+  d.src_pitch = coutp; d.col0 = 0;
   d.N = round_up(ks * coutp, 16);
   const long elems = (long)(cin / 8) * (ks + (ks + 1) / 2) * d.N * 16;
   d.blk0 = p->t3_blocks;
@@ -363,6 +372,22 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   if (g_use_tc && g_use_pw && k == 1 && conv1x1_supported(a)) return launch_conv1x1(a, p->st);
   if (g_use_tc && g_use_c3 && t3_off >= 0 && coutp <= g_c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
   if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
+  if (g_use_tc && tc_off >= 0 && coutp == 256) {     // two launches over the two halves of the output channels (add_tc)
+    ConvArgs h0 = a;
+    h0.coutp = 128;
+    if (conv_tc_supported(h0)) {
+      ConvArgs h1 = h0;
+      h1.out += 128;
+      if (h1.bias) h1.bias += 128;
+      if (h1.res) h1.res += 128;
+      if (h1.omask) h1.omask += 128;
+      if (h1.add) h1.add += 128;
+      if (h1.addmask) h1.addmask += 128;
+      count_launch(1);
+      MSAU_TRY(launch_conv_tc(h0, p->pktc + tc_off, p->st));
+      return launch_conv_tc(h1, p->pktc + tc_off + tc_half_elems(k * k, c1 + c2), p->st);
+    }
+  }
   return launch_conv(a, p->st);
 }
 
@@ -412,6 +437,20 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
   a.skip_flag = skip_flag;
+  if (g_use_tc && a.cb == 256 && cb < 0 && !wgrad_tc_supported(a)) {
+    // the tensor-core kernels take up to 128 output channels: run the two halves of a 256-channel dY separately
+    WgradArgs h = a;
+    h.cb = 128;
+    if (wgrad_tc_supported(h)) {
+      const long base_w = w_off_override >= 0 ? w_off_override : L.w_off, base_b = b_off_override >= 0 ? b_off_override : L.b_off;
+      for (int hf = 0; hf < 2; ++hf) {
+        const int lim = L.cout - 128 * hf < 0 ? 0 : (L.cout - 128 * hf > 128 ? 128 : L.cout - 128 * hf);
+        MSAU_TRY(layer_wgrad(p, L, which, src, psrc, nchw, c_logical, reluA, dy, pdy, dymask, pm, H, W, base_w + 128L * hf * cin * kk,
+                             base_b + 128 * hf, cb_off + 128 * hf, 128, lim, skip_flag));
+      }
+      return MSAU_OK;
+    }
+  }
   count_launch(1);
   MSAU_TRY(wgrad_fork(p));
   if (g_use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->wst);

@@ -1084,31 +1084,8 @@ static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t 
   return MSAU_OK;
 }
 
-bool wgrad_tc_supported(const WgradArgs& a) {
-  if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
-  if (a.Ha != a.Hq || a.Wa != a.Wq) return false;
-  if (a.b_s2d) {
-    if (a.cb != 4 * a.cph || (a.cph & 7) || a.maskB || a.kh != 2 || a.kw != 2) return false;
-    if (a.Hb > 2 * a.Hq || a.Hb < 2 * a.Hq - 1 || a.Wb > 2 * a.Wq || a.Wb < 2 * a.Wq - 1) return false;
-  } else if (a.Hb != a.Hq || a.Wb != a.Wq) return false;
-  if ((a.ca & 7) || (a.cb & 7) || a.cb > 128 || a.kw > 4 || a.kh > 4) return false;
-  const int nyp = a.cb >> 3;
-  if (256 % nyp) return false;
-  if (!a.a_nchw && (a.pa & 3)) return false;
-  if (a.pb & 3) return false;
-  if (a.dila < 1) return false;
-  return true;
-}
-
-int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
-  MSAU_CHECK_ARG(wgrad_tc_supported(a), "wgrad_tc: unsupported shape");
-  {
-    Wg3Tile t3;
-    if (wgrad_tc3_config(a, t3)) return launch_wgrad_tc3(a, t3, st);
-    Wg2Tile t2;
-    if (wgrad_tc2_config(a, t2)) return launch_wgrad_tc2(a, t2, st);
-  }
-  WgTile t;
+// tile geometry of the generic kernel; false when it does not fit shared memory / TMEM (large dilation on a wide dY)
+static bool wg_config(const WgradArgs& a, WgTile& t, size_t& smem, int& ctas_out) {
   t.N = a.cb;                           // M = 64 allows any multiple of 8
   t.ny_planes = a.cb >> 3;
   int px_budget = 16384 / a.cb;         // dY tile <= 32 KB of bf16
@@ -1141,8 +1118,50 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   int cols = a.kh * t.N;
   t.tmem_cols = 32;
   while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
-  const size_t smem = (size_t)t.stage_bytes * 2 + 1024;
-  MSAU_CHECK_ARG(smem <= 200 * 1024 && t.tmem_cols <= 512, "wgrad_tc: tile does not fit (smem %zu B, tmem %u cols)", smem, t.tmem_cols);
+  smem = (size_t)t.stage_bytes * 2 + 1024;
+  ctas_out = ctas;
+  return smem <= 200 * 1024 && t.tmem_cols <= 512;
+}
+
+bool wgrad_tc_supported(const WgradArgs& a) {
+  if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
+  if (a.Ha != a.Hq || a.Wa != a.Wq) return false;
+  if (a.b_s2d) {
+    if (a.cb != 4 * a.cph || (a.cph & 7) || a.maskB || a.kh != 2 || a.kw != 2) return false;
+    if (a.Hb > 2 * a.Hq || a.Hb < 2 * a.Hq - 1 || a.Wb > 2 * a.Wq || a.Wb < 2 * a.Wq - 1) return false;
+  } else if (a.Hb != a.Hq || a.Wb != a.Wq) return false;
+  if ((a.ca & 7) || (a.cb & 7) || a.cb > 128 || a.kw > 4 || a.kh > 4) return false;
+  const int nyp = a.cb >> 3;
+  if (256 % nyp) return false;
+  if (!a.a_nchw && (a.pa & 3)) return false;
+  if (a.pb & 3) return false;
+  if (a.dila < 1) return false;
+  {
+    Wg3Tile t3;
+    if (wgrad_tc3_config(a, t3)) return true;
+    Wg2Tile t2;
+    if (wgrad_tc2_config(a, t2)) return true;
+  }
+  WgTile t;
+  size_t smem;
+  int ctas;
+  return wg_config(a, t, smem, ctas);
+}
+
+int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
+  MSAU_CHECK_ARG(wgrad_tc_supported(a), "wgrad_tc: unsupported shape");
+  {
+    Wg3Tile t3;
+    if (wgrad_tc3_config(a, t3)) return launch_wgrad_tc3(a, t3, st);
+    Wg2Tile t2;
+    if (wgrad_tc2_config(a, t2)) return launch_wgrad_tc2(a, t2, st);
+  }
+  WgTile t;
+  size_t smem = 0;
+  int ctas = 0;
+  const bool fits = wg_config(a, t, smem, ctas);
+  const int planes = a.ca >> 3;
+  MSAU_CHECK_ARG(fits, "wgrad_tc: tile does not fit (smem %zu B, tmem %u cols)", smem, t.tmem_cols);
   static bool attr = false;
   if (!attr) {
     MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -11,8 +11,9 @@ B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 for kv in sys.argv[3:]:                      # engine options, e.g. wgrad_side_stream=0 lrn_coop=0
     k, v = kv.split("=")
     _lib.set_option(k, int(v))
-cfg = om.MsauConfig()
-m = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=8, scale_space_num=4, res_depth=2))
+S, R = int(os.environ.get("MSAU_S", 4)), int(os.environ.get("MSAU_R", 2))     # MSAU_S=6 MSAU_R=3: the wrapper-default model
+cfg = om.MsauConfig(scale_space_num=S, res_depth=R)
+m = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=8, scale_space_num=S, res_depth=R))
 m.load_state_dict(om.init_state_dict(cfg, 0)); m = m.cuda().train()
 x, labels = synth_input(cfg.channels, cfg.n_class, B, 512, 512, 3); x, labels = x.cuda(), labels.cuda()
 for _ in range(3): m.train_step(x, labels)

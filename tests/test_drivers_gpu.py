@@ -96,6 +96,25 @@ def test_extract_value_matches_oracle(seed, n_class, noise):
     assert any(v[0] for v in want)
 
 
+def test_extract_value_degenerate_inputs():
+    """No foreground pixel at all, only specks below the area threshold, and a 2-class map (no field classes)."""
+    H, W = 40, 56
+    lm = np.zeros((H, W), np.uint16); lm[5:9, 4:30] = 1
+    cm = np.zeros((H, W), np.uint16); cm[5:9, 4:30] = np.arange(1, 27)[None, :]
+    lines = [dict(box=[4, 5, 30, 9], text="abcdefghijklmnopqrstuvwxyz", type=0, value=0)]
+    pm = np.zeros((H, W, 5), np.float32); pm[:, :, 0] = 1.0
+    values, mask = kv_model.KVModel._extract_value(lm, cm, [dict(l) for l in lines], pm, 5)
+    assert values == [("", None, None, None)] * 5 and mask.shape == (H, W, 5) and mask[:, :, 1:].sum() == 0
+    pm2 = pm.copy(); pm2[6, 10, 0] = 0.0; pm2[6, 10, 3] = 1.0; pm2[6, 11, 0] = 0.0; pm2[6, 11, 3] = 1.0     # area 2 < 5
+    values, mask = kv_model.KVModel._extract_value(lm, cm, [dict(l) for l in lines], pm2, 5)
+    assert all(v[0] == "" for v in values) and mask[:, :, 1:].sum() == 0
+    pm3 = pm.copy(); pm3[5:9, 4:30, 0] = 0.0; pm3[5:9, 4:30, 3] = 1.0                                        # one clean field
+    values, mask = kv_model.KVModel._extract_value(lm, cm, [dict(l) for l in lines], pm3, 5)
+    assert values[3][0] == lines[0]["text"] and values[3][1] == [[4, 5, 30, 9]] and mask[:, :, 3].sum() == 4 * 26
+    values, mask = kv_model.KVModel._extract_value(lm, cm, [dict(l) for l in lines], pm[:, :, :2], 2)
+    assert values == [("", None, None, None)] * 2 and mask.shape == (H, W, 2)
+
+
 def test_train_and_evaluate_loop():
     cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
     model = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))

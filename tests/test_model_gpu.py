@@ -368,3 +368,30 @@ def test_graph_train_step_matches_eager(golden_dir):
     assert le[-1] != le[0]
     with pytest.raises(_lib.MsauError):
         ms.train_step(batches[1][0], batches[1][1], use_graph="static")
+
+
+def test_s6r3_deep_levels(tc):
+    """Wrapper-default depth (S=6, R=3) on a 256x256 page, where the 128- and 256-channel levels are 16x16 and 8x8 maps: wide
+    enough for the tensor-core kernels, so the 256-column convs run as two 128-column launches (forward, data gradient and
+    weight gradient).  Logits, loss and every parameter-gradient norm against the torch-fp32 oracle."""
+    cfg = om.MsauConfig(channels=16, n_class=5, scale_space_num=6, res_depth=3, feat_root=8)
+    sd = om.init_state_dict(cfg, 31)
+    x, labels = synth_input(cfg.channels, cfg.n_class, 1, 256, 256, 32)
+    m = build(cfg, sd).train()
+    _, logits, aux = m(x.cuda())
+    loss = m.loss(logits, aux, labels.cuda())
+    loss.backward()
+    ref_loss, ref_logits, ref_aux, ref_grads = om.loss_and_grads(sd, cfg, x, labels)
+    assert (logits.cpu() - ref_logits).abs().max().item() <= LOGIT_ATOL
+    assert (aux.cpu() - ref_aux).abs().max().item() <= LOGIT_ATOL
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-4 * max(1.0, float(ref_loss))
+    named = dict(m.named_parameters())
+    keys = [k for k, _ in om.param_schema(cfg)]
+    got = np.array([0.0 if named[k].grad is None else float(named[k].grad.double().norm()) for k in keys])
+    want = np.array([0.0 if ref_grads[k] is None else float(ref_grads[k].double().norm()) for k in keys])
+    np.testing.assert_allclose(got, want, rtol=3e-2 if tc else 2e-3, atol=2e-5 if tc else 2e-6)
+    for k in ("msau_net.blocks.0.downsamplingblock.conv_res_list.5.conv_res_list.1.custom_conv.weight",
+              "msau_net.blocks.1.downsamplingblock.conv1s.5.conv.weight",
+              "msau_net.blocks.1.upsamplingblock.deconvs.4.conv.weight"):
+        d = (named[k].grad.cpu() - ref_grads[k]).double().norm().item() / ref_grads[k].double().norm().item()
+        assert d <= (3e-2 if tc else 2e-3), (k, d)

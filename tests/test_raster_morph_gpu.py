@@ -195,6 +195,48 @@ def test_bert_row_id_path_equals_dense_path():
     assert abs(l0 - float(ref_loss)) <= 1e-4 * max(1.0, float(ref_loss)) and l2 < l0 and np.isfinite(l1)
 
 
+def test_bert_row_id_path_edge_cases():
+    """An empty page (every id -1) next to a page covered by ONE box: the empty page contributes the bias-only response, the
+    first-layer weight gradient equals that of the dense run, and out-of-range table sizes are refused."""
+    import msau_b200
+    from oracle import model as om
+    D, H, W = 768, 32, 32
+    table = 0.3 * torch.randn(3, D, generator=torch.Generator().manual_seed(1)).cuda()
+    ids = torch.full((2, H, W), -1, dtype=torch.int16, device="cuda")
+    ids[1, 4:20, 3:29] = 2
+    dense = torch.zeros(2, D, H, W, device="cuda")
+    dense[1, :, 4:20, 3:29] = table[2][:, None, None]
+    labels = torch.randint(0, 5, (2, H, W), generator=torch.Generator().manual_seed(2)).cuda()
+    labels[:, 0, 0] = 1
+    cfg = om.MsauConfig(channels=D)
+    sd = om.init_state_dict(cfg, 8)
+    kw = dict(final_act="softmax", featRoot=8, scale_space_num=4, res_depth=2)
+    ma = msau_b200.MSAUWrapper(D, 5, kw); ma.load_state_dict(sd); ma = ma.cuda().train()
+    mb = msau_b200.MSAUWrapper(D, 5, kw); mb.load_state_dict(sd); mb = mb.cuda().train()
+    mb.set_feature_table(table)
+    pl, xc, lg_b, _, _, _ = mb._run_forward(ids, 3, True, False)
+    mb._last = (pl, xc, 3, 0, 0)
+    loss_b = mb._backward_from_last(labels)
+    _, lg_a, aux_a = ma(dense)
+    loss_a = ma.loss(lg_a, aux_a, labels)
+    loss_a.backward()
+    assert (lg_a - lg_b).abs().max().item() <= 5e-4 and abs(float(loss_a.detach()) - float(loss_b)) <= 1e-4
+    k = "msau_net.blocks.0.downsamplingblock.conv1s.0.conv.weight"
+    ga = dict(ma.named_parameters())[k].grad
+    n = ga.numel()
+    gb = mb.flat_grads[:0]
+    off = 0
+    for kk, p in mb.named_parameters():
+        if kk == k:
+            gb = mb.flat_grads[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    assert gb.numel() == n and (ga - gb).double().norm().item() <= 3e-2 * ga.double().norm().item()
+    with pytest.raises(ValueError):
+        mb.set_feature_table(torch.zeros(40000, D))
+    with pytest.raises(ValueError):
+        mb.set_feature_table(torch.zeros(3, D + 1))
+
+
 @pytest.fixture(scope="module")
 def mgold(golden_dir):
     z = np.load(os.path.join(golden_dir, "morph.npz"))
