@@ -140,11 +140,16 @@ class KVModel:
     @staticmethod
     def _dev_components(pred_class: torch.Tensor, n_class: int, max_labels: int):
         """closing + labelling of every foreground class map in one batch (kv_model.py:174-177) ->
-        (labels int32 [n_maps,H,W] on the device, component counts [n_maps] and bounding boxes [n_maps, n, 4] on the host)."""
+        (labels int32 [n_maps,H,W] on the device, component counts [n_maps] and bounding boxes [n_maps, n, 4] on the host, the
+        label capacity actually used: the labelling is repeated with a larger box table when a map has more components)."""
         maps = torch.stack([morph.class_equals(pred_class[None], c)[0] for c in range(2, n_class)])
-        labels, n_lab, bboxes = morph.ccl_batch(morph.closing_batch(maps, (1, 3)), max_labels)
+        closed = morph.closing_batch(maps, (1, 3))
+        labels, n_lab, bboxes = morph.ccl_batch(closed, max_labels)
         n_lab_h = n_lab.cpu().numpy()
-        return labels, n_lab_h, bboxes[:, :max(int(n_lab_h.max()), 1)].cpu().numpy()
+        if int(n_lab_h.max()) > max_labels:          # a noisy map (untrained weights): boxes of every component are needed
+            max_labels = 1 << (int(n_lab_h.max()) - 1).bit_length()
+            labels, n_lab, bboxes = morph.ccl_batch(closed, max_labels)
+        return labels, n_lab_h, bboxes[:, :max(int(n_lab_h.max()), 1)].cpu().numpy(), max_labels
 
     @staticmethod
     def _dev_select(labels, line_mask, slot_of: np.ndarray, n_slots: int, num_lines: int):
@@ -194,9 +199,7 @@ class KVModel:
             l["id"] = i + 1
         if n_maps <= 0:
             return values, None
-        labels, n_lab_h, bb_h = cls._dev_components(pred_class, n_class, max_labels)
-        if int(n_lab_h.max()) > max_labels:
-            raise RuntimeError(f"_extract_value: {int(n_lab_h.max())} components in one class map, max_labels={max_labels}")
+        labels, n_lab_h, bb_h, max_labels = cls._dev_components(pred_class, n_class, max_labels)
         # ---- pick components per class from the bounding boxes (kv_model.py:181-205)
         slot_of = np.full((n_maps, max_labels + 1), -1, np.int32)
         picked = {}                                       # c -> [component ids, best first then alternatives]

@@ -1,6 +1,7 @@
 """Secondary measurements (BASELINE.json configs 0, 2, 3, 4): one JSON object on stdout.
 
   c1  chargrid inference, 1 page 512x512                      -> ms / page (latency), pages/s at batch 16
+      + KVModel.predict end to end on one page (reference inference API)
   c3  BERT-grid (768-channel dense input) train step, batch 8  -> pages/s
   s6r3  the wrapper-default model (S=6, R=3: levels of 8..256 channels), chargrid train step, batch 16 -> pages/s
   c4  R1 rasterisation of 256 pages (~200 boxes) + closing(1,3) + 4-connected labelling of 3 class maps per page
@@ -60,6 +61,28 @@ def main():
         out["c5_inference_1024x768_b64"] = dict(ms=ms64, pages_per_s=64 / (ms64 * 1e-3))
         del x64, x16, x1
     torch.cuda.empty_cache()
+    # c1 through the reference's inference API: KVModel.predict on one synthetic FUNSD-shaped page (198 text lines): JSON lines ->
+    # R3 masks -> one-hot -> network -> arg-max -> closing + labelling per class -> _extract_value -> field strings
+    from msau_b200 import kv_model
+    charset = "".join(chr(c) for c in range(33, 127) if chr(c) != "$") + chr(161)
+    words, _ = orr.synth_page(11, 512, 512, 198)
+    texts = ["".join(charset[c - 2] for c in ch) for ch in words["chars"]]
+    page = dict(lines=[dict(box=[int(words["x"][i]), int(words["y"][i]), int(words["x"][i] + words["w"][i]),
+                                 int(words["y"][i] + words["h"][i])], text=texts[i], type=0, value=0) for i in range(len(texts))])
+    kv = kv_model.KVModel()
+    kv.net = m
+    kv.load(model_weight=None, charset=None, n_class=cfg.n_class)
+    kv.set_charset(charset)
+    import copy
+
+    def kv_predict():
+        return kv.predict((copy.deepcopy(page), None))
+
+    with torch.no_grad():
+        ms_kv = timed(kv_predict, reps=10)
+        im = kv._generate_masks_from_label(copy.deepcopy(page), as_numpy=False)[0]
+    out["c1_kv_predict_one_page"] = dict(ms=ms_kv, grid=list(im.shape), lines=len(texts),
+                                         note="KVModel.predict: JSON lines -> R3 masks -> network -> closing / labelling -> field values, host syncs included")
     # c3
     cfg3 = om.MsauConfig(channels=768)
     m3 = msau_b200.MSAUWrapper(768, 5, kw)

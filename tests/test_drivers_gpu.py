@@ -115,6 +115,25 @@ def test_extract_value_degenerate_inputs():
     assert values == [("", None, None, None)] * 2 and mask.shape == (H, W, 2)
 
 
+def test_extract_value_many_components():
+    """A salt-and-pepper class map (what untrained weights predict) has more components than the default box table holds:
+    the labelling is repeated with a larger table and the result still equals the oracle's."""
+    from oracle import kv as okv
+    rng = np.random.RandomState(3)
+    H, W = 96, 120
+    cls_map = rng.randint(0, 5, (H, W))
+    pm = np.zeros((H, W, 5), np.float32)
+    pm[np.arange(H)[:, None], np.arange(W)[None, :], cls_map] = 1.0
+    lm = np.zeros((H, W), np.uint16); lm[10:14, 5:100] = 1; lm[30:34, 5:100] = 2
+    cm = np.zeros((H, W), np.uint16); cm[10:14, 5:100] = np.arange(1, 96)[None, :]; cm[30:34, 5:100] = np.arange(1, 96)[None, :]
+    lines = [dict(box=[5, 10, 100, 14], text="a" * 95, type=0, value=0), dict(box=[5, 30, 100, 34], text="b" * 95, type=0, value=0)]
+    want, want_mask = okv.extract_value(lm, cm, [dict(l) for l in lines], pm, 5)
+    labels, n_lab, bb, cap = kv_model.KVModel._dev_components(torch.from_numpy(cls_map.astype(np.uint8)).cuda(), 5, 64)
+    assert int(n_lab.max()) > 64 and cap >= int(n_lab.max()) and bb.shape[1] == int(n_lab.max())
+    got, got_mask = kv_model.KVModel._extract_value(lm, cm, [dict(l) for l in lines], pm, 5)
+    assert [tuple(v) for v in got] == [tuple(v) for v in want] and np.array_equal(got_mask, want_mask)
+
+
 def test_train_and_evaluate_loop():
     cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
     model = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))

@@ -22,7 +22,7 @@ class HostKV(KVModel):
         bb = np.zeros((n_class - 2, max(int(n_lab.max()), 1), 4), np.int32)
         for c in range(2, n_class):
             bb[c - 2, :n_lab[c - 2]] = res[c][2]
-        return labels, n_lab, bb
+        return labels, n_lab, bb, max_labels
 
     @staticmethod
     def _dev_select(labels, line_mask, slot_of, n_slots, num_lines):
