@@ -208,17 +208,19 @@ class KVModel:
             n = int(n_lab_h[c - 2])
             if n == 0:
                 continue
-            objects = morph.objects_from_bboxes(n, bb_h[c - 2])
-            area = [(o[1].stop - o[1].start) * (o[0].stop - o[0].start) for o in objects]
+            bb = bb_h[c - 2, :n].astype(np.int64)             # y0, y1, x0, x1 (half-open), one row per component
+            area = (bb[:, 3] - bb[:, 2]) * (bb[:, 1] - bb[:, 0])           # morph_util.area, same integers as the reference's list
             multi = c in cls.multiple_lines_fields
-            order = np.argsort([-np.mean([o[0].stop, o[0].start]) for o in objects]) if multi else np.argsort(area)
+            # np.argsort on the same values in the same order as the reference's Python lists (ties break identically);
+            # ycenter = np.mean([stop, start]) = (y0 + y1) / 2 exactly
+            order = np.argsort(-((bb[:, 1] + bb[:, 0]) / 2.0)) if multi else np.argsort(area)
             best = int(order[-1])
             if area[best] < 5:
                 continue
             alts = [int(k) for k in order[:-1] if area[int(k)] > 5] if (multi and n > 1) else []
             for k in alts + [best]:
-                o = objects[k]
-                boxes_for_field[c].append([o[1].start, o[0].start, o[1].stop, o[0].stop])
+                y0, y1, x0, x1 = (int(v) for v in bb[k])
+                boxes_for_field[c].append([x0, y0, x1, y1])
             picked[c] = [best] + alts
             for k in picked[c]:
                 slot_of[c - 2, k + 1] = n_slots
