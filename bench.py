@@ -79,10 +79,10 @@ class ClockSampler:
 
 
 def synth_records(first_seed, n):
-    from oracle import raster as orr
+    from bench_inputs import synth_page
     wp, lp = [], []
     for i in range(n):
-        w, l = orr.synth_page(first_seed + i, H, W, 198)
+        w, l = synth_page(first_seed + i, H, W, 198)
         wp.append(w); lp.append(l)
     return wp, lp
 
@@ -155,7 +155,6 @@ def main():
 
     import msau_b200
     from msau_b200 import _lib, raster
-    from oracle import model as om
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,16 +182,17 @@ def main():
             return float(t)
         return ms
 
-    cfg = om.MsauConfig(**CFG)
-    model = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=cfg.feat_root,
-                                                                  scale_space_num=cfg.scale_space_num, res_depth=cfg.res_depth))
-    model.load_state_dict(om.init_state_dict(cfg, 0))     # identical replicas on every rank
+    # nothing under oracle/ is touched by this arm: the wrapper's own initialiser draws the reference's init distributions
+    # (model/layers/layers.py:33-36,59-60) from a seeded CPU generator -> identical replicas on every rank
+    model = msau_b200.MSAUWrapper(CFG["channels"], CFG["n_class"], dict(final_act="softmax", featRoot=CFG["feat_root"],
+                                                                          scale_space_num=CFG["scale_space_num"], res_depth=CFG["res_depth"]))
+    model.reset_parameters(seed=0)
     model = model.to(dev).train()
     pg = dist.group.WORLD if world > 1 else None
 
     # ---- synthetic pages for this rank: records on the host, dense grid rasterised once for the resident run
     words, lines = synth_records(rank * P, P)
-    table = torch.eye(cfg.channels, dtype=torch.float64, device=dev)
+    table = torch.eye(CFG["channels"], dtype=torch.float64, device=dev)
     grid, label, _ = raster.rasterize_word_chargrid(words, lines, table, out_hw=(H, W), layout="nchw", device=dev)
     labels64 = label.long()
 
