@@ -15,7 +15,7 @@ namespace msau {
 // PX pixels per thread and iteration (256 pixels apart, so every load / store instruction of a warp is still one contiguous
 // run): PX x more independent 16-byte loads in flight before the FMA chain starts.
 template <int CO, int PX>
-__global__ void __launch_bounds__(256) conv1x1_kernel(const ConvArgs a, long npix) {
+__global__ void __launch_bounds__(256, CO == 8 ? 3 : (CO == 16 ? 2 : 1)) conv1x1_kernel(const ConvArgs a, long npix) {
   extern __shared__ __align__(16) float wsm[];                 // [cin][CO]
   if (a.skip_flag && *a.skip_flag == 0) return;
   const int cin = a.c1 + a.c2;
