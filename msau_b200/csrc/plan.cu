@@ -338,7 +338,7 @@ static bool g_side_stream = true;  // weight-gradient kernels on a side stream, 
 static bool g_fuse_mask = true;    // coupling dgrad applies the ReLU mask of the residual block it feeds (no relu_mask pass)
 static bool g_use_pw = true;       // 1x1 convs on the fp32 streaming kernel (conv1x1.cu)
 static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
-static int g_c3_max = 32;        // ... for at most this many output channels (measured: 16 -> 32 is worth 0.16 ms per step, 64 nothing)
+static int g_c3_max = 16;        // ... for at most this many output channels (option conv3_max_channels: 32 is worth 0.06-0.16 ms per step, 64 nothing)
 
 struct ConvOpt {
   bool relu1 = false, relu = false, relu2 = false;
