@@ -70,3 +70,31 @@ def test_reference_quirks():
     m = msau_b200.MSAUWrapper(12, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))
     with pytest.raises(msau_b200.MsauError):   # no CPU fallback
         m(torch.zeros(1, 12, 16, 16))
+
+
+def test_no_cpu_fallback_anywhere():
+    """Every public entry point fails loudly on a machine without a GPU instead of computing on the host."""
+    import numpy as np
+    from msau_b200 import kv_model, morph, raster
+    m = msau_b200.MSAUWrapper(12, 5, dict(final_act="softmax", featRoot=8, scale_space_num=3, res_depth=2))
+    x = torch.zeros(1, 12, 16, 16)
+    lab = torch.ones(1, 16, 16, dtype=torch.int64)
+    for call in (lambda: m.train_step(x, lab), lambda: m.train_step(x, lab, use_graph=True), lambda: m.predict_classes(x),
+                 lambda: m.predict_classes_graph(x), lambda: m.set_feature_table(torch.zeros(3, 12)),
+                 lambda: m.loss(x, x, lab)):
+        with pytest.raises(msau_b200.MsauError):
+            call()
+    if not torch.cuda.is_available():
+        with pytest.raises(msau_b200.MsauError):
+            raster.rasterize_kv([np.array([[0, 0, 10, 10]], np.float64)], [[np.array([3], np.int32)]])
+        with pytest.raises((msau_b200.MsauError, AssertionError, RuntimeError)):
+            morph.r_closing(np.zeros((8, 8), bool), (1, 3))
+        with pytest.raises((msau_b200.MsauError, AssertionError, RuntimeError)):
+            kv_model.KVModel._extract_value(np.zeros((8, 8), np.uint16), np.zeros((8, 8), np.uint16), [], np.zeros((8, 8, 5), np.float32), 5)
+
+
+def test_s6r3_defaults_are_plannable_and_counted():
+    """The wrapper's own defaults (model/model.py:406-408: S=6, R=3, featRoot=8) build the reference's 13.08 M-parameter schema."""
+    m = msau_b200.MSAUWrapper(96, 5, dict(final_act="softmax"))
+    assert m.scale_space_num == 6 and m.res_depth == 3 and m.featRoot == 8
+    assert m.flat_params.numel() == 13083687          # SURVEY.md section 8(d): 13.08 M
