@@ -134,6 +134,81 @@ def run_reference(args):
         e2e=dict(value=val, unit="pages/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
 
 
+
+# --------------------------------------------------------------------------------------------- extra legs
+def bench_c5(model, raster, rank, dev, timed, world, reps):
+    """BASELINE.json configs[4]: 1024x768 chargrid inference, 64 pages per GPU (replicas only).  The pages are rasterised on the
+    device into int16 channel-id maps once; a step = predict_classes (arg-max class map, uint8) over the 64 resident pages."""
+    import torch
+    from bench_inputs import synth_page
+    Hc, Wc, n = 1024, 768, 64
+    wp, lp = [], []
+    for i in range(n):
+        w, l = synth_page(5000 + rank * n + i, Hc, Wc, 198)
+        wp.append(w); lp.append(l)
+    table = torch.eye(CFG["channels"], dtype=torch.float64, device=dev)
+    ids, _, _ = raster.rasterize_word_chargrid(wp, lp, table, out_hw=(Hc, Wc), layout="ids", device=dev)
+    model.eval()
+    chunk = 16
+
+    def step():
+        return model.predict_classes(ids, layout=2, pages_per_call=chunk)
+    for _ in range(2):
+        step()
+    ms = timed(step, reps) / reps
+    model.train()
+    return dict(value=world * n / (ms * 1e-3), unit="pages/s", pages_per_gpu=n, pages_per_call=chunk, ms_per_step=ms,
+                input="int16 channel-id maps [64,1024,768] resident in HBM (R1 rasterised on the device)", output="uint8 arg-max maps")
+
+
+def gpu_library_baseline(grid, labels64, dev):
+    """The reference step through PyTorch-eager on the same GPU (cuDNN / cuBLAS / ATen fp32, TF32 off): the oracle port of
+    model/model.py + train_chargrid_funsd_msau.py:46-59 with its tensors on the device.  Batch 16 (mean over pages of the per-page
+    loss) and page by page (the reference's own loop).  Same pages, same init as the native arm."""
+    import torch
+    from oracle import model as om
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = om.MsauConfig(**CFG)
+    sd = {k: v.to(dev) for k, v in om.init_state_dict(cfg, 0).items()}
+    m = {k: torch.zeros_like(v) for k, v in sd.items()}
+    v = {k: torch.zeros_like(t) for k, t in sd.items()}
+    dead = f"msau_net.blocks.{cfg.num_blocks - 1}.downsamplingblock.layer_attentions."
+    step_no = [0]
+
+    def step(x, lab):
+        _, _, _, grads = om.loss_and_grads(sd, cfg, x, lab)
+        grads = {k: (None if k.startswith(dead) else g) for k, g in grads.items()}
+        step_no[0] += 1
+        om.clip_adam_step(sd, grads, m, v, step=step_no[0])
+
+    def time_it(fn, reps):
+        fn(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    B = grid.shape[0]
+    out = dict(unit="pages/s", what="oracle port of the reference step on cuda (PyTorch-eager: cuDNN conv, ATen LRN / attention / CE / "
+                                    "clip / Adam), fp32, TF32 off, same B200, CUDA events", kind="port")
+    try:
+        ms_b = time_it(lambda: step(grid, labels64), 3)
+        out.update(value=B / (ms_b * 1e-3), ms_per_step=ms_b, batch=B)
+    except torch.cuda.OutOfMemoryError as e:
+        out.update(value=None, batch_error=str(e)[:120])
+        torch.cuda.empty_cache()
+    ms_p = time_it(lambda: [step(grid[i:i + 1], labels64[i:i + 1]) for i in range(min(B, 4))], 2) / min(B, 4)
+    out.update(page_by_page_value=1e3 / ms_p, page_by_page_ms=ms_p)
+    del sd, m, v
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------------- native arm
 def main():
     ap = argparse.ArgumentParser()
@@ -144,7 +219,11 @@ def main():
     ap.add_argument("--pages", type=int, default=PAGES_PER_GPU, help="pages per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-dense", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the CUDA-graph replay of fwd+loss+bwd")
+    ap.add_argument("--no-graph", action="store_true", help="eager kernel launches instead of the CUDA-graph replay of the step")
+    ap.add_argument("--no-graph-tail", action="store_true", help="keep the all-reduce and clip + Adam outside the CUDA graph")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --pages per GPU (default 16); strong: global batch 16 split over the GPUs (16/N pages per GPU)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / configs[4] / library-GPU-baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -169,6 +248,9 @@ def main():
         import datetime
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
     K, Wm, P = args.steps, max(args.warmup, 3), args.pages
+    if args.scaling == "strong":
+        P = max(PAGES_PER_GPU // world, 1)
+    tail = not args.no_graph_tail
 
     def barrier():
         if world > 1:
@@ -201,7 +283,8 @@ def main():
     graph_static = "static"     # the resident batch is the same tensor every step: the graph reads it in place
 
     def step_resident():
-        return model.train_step(grid, labels64, process_group=pg, world_size=world, use_graph=False if args.no_graph else graph_static)
+        return model.train_step(grid, labels64, process_group=pg, world_size=world, use_graph=False if args.no_graph else graph_static,
+                                graph_tail=tail)
 
     def step_resident_eager():
         return model.train_step(grid, labels64, process_group=pg, world_size=world)
@@ -252,7 +335,7 @@ def main():
         g = raster.raster_features(wb, geom, table, (H, W), True, "ids")
         lab = raster.raster_labels(lb, geom, (H, W))
         h2d[0] = wb.h_bytes + lb.h_bytes
-        loss = model.train_step(g, lab, layout=2, process_group=pg, world_size=world, use_graph=not args.no_graph)
+        loss = model.train_step(g, lab, layout=2, process_group=pg, world_size=world, use_graph=not args.no_graph, graph_tail=tail)
         return float(loss)            # D2H read of the step's result
 
     for _ in range(2):
@@ -286,13 +369,13 @@ def main():
     # every rank runs the pass (the step contains the all-reduce); rank 0 reports its own kernels
     # (weight gradients normally overlap the data-gradient chain on a side stream; serialise them here so that every
     #  kernel's events measure that kernel alone)
-    _lib.set_option("wgrad_side_stream", 0)
+    model.set_option("wgrad_side_stream", 0)
     _lib.profile_enable(True)
     for _ in range(K):
         step_resident_eager()
     rep = _lib.profile_report()
     _lib.profile_enable(False)
-    _lib.set_option("wgrad_side_stream", 1)
+    model.set_option("wgrad_side_stream", 1)
     if rank == 0:
         pk = peaks()
         tot = sum(v["ms"] for v in rep.values())
@@ -309,15 +392,49 @@ def main():
             ach = tv["flops"] / (tv["ms"] * 1e-3) / 1e12
             roof = dict(bound="tensor", achieved=ach, peak=pk["tf"], unit="TFLOP/s", frac=ach / pk["tf"], traffic=None)
         try:   # DRAM bytes per launch of this kernel family, from the committed ncu launch list of the same step
-            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r1.json"))).get(top)
+            tfile = "traffic_r2.json" if os.path.exists(os.path.join(ROOT, "profiles", "traffic_r2.json")) else "traffic_r1.json"
+            tr = json.load(open(os.path.join(ROOT, "profiles", tfile))).get(top)
             if tr:
                 roof["traffic"] = tr["dram_bytes_per_launch"]
-                roof["traffic_source"] = "profiles/traffic_r1.json: " + tr["source"]
+                roof["traffic_source"] = f"profiles/{tfile}: " + tr["source"]
                 roof["algorithmic_bytes_per_launch"] = tv["bytes"] / tv["launches"]
         except Exception:
             pass
         roof.update(kernel=top, peak_source=pk["src"], launches=tv["launches"], avg_launch_ms=tv["ms"] / tv["launches"],
                     share_of_step=tv["ms"] / tot, pass_="separate K-step pass with CUDA events around every launch, single stream")
+    barrier()
+
+
+    # ---- extra legs (all outside the timed region above; every rank takes part where a collective is involved)
+    strong = c5 = gpu_lib = None
+    if not args.no_extras:
+        # (1) strong scaling of configs[1]: global batch 16 split over the GPUs
+        Ps = max(PAGES_PER_GPU // world, 1)
+        if world == 1 and P == PAGES_PER_GPU:
+            strong = dict(pages_per_gpu=Ps, global_batch=Ps * world, ms_per_step=ms_step, value=value, unit="pages/s")
+        else:
+            gs, ls = grid[:Ps].contiguous(), labels64[:Ps].contiguous()
+
+            def step_strong():
+                return model.train_step(gs, ls, process_group=pg, world_size=world, use_graph=False if args.no_graph else "static",
+                                        graph_tail=tail)
+            for _ in range(3):
+                step_strong()
+            ms_s = timed(step_strong, K) / K
+            strong = dict(pages_per_gpu=Ps, global_batch=Ps * world, ms_per_step=ms_s, value=Ps * world / (ms_s * 1e-3), unit="pages/s")
+            del gs, ls
+        # (2) BASELINE.json configs[4]: 1024x768 chargrid inference, 64 pages per GPU, replicas (no collective)
+        try:
+            c5 = bench_c5(model, raster, rank, dev, timed, world, max(3, K // 3))
+        except Exception as e:  # noqa: BLE001
+            c5 = dict(error=f"{type(e).__name__}: {e}")
+    if rank == 0 and world == 1 and not args.no_extras:
+        # (3) library-GPU baseline: the reference network written with torch ops (oracle port), same B200, cuDNN / cuBLAS fp32,
+        #     TF32 off -- the "PyTorch-eager on the same GPU" bar of SURVEY.md 2b.  A reported baseline, like cpu_baseline.
+        try:
+            gpu_lib = gpu_library_baseline(grid, labels64, dev)
+        except Exception as e:  # noqa: BLE001
+            gpu_lib = dict(error=f"{type(e).__name__}: {e}")
     barrier()
 
     cpu = None
@@ -328,16 +445,24 @@ def main():
                           "torch-CPU fp32 oracle port of train_chargrid_funsd_msau.py:46-59")
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit="pages/s", n_gpus=world, steps=K, warmup=Wm, ms_per_step=ms_step,
-                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                   config=dict(workload="MSAU chargrid training step, batch 16 synthetic 512x512 pages per GPU (BASELINE.json configs[1])",
+                   higher_is_better=True, scaling=args.scaling, vs_baseline=None,
+                   dtype="f32 storage; tcgen05 bf16x3 split (hi*hi + lo*hi + hi*lo, fp32 accumulate) in forward / data gradients, "
+                         "single-term bf16 operands in weight gradients and attention backward",
+                   data="synthetic",
+                   config=dict(workload=f"MSAU chargrid training step, batch {P} synthetic 512x512 pages per GPU (BASELINE.json configs[1])",
                                model_kwargs=CFG, pages_per_gpu=P, global_batch=world * P, parallelism=f"dp{world}",
                                l2="inputs (1.6 GB) and activations (>30 GB) are larger than L2; no flush needed",
                                step="fwd + masked CE (main+aux) + bwd + NCCL all-reduce (N>1) + clip_grad_norm(1.0) + Adam(1e-4)",
                                launch=(graph_note or "eager kernel launches") if args.no_graph else
-                                      "fwd + loss + bwd replayed from a CUDA graph (all-reduce, clip + Adam eager); gpu_launches counts "
-                                      "the graph's kernels per replay"),
+                                      ("the whole step (fwd + loss + bwd + all-reduce + clip + Adam) replayed from ONE CUDA graph" if tail else
+                                       "fwd + loss + bwd replayed from a CUDA graph (all-reduce, clip + Adam eager)") +
+                                      "; gpu_launches counts the graph's kernels per replay"),
                    e2e=e2e, e2e_dense=e2e_dense, gpu_launches=int(launches), roofline=roof, kernel_breakdown=breakdown,
+                   strong_scaling=strong, c5_inference_1024x768=c5, gpu_library_baseline=gpu_lib,
                    cpu_baseline=cpu, clocks=clocks)
+        if e2e_dense is not None:     # the reference's literal input format next to the record-fed number, in the key the driver reads
+            out["e2e"]["dense_input_value"] = e2e_dense["value"]
+            out["e2e"]["dense_input_h2d_bytes_per_step"] = e2e_dense["h2d_bytes_per_step"]
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

@@ -97,11 +97,55 @@ int msau_loss_backward(MsauPlan* plan, const float* x, int x_layout, const void*
                        float loss_scale, void* workspace, size_t workspace_bytes, float* loss,
                        float* grads, void* stream);
 
+/* Generalised loss + backward: MSAUWrapper.loss (mode 0, above) or UNetLoss.forward of the alternative trainer
+ * (mode 1; model/training/cost.py:35-65, called from model/training/trainer.py:124-137):
+ *     loss = weight_main * CrossEntropyLoss(logits, tgt) + weight_aux * CrossEntropyLoss(aux_logits, aux_tgt)
+ * over ALL pixels of the batch (class 0 included), the reference's 0.5 / 0.5 (cost.py:61), optional class weights with
+ * torch's weighted-mean reduction (cost.py:27-31).  labels / labels_aux are the arg-max class maps of the reference's one-hot
+ * targets (cost.py:41,52; msau_onehot_argmax); labels_aux NULL = labels.  n_class <= 32.
+ *   loss_main    optional device float: the main head's own cross-entropy (UNetLoss's `final_loss`, cost.py:57-60)
+ *   accuracy     optional device int32[2] = {pixels with label != 0 whose arg-max equals the label, pixels with label != 0}
+ *                (cost.py:44-50; evaluate() of train...py:133-159 computes the same ratio)
+ * A label outside [0, n_class) contributes nothing and raises bit 0 of the plan's sticky error flags (torch raises). */
+typedef struct MsauLossSpec {
+  int mode;                       /* 0 = MSAUWrapper.loss, 1 = UNetLoss */
+  float weight_main, weight_aux;  /* mode 1 only (0.5 / 0.5 in the reference) */
+  const float* h_class_weights;   /* mode 1 only: HOST pointer to n_class floats, or NULL */
+} MsauLossSpec;
+int msau_loss_backward_ex(MsauPlan* plan, const float* x, int x_layout, const void* labels, const void* labels_aux,
+                          int label_dtype, const MsauLossSpec* spec, float loss_scale, void* workspace,
+                          size_t workspace_bytes, float* loss, float* loss_main, int32_t* accuracy, float* grads,
+                          void* stream);
+/* reads and clears the plan's sticky device error flags (synchronises with the device; not a data-path call) */
+int msau_plan_error_flags(MsauPlan* plan, int* h_flags);
+
 /* nn.utils.clip_grad_norm(params, 1.0) + torch.optim.Adam.step()   train...py:24-26,58-59.
  * `scratch` >= 4 KiB; total_norm (device float, pre-clip norm) may be NULL. */
 int msau_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                         int step, float lr, float beta1, float beta2, float eps, float max_norm,
                         float* scratch, float* total_norm, void* stream);
+
+/* get_optimizer (model/training/optimizer.py:4-30) on the flat buffers, one fused kernel pair:
+ *   kind 0  torch.optim.Adam     state1 = exp_avg, state2 = exp_avg_sq, beta1 / beta2 / eps
+ *   kind 1  torch.optim.RMSprop  state2 = square_avg, beta1 = alpha (0.99), eps (1e-8); momentum 0, not centred (:14-16, the default)
+ *   kind 2  torch.optim.SGD      state1 = momentum buffer, beta1 = momentum (0.9), dampening 0 (:8-13)
+ * weight_decay: g += weight_decay * p (the reference passes lr_decay_rate here, :7,12,16,21); max_norm > 0 applies
+ * clip_grad_norm_ first (the alternative trainer does not clip: pass 0).  The step count (Adam's bias correction, SGD's first
+ * step) comes from `step` (1-based, host) or, when step_dev is not NULL, from that device counter, which the call increments
+ * first -- that form can be captured into a CUDA graph.  Trainer.adjust_lr (trainer.py:45-49) is the caller's `lr`. */
+int msau_optimizer_step(int kind, float* params, float* grads, float* state1, float* state2, long long n, int step,
+                        int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        float max_norm, float* scratch, float* total_norm, void* stream);
+
+/* torch.argmax(tgt, dim=1) on one-hot targets [B, C, H, W] (cost.py:41,52), or -- channels_last = 1 -- np.argmax(pred_mask,
+ * axis=-1) on a [B, H, W, C] probability map (kv_model.py:162): dtype 0 = uint8, 1 = int64, 2 = float32; out uint8 [B, H, W],
+ * first maximum wins. */
+int msau_onehot_argmax(const void* onehot, int dtype, int batch, int channels, long long npix_per_page, int channels_last,
+                       uint8_t* out, void* stream);
+/* evaluate() of train_chargrid_funsd_msau.py:133-159 on the device: confusion[label][pred] += 1 over the pixels with
+ * label != 0 (int64 [n_class][n_class], accumulated; accuracy = trace / sum, micro precision = micro recall = accuracy). */
+int msau_confusion_counts(const uint8_t* pred, const void* labels, int label_dtype, long long n, int n_class,
+                          long long* confusion, void* stream);
 
 /* SelfAttentionBlock.forward (model/layers/attention.py:138-162) as a stand-alone operator on
  * channels-last tensors (the fused tcgen05 kernels the plan uses; the N x N map is never materialised).
@@ -202,8 +246,11 @@ int msau_kv_char_range(const uint16_t* char_mask, const uint8_t* new_mask, int h
                        int n_queries, int32_t* out, void* stream);
 
 /* Engine options.  "tensor_core_conv" (default 1): run the convolutions that fit on the tcgen05 implicit-GEMM
- * kernel; 0 = every convolution on the fp32 CUDA-core kernel (used by the parity tests to cross-check). */
+ * kernel; 0 = every convolution on the fp32 CUDA-core kernel (used by the parity tests to cross-check).  Options are
+ * per plan: msau_set_option edits the defaults that msau_plan_create copies into a new plan (existing plans are not
+ * touched), msau_plan_set_option edits one plan; there is no other mutable global state. */
 int msau_set_option(const char* name, int value);
+int msau_plan_set_option(MsauPlan* plan, const char* name, int value);
 
 /* Per-kernel timing for bench.py's roofline report: when enabled every launch is bracketed by CUDA events on
  * its stream; msau_profile_report synchronises the device and writes a JSON object

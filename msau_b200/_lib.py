@@ -15,7 +15,8 @@ SYMBOLS = [
     "msau_last_error", "msau_version", "msau_launch_count", "msau_launch_count_add",
     "msau_plan_create", "msau_plan_destroy", "msau_param_count", "msau_param_info", "msau_plan_set_feature_table",
     "msau_workspace_bytes",
-    "msau_forward", "msau_loss_backward", "msau_clip_adam_step",
+    "msau_forward", "msau_loss_backward", "msau_loss_backward_ex", "msau_plan_error_flags", "msau_clip_adam_step",
+    "msau_optimizer_step", "msau_onehot_argmax", "msau_confusion_counts", "msau_plan_set_option",
     "msau_raster_geometry", "msau_raster_features", "msau_raster_labels",
     "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
     "msau_rect_filter", "msau_class_equals", "msau_ccl4", "msau_kv_select_components", "msau_kv_char_range",
@@ -28,6 +29,10 @@ SYMBOLS = [
 class MsauConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("channels", "n_class", "scale_space_num", "res_depth", "feat_root",
                                        "filter_size", "pool_size", "num_blocks")]
+
+
+class MsauLossSpec(C.Structure):
+    _fields_ = [("mode", C.c_int), ("weight_main", C.c_float), ("weight_aux", C.c_float), ("h_class_weights", C.POINTER(C.c_float))]
 
 
 class MsauError(RuntimeError):
@@ -64,6 +69,12 @@ def lib() -> C.CDLL:
     L.msau_forward.argtypes = [vp, vp, i32, vp, vp, sz, i32, vp, vp, vp, vp, vp]
     L.msau_loss_backward.argtypes = [vp, vp, i32, vp, i32, f32, vp, sz, vp, vp, vp]
     L.msau_clip_adam_step.argtypes = [vp, vp, vp, vp, i64, i32, f32, f32, f32, f32, f32, vp, vp, vp]
+    L.msau_loss_backward_ex.argtypes = [vp, vp, i32, vp, vp, i32, C.POINTER(MsauLossSpec), f32, vp, sz, vp, vp, vp, vp, vp]
+    L.msau_plan_error_flags.argtypes = [vp, C.POINTER(i32)]
+    L.msau_optimizer_step.argtypes = [i32, vp, vp, vp, vp, i64, i32, vp, f32, f32, f32, f32, f32, f32, vp, vp, vp]
+    L.msau_onehot_argmax.argtypes = [vp, i32, i32, i32, i64, i32, vp, vp]
+    L.msau_confusion_counts.argtypes = [vp, vp, i32, i64, i32, vp, vp]
+    L.msau_plan_set_option.argtypes = [vp, C.c_char_p, i32]
     L.msau_raster_geometry.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, vp]
     L.msau_raster_features.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp]
     L.msau_raster_labels.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, vp]

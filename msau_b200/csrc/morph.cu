@@ -9,9 +9,11 @@
 // [i - size//2 - origin, i - size//2 - origin + size - 1], samples outside the image are 0; label() is
 // 4-connected and numbers components by the raster position of their first pixel.
 //
-// CCL = union-find with atomicMin linking (the root of a component is its smallest linear index, which
-// is exactly SciPy's ordering key) -> flatten -> rank the roots with a ballot/popc prefix count ->
-// relabel + bounding boxes.
+// CCL: (1) every CTA labels one 64 x 64 tile in shared memory -- row runs from warp ballots, vertical links by a
+// shared-memory union-find whose root is the smallest raster index (exactly SciPy's ordering key) -- and writes each
+// pixel's tile-local root as a global index; (2) a small kernel links the tiles along their borders in global memory
+// (atomicMin union-find over root indices only); (3) roots are ranked with a ballot/popc prefix count; (4) every pixel
+// looks up the rank of its root; run starts update the bounding boxes (one set of atomics per row run, not per pixel).
 #include <limits.h>
 
 #include "../../include/msau_b200.h"
@@ -40,9 +42,51 @@ __global__ void __launch_bounds__(256) rect_filter_kernel(const uint8_t* __restr
   out[idx] = (uint8_t)v;
 }
 
+// 4 outputs per thread for 1-row windows on rows whose width is a multiple of 4 (the call site's (1, 3) closing, kv_model.py:176):
+// sw + 3 byte loads instead of 4 sw, one 32-bit store
+__global__ void __launch_bounds__(256) rect_filter_row4_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, long total4,
+                                                                int sw, int c0, int is_max) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total4) return;
+  const int W4 = W >> 2;
+  const long row = q / W4;
+  const int x = (int)(q - row * W4) << 2;
+  const uint8_t* src = in + row * W;
+  int v[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {
+    const int xx = x + c0 + i;
+    v[i] = (i < sw + 3 && xx >= 0 && xx < W) ? (int)__ldg(src + xx) : 0;
+  }
+  uint32_t packed = 0;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    int r = is_max ? 0 : 255;
+#pragma unroll
+    for (int d = 0; d < 8; ++d)
+      if (d < sw) r = is_max ? max(r, v[o + d]) : min(r, v[o + d]);
+    packed |= (uint32_t)r << (8 * o);
+  }
+  reinterpret_cast<uint32_t*>(out)[q] = packed;
+}
+
 __global__ void __launch_bounds__(256) class_equals_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, long n, int cls) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[i] == cls ? 1 : 0;
+  const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + i));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint32_t o = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) o |= (((w[k] >> (8 * b)) & 0xffu) == (uint32_t)cls ? 1u : 0u) << (8 * b);
+      r[k] = o;
+    }
+    *reinterpret_cast<uint4*>(out + i) = make_uint4(r[0], r[1], r[2], r[3]);
+  } else {
+    for (long k = i; k < n && k < i + 16; ++k) out[k] = in[k] == cls ? 1 : 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------- CCL
@@ -64,33 +108,117 @@ __device__ __forceinline__ void uf_union(int32_t* L, int a, int b) {
   }
 }
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict__ bin, int32_t* __restrict__ L, long total, long npix) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  L[idx] = bin[idx] ? (int32_t)(idx % npix) : -1;
+constexpr int CT = 64;                    // tile edge
+constexpr int CT_PIX = CT * CT;           // 4096 pixels, 16 per thread
+
+__device__ __forceinline__ int suf_find(const volatile int* L, int a) {
+  int p = L[a];
+  while (p != a) { a = p; p = L[a]; }
+  return a;
+}
+__device__ __forceinline__ void suf_union(int* L, int a, int b) {
+  while (true) {
+    a = suf_find(L, a);
+    b = suf_find(L, b);
+    if (a == b) return;
+    if (a > b) { const int t = a; a = b; b = t; }
+    const int old = atomicMin(L + b, a);
+    if (old == b) return;
+    b = old;
+  }
 }
 
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ bin, int32_t* __restrict__ L, int H, int W, long total) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+// (1) tile-local labelling.  grid = (tiles_x, tiles_y, n_maps), 256 threads: warp w owns tile rows w, w + 8, ..., a lane two
+// adjacent 32-pixel halves of the row.  L[p] = global raster index of p's tile-local root, -1 for background.
+__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint8_t* __restrict__ bin, int32_t* __restrict__ L, int H, int W) {
+  __shared__ int lab[CT_PIX];
+  __shared__ uint32_t rowbits[CT][2];
   const long npix = (long)H * W;
-  const long m = idx / npix;
-  const int p = (int)(idx - m * npix);
-  const uint8_t* b = bin + m * npix;
-  if (!b[p]) return;
-  int32_t* Lm = L + m * npix;
-  const int y = p / W, x = p - y * W;
-  if (x > 0 && b[p - 1]) uf_union(Lm, p, p - 1);
-  if (y > 0 && b[p - W]) uf_union(Lm, p, p - W);
+  const uint8_t* b = bin + (long)blockIdx.z * npix;
+  int32_t* Lm = L + (long)blockIdx.z * npix;
+  const int x0 = blockIdx.x * CT, y0 = blockIdx.y * CT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // pass 1: foreground bits of every row half + run-start labels
+  for (int r = warp; r < CT; r += 8) {
+    const int gy = y0 + r;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gx = x0 + 32 * h + lane;
+      const bool fg = gy < H && gx < W && b[(long)gy * W + gx] != 0;
+      const uint32_t bits = __ballot_sync(0xffffffffu, fg);
+      if (lane == 0) rowbits[r][h] = bits;
+      // run start inside this 32-pixel half: one past the highest background bit below the lane
+      const uint32_t z = ~bits & ((1u << lane) - 1u);
+      const int start = z ? 32 - __clz(z) : 0;
+      lab[r * CT + 32 * h + lane] = fg ? r * CT + 32 * h + start : -1;
+    }
+  }
+  __syncthreads();
+  // pass 2: links.  A run that crosses the middle of the row joins its halves; a pixel links to the pixel above unless its left
+  // and upper-left neighbours are foreground too (then the left neighbour makes the same connection)
+  for (int r = warp; r < CT; r += 8) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t cur = rowbits[r][h];
+      const bool fg = (cur >> lane) & 1u;
+      if (!fg) continue;
+      const int i = r * CT + 32 * h + lane;
+      if (h == 1 && lane == 0 && (rowbits[r][0] >> 31)) suf_union(lab, i, i - 1);
+      if (r > 0) {
+        const uint32_t up = rowbits[r - 1][h];
+        if ((up >> lane) & 1u) {
+          bool left, upleft;
+          if (lane > 0) { left = (cur >> (lane - 1)) & 1u; upleft = (up >> (lane - 1)) & 1u; }
+          else if (h == 1) { left = rowbits[r][0] >> 31; upleft = rowbits[r - 1][0] >> 31; }
+          else { left = false; upleft = false; }
+          if (!(left && upleft)) suf_union(lab, i, i - CT);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // pass 3: roots -> global indices
+  for (int r = warp; r < CT; r += 8) {
+    const int gy = y0 + r;
+    if (gy >= H) break;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int gx = x0 + 32 * h + lane;
+      if (gx >= W) continue;
+      const int i = r * CT + 32 * h + lane;
+      int out = -1;
+      if (lab[i] >= 0) {
+        const int root = suf_find(lab, i);
+        out = (y0 + (root >> 6)) * W + x0 + (root & (CT - 1));
+      }
+      Lm[(long)gy * W + gx] = out;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256) ccl_flatten_kernel(int32_t* __restrict__ L, long total, long npix) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  if (L[idx] < 0) return;
-  int32_t* Lm = L + (idx / npix) * npix;
-  const int p = (int)(idx % npix);
-  Lm[p] = uf_find(Lm, p);
+// (2) links across tile borders: one thread per pixel of every tile's first column / first row
+__global__ void __launch_bounds__(256) ccl_border_kernel(const uint8_t* __restrict__ bin, int32_t* __restrict__ L, int H, int W, int tiles_x,
+                                                          int tiles_y) {
+  const long npix = (long)H * W;
+  const uint8_t* b = bin + (long)blockIdx.z * npix;
+  int32_t* Lm = L + (long)blockIdx.z * npix;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;       // [0, tiles_x * H) vertical borders, then tiles_y * W horizontal ones
+  const int nv = tiles_x * H;
+  int x, y;
+  bool vertical;
+  if (t < nv) { vertical = true; x = (t / H) * CT; y = t - (t / H) * H; }
+  else if (t < nv + tiles_y * W) { vertical = false; const int u = t - nv; y = (u / W) * CT; x = u - (u / W) * W; }
+  else return;
+  const int p = y * W + x;
+  if (!b[p]) return;
+  if (vertical) {
+    if (x > 0 && b[p - 1]) uf_union(Lm, p, p - 1);
+  } else {
+    if (y > 0 && b[p - W]) {
+      const bool left = x > 0 && b[p - 1], upleft = x > 0 && b[p - W - 1];
+      if (!(left && upleft)) uf_union(Lm, p, p - W);
+    }
+  }
 }
 
 // roots per 1024-pixel chunk
@@ -160,22 +288,42 @@ __global__ void __launch_bounds__(256) ccl_bbox_init_kernel(int32_t* __restrict_
   bboxes[i] = (i & 1) ? 0 : INT_MAX;   // y0, y1, x0, x1 -> min slots start at INT_MAX, max slots at 0
 }
 
+// (4) labels[p] = rank of p's root; the first pixel of every row run (within a warp's 32 pixels) updates the bounding box
 __global__ void __launch_bounds__(256) ccl_relabel_kernel(const int32_t* __restrict__ L, int32_t* __restrict__ labels, int H, int W,
                                                            long total, int32_t* __restrict__ bboxes, int max_labels) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
   const long npix = (long)H * W;
-  const long m = idx / npix;
-  const int p = (int)(idx - m * npix);
-  const int r = L[idx];
-  if (r < 0) { labels[idx] = 0; return; }
-  const int lab = labels[m * npix + r];    // the root's own entry already holds its final value
-  if (r != p) labels[idx] = lab;
-  if (bboxes && lab <= max_labels) {
+  const long m = idx < total ? idx / npix : 0;
+  const int p = idx < total ? (int)(idx - m * npix) : 0;
+  int lab = 0;
+  int r = -1;
+  if (idx < total) {
+    r = L[idx];
+    if (r >= 0) {
+      const int32_t* Lm = L + m * npix;
+      int q = Lm[r];
+      while (q != r) { r = q; q = Lm[r]; }
+      lab = labels[m * npix + r];      // the root's own entry already holds its final value (ccl_rank_kernel)
+      if (r != p) labels[idx] = lab;
+    } else {
+      labels[idx] = 0;
+    }
+  }
+  if (!bboxes) return;
+  // runs: consecutive lanes with the same map, row and (non-zero) label
+  const int lane = threadIdx.x & 31;
+  const int y = p / W, x = p - y * W;
+  const long key = lab ? (m * H + y) * (long)(INT_MAX / 2) + lab : -1 - lane;      // distinct for background lanes
+  const long prev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool start = lab != 0 && (lane == 0 || prev != key || x == 0);
+  const uint32_t starts = __ballot_sync(0xffffffffu, start || lab == 0);          // a background lane ends a run as well
+  if (start && lab <= max_labels) {
+    const uint32_t above = starts & ~((2u << lane) - 1u);                          // next boundary above this lane
+    int len = (above ? __ffs(above) - 1 : 32) - lane;
+    if (x + len > W) len = W - x;                                                  // the run ends with its image row
     int32_t* bb = bboxes + (m * max_labels + lab - 1) * 4;
-    const int y = p / W, x = p - y * W;
     atomicMin(bb + 0, y); atomicMax(bb + 1, y + 1);
-    atomicMin(bb + 2, x); atomicMax(bb + 3, x + 1);
+    atomicMin(bb + 2, x); atomicMax(bb + 3, x + len);
   }
 }
 
@@ -192,6 +340,10 @@ extern "C" int msau_rect_filter(const uint8_t* in, uint8_t* out, int n_maps, int
                  "rect_filter: invalid origin");
   const long total = (long)n_maps * height * width;
   count_launch(1);
+  if (size_h == 1 && origin_h == 0 && size_w <= 8 && (width & 3) == 0 && ((uintptr_t)out & 3) == 0)
+    rect_filter_row4_kernel<<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, width, total / 4, size_w, -(size_w / 2) - origin_w,
+                                                                                   is_max);
+  else
   rect_filter_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, height, width, total, size_h, size_w,
                                                                         -(size_h / 2) - origin_h, -(size_w / 2) - origin_w, is_max);
   MSAU_CUDA_TRY(cudaGetLastError());
@@ -201,7 +353,7 @@ extern "C" int msau_rect_filter(const uint8_t* in, uint8_t* out, int n_maps, int
 extern "C" int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int cls, void* stream) {
   MSAU_CHECK_ARG(class_map && out && n >= 1, "class_equals: bad argument");
   count_launch(1);
-  class_equals_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(class_map, out, n, cls);
+  class_equals_kernel<<<cdiv(cdiv(n, 16), 256), 256, 0, (cudaStream_t)stream>>>(class_map, out, n, cls);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }
@@ -215,10 +367,13 @@ extern "C" int msau_ccl4(const uint8_t* binary, int n_maps, int height, int widt
   const int nchunks = cdiv(npix, 1024);
   int32_t* L = scratch;
   int32_t* counts = scratch + total;
+  const int tiles_x = cdiv(width, CT), tiles_y = cdiv(height, CT);
+  MSAU_CHECK_ARG(n_maps <= 65535 && tiles_y <= 65535, "ccl4: at most 65535 maps per call");
   count_launch(7);
-  ccl_init_kernel<<<cdiv(total, 256), 256, 0, st>>>(binary, L, total, npix);
-  ccl_merge_kernel<<<cdiv(total, 256), 256, 0, st>>>(binary, L, height, width, total);
-  ccl_flatten_kernel<<<cdiv(total, 256), 256, 0, st>>>(L, total, npix);
+  ccl_tile_kernel<<<dim3(tiles_x, tiles_y, n_maps), 256, 0, st>>>(binary, L, height, width);
+  if (tiles_x > 1 || tiles_y > 1)
+    ccl_border_kernel<<<dim3(cdiv((long)tiles_x * height + (long)tiles_y * width, 256), 1, n_maps), 256, 0, st>>>(binary, L, height, width,
+                                                                                                                 tiles_x, tiles_y);
   ccl_count_kernel<<<dim3(nchunks, n_maps), 1024, 0, st>>>(L, npix, nchunks, counts);
   ccl_scan_kernel<<<n_maps, 1024, 0, st>>>(counts, nchunks, n_labels);
   ccl_rank_kernel<<<dim3(nchunks, n_maps), 1024, 0, st>>>(L, npix, nchunks, counts, labels);

@@ -43,7 +43,8 @@ int launch_pack(const float* params, float* packed, const PackDesc* d_descs, int
 
 static constexpr int kNormBlocks = 296;
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, float* __restrict__ partial) {
+// block 0 also advances the device-side step counter (graph-captured steps cannot take the step count as an argument)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long n, float* __restrict__ partial, int* __restrict__ step_dev) {
   double s = 0.0;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
     const float x = g[i];
@@ -56,46 +57,81 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[blockIdx.x] = (float)sh[0];
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = (float)sh[0];
+    if (blockIdx.x == 0 && step_dev) *step_dev += 1;
+  }
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
-                                                    float* __restrict__ v, long n, float step_size, float inv_sqrt_bc2, float b1,
-                                                    float b2, float eps, float max_norm, const float* __restrict__ partial,
-                                                    int n_partial, float* __restrict__ total_norm_out) {
+// kind 0: torch.optim.Adam            m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// kind 1: torch.optim.RMSprop         v = a v + (1-a) g^2 ; p -= lr * g / (sqrt(v) + eps)          (momentum 0, not centered; a = b1)
+// kind 2: torch.optim.SGD(momentum)   buf = mu buf + g (buf = g at step 1) ; p -= lr * buf          (dampening 0; mu = b1)
+// weight decay (all kinds, torch semantics): g += wd * p before the moment updates.  max_norm > 0: clip_grad_norm_ first.
+__global__ void __launch_bounds__(256) optim_kernel(int kind, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                     float* __restrict__ v, long n, int step_host, const int* __restrict__ step_dev, float lr,
+                                                     float b1, float b2, float eps, float wd, float max_norm,
+                                                     const float* __restrict__ partial, int n_partial, float* __restrict__ total_norm_out) {
   // every block re-derives the same global norm from the fixed-order partials => identical on all ranks
-  __shared__ float coef_s;
+  __shared__ float coef_s, step_size_s, inv_sqrt_bc2_s;
+  __shared__ int step_s;
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < n_partial; ++i) s += (double)partial[i];
     const float total = (float)sqrt(s);
-    float c = max_norm / (total + 1e-6f);
+    float c = max_norm > 0.f ? max_norm / (total + 1e-6f) : 1.f;
     coef_s = c > 1.f ? 1.f : c;
     if (blockIdx.x == 0 && total_norm_out) *total_norm_out = total;
+    const int t = step_dev ? *step_dev : step_host;
+    step_s = t;
+    if (kind == 0) {
+      const double bc1 = 1.0 - pow((double)b1, (double)t), bc2 = 1.0 - pow((double)b2, (double)t);
+      step_size_s = (float)((double)lr / bc1);
+      inv_sqrt_bc2_s = (float)(1.0 / sqrt(bc2));
+    } else {
+      step_size_s = lr; inv_sqrt_bc2_s = 1.f;
+    }
   }
   __syncthreads();
-  const float coef = coef_s;
+  const float coef = coef_s, step_size = step_size_s, inv_sqrt_bc2 = inv_sqrt_bc2_s;
+  const bool first = step_s <= 1;
   for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
-    const float gi = g[i] * coef;
-    g[i] = gi;   // clip_grad_norm_ scales .grad in place
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] -= step_size * (mi / denom);
+    float gi = g[i] * coef;
+    if (max_norm > 0.f) g[i] = gi;   // clip_grad_norm_ scales .grad in place
+    float pi = p[i];
+    if (wd != 0.f) gi += wd * pi;
+    if (kind == 0) {
+      const float mi = b1 * m[i] + (1.f - b1) * gi;
+      const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+      m[i] = mi; v[i] = vi;
+      pi -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
+    } else if (kind == 1) {
+      const float vi = b1 * v[i] + (1.f - b1) * gi * gi;
+      v[i] = vi;
+      pi -= step_size * (gi / (sqrtf(vi) + eps));
+    } else {
+      const float bi = first ? gi : b1 * m[i] + gi;
+      m[i] = bi;
+      pi -= step_size * bi;
+    }
+    p[i] = pi;
   }
+}
+
+int launch_optim(int kind, float* params, float* grads, float* m, float* v, long n, int step, int* step_dev, float lr, float b1, float b2,
+                 float eps, float wd, float max_norm, float* partial, float* total_norm_out, cudaStream_t st) {
+  MSAU_CHECK_ARG(kind >= 0 && kind <= 2, "optimizer: kind must be 0 (Adam), 1 (RMSprop) or 2 (SGD with momentum)");
+  MSAU_CHECK_ARG(step_dev || step >= 1, "optimizer: step must be >= 1 (or pass a device step counter)");
+  ProfScope ps("clip_adam_kernels", 0, (double)n * 4.0 * (kind == 0 ? 8 : 6), st);
+  sumsq_kernel<<<kNormBlocks, 256, 0, st>>>(grads, n, partial, step_dev);
+  optim_kernel<<<kNormBlocks, 256, 0, st>>>(kind, params, grads, m, v, n, step, step_dev, lr, b1, b2, eps, wd, max_norm, partial, kNormBlocks,
+                                            total_norm_out);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
 }
 
 int launch_clip_adam(float* params, float* grads, float* m, float* v, long n, int step, float lr, float b1, float b2, float eps,
                      float max_norm, float* partial, float* total_norm_out, cudaStream_t st) {
-  MSAU_CHECK_ARG(step >= 1, "adam: step must be >= 1");
-  ProfScope ps("clip_adam_kernels", 0, (double)n * 4.0 * 8, st);
-  sumsq_kernel<<<kNormBlocks, 256, 0, st>>>(grads, n, partial);
-  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
-  adam_kernel<<<kNormBlocks, 256, 0, st>>>(params, grads, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps, max_norm,
-                                           partial, kNormBlocks, total_norm_out);
-  MSAU_CUDA_TRY(cudaGetLastError());
-  return MSAU_OK;
+  return launch_optim(0, params, grads, m, v, n, step, nullptr, lr, b1, b2, eps, 0.f, max_norm, partial, total_norm_out, st);
 }
 
 }  // namespace msau

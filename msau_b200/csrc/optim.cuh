@@ -16,4 +16,8 @@ struct PackDesc {
 int launch_pack(const float* params, float* packed, const PackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st);
 int launch_clip_adam(float* params, float* grads, float* m, float* v, long n, int step, float lr, float b1, float b2, float eps,
                      float max_norm, float* partial /*>= 1024 floats*/, float* total_norm_out, cudaStream_t st);
+// kind 0 Adam / 1 RMSprop (b1 = alpha) / 2 SGD with momentum (b1 = momentum); step_dev: optional device step counter (incremented by the
+// call; for CUDA-graph capture), else `step` (1-based) from the host; max_norm <= 0: no gradient clipping
+int launch_optim(int kind, float* params, float* grads, float* m, float* v, long n, int step, int* step_dev, float lr, float b1, float b2,
+                 float eps, float wd, float max_norm, float* partial, float* total_norm_out, cudaStream_t st);
 }  // namespace msau

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "../../include/msau_b200.h"
@@ -107,12 +108,26 @@ struct Block {
   Tensor logits;
 };
 
+// Engine options live in the plan (two plans with different options can run side by side, one host thread per GPU);
+// msau_set_option only edits the defaults a plan copies at msau_plan_create, msau_plan_set_option edits one plan.
+struct EngineOpts {
+  int use_tc = 1;        // tensor_core_conv: tcgen05 kernels where they apply (0 = fp32 CUDA-core cross-check path)
+  int structured = 1;    // structured_first_layer: one-hot inputs through the id-gather first layer (first_layer.cu)
+  int side_stream = 1;   // wgrad_side_stream: weight-gradient kernels on a plan-owned side stream
+  int fuse_mask = 1;     // fuse_relu_mask: gradient writers apply the ReLU mask of the tensor they feed
+  int use_pw = 1;        // pointwise_conv: 1x1 convs of the narrow levels on the fp32 streaming kernel (conv1x1.cu)
+  int use_c3 = 1;        // conv3_fold: kx-folded 3x3 kernel (conv3_tc.cu) where it applies
+  int c3_max = 16;       // conv3_max_channels: ... for at most this many output channels
+  int lrn_coop = 1;      // 0 = thread-per-pixel LRN kernels only, 1 = lane-cooperative where it wins, 2 = from 8 channels up
+  int fuse_lrn = 1;      // fuse_lrn: LRN of a dilated first conv computed in that conv's epilogue (z1 and y1 written by one kernel)
+};
 }  // namespace msau
 
 using namespace msau;
 
 struct MsauPlan {
   MsauConfig cfg;
+  EngineOpts opt;
   int B, H, W;
   std::vector<int> Hl, Wl;
   std::vector<Block> blocks;
@@ -151,6 +166,8 @@ struct MsauPlan {
   const float* ftable = nullptr; int ftable_rows = 0;
   float* tabP = nullptr; float* tabH = nullptr; long tab_cap = 0;   // plan-owned scratch: projected taps / row histogram
   const short* first_ids = nullptr;  // ... and the id map it used (plan workspace, or the caller's with x_layout 2)
+  int lp = 8;                        // channel pitch of the logits tensors: 8 / 16 / 32 >= n_class
+  int* d_flags = nullptr;            // plan-owned sticky device error flags (bit 0: a label was out of range)
 
   Tensor alloc(int C, int Hh, int Ww) {
     Tensor t;
@@ -240,9 +257,9 @@ static long add_tc3(MsauPlan* p, long src_off, int cin, int coutp, int ks = 3) {
 //   fwd   [tap][c1p + c2p][coutp]                     rows = input channels of [src1 | src2]
 //   dgrad [flipped tap][coutp][c_s p] per source s     rows = output channels, cols = that source's channels
 static void setup_conv(MsauPlan* p, ConvLayer& L, int cout, int cin1, int cin2, int k, int dil, bool need_d1, bool need_d2,
-                       int c1p_override = 0) {
+                       int c1p_override = 0, int coutp_override = 0) {
   L.cout = cout; L.cin1 = cin1; L.cin2 = cin2; L.k = k; L.dil = dil;
-  L.coutp = pad8(cout);
+  L.coutp = coutp_override ? coutp_override : pad8(cout);
   L.c1p = c1p_override ? c1p_override : pad4(cin1);
   L.c2p = cin2 ? pad4(cin2) : 0;
   const int cin = cin1 + cin2;
@@ -332,13 +349,22 @@ static void setup_attn(MsauPlan* p, AttnLayer& at, int C) {
 }
 
 // ------------------------------------------------------------------ launch helpers
-static bool g_use_tc = true;
-static bool g_structured = true;   // one-hot inputs: id-gather first layer (first_layer.cu)
-static bool g_side_stream = true;  // weight-gradient kernels on a side stream, overlapping the data-gradient chain
-static bool g_fuse_mask = true;    // coupling dgrad applies the ReLU mask of the residual block it feeds (no relu_mask pass)
-static bool g_use_pw = true;       // 1x1 convs on the fp32 streaming kernel (conv1x1.cu)
-static bool g_use_c3 = true;     // kx-folded 3x3 kernel (conv3_tc.cu) where it applies
-static int g_c3_max = 16;        // ... for at most this many output channels (option conv3_max_channels: 32 is worth 0.06-0.16 ms per step, 64 nothing)
+static EngineOpts g_defaults;
+static std::mutex g_defaults_mu;
+
+static int set_opt(EngineOpts& o, const char* name, int value) {
+  if (!strcmp(name, "tensor_core_conv")) { o.use_tc = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "conv3_fold")) { o.use_c3 = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "pointwise_conv")) { o.use_pw = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "wgrad_side_stream")) { o.side_stream = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "structured_first_layer")) { o.structured = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "fuse_relu_mask")) { o.fuse_mask = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "lrn_coop")) { o.lrn_coop = value; return MSAU_OK; }
+  if (!strcmp(name, "conv3_max_channels")) { o.c3_max = value; return MSAU_OK; }
+  if (!strcmp(name, "fuse_lrn")) { o.fuse_lrn = value != 0; return MSAU_OK; }
+  set_error("set_option: unknown option '%s'", name);
+  return MSAU_ERR_ARG;
+}
 
 struct ConvOpt {
   bool relu1 = false, relu = false, relu2 = false;
@@ -368,11 +394,10 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.accumulate = o.accumulate;
   a.skip_flag = skip_flag;
   count_launch(1);
-  { static bool init = false; if (!init) { const char* e = getenv("MSAU_C3_MAX"); if (e) g_c3_max = atoi(e); init = true; } }
-  if (g_use_tc && g_use_pw && k == 1 && conv1x1_supported(a)) return launch_conv1x1(a, p->st);
-  if (g_use_tc && g_use_c3 && t3_off >= 0 && coutp <= g_c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
-  if (g_use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
-  if (g_use_tc && tc_off >= 0 && coutp == 256) {     // two launches over the two halves of the output channels (add_tc)
+  if (p->opt.use_tc && p->opt.use_pw && k == 1 && conv1x1_supported(a)) return launch_conv1x1(a, p->st);
+  if (p->opt.use_tc && p->opt.use_c3 && t3_off >= 0 && coutp <= p->opt.c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
+  if (p->opt.use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
+  if (p->opt.use_tc && tc_off >= 0 && coutp == 256) {     // two launches over the two halves of the output channels (add_tc)
     ConvArgs h0 = a;
     h0.coutp = 128;
     if (conv_tc_supported(h0)) {
@@ -437,7 +462,7 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
   a.skip_flag = skip_flag;
-  if (g_use_tc && a.cb == 256 && cb < 0 && !wgrad_tc_supported(a)) {
+  if (p->opt.use_tc && a.cb == 256 && cb < 0 && !wgrad_tc_supported(a)) {
     // the tensor-core kernels take up to 128 output channels: run the two halves of a 256-channel dY separately
     WgradArgs h = a;
     h.cb = 128;
@@ -453,7 +478,7 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   }
   count_launch(1);
   MSAU_TRY(wgrad_fork(p));
-  if (g_use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->wst);
+  if (p->opt.use_tc && wgrad_tc_supported(a)) return launch_wgrad_tc(a, p->wst);
   return launch_wgrad(a, p->wst);
 }
 
@@ -522,14 +547,14 @@ static int coupl_bwd(MsauPlan* p, const ConvLayer& L, const Tensor& prev, const 
   if (mask_prev) { o.omask = p->A(prev); o.pom = prev.C; }
   MSAU_TRY(layer_dgrad(p, L, 1, dy, out.C, nullptr, 0, prev, o));
   o.omask = nullptr; o.pom = 0;
-  *mask_cur = g_fuse_mask && !p->written[cur.id];
+  *mask_cur = p->opt.fuse_mask && !p->written[cur.id];
   if (*mask_cur) { o.omask = p->A(cur); o.pom = cur.C; }
   MSAU_TRY(layer_dgrad(p, L, 2, dy, out.C, nullptr, 0, cur, o));
   return MSAU_OK;
 }
 
 static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out) {
-  if (g_use_tc && L.tc_m >= 0) {
+  if (p->opt.use_tc && L.tc_m >= 0) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.src1 = p->A(in); a.c1 = L.cinp; a.p1 = in.C; a.c1_logical = L.cinp;
@@ -565,7 +590,7 @@ static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
 static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const Tensor& out, bool mask_in = false) {
   // weights: dW[ci][co][ky][kx] = sum_q x[q][ci] * dOut[2q - 1 + (ky,kx)][co]
   bool w_done = false;
-  if (g_use_tc && L.tc_m >= 0) {
+  if (p->opt.use_tc && L.tc_m >= 0) {
     // = weight gradient of the merged 2x2-tap forward conv: A = x (taps (ty,tx) read x[q + (ty,tx)]), B = space-to-depth
     // view of dOut; the kernel maps (tap, phase) back to (ky, kx) and folds the bias gradient into the dOut loader
     WgradArgs a;
@@ -603,7 +628,7 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
     count_launch(1);
     MSAU_TRY(launch_colsum(p->G(out), p->npix(out), out.C, L.cout, p->gparams + L.b_off, p->st));
   }
-  if (g_use_tc && L.tc_dm >= 0) {
+  if (p->opt.use_tc && L.tc_dm >= 0) {
     ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.src1 = p->G(out); a.c1 = 4 * L.coutp; a.p1 = out.C; a.c1_logical = a.c1;
@@ -673,7 +698,7 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   MSAU_CHECK_ARG(cfg->num_blocks >= 2 && cfg->num_blocks <= 8, "plan_create: num_blocks must be in [2,8]");
   MSAU_CHECK_ARG(cfg->scale_space_num >= 2 && cfg->res_depth >= 1, "plan_create: need scale_space_num >= 2, res_depth >= 1");
   MSAU_CHECK_ARG(cfg->feat_root >= 8 && cfg->feat_root % 8 == 0, "plan_create: feat_root must be a multiple of 8");
-  MSAU_CHECK_ARG(cfg->n_class >= 2 && cfg->n_class <= 8, "plan_create: n_class must be in [2,8]");
+  MSAU_CHECK_ARG(cfg->n_class >= 2 && cfg->n_class <= 32, "plan_create: n_class must be in [2,32]");
   MSAU_CHECK_ARG(cfg->channels >= 1, "plan_create: channels must be >= 1");
   const int S = cfg->scale_space_num, R = cfg->res_depth, NB = cfg->num_blocks;
   const int fa = cfg->feat_root << (S - 1), da = fa / 8;
@@ -690,6 +715,8 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   }
   MsauPlan* p = new MsauPlan();
   p->cfg = *cfg; p->B = batch; p->H = height; p->W = width;
+  { std::lock_guard<std::mutex> lk(g_defaults_mu); p->opt = g_defaults; }
+  p->lp = cfg->n_class <= 8 ? 8 : (cfg->n_class <= 16 ? 16 : 32);
   p->Hl.resize(S); p->Wl.resize(S);
   p->Hl[0] = height; p->Wl[0] = width;
   for (int l = 1; l < S; ++l) { p->Hl[l] = (p->Hl[l - 1] + 1) / 2; p->Wl[l] = (p->Wl[l - 1] + 1) / 2; }
@@ -709,8 +736,8 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
     for (int l = 0; l < S; ++l) {
       const int f = cfg->feat_root << l;
       const int cin = l == 0 ? cin0 : (cfg->feat_root << (l - 1));
-      // blocks >= 1 read the previous block's logits, stored with pitch 8
-      setup_conv(p, blk.down[l].conv1, f, cin, 0, 3, 1 << l, !(b == 0 && l == 0), false, (b > 0 && l == 0) ? 8 : 0);
+      // blocks >= 1 read the previous block's logits, stored with pitch lp
+      setup_conv(p, blk.down[l].conv1, f, cin, 0, 3, 1 << l, !(b == 0 && l == 0), false, (b > 0 && l == 0) ? p->lp : 0);
     }
     if (b > 0)
       for (int l = 0; l < S; ++l) {
@@ -737,7 +764,7 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
       setup_deconv(p, blk.up[l].deconv, 2 * f, f);
     }
   }
-  for (int b = 0; b < NB; ++b) setup_conv(p, p->blocks[b].end, cfg->n_class, cfg->feat_root, 0, 4, 1, true, false);
+  for (int b = 0; b < NB; ++b) setup_conv(p, p->blocks[b].end, cfg->n_class, cfg->feat_root, 0, 4, 1, true, false, 0, p->lp);
 
   // ---- activations ----
   for (int b = 0; b < NB; ++b) {
@@ -766,10 +793,10 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
       U.ur = p->alloc(f, Hh, Ww);
       U.uc = b > 0 ? p->alloc(f, Hh, Ww) : U.ur;
     }
-    blk.logits = p->alloc(8, height, width);
+    blk.logits = p->alloc(p->lp, height, width);
   }
   p->written.assign(p->n_tensors, 0);
-  p->misc_floats = round_up(loss_partial_count(batch, (long)height * width) + 2 * batch + 2048, 64);
+  p->misc_floats = round_up(2 * loss_partial_count(batch, (long)height * width) + round_up((int)loss_scratch_ints(batch), 64) + 2048, 64);
   p->attn_scratch_off = p->misc_floats;
   if (attn_tc_supported(fa, da))
     p->misc_floats += (long)((attn_tc_scratch_bytes(batch, p->Hl[S - 1] * p->Wl[S - 1], fa) + 255) / 256 * 64);
@@ -782,6 +809,8 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   }
   // descriptor table: the only device memory the plan owns
   cudaError_t e = cudaMalloc(&p->d_descs, sizeof(PackDesc) * p->descs.size());
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_flags, 64);
+  if (e == cudaSuccess) e = cudaMemset(p->d_flags, 0, 64);
   if (e == cudaSuccess) e = cudaMemcpy(p->d_descs, p->descs.data(), sizeof(PackDesc) * p->descs.size(), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && !p->tc_descs.empty()) {
     e = cudaMalloc(&p->d_tc_descs, sizeof(TcPackDesc) * p->tc_descs.size());
@@ -796,6 +825,7 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
   if (e != cudaSuccess) {
     set_error("plan_create: descriptor upload failed: %s", cudaGetErrorString(e));
     if (p->d_descs) cudaFree(p->d_descs);
+    if (p->d_flags) cudaFree(p->d_flags);
     if (p->d_tc_descs) cudaFree(p->d_tc_descs);
     if (p->d_t3_descs) cudaFree(p->d_t3_descs);
     delete p;
@@ -808,6 +838,7 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
 extern "C" void msau_plan_destroy(MsauPlan* p) {
   if (!p) return;
   if (p->d_descs) cudaFree(p->d_descs);
+  if (p->d_flags) cudaFree(p->d_flags);
   if (p->d_tc_descs) cudaFree(p->d_tc_descs);
   if (p->d_t3_descs) cudaFree(p->d_t3_descs);
   if (p->tabP) cudaFree(p->tabP);
@@ -859,7 +890,7 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
   MSAU_CUDA_TRY(cudaMemsetAsync(p->pk, 0, sizeof(float) * p->packed_floats, p->st));
   count_launch(1);
   MSAU_TRY(launch_pack(params, p->pk, p->d_descs, (int)p->descs.size(), p->pack_blocks, p->st));
-  if (g_use_tc) {
+  if (p->opt.use_tc) {
     count_launch(1);
     MSAU_TRY(launch_pack_tc(p->pk, p->pktc, p->d_tc_descs, (int)p->tc_descs.size(), p->tc_blocks, p->st));
     if (!p->t3_descs.empty()) {
@@ -898,7 +929,7 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
           p->first_skip = flag;
           p->first_ids = reinterpret_cast<const short*>(x);
         } else {
-        if (g_use_tc && g_structured && p->ids_off >= 0) {
+        if (p->opt.use_tc && p->opt.structured && p->ids_off >= 0) {
           // chargrid input: scan for one-hot structure, then the id-gather conv; the dense kernel below skips itself
           short* ids = reinterpret_cast<short*>(p->misc + p->ids_off);
           int* flag = reinterpret_cast<int*>(p->misc + p->ids_off) + (((long)p->B * p->H * p->W + 1) / 2 + 8);
@@ -918,7 +949,7 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
         MSAU_TRY(layer_fwd(p, L.conv1, src, nullptr, L.z1, o));
       }
       count_launch(1);
-      MSAU_TRY(launch_lrn_fwd(p->A(L.z1), p->A(L.y1), p->npix(L.z1), L.z1.C, p->st));
+      MSAU_TRY(launch_lrn_fwd(p->A(L.z1), p->A(L.y1), p->npix(L.z1), L.z1.C, p->opt.lrn_coop, p->st));
       MSAU_TRY(res_fwd(p, L.res, L.y1, L.a, L.rr));
       if (b > 0) {
         const Tensor& pd = (l == S - 1) ? prev->att : prev->down[l].cc;
@@ -930,7 +961,7 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
           ConvOpt oa;
           MSAU_TRY(layer_fwd(p, blk.attn.fg, L.cc, nullptr, blk.fg, oa));
           MSAU_TRY(layer_fwd(p, blk.attn.h, L.cc, nullptr, blk.hh, oa));
-          if (g_use_tc && attn_tc_supported(blk.attn.C, blk.attn.d)) {
+          if (p->opt.use_tc && attn_tc_supported(blk.attn.C, blk.attn.d)) {
             count_launch(3);
             MSAU_TRY(launch_attn_tc_fwd(p->A(blk.fg), p->A(blk.hh), p->A(L.cc), p->B, L.cc.H * L.cc.W, blk.attn.C, blk.attn.d,
                                         p->A(blk.mrow), p->A(blk.att), p->misc + p->attn_scratch_off, p->st));
@@ -964,18 +995,20 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
   const long npp = (long)p->H * p->W;
   if (aux) {
     count_launch(1);
-    MSAU_TRY(launch_head(p->A(p->blocks[NB - 2].logits), 8, cfg.n_class, p->B, npp, aux, nullptr, nullptr, p->st));
+    MSAU_TRY(launch_head(p->A(p->blocks[NB - 2].logits), p->lp, cfg.n_class, p->B, npp, aux, nullptr, nullptr, p->st));
   }
   if (logits || probs || argmax) {
     count_launch(1);
-    MSAU_TRY(launch_head(p->A(p->blocks[NB - 1].logits), 8, cfg.n_class, p->B, npp, logits, probs, argmax, p->st));
+    MSAU_TRY(launch_head(p->A(p->blocks[NB - 1].logits), p->lp, cfg.n_class, p->B, npp, logits, probs, argmax, p->st));
   }
   return MSAU_OK;
 }
 
-extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, const void* labels, int label_dtype, float loss_scale,
-                                  void* workspace, size_t workspace_bytes, float* loss, float* grads, void* stream) {
-  MSAU_CHECK_ARG(p && x && labels && loss && grads, "loss_backward: null argument");
+extern "C" int msau_loss_backward_ex(MsauPlan* p, const float* x, int x_layout, const void* labels, const void* labels_aux,
+                                     int label_dtype, const MsauLossSpec* spec, float loss_scale, void* workspace, size_t workspace_bytes,
+                                     float* loss, float* loss_main, int32_t* accuracy, float* grads, void* stream) {
+  MSAU_CHECK_ARG(p && x && labels && loss && grads && spec, "loss_backward: null argument");
+  MSAU_CHECK_ARG(label_dtype == 0 || label_dtype == 1, "loss_backward: label_dtype must be 0 (uint8) or 1 (int64)");
   MSAU_TRY(bind(p, workspace, workspace_bytes, 1, stream));
   const MsauConfig& cfg = p->cfg;
   const int S = cfg.scale_space_num, NB = cfg.num_blocks;
@@ -983,7 +1016,7 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
   std::fill(p->written.begin(), p->written.end(), 0);
   MSAU_CUDA_TRY(cudaMemsetAsync(grads, 0, sizeof(float) * p->n_params, p->st));
   p->wst = p->st;
-  if (g_side_stream) {
+  if (p->opt.side_stream) {
     if (!p->side) {
       MSAU_CUDA_TRY(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
       MSAU_CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -995,11 +1028,16 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
   {
     Block& last = p->blocks[NB - 1];
     Block& auxb = p->blocks[NB - 2];
-    int* counts = reinterpret_cast<int*>(p->misc);
-    float* partial = p->misc + round_up(p->B, 64);
+    int* ints = reinterpret_cast<int*>(p->misc);
+    float* partial = p->misc + round_up((int)loss_scratch_ints(p->B), 64);
+    LossSpec ls;
+    ls.mode = spec->mode; ls.w_main = spec->weight_main; ls.w_aux = spec->weight_aux;
+    ls.class_weights = spec->h_class_weights;
     count_launch(3);
-    MSAU_TRY(launch_loss(p->A(last.logits), p->A(auxb.logits), cfg.n_class, labels, label_dtype, p->B, npp, loss_scale,
-                         p->G(last.logits), p->G(auxb.logits), counts, partial, loss, p->st));
+    MSAU_TRY(launch_loss(p->A(last.logits), p->A(auxb.logits), p->lp, cfg.n_class, labels, labels_aux ? labels_aux : labels, label_dtype,
+                         p->B, npp, loss_scale, ls, p->G(last.logits), p->G(auxb.logits), ints, p->d_flags, partial, loss, loss_main, p->st));
+    if (accuracy)
+      MSAU_CUDA_TRY(cudaMemcpyAsync(accuracy, ints + 2L * p->B * 32, 2 * sizeof(int), cudaMemcpyDeviceToDevice, p->st));
     p->touch(last.logits); p->touch(auxb.logits);
   }
   for (int b = NB - 1; b >= 0; --b) {
@@ -1008,19 +1046,19 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
     // ---- 4x4 head ----
     {
       const Tensor& src = blk.up[0].uc;
-      MSAU_TRY(layer_wgrad(p, blk.end, 1, p->A(src), src.C, 0, blk.end.c1p, false, p->G(blk.logits), 8, nullptr, 0, p->H, p->W));
+      MSAU_TRY(layer_wgrad(p, blk.end, 1, p->A(src), src.C, 0, blk.end.c1p, false, p->G(blk.logits), p->lp, nullptr, 0, p->H, p->W));
       ConvOpt o;
       // up-tower outputs uc (post-ReLU) have two gradient writers, this head / the deconv below and the next block's coupling:
       // each masks its own contribution, so the relu_mask pass over G(uc) is not needed
-      if (g_fuse_mask) { o.omask = p->A(src); o.pom = src.C; }
-      MSAU_TRY(layer_dgrad(p, blk.end, 1, p->G(blk.logits), 8, nullptr, 0, src, o));
+      if (p->opt.fuse_mask) { o.omask = p->A(src); o.pom = src.C; }
+      MSAU_TRY(layer_dgrad(p, blk.end, 1, p->G(blk.logits), p->lp, nullptr, 0, src, o));
     }
     // ---- up tower (forward ran l = S-2..0, so backward runs l = 0..S-2) ----
     for (int l = 0; l <= S - 2; ++l) {
       UpLevel& U = blk.up[l];
       const Tensor& xin = (l == S - 2) ? blk.down[S - 1].cc : blk.up[l + 1].uc;
-      bool pre = (b == 0) && g_fuse_mask;       // block 0: uc IS the residual block's output ur
-      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc, &pre, g_fuse_mask, g_fuse_mask));
+      bool pre = (b == 0) && p->opt.fuse_mask;       // block 0: uc IS the residual block's output ur
+      if (b > 0) MSAU_TRY(coupl_bwd(p, U.coupl, prev->up[l].uc, U.ur, U.uc, &pre, p->opt.fuse_mask, p->opt.fuse_mask));
       MSAU_TRY(res_bwd(p, U.res, U.u, U.a, U.ur, pre));
       p->touch(U.u);
       // conv1s on cat[dw[l], deconv]
@@ -1030,7 +1068,7 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       ConvOpt o;
       MSAU_TRY(layer_dgrad(p, U.conv1, 1, p->G(U.u), U.u.C, nullptr, 0, skip, o));
       MSAU_TRY(layer_dgrad(p, U.conv1, 2, p->G(U.u), U.u.C, nullptr, 0, U.d, o));
-      MSAU_TRY(deconv_bwd(p, U.deconv, xin, U.d, g_fuse_mask && l < S - 2));   // xin = uc of level l+1 (l = S-2: the deepest cc)
+      MSAU_TRY(deconv_bwd(p, U.deconv, xin, U.d, p->opt.fuse_mask && l < S - 2));   // xin = uc of level l+1 (l = S-2: the deepest cc)
     }
     // ---- down tower, deepest level first ----
     for (int l = S - 1; l >= 0; --l) {
@@ -1039,7 +1077,7 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
         if (p->written[blk.att.id]) {   // only the next block's coupling reads the attention output
           const AttnLayer& at = blk.attn;
           const int N = L.cc.H * L.cc.W;
-          if (g_use_tc && attn_tc_supported(at.C, at.d)) {
+          if (p->opt.use_tc && attn_tc_supported(at.C, at.d)) {
             count_launch(3);
             MSAU_TRY(launch_attn_tc_bwd(p->A(blk.fg), p->A(blk.hh), p->G(blk.att), p->A(blk.mrow), p->B, N, at.C, at.d, p->G(blk.fg),
                                         p->G(blk.hh), p->misc + p->attn_scratch_off, p->st));
@@ -1065,7 +1103,7 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       }
       // the pool gradient is the last contribution to G(cc) (the skip connection and the next block's coupling came earlier):
       // it also applies the mask of the ReLU that produced cc, so the relu_mask pass of coupl_bwd / res_bwd is skipped
-      const bool pool_masks = g_fuse_mask && l < S - 1;
+      const bool pool_masks = p->opt.fuse_mask && l < S - 1;
       if (l < S - 1) {
         count_launch(1);
         MSAU_TRY(launch_pool_bwd(p->A(L.cc), p->G(L.pooled), p->G(L.cc), p->B, L.cc.H, L.cc.W, L.cc.C, p->touch(L.cc), pool_masks, p->st));
@@ -1077,7 +1115,7 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
       }
       MSAU_TRY(res_bwd(p, L.res, L.y1, L.a, L.rr, pre));
       count_launch(1);
-      MSAU_TRY(launch_lrn_bwd(p->A(L.z1), p->G(L.y1), p->G(L.z1), p->npix(L.z1), L.z1.C, p->st));
+      MSAU_TRY(launch_lrn_bwd(p->A(L.z1), p->G(L.y1), p->G(L.z1), p->npix(L.z1), L.z1.C, p->opt.lrn_coop, p->st));
       if (b == 0 && l == 0) {
         const int c1 = pad4(cfg.channels);
         if (x_layout == 3) {
@@ -1110,6 +1148,21 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
   return MSAU_OK;
 }
 
+extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, const void* labels, int label_dtype, float loss_scale,
+                                  void* workspace, size_t workspace_bytes, float* loss, float* grads, void* stream) {
+  MsauLossSpec spec;
+  spec.mode = 0; spec.weight_main = 1.f; spec.weight_aux = 1.f; spec.h_class_weights = nullptr;
+  return msau_loss_backward_ex(p, x, x_layout, labels, nullptr, label_dtype, &spec, loss_scale, workspace, workspace_bytes, loss, nullptr, nullptr,
+                               grads, stream);
+}
+
+extern "C" int msau_plan_error_flags(MsauPlan* p, int* h_flags) {
+  MSAU_CHECK_ARG(p && h_flags, "plan_error_flags: null argument");
+  MSAU_CUDA_TRY(cudaMemcpy(h_flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+  if (*h_flags) MSAU_CUDA_TRY(cudaMemset(p->d_flags, 0, sizeof(int)));
+  return MSAU_OK;
+}
+
 extern "C" int msau_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, long long n, int step, float lr,
                                    float beta1, float beta2, float eps, float max_norm, float* scratch, float* total_norm,
                                    void* stream) {
@@ -1117,6 +1170,31 @@ extern "C" int msau_clip_adam_step(float* params, float* grads, float* exp_avg, 
   count_launch(2);
   return launch_clip_adam(params, grads, exp_avg, exp_avg_sq, n, step, lr, beta1, beta2, eps, max_norm, scratch, total_norm,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msau_optimizer_step(int kind, float* params, float* grads, float* state1, float* state2, long long n, int step,
+                                   int32_t* step_dev, float lr, float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                                   float* scratch, float* total_norm, void* stream) {
+  MSAU_CHECK_ARG(params && grads && scratch, "optimizer_step: null argument");
+  MSAU_CHECK_ARG((kind == 1 || state1) && (kind == 2 || state2), "optimizer_step: missing optimiser state buffer");
+  count_launch(2);
+  return launch_optim(kind, params, grads, state1, state2, n, step, step_dev, lr, beta1, beta2, eps, weight_decay, max_norm, scratch,
+                      total_norm, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msau_onehot_argmax(const void* onehot, int dtype, int batch, int channels, long long npix_per_page, int channels_last,
+                                  uint8_t* out, void* stream) {
+  MSAU_CHECK_ARG(onehot && out && batch >= 1 && npix_per_page >= 1, "onehot_argmax: bad argument");
+  count_launch(1);
+  return launch_onehot_argmax(onehot, dtype, batch, channels, npix_per_page, channels_last, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int msau_confusion_counts(const uint8_t* pred, const void* labels, int label_dtype, long long n, int n_class,
+                                     long long* confusion, void* stream) {
+  MSAU_CHECK_ARG(pred && labels && confusion && n >= 0, "confusion_counts: bad argument");
+  MSAU_CHECK_ARG(label_dtype == 0 || label_dtype == 1, "confusion_counts: label_dtype must be 0 (uint8) or 1 (int64)");
+  count_launch(1);
+  return launch_confusion(pred, labels, label_dtype, n, n_class, confusion, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // SelfAttentionBlock as a stand-alone operator (model/layers/attention.py:152-162), tensor-core path
@@ -1173,14 +1251,11 @@ extern "C" int msau_debug_tensor(const MsauPlan* p, int id, long long* off, int*
 
 extern "C" int msau_set_option(const char* name, int value) {
   MSAU_CHECK_ARG(name, "set_option: null name");
-  if (!strcmp(name, "tensor_core_conv")) { g_use_tc = value != 0; return MSAU_OK; }
-  if (!strcmp(name, "conv3_fold")) { g_use_c3 = value != 0; return MSAU_OK; }
-  if (!strcmp(name, "pointwise_conv")) { g_use_pw = value != 0; return MSAU_OK; }
-  if (!strcmp(name, "wgrad_side_stream")) { g_side_stream = value != 0; return MSAU_OK; }
-  if (!strcmp(name, "structured_first_layer")) { g_structured = value != 0; return MSAU_OK; }
-  if (!strcmp(name, "fuse_relu_mask")) { g_fuse_mask = value != 0; return MSAU_OK; }
-  if (!strcmp(name, "lrn_coop")) { g_lrn_coop = value; return MSAU_OK; }
-  if (!strcmp(name, "conv3_max_channels")) { g_c3_max = value; return MSAU_OK; }
-  set_error("set_option: unknown option '%s'", name);
-  return MSAU_ERR_ARG;
+  std::lock_guard<std::mutex> lk(g_defaults_mu);
+  return set_opt(g_defaults, name, value);
+}
+
+extern "C" int msau_plan_set_option(MsauPlan* p, const char* name, int value) {
+  MSAU_CHECK_ARG(p && name, "plan_set_option: null argument");
+  return set_opt(p->opt, name, value);
 }

@@ -244,18 +244,16 @@ static void lrn_coop_launch(const float* z, const float* gy, float* out, long np
                                                                  reinterpret_cast<float4*>(out), nquad);
 }
 
-int g_lrn_coop = 1;   // msau_set_option("lrn_coop", v): 0 = thread-per-pixel kernels only, 1 = cooperative where it wins, 2 = from 8 channels up
-
 template <bool BWD>
-static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, cudaStream_t st) {
+static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, int C, int coop, cudaStream_t st) {
   const int grid = cdiv(npix, 256);
   ProfScope ps(BWD ? "lrn_bwd_kernel" : "lrn_fwd_kernel", C, C, 0, 0, (int)(npix >> 10), 0, (double)npix * C * (BWD ? 12 : 6),
                (double)npix * C * 4.0 * (BWD ? 3 : 2), st);
   // measured (B = 16, 512^2 pages, profiles/README.md): the cooperative kernel wins from 16 channels up in the forward pass
   // (25 vs 29 us at 16, 15 vs 23 us at 32, 12 vs 19 us at 64) and from 32 channels up in the backward pass (35 vs 66 us at
   // 32, 21 vs 41 us at 64; 58 vs 54 us at 16); at 8 channels the thread-per-pixel kernels already stream at 5-5.9 TB/s
-  const int coop_min = g_lrn_coop == 2 ? 8 : (BWD ? 32 : 16);
-  if (g_lrn_coop && C >= coop_min && (C == 8 || C == 16 || C == 32 || C == 64 || C == 128)) {
+  const int coop_min = coop == 2 ? 8 : (BWD ? 32 : 16);
+  if (coop && C >= coop_min && (C == 8 || C == 16 || C == 32 || C == 64 || C == 128)) {
     switch (C) {
       case 8: lrn_coop_launch<8, BWD>(z, gy, out, npix, st); break;
       case 16: lrn_coop_launch<16, BWD>(z, gy, out, npix, st); break;
@@ -287,8 +285,8 @@ static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, 
   return MSAU_OK;
 }
 
-int launch_lrn_fwd(const float* z, float* y, long npix, int C, cudaStream_t st) { return lrn_dispatch<false>(z, nullptr, y, npix, C, st); }
-int launch_lrn_bwd(const float* z, const float* gy, float* gz, long npix, int C, cudaStream_t st) { return lrn_dispatch<true>(z, gy, gz, npix, C, st); }
+int launch_lrn_fwd(const float* z, float* y, long npix, int C, int coop, cudaStream_t st) { return lrn_dispatch<false>(z, nullptr, y, npix, C, coop, st); }
+int launch_lrn_bwd(const float* z, const float* gy, float* gz, long npix, int C, int coop, cudaStream_t st) { return lrn_dispatch<true>(z, gy, gz, npix, C, coop, st); }
 
 // ------------------------------------------------------------------------------------------- pool
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
@@ -458,144 +456,305 @@ int launch_colsum(const float* g, long npix, int C, int c_lim, float* out, cudaS
 }
 
 // ------------------------------------------------------------------------------------------- head
-// logits NHWC (pitch P, n_class <= 8 used) -> NCHW logits / softmax probabilities / uint8 argmax.
-// One thread per pixel: reads 32 B, writes n_class strided planes (coalesced across the warp).
-__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ lg, int P, int n_class, long npix_per_page, int B,
+// logits NHWC (pitch P = 8 / 16 / 32, n_class <= P used) -> NCHW logits / softmax probabilities / uint8 argmax.
+// One thread per pixel: reads P * 4 B, writes n_class strided planes (coalesced across the warp).
+template <int P>
+__device__ __forceinline__ void load_pixel(const float* __restrict__ src, long idx, float* v) {
+  const float4* s4 = reinterpret_cast<const float4*>(src + idx * P);
+#pragma unroll
+  for (int i = 0; i < P / 4; ++i) {
+    const float4 t = __ldg(s4 + i);
+    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+  }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ lg, int n_class, long npix_per_page, int B,
                                                     float* __restrict__ logits_nchw, float* __restrict__ probs_nchw,
                                                     uint8_t* __restrict__ argmax) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= npix_per_page * B) return;
   const int b = (int)(idx / npix_per_page);
   const long p = idx - (long)b * npix_per_page;
-  float v[8];
-  const float4 a = __ldg(reinterpret_cast<const float4*>(lg + idx * P));
-  const float4 c = __ldg(reinterpret_cast<const float4*>(lg + idx * P) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  float v[P];
+  load_pixel<P>(lg, idx, v);
   float m = v[0]; int am = 0;
 #pragma unroll
-  for (int k = 1; k < 8; ++k)
+  for (int k = 1; k < P; ++k)
     if (k < n_class && v[k] > m) { m = v[k]; am = k; }   // first maximum wins (numpy / torch argmax)
   if (argmax) argmax[idx] = (uint8_t)am;
   float* lo = logits_nchw ? logits_nchw + (long)b * n_class * npix_per_page + p : nullptr;
   if (lo) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < P; ++k)
       if (k < n_class) lo[k * npix_per_page] = v[k];
   }
   if (probs_nchw) {
-    float e[8]; float s = 0.f;
+    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { e[k] = k < n_class ? expf(v[k] - m) : 0.f; s += e[k]; }
+    for (int k = 0; k < P; ++k) { v[k] = k < n_class ? expf(v[k] - m) : 0.f; s += v[k]; }
     const float inv = 1.f / s;
     float* po = probs_nchw + (long)b * n_class * npix_per_page + p;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (k < n_class) po[k * npix_per_page] = e[k] * inv;
+    for (int k = 0; k < P; ++k)
+      if (k < n_class) po[k * npix_per_page] = v[k] * inv;
   }
 }
 
 int launch_head(const float* lg, int P, int n_class, int B, long npix_per_page, float* logits_nchw, float* probs_nchw, uint8_t* argmax, cudaStream_t st) {
-  MSAU_CHECK_ARG(P == 8 && n_class <= 8, "head: logits pitch must be 8 and n_class <= 8 (got %d, %d)", P, n_class);
-  ProfScope ps("head_kernel", 0, (double)npix_per_page * B * (32.0 + 4.0 * n_class * ((logits_nchw ? 1 : 0) + (probs_nchw ? 1 : 0)) + (argmax ? 1 : 0)), st);
-  head_kernel<<<cdiv(npix_per_page * B, 256), 256, 0, st>>>(lg, P, n_class, npix_per_page, B, logits_nchw, probs_nchw, argmax);
+  MSAU_CHECK_ARG((P == 8 || P == 16 || P == 32) && n_class <= P, "head: logits pitch must be 8, 16 or 32 and n_class <= pitch (got %d, %d)", P, n_class);
+  ProfScope ps("head_kernel", 0, (double)npix_per_page * B * (4.0 * P + 4.0 * n_class * ((logits_nchw ? 1 : 0) + (probs_nchw ? 1 : 0)) + (argmax ? 1 : 0)), st);
+  const int grid = cdiv(npix_per_page * B, 256);
+  if (P == 8) head_kernel<8><<<grid, 256, 0, st>>>(lg, n_class, npix_per_page, B, logits_nchw, probs_nchw, argmax);
+  else if (P == 16) head_kernel<16><<<grid, 256, 0, st>>>(lg, n_class, npix_per_page, B, logits_nchw, probs_nchw, argmax);
+  else head_kernel<32><<<grid, 256, 0, st>>>(lg, n_class, npix_per_page, B, logits_nchw, probs_nchw, argmax);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }
 
 // ------------------------------------------------------------------------------------------- loss
-// stage 1: kept-pixel count per page ; stage 2: per-pixel log-softmax NLL for both heads + dlogits,
-// per-block partial sums ; stage 3: fixed-order final sum (deterministic).
+// Two loss definitions share these kernels (LossSpec::mode):
+//   0  MSAUWrapper.loss (model/model.py:446-459): CE(main) + CE(aux) over the pixels with label != 0, mean over the kept
+//      pixels of a page, mean over pages;
+//   1  UNetLoss (model/training/cost.py:35-65): w_main * CrossEntropyLoss(logits, tgt) + w_aux * CrossEntropyLoss(aux,
+//      aux_tgt) over ALL pixels of the batch (label 0 is a class like any other), optional class weights with torch's
+//      weighted-mean reduction  sum_p w[t_p] nll_p / sum_p w[t_p];  labels = argmax of the one-hot targets (:41,:52).
+// stage 1: class histogram per (head, page) -- integer atomics, so the denominators are exact and deterministic;
+// stage 2: per-pixel log-softmax NLL of both heads + dlogits + per-block partial sums; stage 3: fixed-order final sum.
+// Out-of-range labels (negative or >= n_class; torch raises) contribute nothing and raise the plan's error flag;
+// the masked accuracy of cost.py:44-50 / train...py:135-159 (argmax == label over label != 0) is counted on the way.
 template <typename LT>
-__global__ void __launch_bounds__(256) count_kept_kernel(const LT* __restrict__ labels, long npix_per_page, int* __restrict__ counts) {
+__global__ void __launch_bounds__(256) class_hist_kernel(const LT* __restrict__ labels, const LT* __restrict__ labels_aux, long npix_per_page,
+                                                         int n_class, int* __restrict__ hist /* [2][B][32] */, int B, int* __restrict__ flags) {
+  __shared__ int sh[64];
   const int b = blockIdx.y;
-  const LT* l = labels + (long)b * npix_per_page;
-  int c = 0;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix_per_page; i += (long)gridDim.x * blockDim.x) c += (l[i] != 0);
-  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(counts + b, c);
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const LT* l0 = labels + (long)b * npix_per_page;
+  const LT* l1 = labels_aux ? labels_aux + (long)b * npix_per_page : nullptr;
+  bool bad = false;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix_per_page; i += (long)gridDim.x * blockDim.x) {
+    const long long a = (long long)l0[i];
+    if (a < 0 || a >= n_class) bad = true; else atomicAdd(&sh[(int)a], 1);
+    if (l1) {
+      const long long c = (long long)l1[i];
+      if (c < 0 || c >= n_class) bad = true; else atomicAdd(&sh[32 + (int)c], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64 && sh[threadIdx.x]) atomicAdd(hist + ((threadIdx.x >> 5) * B + b) * 32 + (threadIdx.x & 31), sh[threadIdx.x]);
+  if (bad) atomicOr(flags, 1);
 }
 
-__device__ __forceinline__ float ce_head(const float* __restrict__ src, long idx, int n_class, int lab, float scale,
-                                         float gscale, float4& g0, float4& g1) {
-  float v[8];
-  const float4 a = __ldg(reinterpret_cast<const float4*>(src + idx * 8));
-  const float4 c = __ldg(reinterpret_cast<const float4*>(src + idx * 8) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
-  float m = v[0];
+template <int P>
+__device__ __forceinline__ float ce_head(const float* __restrict__ src, float* __restrict__ dst, long idx, int n_class, int lab, float scale,
+                                         float gscale, bool active, int* correct) {
+  float4* d4 = reinterpret_cast<float4*>(dst + idx * P);
+  if (!active) {
 #pragma unroll
-  for (int k = 1; k < 8; ++k) if (k < n_class) m = fmaxf(m, v[k]);
-  float e[8]; float s = 0.f; float vl = 0.f;
+    for (int i = 0; i < P / 4; ++i) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return 0.f;
+  }
+  float v[P];
+  load_pixel<P>(src, idx, v);
+  float m = v[0]; int am = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { e[k] = k < n_class ? expf(v[k] - m) : 0.f; s += e[k]; if (k == lab) vl = v[k]; }
+  for (int k = 1; k < P; ++k) if (k < n_class && v[k] > m) { m = v[k]; am = k; }
+  if (correct && lab != 0 && am == lab) ++*correct;
+  float s = 0.f, vl = 0.f;
+#pragma unroll
+  for (int k = 0; k < P; ++k) { if (k == lab) vl = v[k]; v[k] = k < n_class ? expf(v[k] - m) : 0.f; s += v[k]; }
   const float gs = scale * gscale;
   const float inv = gs / s;
-  float gq[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) gq[k] = e[k] * inv - (k == lab ? gs : 0.f);
-  g0 = make_float4(gq[0], gq[1], gq[2], gq[3]);
-  g1 = make_float4(gq[4], gq[5], gq[6], gq[7]);
+  for (int k = 0; k < P; ++k) v[k] = v[k] * inv - (k == lab ? gs : 0.f);
+#pragma unroll
+  for (int i = 0; i < P / 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   return (logf(s) + m - vl) * scale;
 }
 
-template <typename LT>
+struct LossDev {
+  int mode; float w_main, w_aux;
+  float cw[32];      // class weights (all 1 when absent)
+  int has_cw;
+};
+
+template <typename LT, int P>
 __global__ void __launch_bounds__(256) ce_kernel(const float* __restrict__ lg, const float* __restrict__ la, int n_class,
-                                                  const LT* __restrict__ labels, const int* __restrict__ counts, long npix_per_page, int B,
-                                                  float gscale, float* __restrict__ dlg, float* __restrict__ dla, float* __restrict__ partial) {
+                                                  const LT* __restrict__ labels, const LT* __restrict__ labels_aux, const int* __restrict__ hist,
+                                                  long npix_per_page, int B, float gscale, const LossDev spec, float* __restrict__ dlg,
+                                                  float* __restrict__ dla, float* __restrict__ partial, int* __restrict__ acc_counts) {
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  float loss = 0.f;
+  // denominators (identical in every thread: fixed-order sums over the integer histogram)
+  __shared__ float den_s[2][64];   // mode 0: per page (B <= 64 cached, else recomputed); mode 1: [head][0]
+  if (spec.mode == 1) {
+    if (threadIdx.x < 2) {
+      double d = 0.0;
+      for (int b = 0; b < B; ++b)
+        for (int c = 0; c < n_class; ++c) d += (double)spec.cw[c] * (double)hist[(threadIdx.x * B + b) * 32 + c];
+      den_s[threadIdx.x][0] = (float)d;
+    }
+  } else if (threadIdx.x < 64 && threadIdx.x < B) {
+    int kept = 0;
+    for (int c = 1; c < n_class; ++c) kept += hist[threadIdx.x * 32 + c];
+    den_s[0][threadIdx.x] = (float)kept;
+  }
+  __syncthreads();
+  float loss = 0.f, loss_main = 0.f;
+  int correct = 0, kept = 0;
   if (idx < npix_per_page * B) {
     const int b = (int)(idx / npix_per_page);
-    const int lab = (int)labels[idx];
-    float4 z0 = make_float4(0.f, 0.f, 0.f, 0.f), z1 = z0, y0 = z0, y1 = z0;
-    if (lab != 0) {
-      const float scale = 1.f / ((float)counts[b] * (float)B);
-      loss += ce_head(lg, idx, n_class, lab, scale, gscale, z0, z1);
-      loss += ce_head(la, idx, n_class, lab, scale, gscale, y0, y1);
+    const long long l0 = (long long)labels[idx];
+    const long long l1 = labels_aux ? (long long)labels_aux[idx] : l0;
+    const bool ok0 = l0 >= 0 && l0 < n_class, ok1 = l1 >= 0 && l1 < n_class;
+    if (spec.mode == 0) {
+      const bool act = ok0 && l0 != 0;
+      float den;
+      if (b < 64) den = den_s[0][b];
+      else { int k = 0; for (int c = 1; c < n_class; ++c) k += hist[b * 32 + c]; den = (float)k; }
+      const float scale = act ? 1.f / (den * (float)B) : 0.f;
+      loss_main = ce_head<P>(lg, dlg, idx, n_class, (int)l0, scale, gscale, act, &correct);
+      loss = loss_main + ce_head<P>(la, dla, idx, n_class, (int)l0, scale, gscale, act, nullptr);
+      kept += act ? 1 : 0;
+    } else {
+      const float s0 = ok0 ? spec.w_main * spec.cw[ok0 ? (int)l0 : 0] / den_s[0][0] : 0.f;
+      const float s1 = ok1 ? spec.w_aux * spec.cw[ok1 ? (int)l1 : 0] / den_s[1][0] : 0.f;
+      loss_main = ce_head<P>(lg, dlg, idx, n_class, (int)l0, s0, gscale, ok0, &correct);
+      loss = loss_main + ce_head<P>(la, dla, idx, n_class, (int)l1, s1, gscale, ok1 && spec.w_aux != 0.f, nullptr);
+      kept += (ok0 && l0 != 0) ? 1 : 0;
     }
-    reinterpret_cast<float4*>(dlg + idx * 8)[0] = z0; reinterpret_cast<float4*>(dlg + idx * 8)[1] = z1;
-    reinterpret_cast<float4*>(dla + idx * 8)[0] = y0; reinterpret_cast<float4*>(dla + idx * 8)[1] = y1;
   }
-  __shared__ float ws[8];
-  for (int o = 16; o; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = loss;
+  __shared__ float ws[8], wm[8];
+  __shared__ int wc[8], wk[8];
+  for (int o = 16; o; o >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    loss_main += __shfl_xor_sync(0xffffffffu, loss_main, o);
+    correct += __shfl_xor_sync(0xffffffffu, correct, o);
+    kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  }
+  if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = loss; wm[threadIdx.x >> 5] = loss_main; wc[threadIdx.x >> 5] = correct; wk[threadIdx.x >> 5] = kept; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < 8; ++i) s += ws[i];
+    float s = 0.f, sm = 0.f; int c = 0, k = 0;
+    for (int i = 0; i < 8; ++i) { s += ws[i]; sm += wm[i]; c += wc[i]; k += wk[i]; }
     partial[blockIdx.x] = s;
+    partial[gridDim.x + blockIdx.x] = sm;
+    if (c) atomicAdd(acc_counts, c);
+    if (k) atomicAdd(acc_counts + 1, k);
   }
 }
 
-__global__ void __launch_bounds__(1024) final_sum_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
-  __shared__ double sh[1024];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < n; i += 1024) s += (double)partial[i];
-  sh[threadIdx.x] = s;
+// out[0] = sum of partial[0..n) (the loss), out[1] = main_scale * sum of partial[n..2n) (the main head's own term)
+__global__ void __launch_bounds__(1024) final_sum_kernel(const float* __restrict__ partial, int n, float main_scale, float* __restrict__ out,
+                                                         float* __restrict__ out_main) {
+  __shared__ double sh[1024], shm[1024];
+  double s = 0.0, sm = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) { s += (double)partial[i]; sm += (double)partial[n + i]; }
+  sh[threadIdx.x] = s; shm[threadIdx.x] = sm;
   __syncthreads();
   for (int o = 512; o; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    if (threadIdx.x < o) { sh[threadIdx.x] += sh[threadIdx.x + o]; shm[threadIdx.x] += shm[threadIdx.x + o]; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *out = (float)sh[0];
+  if (threadIdx.x == 0) {
+    *out = (float)sh[0];
+    if (out_main) *out_main = (float)(shm[0] * (double)main_scale);
+  }
 }
 
-int loss_partial_count(int B, long npix_per_page) { return cdiv(npix_per_page * B, 256); }
+int loss_partial_count(int B, long npix_per_page) { return cdiv(npix_per_page * B, 256); }   // the partial buffer holds 2x this many floats
+long loss_scratch_ints(int B) { return 2L * B * 32 + 8; }   // histogram [2][B][32] + {correct, kept}
 
-int launch_loss(const float* lg, const float* la, int n_class, const void* labels, int label_is_i64, int B, long npix_per_page,
-                float gscale, float* dlg, float* dla, int* counts, float* partial, float* loss_out, cudaStream_t st) {
-  MSAU_CHECK_ARG(n_class <= 8, "loss: n_class <= 8 supported");
-  MSAU_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(int) * B, st));
-  ProfScope ps("loss_kernels", 0, (double)npix_per_page * B * (4 * 32.0 + 2.0 * (label_is_i64 ? 8 : 1)), st);
+template <typename LT>
+static int loss_typed(const float* lg, const float* la, int P, int n_class, const LT* labels, const LT* labels_aux, int B, long npix_per_page,
+                      float gscale, const LossDev& spec, float* dlg, float* dla, int* ints, int* flags, float* partial, float* loss_out, float* loss_main_out, cudaStream_t st) {
   const int nblk = loss_partial_count(B, npix_per_page);
+  int* hist = ints;
+  int* acc = ints + 2L * B * 32;
   dim3 cg(min(cdiv(npix_per_page, 256), 64), B);
-  if (label_is_i64) {
-    count_kept_kernel<long long><<<cg, 256, 0, st>>>((const long long*)labels, npix_per_page, counts);
-    ce_kernel<long long><<<nblk, 256, 0, st>>>(lg, la, n_class, (const long long*)labels, counts, npix_per_page, B, gscale, dlg, dla, partial);
-  } else {
-    count_kept_kernel<uint8_t><<<cg, 256, 0, st>>>((const uint8_t*)labels, npix_per_page, counts);
-    ce_kernel<uint8_t><<<nblk, 256, 0, st>>>(lg, la, n_class, (const uint8_t*)labels, counts, npix_per_page, B, gscale, dlg, dla, partial);
+  class_hist_kernel<LT><<<cg, 256, 0, st>>>(labels, spec.mode == 1 ? labels_aux : nullptr, npix_per_page, n_class, hist, B, flags);
+#define MSAU_CE(PV) ce_kernel<LT, PV><<<nblk, 256, 0, st>>>(lg, la, n_class, labels, spec.mode == 1 ? labels_aux : nullptr, hist, npix_per_page, B, gscale, spec, dlg, dla, partial, acc)
+  if (P == 8) MSAU_CE(8); else if (P == 16) MSAU_CE(16); else MSAU_CE(32);
+#undef MSAU_CE
+  final_sum_kernel<<<1, 1024, 0, st>>>(partial, nblk, (spec.mode == 1 && spec.w_main != 0.f) ? 1.f / spec.w_main : 1.f, loss_out, loss_main_out);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+int launch_loss(const float* lg, const float* la, int P, int n_class, const void* labels, const void* labels_aux, int label_dtype, int B,
+                long npix_per_page, float gscale, const LossSpec& hs, float* dlg, float* dla, int* ints, int* flags, float* partial,
+                float* loss_out, float* loss_main_out, cudaStream_t st) {
+  MSAU_CHECK_ARG((P == 8 || P == 16 || P == 32) && n_class <= P && n_class <= 32, "loss: logits pitch 8/16/32 and n_class <= 32 supported");
+  MSAU_CHECK_ARG(hs.mode == 0 || hs.mode == 1, "loss: mode must be 0 (MSAUWrapper.loss) or 1 (UNetLoss)");
+  LossDev spec;
+  spec.mode = hs.mode; spec.w_main = hs.w_main; spec.w_aux = hs.w_aux; spec.has_cw = hs.class_weights != nullptr;
+  for (int c = 0; c < 32; ++c) spec.cw[c] = (hs.class_weights && c < n_class) ? hs.class_weights[c] : 1.f;
+  // `flags` is sticky across calls: only msau_plan_error_flags clears it
+  MSAU_CUDA_TRY(cudaMemsetAsync(ints, 0, sizeof(int) * (2L * B * 32 + 2), st));
+  ProfScope ps("loss_kernels", 0, (double)npix_per_page * B * (4.0 * 4 * P + 2.0 * (label_dtype == 1 ? 8 : 1)), st);
+  if (label_dtype == 1)
+    return loss_typed<long long>(lg, la, P, n_class, (const long long*)labels, (const long long*)labels_aux, B, npix_per_page, gscale, spec, dlg,
+                                 dla, ints, flags, partial, loss_out, loss_main_out, st);
+  return loss_typed<uint8_t>(lg, la, P, n_class, (const uint8_t*)labels, (const uint8_t*)labels_aux, B, npix_per_page, gscale, spec, dlg, dla,
+                             ints, flags, partial, loss_out, loss_main_out, st);
+}
+
+// ------------------------------------------------------------------------------------------- driver-side helpers
+// tgt = torch.argmax(tgt, dim=1) on [B, C, H, W] one-hot targets (cost.py:41,52): first maximum wins
+template <typename T>
+__global__ void __launch_bounds__(256) onehot_argmax_kernel(const T* __restrict__ t, int C, long npix_per_page, long total, long stride_c,
+                                                            long stride_p, uint8_t* __restrict__ out) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long b = idx / npix_per_page, p = idx - b * npix_per_page;
+  const T* s = t + b * C * npix_per_page + p * stride_p;
+  T m = s[0]; int am = 0;
+  for (int c = 1; c < C; ++c) { const T v = s[(long)c * stride_c]; if (v > m) { m = v; am = c; } }
+  out[idx] = (uint8_t)am;
+}
+
+int launch_onehot_argmax(const void* t, int dtype, int B, int C, long npix_per_page, int channels_last, uint8_t* out, cudaStream_t st) {
+  MSAU_CHECK_ARG(C >= 1 && C <= 255, "onehot_argmax: 1..255 classes");
+  const long total = (long)B * npix_per_page;
+  const int grid = cdiv(total, 256);
+  const long sc = channels_last ? 1 : npix_per_page, sp = channels_last ? C : 1;
+  ProfScope ps("onehot_argmax_kernel", 0, (double)total * (C * (dtype == 1 ? 8.0 : dtype == 2 ? 4.0 : 1.0) + 1.0), st);
+  if (dtype == 1) onehot_argmax_kernel<long long><<<grid, 256, 0, st>>>((const long long*)t, C, npix_per_page, total, sc, sp, out);
+  else if (dtype == 2) onehot_argmax_kernel<float><<<grid, 256, 0, st>>>((const float*)t, C, npix_per_page, total, sc, sp, out);
+  else if (dtype == 0) onehot_argmax_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)t, C, npix_per_page, total, sc, sp, out);
+  else { set_error("onehot_argmax: dtype must be 0 (uint8), 1 (int64) or 2 (float32)"); return MSAU_ERR_ARG; }
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
+// masked accuracy + confusion counts of evaluate() (train_chargrid_funsd_msau.py:133-159): pixels with label != 0 only.
+// confusion int64 [n_class][n_class] (row = label, column = prediction), accumulated (the caller zeroes it per evaluation)
+template <typename LT>
+__global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restrict__ pred, const LT* __restrict__ labels, long n, int n_class,
+                                                        unsigned long long* __restrict__ conf) {
+  extern __shared__ unsigned int shc[];
+  const int cells = n_class * n_class;
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) shc[i] = 0;
+  __syncthreads();
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long long l = (long long)labels[i];
+    const int pr = pred[i];
+    if (l > 0 && l < n_class && pr < n_class) atomicAdd(&shc[(int)l * n_class + pr], 1u);
   }
-  final_sum_kernel<<<1, 1024, 0, st>>>(partial, nblk, loss_out);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cells; i += blockDim.x)
+    if (shc[i]) atomicAdd(conf + i, (unsigned long long)shc[i]);
+}
+
+int launch_confusion(const uint8_t* pred, const void* labels, int label_dtype, long n, int n_class, long long* conf, cudaStream_t st) {
+  MSAU_CHECK_ARG(n_class >= 1 && n_class <= 32, "confusion: n_class <= 32");
+  int grid = cdiv(n, 256 * 8);
+  if (grid > 8 * sm_count()) grid = 8 * sm_count();
+  if (grid < 1) grid = 1;
+  const size_t sh = sizeof(unsigned int) * n_class * n_class;
+  ProfScope ps("confusion_kernel", 0, (double)n * (1.0 + (label_dtype == 1 ? 8 : 1)), st);
+  if (label_dtype == 1) confusion_kernel<long long><<<grid, 256, sh, st>>>(pred, (const long long*)labels, n, n_class, (unsigned long long*)conf);
+  else confusion_kernel<uint8_t><<<grid, 256, sh, st>>>(pred, (const uint8_t*)labels, n, n_class, (unsigned long long*)conf);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

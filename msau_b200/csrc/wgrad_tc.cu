@@ -700,7 +700,7 @@ static int launch_wgrad_tc2(const WgradArgs& a, const Wg2Tile& t0, cudaStream_t 
   dim3 grid(ctas, planes);
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb) * (a.maskB ? 2 : 1)) * 4.0;
-  ProfScope ps("wgrad_tc2_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc2_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
   if (a.a_nchw) wgrad_tc2_kernel<true><<<grid, WG_THREADS, smem, st>>>(a, t);
   else wgrad_tc2_kernel<false><<<grid, WG_THREADS, smem, st>>>(a, t);
   MSAU_CUDA_TRY(cudaGetLastError());
@@ -1078,7 +1078,7 @@ static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t 
   dim3 grid(ctas, planes);
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * a.ca + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb)) * 4.0;
-  ProfScope ps("wgrad_tc3_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, 2, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc3_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, 2, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
   wgrad_tc3_kernel<<<grid, WG3_THREADS, smem, st>>>(a, t);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -1170,7 +1170,7 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   dim3 grid(ctas, planes);
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + npq * a.cb * (a.maskB ? 2 : 1)) * 4.0;
-  ProfScope ps("wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, 2.0 * npq * a.kh * a.kw * a.ca * a.cb, wbytes, st);
+  ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
   wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(a, t);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;

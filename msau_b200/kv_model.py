@@ -16,9 +16,23 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import torch
 
-from . import morph, raster
+from . import _lib, morph, raster
 
-CLASS_NAMES = None   # inference/postprocess.py:2-5 is a project-specific table; callers pass their own
+# inference/postprocess.py:2-5 -- the reference's (project-specific) class table; assign another list to use other field names
+CLASS_NAMES = ['NUL', 'k_bank_name', 'v_bank_name', 'k_bank_branch_name', 'v_bank_branch_name', 'k_account_number',
+               'v_account_number', 'k_account_type', 'v_account_type', 'k_account_name', 'v_account_name',
+               'k_account_name_kana', 'v_account_name_kana', 'k_branch', 'v_branch', 'k_financial_institution',
+               'v_financial_institution']
+
+
+def post_process_kv(values):
+    """inference/postprocess.py:8-15: the value classes (odd class ids > 1) keyed by their field name."""
+    results = {}
+    for idx, v in enumerate(values):
+        if idx % 2 == 1 and idx > 1:
+            field_name = CLASS_NAMES[idx - 1][2:] if len(CLASS_NAMES) > idx - 1 else str(idx - 1)
+            results[field_name] = v[0]
+    return results
 
 
 class KVModel:
@@ -290,7 +304,12 @@ class KVModel:
                 return m.cuda().contiguous()
             return torch.from_numpy(np.ascontiguousarray(np.asarray(m).astype(np.uint16)).view(np.int16)).cuda()
 
-        pred_class = pm.argmax(dim=-1).to(torch.uint8).contiguous()          # first maximum wins, like np.argmax (:162)
+        # np.argmax(pred_mask, axis=-1) (:162, first maximum wins) with the engine's arg-max kernel on the channels-last map
+        pm = pm.to(torch.float32).contiguous()
+        pred_class = torch.empty(tuple(pm.shape[:2]), dtype=torch.uint8, device=pm.device)
+        with torch.cuda.device(pm.device):
+            _lib.check(_lib.lib().msau_onehot_argmax(pm.data_ptr(), 2, 1, n_class, pm.shape[0] * pm.shape[1], 1, pred_class.data_ptr(),
+                                                     _lib.current_stream()))
         values, new_mask = KVModel.extract_value_device(dev16(line_mask), dev16(char_mask), label_lines, pred_class, n_class,
                                                         num_classes)
         new_pred_mask = np.zeros(tuple(pm.shape))
@@ -308,5 +327,5 @@ class KVModel:
         with torch.no_grad():
             pred_class = self.predict_maps(input_im[None])[0]
         values, _ = self.extract_value_device(line_mask, char_mask, label_lines, pred_class, self.n_class, self.n_class)
-        kv_results = {i: v[0] for i, v in enumerate(values) if v[0]}
+        kv_results = post_process_kv(values)                  # kv_model.py:315
         return kv_results, None

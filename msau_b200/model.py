@@ -92,15 +92,28 @@ class _Plan:
             _lib.check(_lib.lib().msau_plan_create(C.byref(cfg), B, H, W, C.byref(self.handle)))
         self.ws: Optional[torch.Tensor] = None
         self.ws_training = False
+        self.generation = 0          # bumped whenever the workspace is (re)allocated: CUDA graphs captured before are stale
 
     def workspace(self, training: bool) -> torch.Tensor:
         if self.ws is None or (training and not self.ws_training):
+            # an inference-sized workspace grows when the plan is first used for training.  Captured CUDA graphs have the old
+            # pointers baked in, so every graph entry records the generation it was captured at and is re-captured (never
+            # replayed) once it differs -- see MSAUWrapper._graph_entry
             n = C.c_size_t()
             _lib.check(_lib.lib().msau_workspace_bytes(self.handle, int(training), C.byref(n)))
             self.ws = None
             self.ws = torch.empty(n.value + 256, dtype=torch.uint8, device=self.device)
             self.ws_training = training
+            self.generation += 1
         return self.ws
+
+    def set_option(self, name: str, value: int) -> None:
+        _lib.check(_lib.lib().msau_plan_set_option(self.handle, name.encode(), int(value)))
+
+    def error_flags(self) -> int:
+        v = C.c_int(0)
+        _lib.check(_lib.lib().msau_plan_error_flags(self.handle, C.byref(v)))
+        return v.value
 
     def ws_ptr(self, training: bool) -> Tuple[int, int]:
         ws = self.workspace(training)
@@ -169,7 +182,11 @@ class MSAUWrapper(torch.nn.Module):
         self._last = None            # (plan, x, layout) of the last training forward
         self._loss_value = None
         self._anchor = None
-        self._adam = None            # (exp_avg, exp_avg_sq, step, scratch)
+        self._adam = None            # fused optimiser state: dict(kind, s1, s2, step_dev, scratch, total)
+        self._options: Dict[str, int] = {}   # engine options of this model's plans (msau_plan_set_option)
+        self._grad_new: Optional[torch.Tensor] = None   # what the backward kernels of loss() wrote (accumulated into flat_grads)
+        self._acc = None             # device int32[2]: {correct, kept} of the last loss (masked accuracy)
+        self._loss_main = None
         self._table = None           # fp32 [rows, channels] feature table of a box-constant (BERT-grid) batch, layout 3
         self._graphs = {}            # (B, H, W, layout, dtype) -> (CUDAGraph, static input, static class map)
         self._train_graphs = {}      # ... -> (CUDAGraph of forward + loss + backward, static x, static labels, loss, launches)
@@ -199,7 +216,7 @@ class MSAUWrapper(torch.nn.Module):
             p.data = self._flat[off:off + n].view(shape)
             off += n
         self._flat_grad = None
-        self._adam = None
+        self._grad_new = None
         for p in self._param_list:
             p.grad = None
 
@@ -234,8 +251,13 @@ class MSAUWrapper(torch.nn.Module):
         new_flat = fn(self._flat)
         if new_flat.dtype != torch.float32:
             raise TypeError("msau_b200 parameters are fp32 only")
+        if new_flat.device == self._flat.device and new_flat.data_ptr() == self._flat.data_ptr():
+            return self                                  # no-op move (.cuda() on a CUDA model): plans, graphs, optimiser state stay
         self._flat = new_flat.contiguous()
         self._rebind()
+        if self._adam is not None:                       # the optimiser state follows the parameters
+            for k in ("s1", "s2", "step_dev", "scratch", "total"):
+                self._adam[k] = self._adam[k].to(self._flat.device)
         self._plans = {}
         self._graphs = {}
         self._train_graphs = {}
@@ -275,6 +297,15 @@ class MSAUWrapper(torch.nn.Module):
         return self._flat_grad
 
     # ------------------------------------------------------------------ engine plumbing
+    def set_option(self, name: str, value: int) -> None:
+        """Engine option of THIS model's plans (msau_plan_set_option; include/msau_b200.h lists the names).  Options are
+        per plan, so two models with different options can run side by side; captured CUDA graphs are dropped."""
+        self._options[name] = int(value)
+        for pl in self._plans.values():
+            pl.set_option(name, value)
+        self._graphs = {}
+        self._train_graphs = {}
+
     def _plan(self, B: int, H: int, W: int) -> _Plan:
         if not self._flat.is_cuda:
             raise _lib.MsauError("msau_b200 has no CPU path: move the model to a CUDA device first (.cuda() / .to('cuda'))")
@@ -284,6 +315,8 @@ class MSAUWrapper(torch.nn.Module):
             pl = _Plan(self._cfg, B, H, W, self._flat.device)
             n = int(_lib.lib().msau_param_count(pl.handle))
             assert n == self._numel, (n, self._numel)
+            for name, value in self._options.items():
+                pl.set_option(name, value)
             self._plans[key] = pl
         return pl
 
@@ -372,15 +405,28 @@ class MSAUWrapper(torch.nn.Module):
             out[b0:b0 + chunk.shape[0]] = self._run_forward(chunk, layout, False, False, want_argmax=True, want_logits=False)[5]
         return out
 
+    def _graph_entry(self, table: dict, key, pl_shape):
+        """A captured graph is only valid for the workspace it was captured with: entries remember the plan's workspace
+        generation and are dropped once the workspace has been reallocated (inference plan later used for training)."""
+        ent = table.get(key)
+        if ent is not None and ent[0] != self._plan(*pl_shape).generation:
+            del table[key]
+            ent = None
+        return ent
+
     def predict_classes_graph(self, inp, layout: int = 0):
         """``predict_classes`` replayed from a CUDA graph: the ~150 kernel launches of one inference forward are captured once
         per (B, H, W, layout) and replayed with a single launch, which takes the host out of the latency of small batches
         (BASELINE.json config 1: one 512x512 page).  The input is copied into the graph's static buffer, the class map comes
         back as a fresh tensor; parameters are read from the flat buffer at every replay, so ``load_state_dict`` / training
-        steps between calls are seen."""
+        steps between calls are seen.  ``layout=3`` is refused: the feature table's pointer and row count would be baked into
+        the graph while ``set_feature_table`` swaps the table per batch (use ``predict_classes``)."""
+        if layout == 3:
+            raise _lib.MsauError("predict_classes_graph does not take layout 3 (the per-batch feature table cannot be captured); "
+                                 "use predict_classes")
         B, H, W = self._check_input(inp, layout)
         key = (B, H, W, layout, inp.dtype)
-        ent = self._graphs.get(key)
+        ent = self._graph_entry(self._graphs, key, (B, H, W))
         if ent is None:
             static_in = inp.contiguous().clone()
             side = torch.cuda.Stream(device=inp.device)
@@ -392,148 +438,317 @@ class MSAUWrapper(torch.nn.Module):
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
                 static_out = self._run_forward(static_in, layout, False, False, want_argmax=True, want_logits=False)[5]
-            ent = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = ent
+            ent = self._graphs[key] = (self._plan(B, H, W).generation, graph, static_in, static_out)
+        _, graph, static_in, static_out = ent
         static_in.copy_(inp)
         graph.replay()
         return static_out.clone()
 
-    def _backward_from_last(self, labels: torch.Tensor, loss_scale: float = 1.0) -> torch.Tensor:
-        if self._last is None:
-            raise _lib.MsauError("loss/backward needs a preceding forward() in training mode with grad enabled")
-        pl, x, layout = self._last[:3]
+    # ------------------------------------------------------------------ loss + backward
+    @staticmethod
+    def _label_tensor(labels: torch.Tensor, device) -> Tuple[torch.Tensor, int]:
         if labels.dim() == 2:
             labels = labels.unsqueeze(0)
-        if tuple(labels.shape) != (pl.B, pl.H, pl.W):
-            raise ValueError(f"label_mask shape {tuple(labels.shape)} != {(pl.B, pl.H, pl.W)}")
         if labels.dtype == torch.uint8:
             ld = 0
         else:
             labels = labels.to(torch.int64)
             ld = 1
-        labels = labels.to(x.device).contiguous()
+        return labels.to(device).contiguous(), ld
+
+    def _backward_from_last(self, labels: torch.Tensor, loss_scale: float = 1.0, grads: Optional[torch.Tensor] = None,
+                            loss_spec: Optional[dict] = None, labels_aux: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """msau_loss_backward_ex on the plan of the last training forward.  ``loss_spec`` None = MSAUWrapper.loss
+        (model/model.py:446-459); dict(mode=1, weight_main, weight_aux, class_weights) = UNetLoss (model/training/cost.py:35-65)."""
+        if self._last is None:
+            raise _lib.MsauError("loss/backward needs a preceding forward() in training mode with grad enabled")
+        pl, x, layout = self._last[:3]
+        labels, ld = self._label_tensor(labels, x.device)
+        if tuple(labels.shape) != (pl.B, pl.H, pl.W):
+            raise ValueError(f"label_mask shape {tuple(labels.shape)} != {(pl.B, pl.H, pl.W)}")
+        la_ptr = 0
+        if labels_aux is not None:
+            labels_aux, ld2 = self._label_tensor(labels_aux, x.device)
+            if ld2 != ld or labels_aux.shape != labels.shape:
+                raise ValueError("aux targets must have the shape and dtype of the main targets")
+            la_ptr = labels_aux.data_ptr()
+        spec = _lib.MsauLossSpec(0, 1.0, 1.0, None)
+        cw = None
+        if loss_spec:
+            spec.mode = int(loss_spec.get("mode", 1))
+            spec.weight_main = float(loss_spec.get("weight_main", 0.5))
+            spec.weight_aux = float(loss_spec.get("weight_aux", 0.5))
+            if loss_spec.get("class_weights") is not None:
+                w = [float(v) for v in loss_spec["class_weights"]]
+                if len(w) != self.n_class:
+                    raise ValueError(f"class_weights needs {self.n_class} entries")
+                cw = (C.c_float * len(w))(*w)
+                spec.h_class_weights = C.cast(cw, C.POINTER(C.c_float))
         ws, ws_bytes = pl.ws_ptr(True)
-        loss = torch.empty((), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().msau_loss_backward(pl.handle, x.data_ptr(), layout, labels.data_ptr(), ld, float(loss_scale), ws,
-                                                     ws_bytes, loss.data_ptr(), self.flat_grads.data_ptr(),
-                                                     _lib.current_stream()))
+        dev = x.device
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        self._loss_main = torch.empty((), dtype=torch.float32, device=dev)
+        self._acc = torch.empty(2, dtype=torch.int32, device=dev)
+        g = self.flat_grads if grads is None else grads
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().msau_loss_backward_ex(pl.handle, x.data_ptr(), layout, labels.data_ptr(), la_ptr, ld, C.byref(spec),
+                                                        float(loss_scale), ws, ws_bytes, loss.data_ptr(), self._loss_main.data_ptr(),
+                                                        self._acc.data_ptr(), g.data_ptr(), _lib.current_stream()))
         return loss
+
+    def check_labels(self) -> None:
+        """Raises if any label seen by a loss call since the last check was outside [0, n_class) (torch's CrossEntropyLoss
+        raises at once; here such pixels contribute nothing and a sticky device flag records them).  Synchronises."""
+        bad = 0
+        for pl in self._plans.values():
+            bad |= pl.error_flags()
+        if bad & 1:
+            raise IndexError(f"label_mask holds a class index outside [0, {self.n_class})")
+
+    def last_accuracy(self) -> float:
+        """Masked pixel accuracy of the last loss call: argmax(logits) == label over label != 0 (UNetLoss cost.py:44-50;
+        evaluate() train_chargrid_funsd_msau.py:133-159), counted inside the loss kernel.  One 8-byte D2H read."""
+        if self._acc is None:
+            raise _lib.MsauError("last_accuracy() needs a preceding loss / train_step")
+        c, k = (int(v) for v in self._acc.tolist())
+        return c / k if k else float("nan")
+
+    def _scratch_grads(self) -> torch.Tensor:
+        if self._grad_new is None or self._grad_new.device != self._flat.device:
+            self._grad_new = torch.zeros_like(self._flat)
+        return self._grad_new
 
     def loss(self, out_grid, out_grid_aux, label_mask):
         """model/model.py:446-459 (mean over pages for B>1).  ``out_grid`` / ``out_grid_aux`` must be the logits
         returned by the immediately preceding ``forward``; the value and the gradients come from one fused
-        CUDA pass, the returned scalar carries a grad_fn so ``loss.backward()`` fills ``p.grad``."""
+        CUDA pass, the returned scalar carries a grad_fn so ``loss.backward()`` fills ``p.grad`` -- accumulating into an
+        existing ``p.grad`` like autograd does when ``zero_grad`` was not called.  A label outside [0, n_class) raises
+        IndexError (one flag read per call; the fused ``train_step`` path leaves that check to ``check_labels()``)."""
         if self._last is None or out_grid.data_ptr() != self._last[3] or out_grid_aux.data_ptr() != self._last[4]:
             raise _lib.MsauError("loss(): pass the logits returned by the preceding forward() (training mode, grad enabled)")
-        self._loss_value = self._backward_from_last(label_mask)
+        self._loss_value = self._backward_from_last(label_mask, grads=self._scratch_grads())
+        self._last[0].error_flags() and self._raise_bad_label()
         if self._anchor is None or self._anchor.device != self._flat.device:
             self._anchor = torch.zeros((), device=self._flat.device, requires_grad=True)
         return _LossBackward.apply(self._anchor, self, label_mask)
+
+    def _raise_bad_label(self):
+        raise IndexError(f"label_mask holds a class index outside [0, {self.n_class})")
+
+    def unet_loss(self, logits, tgt, aux_logits=None, aux_tgt=None, class_weights=None, weight_main: float = 0.5,
+                  weight_aux: float = 0.5):
+        """UNetLoss.forward (model/training/cost.py:35-65) on the logits of the preceding ``forward``: targets are one-hot
+        [B, n_class, H, W] (arg-max taken on the device, :41,:52) or already class maps [B, H, W]; returns
+        ``(acc, loss, final_loss)`` like the reference -- ``loss`` carries a grad_fn, ``acc`` is a Python float (the reference
+        computes it on the host too), ``final_loss`` the main head's own term (None without aux logits)."""
+        if self._last is None or logits.data_ptr() != self._last[3]:
+            raise _lib.MsauError("unet_loss(): pass the logits returned by the preceding forward() (training mode, grad enabled)")
+        if aux_logits is not None and aux_logits.data_ptr() != self._last[4]:
+            raise _lib.MsauError("unet_loss(): aux_logits must be the aux logits of the preceding forward()")
+        t = self.onehot_argmax(tgt) if tgt.dim() == 4 else tgt
+        ta = None
+        if aux_logits is not None and aux_tgt is not None:
+            ta = self.onehot_argmax(aux_tgt) if aux_tgt.dim() == 4 else aux_tgt
+            if ta.dtype != t.dtype:
+                ta = ta.to(t.dtype)
+        spec = dict(mode=1, weight_main=weight_main if aux_logits is not None else 1.0,
+                    weight_aux=weight_aux if aux_logits is not None else 0.0, class_weights=class_weights)
+        self._loss_value = self._backward_from_last(t, grads=self._scratch_grads(), loss_spec=spec, labels_aux=ta)
+        self._last[0].error_flags() and self._raise_bad_label()
+        if self._anchor is None or self._anchor.device != self._flat.device:
+            self._anchor = torch.zeros((), device=self._flat.device, requires_grad=True)
+        loss = _LossBackward.apply(self._anchor, self, t)
+        final = self._loss_main.clone() if aux_logits is not None else None
+        return self.last_accuracy(), loss, final
+
+    def onehot_argmax(self, tgt: torch.Tensor) -> torch.Tensor:
+        """torch.argmax(tgt, dim=1) of one-hot targets as a uint8 class map, on the device (cost.py:41,52)."""
+        dt = {torch.uint8: 0, torch.int64: 1, torch.float32: 2}.get(tgt.dtype)
+        if dt is None:
+            tgt, dt = tgt.to(torch.int64), 1
+        tgt = tgt.to(self._flat.device).contiguous()
+        B, Cc, H, W = tgt.shape
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=tgt.device)
+        with torch.cuda.device(tgt.device):
+            _lib.check(_lib.lib().msau_onehot_argmax(tgt.data_ptr(), dt, B, Cc, H * W, 0, out.data_ptr(), _lib.current_stream()))
+        return out
 
     def _live_mask(self) -> List[bool]:
         dead = f"msau_net.blocks.{self.num_blocks - 1}.downsamplingblock.layer_attentions."
         return [not k.startswith(dead) for k, _ in self._schema]
 
     def _assign_grads(self, scale=None):
-        """p.grad <- views of the flat gradient buffer.  The last block's attention parameters keep grad=None
-        exactly like the reference (their output is never read)."""
-        g = self.flat_grads
+        """loss.backward(): p.grad (views of the flat gradient buffer) += what the backward kernels wrote.  The last block's
+        attention parameters keep grad=None exactly like the reference (their output is never read)."""
+        new = self._scratch_grads()
         if scale is not None:
-            g.mul_(scale.to(g.dtype))
+            new.mul_(scale.to(new.dtype))
+        acc = self.flat_grads
         off = 0
         for p, (_, shape), live in zip(self._param_list, self._schema, self._live_mask()):
             n = p.numel()
             if live:
-                view = g[off:off + n].view(shape)
+                view = acc[off:off + n].view(shape)
+                fresh = new[off:off + n].view(shape)
                 if p.grad is None:
+                    view.copy_(fresh)
                     p.grad = view
-                elif p.grad.data_ptr() != view.data_ptr():
-                    p.grad.add_(view)
+                else:
+                    p.grad.add_(fresh)
             off += n
 
     # ------------------------------------------------------------------ fused training step
+    _OPT_KIND = {"adam": 0, "rmsprop": 1, "momentum": 2, "sgd": 2}
+
     def train_step(self, x: torch.Tensor, labels: torch.Tensor, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
-                   max_norm: float = 1.0, layout: int = 0, process_group=None, world_size: int = 1, use_graph: bool = False):
+                   max_norm: float = 1.0, layout: int = 0, process_group=None, world_size: int = 1, use_graph=False,
+                   optimizer: str = "adam", weight_decay: float = 0.0, loss_spec: Optional[dict] = None,
+                   labels_aux: Optional[torch.Tensor] = None, graph_tail: bool = True):
         """One step of train_chargrid_funsd_msau.py:45-59 on a batch of pages: forward, masked CE (main + aux),
         backward, [NCCL all-reduce of the flat gradient over ``process_group``], clip_grad_norm(max_norm),
         Adam.  Returns the (local-batch) loss as a 0-d CUDA tensor; nothing synchronises with the host.
-        ``use_graph``: forward + loss + backward (~420 kernel launches on two streams) are captured once per input shape into
-        a CUDA graph and replayed with one launch per step, so the step no longer depends on how fast the host can enqueue
-        kernels; the all-reduce and the clip + Adam kernels (which take the step count as an argument) stay eager.
+        ``optimizer`` / ``weight_decay`` / ``loss_spec`` / ``labels_aux`` select the alternative trainer's step instead
+        (model/training/trainer.py:122-137: UNetLoss, RMSprop by default, no clipping -> ``max_norm=0``).
+        ``use_graph``: the whole step -- forward + loss + backward (~400 launches on two streams) and, with ``graph_tail``, the
+        all-reduce and the clip + optimiser kernels (the step count lives in a device counter) -- is captured once per input
+        shape into a CUDA graph and replayed with one launch per step.
         ``use_graph="static"``: the caller keeps feeding the same (refilled) input tensors, so the graph reads them in place."""
+        opt_args = (optimizer, float(lr), tuple(betas), float(eps), float(max_norm), float(weight_decay))
         if use_graph and layout != 3:
-            loss = self._fwd_bwd_graph(x, labels, layout, world_size, use_graph == "static")
-        else:
-            pl, xc, _, _, _, _ = self._run_forward(x, layout, True, False, want_logits=False)
-            self._last = (pl, xc, layout, 0, 0)
-            loss = self._backward_from_last(labels, loss_scale=1.0 / world_size)
+            return self._step_graph(x, labels, layout, world_size, process_group, use_graph == "static", opt_args, loss_spec, labels_aux,
+                                    graph_tail)
+        pl, xc, _, _, _, _ = self._run_forward(x, layout, True, False, want_logits=False)
+        self._last = (pl, xc, layout, 0, 0)
+        loss = self._backward_from_last(labels, loss_scale=1.0 / world_size, loss_spec=loss_spec, labels_aux=labels_aux)
         if world_size > 1:
             torch.distributed.all_reduce(self.flat_grads, group=process_group)
-        self.adam_step(lr, betas, eps, max_norm)
+        self.optimizer_step(*opt_args)
         return loss
 
-    def _fwd_bwd_graph(self, x: torch.Tensor, labels: torch.Tensor, layout: int, world_size: int, static: bool) -> torch.Tensor:
-        """forward(training) + loss + backward as one CUDA-graph launch.  The graph reads private copies of the inputs (every
-        call copies x / labels into them: 12 MB for an id-map batch of 16 pages); with ``static`` it is bound to the caller's
-        own tensors instead, for loops that refill the same buffers in place (no copy; a dense 1.6 GB batch stays put)."""
+    def _step_graph(self, x, labels, layout, world_size, process_group, static, opt_args, loss_spec, labels_aux, graph_tail):
+        """The train step as one CUDA-graph launch.  The graph reads private copies of the inputs (every call copies x / labels
+        into them: 12 MB for an id-map batch of 16 pages); with ``static`` it is bound to the caller's own tensors instead, for
+        loops that refill the same buffers in place (no copy; a dense 1.6 GB batch stays put)."""
         B, H, W = self._check_input(x, layout)
-        if labels.dim() == 2:
-            labels = labels.unsqueeze(0)
-        if labels.dtype != torch.uint8:
-            labels = labels.to(torch.int64)
-        labels = labels.to(x.device)
-        key = (B, H, W, layout, x.dtype, labels.dtype, world_size, static)
-        ent = self._train_graphs.get(key)
+        labels, _ = self._label_tensor(labels, x.device)
+        if labels_aux is not None:
+            labels_aux, _ = self._label_tensor(labels_aux, x.device)
+        spec_key = None if not loss_spec else tuple(sorted((k, tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in loss_spec.items()))
+        key = (B, H, W, layout, x.dtype, labels.dtype, world_size, static, opt_args if graph_tail else None, spec_key,
+               labels_aux is not None, graph_tail)
+        ent = self._graph_entry(self._train_graphs, key, (B, H, W))
         if ent is None:
             if static:
                 if not (x.is_contiguous() and labels.is_contiguous()):
                     raise ValueError("use_graph='static' needs contiguous input tensors")
-                sx, sl = x, labels                        # the caller promises to keep feeding these very tensors
+                sx, sl, sa = x, labels, labels_aux           # the caller promises to keep feeding these very tensors
             else:
                 sx, sl = x.contiguous().clone(), labels.contiguous().clone()
+                sa = labels_aux.contiguous().clone() if labels_aux is not None else None
             dev = x.device
 
-            def fwd_bwd():
+            def body():
                 pl, xc, _, _, _, _ = self._run_forward(sx, layout, True, False, want_logits=False)
                 self._last = (pl, xc, layout, 0, 0)
-                return self._backward_from_last(sl, loss_scale=1.0 / world_size)
+                loss = self._backward_from_last(sl, loss_scale=1.0 / world_size, loss_spec=loss_spec, labels_aux=sa)
+                if graph_tail:
+                    if world_size > 1:
+                        torch.distributed.all_reduce(self.flat_grads, group=process_group)
+                    self.optimizer_step(*opt_args)
+                return loss
 
             self.flat_grads                               # allocate outside the capture
+            self._opt_state(opt_args[0])
+            # warm-up on a side stream: plan, workspace, side stream / events, kernel attributes, NCCL communicator.  The warm-up
+            # must not change the model: parameters, optimiser state and step counter are restored afterwards
+            keep = None
+            if graph_tail:
+                st = self._adam
+                keep = (self._flat.clone(), st["s1"].clone(), st["s2"].clone(), st["step_dev"].clone())
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):                 # warm-up: plan, workspace, side stream / events, kernel attributes
-                fwd_bwd()
+            with torch.cuda.stream(side):
+                body()
             torch.cuda.current_stream(dev).wait_stream(side)
+            if keep is not None:
+                self._flat.copy_(keep[0]); st["s1"].copy_(keep[1]); st["s2"].copy_(keep[2]); st["step_dev"].copy_(keep[3])
             n0 = _lib.launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may call CUDA
-                sloss = fwd_bwd()
-            ent = self._train_graphs[key] = (graph, sx, sl, sloss, _lib.launch_count() - n0)
-        graph, sx, sl, sloss, n_launch = ent
+                sloss = body()
+            pl = self._plan(B, H, W)
+            ent = self._train_graphs[key] = (pl.generation, graph, sx, sl, sa, sloss, _lib.launch_count() - n0, self._acc, self._loss_main)
+        _, graph, sx, sl, sa, sloss, n_launch, acc, lmain = ent
         if static:
             if x.data_ptr() != sx.data_ptr() or labels.data_ptr() != sl.data_ptr():
                 raise _lib.MsauError("use_graph='static': the step must be fed the tensors the graph was captured with")
         else:
             sx.copy_(x)
             sl.copy_(labels)
+            if sa is not None:
+                sa.copy_(labels_aux)
         graph.replay()
+        self._acc, self._loss_main = acc, lmain
         _lib.lib().msau_launch_count_add(n_launch)
+        if not graph_tail:
+            if world_size > 1:
+                torch.distributed.all_reduce(self.flat_grads, group=process_group)
+            self.optimizer_step(*opt_args)
         return sloss.clone()
 
-    def adam_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
-        if self._adam is None:
-            self._adam = [torch.zeros_like(self._flat), torch.zeros_like(self._flat), 0,
-                          torch.empty(2048, dtype=torch.float32, device=self._flat.device),
-                          torch.zeros((), dtype=torch.float32, device=self._flat.device)]
-        m, v, step, scratch, total = self._adam
-        step += 1
-        self._adam[2] = step
+    # ------------------------------------------------------------------ fused optimisers
+    def _opt_state(self, optimizer: str) -> dict:
+        kind = self._OPT_KIND.get(optimizer)
+        if kind is None:
+            raise ValueError(f"optimizer={optimizer!r}: expected one of {sorted(self._OPT_KIND)}")
+        if self._adam is None or self._adam["kind"] != kind or self._adam["s1"].device != self._flat.device:
+            dev = self._flat.device
+            self._adam = dict(kind=kind, s1=torch.zeros_like(self._flat), s2=torch.zeros_like(self._flat),
+                              step_dev=torch.zeros((), dtype=torch.int32, device=dev),
+                              scratch=torch.empty(2048, dtype=torch.float32, device=dev),
+                              total=torch.zeros((), dtype=torch.float32, device=dev))
+        return self._adam
+
+    def optimizer_step(self, optimizer: str = "adam", lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0,
+                       weight_decay: float = 0.0):
+        """clip_grad_norm(max_norm) + optimiser update on the flat buffers (train_chargrid_funsd_msau.py:58-59 with "adam";
+        model/training/optimizer.py:4-30 with "rmsprop" (betas[0] = alpha) or "momentum" (betas[0] = momentum)).  The step count
+        is a device counter, so the call is CUDA-graph capturable.  Returns the pre-clip gradient norm (0-d CUDA tensor)."""
+        st = self._opt_state(optimizer)
         with torch.cuda.device(self._flat.device):
-            _lib.check(_lib.lib().msau_clip_adam_step(self._flat.data_ptr(), self.flat_grads.data_ptr(), m.data_ptr(), v.data_ptr(),
-                                                      self._numel, step, lr, betas[0], betas[1], eps, max_norm, scratch.data_ptr(),
-                                                      total.data_ptr(), _lib.current_stream()))
-        return total
+            _lib.check(_lib.lib().msau_optimizer_step(st["kind"], self._flat.data_ptr(), self.flat_grads.data_ptr(), st["s1"].data_ptr(),
+                                                      st["s2"].data_ptr(), self._numel, 0, st["step_dev"].data_ptr(), lr, betas[0], betas[1],
+                                                      eps, weight_decay, max_norm, st["scratch"].data_ptr(), st["total"].data_ptr(),
+                                                      _lib.current_stream()))
+        return st["total"]
+
+    def adam_step(self, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, max_norm: float = 1.0):
+        return self.optimizer_step("adam", lr, betas, eps, max_norm)
+
+    def optimizer_state_dict(self) -> dict:
+        """State of the fused optimiser (moments + step) for checkpoints -- what ``save_checkpoint`` pickles with the optimizer
+        object in the reference (utils/io_utils.py:83-105).  Keys follow torch: exp_avg / exp_avg_sq (Adam), square_avg (RMSprop),
+        momentum_buffer (SGD), step."""
+        if self._adam is None:
+            return {}
+        st = self._adam
+        names = {0: ("exp_avg", "exp_avg_sq"), 1: (None, "square_avg"), 2: ("momentum_buffer", None)}[st["kind"]]
+        out = dict(kind={0: "adam", 1: "rmsprop", 2: "momentum"}[st["kind"]], step=int(st["step_dev"].item()))
+        for name, key in zip(names, ("s1", "s2")):
+            if name:
+                out[name] = st[key].detach().cpu().clone()
+        return out
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        if not sd:
+            self._adam = None
+            return
+        st = self._opt_state(sd["kind"])
+        names = {0: ("exp_avg", "exp_avg_sq"), 1: (None, "square_avg"), 2: ("momentum_buffer", None)}[st["kind"]]
+        for name, key in zip(names, ("s1", "s2")):
+            if name:
+                st[key].copy_(sd[name].to(st[key].device))
+        st["step_dev"].fill_(int(sd["step"]))
 
 
 MSAU = MSAUWrapper

@@ -298,6 +298,57 @@ def clip_adam_step(sd, grads, m, v, step: int, lr: float = 1e-4, b1: float = 0.9
     return total
 
 
+# ----------------------------------------------------------------------------- alternative trainer (UNetLoss + RMSprop / SGD)
+def unet_loss(logits: Tensor, tgt_onehot: Tensor, aux_logits: Tensor = None, aux_tgt_onehot: Tensor = None, class_weights=None):
+    """UNetLoss.forward, model/training/cost.py:35-65: targets = argmax of the one-hot maps (:41,:52), CrossEntropyLoss over ALL
+    pixels (optionally class-weighted, :27-31), loss = 0.5 final + 0.5 aux (:61), masked accuracy over tgt != 0 (:44-50).
+    Returns (acc float, loss, final_loss or None)."""
+    tgt = torch.argmax(tgt_onehot, dim=1)
+    pred = torch.argmax(logits, dim=1)
+    nz = tgt != 0
+    acc = float((tgt[nz] == pred[nz]).sum().double() / nz.sum().double())
+    w = None if class_weights is None else torch.tensor(class_weights, dtype=logits.dtype, device=logits.device)
+    final = F.cross_entropy(logits, tgt, weight=w)
+    if aux_logits is None:
+        return acc, final, None
+    aux = F.cross_entropy(aux_logits, torch.argmax(aux_tgt_onehot, dim=1), weight=w)
+    return acc, 0.5 * final + 0.5 * aux, final
+
+
+def rmsprop_step(sd, grads, sq, lr: float = 0.001, alpha: float = 0.99, eps: float = 1e-8, weight_decay: float = 0.0):
+    """torch.optim.RMSprop as constructed by get_optimizer (model/training/optimizer.py:14-16): momentum 0, not centred.
+    Parameters whose grad is None are skipped."""
+    for k in sd:
+        if grads[k] is None:
+            continue
+        g = grads[k] if weight_decay == 0.0 else grads[k] + weight_decay * sd[k]
+        sq[k].mul_(alpha).addcmul_(g, g, value=1 - alpha)
+        sd[k].addcdiv_(g, sq[k].sqrt().add_(eps), value=-lr)
+
+
+def sgd_momentum_step(sd, grads, buf, step: int, lr: float = 0.001, momentum: float = 0.9, weight_decay: float = 0.0):
+    """torch.optim.SGD(params, lr, momentum) (optimizer.py:8-13): buf = g at the first step, then momentum * buf + g."""
+    for k in sd:
+        if grads[k] is None:
+            continue
+        g = grads[k] if weight_decay == 0.0 else grads[k] + weight_decay * sd[k]
+        if step == 1:
+            buf[k].copy_(g)
+        else:
+            buf[k].mul_(momentum).add_(g)
+        sd[k].add_(buf[k], alpha=-lr)
+
+
+def unet_loss_and_grads(sd, cfg: MsauConfig, x: Tensor, tgt_onehot: Tensor, aux_tgt_onehot: Tensor, class_weights=None):
+    """forward + UNetLoss + backward (model/training/trainer.py:122-136).  Returns (acc, loss, final_loss, logits, aux, grads)."""
+    leaves = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    logits, aux = msau_forward(leaves, cfg, x)
+    acc, loss, final = unet_loss(logits, tgt_onehot, aux, aux_tgt_onehot, class_weights)
+    loss.backward()
+    grads = {k: leaves[k].grad for k in leaves}
+    return acc, loss.detach(), final.detach(), logits.detach(), aux.detach(), grads
+
+
 # ----------------------------------------------------------------------------- traced forward (debugging aid)
 def msau_forward_trace(sd, cfg: MsauConfig, x: Tensor, retain_grad: bool = False):
     """Same arithmetic as ``msau_forward`` but also returns every intermediate activation, in the order the

@@ -107,6 +107,59 @@ def golden_model(name, cfg, B, H, W, seed, full_grads):
     print(name, "loss", losses, "total_norm", float(total))
 
 
+def synth_onehot_targets(n_class, B, H, W, seed):
+    """one-hot main / aux target maps [B, n_class, H, W] int64 (what the reference's generators hand to Trainer.train)"""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randint(0, n_class, (B, H, W), generator=g)
+    t = t * (torch.rand((B, H, W), generator=g) < 0.5)          # half of the pixels are background (class 0)
+    ta = torch.where(torch.rand((B, H, W), generator=g) < 0.9, t, torch.randint(0, n_class, (B, H, W), generator=g))
+    return torch.nn.functional.one_hot(t, n_class).permute(0, 3, 1, 2).contiguous(), \
+        torch.nn.functional.one_hot(ta, n_class).permute(0, 3, 1, 2).contiguous()
+
+
+def golden_trainer(name, cfg, B, H, W, seed, optimizer, class_weights, steps=2):
+    """The alternative trainer's step (model/training/trainer.py:122-137) with the reference's own UNetLoss and get_optimizer."""
+    from model.training.cost import UNetLoss
+    from model.training.optimizer import get_optimizer
+    sd = om.init_state_dict(cfg, seed)
+    x, _ = synth_input(cfg, B, H, W, seed + 1)
+    tgt, tgt_aux = synth_onehot_targets(cfg.n_class, B, H, W, seed + 2)
+    m = ref_model(cfg, sd)
+    m.train()
+    ck = {"aux_logits": None, "aux_tgt": None}
+    if class_weights is not None:
+        ck["class_weights"] = class_weights
+    crit = UNetLoss(ck)
+    with contextlib.redirect_stdout(io.StringIO()):
+        opt = get_optimizer(m, {"optimizer": optimizer} if optimizer != "rmsprop" else {})
+    out = {}
+    accs, losses, finals = [], [], []
+    for s in range(steps):
+        opt.zero_grad()
+        _, logits, aux = m(x)
+        ck["aux_logits"] = aux
+        ck["aux_tgt"] = tgt_aux
+        acc, loss, final = crit(logits, tgt, ck)
+        loss.backward()
+        if s == 0:
+            out["logits"] = logits.detach().numpy()
+            keys = [k for k, _ in om.param_schema(cfg)]
+            named = dict(m.named_parameters())
+            out["grad_norms"] = np.array([0.0 if named[k].grad is None else float(named[k].grad.double().norm()) for k in keys])
+        opt.step()
+        accs.append(float(acc)); losses.append(float(loss)); finals.append(float(final))
+    keys = [k for k, _ in om.param_schema(cfg)]
+    named = dict(m.named_parameters())
+    out["acc"] = np.array(accs); out["loss"] = np.array(losses); out["final_loss"] = np.array(finals)
+    out["param_sums_after"] = np.array([float(named[k].detach().double().sum()) for k in keys])
+    k0 = "msau_net.blocks.1.upsamplingblock.conv1s.0.custom_conv.weight"
+    out["param_after::" + k0] = named[k0].detach().numpy().copy()
+    meta = dict(cfg=cfg.__dict__, B=B, H=H, W=W, seed=seed, optimizer=optimizer, class_weights=class_weights, steps=steps)
+    out["meta"] = np.array(json.dumps(meta))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "acc", accs, "loss", losses, "final", finals)
+
+
 # ----------------------------------------------------------------------------- rasterisers
 class _Cell:
     def __init__(self, x, y, w, h, ocr_value):
@@ -273,6 +326,16 @@ if __name__ == "__main__":
         golden_morph()
     if want("kv"):
         golden_kv()
+    # alternative trainer (UNetLoss + get_optimizer); 17 classes = the KV checkpoints' class count (inference/postprocess.py:2-5)
+    kv17 = om.MsauConfig(channels=12, n_class=17, scale_space_num=3, res_depth=2, feat_root=8)
+    if want("trainer_rmsprop_c17"):
+        golden_trainer("trainer_rmsprop_c17", kv17, B=2, H=24, W=40, seed=31, optimizer="rmsprop", class_weights=None)
+    if want("trainer_momentum_w_c17"):
+        golden_trainer("trainer_momentum_w_c17", kv17, B=2, H=24, W=40, seed=33, optimizer="momentum",
+                       class_weights=[0.5] + [1.0 + 0.1 * i for i in range(16)])
+    if want("model_s3r2_c12_k17"):
+        golden_model("model_s3r2_c12_k17", kv17, B=2, H=37, W=43, seed=13,
+                     full_grads=["msau_net.end_convs.2.custom_conv.weight", "msau_net.blocks.1.downsamplingblock.conv1s.0.conv.weight"])
     small = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
     if want("model_s3r2_c12"):
         golden_model("model_s3r2_c12", small, B=2, H=37, W=43, seed=11,

@@ -26,7 +26,7 @@ def tc(request):
     _lib.set_option("tensor_core_conv", request.param)
     yield request.param
     _lib.set_option("tensor_core_conv", 1)
-FIXTURES = ["model_s3r2_c12", "model_s4r2_c96", "model_s2r3_c8", "model_s6r3_c16"]
+FIXTURES = ["model_s3r2_c12", "model_s4r2_c96", "model_s2r3_c8", "model_s6r3_c16", "model_s3r2_c12_k17"]
 
 
 def load(golden_dir, name):
@@ -199,7 +199,7 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
         assert (p2.detach() - p1.detach()).abs().max().item() <= tol, k
         if not k.endswith("attention_block.f.conv.bias"):
             assert (p2.detach() - p1.detach()).abs().mean().item() <= 2e-7, k
-    assert abs(float(m2._adam[4]) - float(z["total_norm"])) <= (2e-2 if tc else 2e-3) * float(z["total_norm"])
+    assert abs(float(m2._adam["total"]) - float(z["total_norm"])) <= (2e-2 if tc else 2e-3) * float(z["total_norm"])
     # dead attention params untouched
     dead = [k for k, lv in zip(keys, m2._live_mask()) if not lv]
     for k in dead:
@@ -362,7 +362,8 @@ def test_graph_train_step_matches_eager(golden_dir):
             compare_params()
     assert len(mg._train_graphs) == 1 and len(ms._train_graphs) == 1
     # warm-up + capture enqueue the forward/backward kernels twice more than the eager loop; every replay counts like an eager step
-    assert n_graph == n_eager + 2 * (n_eager - 6) // 3
+    # (the graph holds the 2 optimiser launches as well: graph_tail)
+    assert n_graph == n_eager + 2 * ((n_eager - 6) // 3) + 4
     for a, b, c in zip(le, lg, lst):
         assert abs(a - b) <= 1e-4 * max(1.0, abs(a)) and abs(a - c) <= 1e-4 * max(1.0, abs(a))
     assert le[-1] != le[0]

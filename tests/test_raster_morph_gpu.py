@@ -276,7 +276,7 @@ def test_ccl_batch_against_scipy_full_size():
     """256 x 3 class maps at 512x512 (BASELINE.json config 4): every label map equals scipy.ndimage.label's,
     plus the size-independent properties (labels are 1..n, bbox tight)."""
     from scipy import ndimage
-    maps = np.stack([class_map(100 + i, 512, 512) for i in range(16)])
+    maps = np.stack([class_map(100 + i, 512, 512) for i in range(256)])
     t = torch.from_numpy(maps).cuda()
     for c in (2, 3, 4):
         closed = morph.closing_batch(morph.class_equals(t, c), (1, 3))

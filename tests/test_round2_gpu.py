@@ -1,0 +1,358 @@
+"""Round-2 parity tests through the C ABI: full-size backward precision, the alternative trainer (UNetLoss + RMSprop / SGD),
+17-class heads, per-plan options, graph / workspace lifetime, gradient accumulation, label validation, the bucketed page
+feeder, on-device evaluation and the 2-rank NCCL data-parallel step."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import msau_b200
+from msau_b200 import _lib, raster, train, training
+from oracle import model as om
+from oracle import raster as orr
+from oracle.synth import synth_input
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build(cfg, sd):
+    m = msau_b200.MSAUWrapper(cfg.channels, cfg.n_class, dict(final_act="softmax", featRoot=cfg.feat_root,
+                                                              scale_space_num=cfg.scale_space_num, res_depth=cfg.res_depth))
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def synth_onehot_targets(n_class, B, H, W, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randint(0, n_class, (B, H, W), generator=g)
+    t = t * (torch.rand((B, H, W), generator=g) < 0.5)
+    ta = torch.where(torch.rand((B, H, W), generator=g) < 0.9, t, torch.randint(0, n_class, (B, H, W), generator=g))
+    oh = torch.nn.functional.one_hot
+    return oh(t, n_class).permute(0, 3, 1, 2).contiguous(), oh(ta, n_class).permute(0, 3, 1, 2).contiguous()
+
+
+def rel_l2(a, b):
+    return (a.double() - b.double()).norm().item() / max(b.double().norm().item(), 1e-30)
+
+
+# ------------------------------------------------------------------------------------------------ backward precision
+@pytest.mark.parametrize("tc", [1, 0], ids=["tcgen05", "fp32core"])
+def test_full_size_parameter_gradients_vs_fp64_oracle(tc):
+    """BASELINE size: 512x512 pages, B = 2, S4R2, every parameter gradient against the fp64 oracle.  This is where the
+    single-term bf16 weight-gradient operands are proven: each dW element sums 5e5 pixel products.  The fp32 CUDA-core path
+    (tensor_core_conv = 0: fp32 operands everywhere) runs the same comparison, which separates the bf16 operand rounding from
+    what both paths share: ReLU / max-pool decisions that flip where a pre-activation is within the forward pass's rounding
+    error of zero (each flip changes single pixels of one gradient map completely).  The measured per-tensor errors of both
+    paths are written to gpurun_out/grad_precision_*.json (committed as profiles/grad_precision_r2.json)."""
+    torch.manual_seed(0)
+    cfg = om.MsauConfig()
+    sd = om.init_state_dict(cfg, 0)
+    words, lines = zip(*[orr.synth_page(700 + i, 512, 512, 198) for i in range(2)])
+    grid, label, _ = raster.rasterize_word_chargrid(list(words), list(lines), np.eye(96), out_hw=(512, 512))
+    m = build(cfg, sd).train()
+    m.set_option("tensor_core_conv", tc)
+    _, logits, aux = m(grid)
+    loss = m.loss(logits, aux, label.long())
+    loss.backward()
+    sd64 = {k: v.double() for k, v in sd.items()}
+    torch.set_num_threads(os.cpu_count())
+    ref_loss, ref_logits, _, ref_grads = om.loss_and_grads(sd64, cfg, grid.cpu().double(), label.cpu().long())
+    assert (logits.cpu().double() - ref_logits).abs().max().item() <= 5e-4
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-5 * max(1.0, float(ref_loss))
+    named = dict(m.named_parameters())
+    report = {}
+    for k, g in ref_grads.items():
+        if g is None or named[k].grad is None:
+            assert named[k].grad is None and (g is None or float(g.abs().max()) == 0.0), k
+            continue
+        if float(g.norm()) < 1e-9:          # attention f.conv.bias: analytically zero (soft-max shift invariance)
+            assert float(named[k].grad.abs().max()) < 1e-4, k
+            continue
+        report[k] = rel_l2(named[k].grad.cpu(), g)
+    worst = max(report, key=report.get)
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, f"grad_precision_{'tcgen05' if tc else 'fp32core'}.json"), "w") as f:
+        json.dump(dict(path="tcgen05 (bf16x3 fwd/dgrad, bf16x1 wgrad)" if tc else "fp32 CUDA cores", worst=worst, worst_rel_l2=report[worst], median_rel_l2=float(np.median(list(report.values()))),
+                       per_tensor=report), f, indent=1)
+    assert report[worst] <= (2e-2 if tc else 5e-3), (worst, report[worst])
+    assert float(np.median(list(report.values()))) <= (5e-3 if tc else 1e-3)
+
+
+def test_twenty_step_trajectory_vs_oracle():
+    """20 fused train steps (lr 1e-4, clip 1.0, Adam) on two 256x256 pages against the torch-fp32 oracle's own 20 steps:
+    the loss curve and the parameter drift stay together (Adam normalises the update, so a gradient error of a few 1e-3 moves a
+    weight by a fraction of lr per step)."""
+    cfg = om.MsauConfig()
+    sd = om.init_state_dict(cfg, 2)
+    words, lines = zip(*[orr.synth_page(800 + i, 256, 256, 60) for i in range(2)])
+    grid, label, _ = raster.rasterize_word_chargrid(list(words), list(lines), np.eye(96), out_hw=(256, 256))
+    m = build(cfg, sd).train()
+    lab = label.long()
+    got = [float(m.train_step(grid, lab)) for _ in range(20)]
+    torch.set_num_threads(os.cpu_count())
+    ref = {k: v.clone() for k, v in sd.items()}
+    mm = {k: torch.zeros_like(v) for k, v in ref.items()}
+    vv = {k: torch.zeros_like(v) for k, v in ref.items()}
+    dead = f"msau_net.blocks.{cfg.num_blocks - 1}.downsamplingblock.layer_attentions."
+    want = []
+    xc, lc = grid.cpu(), lab.cpu()
+    for s in range(20):
+        loss, _, _, grads = om.loss_and_grads(ref, cfg, xc, lc)
+        grads = {k: (None if k.startswith(dead) else g) for k, g in grads.items()}
+        om.clip_adam_step(ref, grads, mm, vv, step=s + 1)
+        want.append(float(loss))
+    assert want[-1] < want[0]
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=2e-4)
+    moved = drift = 0.0
+    for k, p in m.state_dict().items():
+        moved += (ref[k] - sd[k]).double().pow(2).sum().item()
+        drift += (p.cpu() - ref[k]).double().pow(2).sum().item()
+    # distance between the two trajectories' end points relative to the distance travelled
+    assert drift ** 0.5 <= 0.1 * moved ** 0.5, (drift ** 0.5, moved ** 0.5)
+
+
+# ------------------------------------------------------------------------------------------------ alternative trainer
+@pytest.mark.parametrize("name", ["trainer_rmsprop_c17", "trainer_momentum_w_c17"])
+def test_alternative_trainer_step_matches_reference(golden_dir, name):
+    """UNetLoss (one-hot targets, 0.5 / 0.5 aux, optional class weights) + RMSprop / SGD-momentum through the fused kernels,
+    against fixtures generated by the reference's own model/training/{cost,optimizer}.py, with a 17-class head."""
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    cfg = om.MsauConfig(**meta["cfg"])
+    sd = om.init_state_dict(cfg, meta["seed"])
+    x, _ = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
+    tgt, tgt_aux = synth_onehot_targets(cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 2)
+    m = training.register(build(cfg, sd).train())
+    crit = training.UNetLoss({"aux_logits": None, "aux_tgt": None, "class_weights": meta["class_weights"]})
+    opt = training.get_optimizer(m, {"optimizer": meta["optimizer"]} if meta["optimizer"] != "rmsprop" else {})
+    keys = [k for k, _ in om.param_schema(cfg)]
+    for s in range(meta["steps"]):
+        opt.zero_grad()
+        _, logits, aux = m(x.cuda())
+        acc, loss, final = crit(logits, tgt.cuda(), {"aux_logits": aux, "aux_tgt": tgt_aux.cuda()})
+        loss.backward()
+        if s == 0:
+            assert np.abs(logits.cpu().numpy() - z["logits"]).max() <= 5e-4
+            named = dict(m.named_parameters())
+            norms = np.array([0.0 if named[k].grad is None else float(named[k].grad.double().norm()) for k in keys])
+            np.testing.assert_allclose(norms, z["grad_norms"], rtol=3e-2, atol=2e-5)
+        opt.step()
+        assert abs(acc - z["acc"][s]) <= 2e-3          # a few arg-max ties may flip
+        assert abs(float(loss) - z["loss"][s]) <= 2e-3 and abs(float(final) - z["final_loss"][s]) <= 2e-3
+    k0 = "msau_net.blocks.1.upsamplingblock.conv1s.0.custom_conv.weight"
+    got = dict(m.named_parameters())[k0].detach().cpu().numpy()
+    lr = 1e-3
+    # RMSprop's first steps move a weight by ~lr * g / |g|; momentum SGD by lr * g: bound the difference by a fraction of a step
+    assert np.abs(got - z["param_after::" + k0]).max() <= (2.2 * lr if meta["optimizer"] == "rmsprop" else 1e-5)
+    assert np.abs(got - z["param_after::" + k0]).mean() <= (0.05 * lr if meta["optimizer"] == "rmsprop" else 1e-6)
+
+    # the fused path (Trainer.train's step) lands on the same parameters as the autograd-style loop above
+    m2 = build(cfg, sd).train()
+    t8, a8 = m2.onehot_argmax(tgt.cuda()), m2.onehot_argmax(tgt_aux.cuda())
+    assert torch.equal(t8.cpu().long(), tgt.argmax(1)) and torch.equal(a8.cpu().long(), tgt_aux.argmax(1))
+    for s in range(meta["steps"]):
+        m2.train_step(x.cuda(), t8, loss_spec=dict(mode=1, weight_main=0.5, weight_aux=0.5, class_weights=meta["class_weights"]),
+                      labels_aux=a8, **opt.fused_args())
+        assert abs(m2.last_accuracy() - z["acc"][s]) <= 2e-3
+    for (k, p2), p1 in zip(m2.named_parameters(), m.parameters()):
+        assert (p2.detach() - p1.detach()).abs().max().item() <= (2.2 * lr if meta["optimizer"] == "rmsprop" else 1e-5), k
+
+
+def test_trainer_loop_runs_and_schedules_lr(tmp_path):
+    """Trainer.train over a tiny in-memory data provider: step-decay LR (trainer.py:45-49), best-val / every-8 checkpoints."""
+    cfg = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    sd = om.init_state_dict(cfg, 41)
+
+    class Provider:
+        size_val, batchsize_tr = 1, 2
+
+        def __init__(self):
+            self.i = 0
+
+        def next_data(self, which):
+            self.i += 1
+            x, _ = synth_input(cfg.channels, cfg.n_class, 2, 32, 40, 50 + self.i % 3)
+            t, ta = synth_onehot_targets(cfg.n_class, 2, 32, 40, 60 + self.i % 3)
+            return x, t, ta
+
+        def restart_val_runner(self):
+            pass
+
+        def stop_all(self):
+            pass
+
+    m = build(cfg, sd)
+    tr = training.Trainer(m, opt_kwargs={}, cost_kwargs={})
+    tr.train(Provider(), str(tmp_path), batch_steps_per_epoch=3, epochs=12)
+    assert len(tr.history) == 12
+    assert tr.history[0]["lr"] == 0.001 and abs(tr.history[10]["lr"] - 0.00095) < 1e-12
+    assert tr.history[-1]["train_loss"] < tr.history[0]["train_loss"]
+    assert os.path.exists(os.path.join(str(tmp_path), "model1")) and os.path.exists(os.path.join(str(tmp_path), "model8"))
+    m3 = build(cfg, sd)
+    m3.load_weights(os.path.join(str(tmp_path), "model8"))
+
+
+# ------------------------------------------------------------------------------------------------ engine plumbing
+def test_per_plan_options_do_not_leak():
+    """Two models with different engine options run side by side (no process-global switch): the fp32-core model and the
+    tensor-core model each keep their own kernels, and both agree with the oracle."""
+    cfg = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    sd = om.init_state_dict(cfg, 11)
+    x, _ = synth_input(cfg.channels, cfg.n_class, 1, 37, 43, 12)
+    a, b = build(cfg, sd).eval(), build(cfg, sd).eval()
+    a.set_option("tensor_core_conv", 0)
+    ref, _ = om.msau_forward(sd, cfg, x)
+    with torch.no_grad():
+        la0 = a(x.cuda())[1].cpu()
+        lb0 = b(x.cuda())[1].cpu()
+        la1 = a(x.cuda())[1].cpu()
+    assert torch.equal(la0, la1)
+    assert not torch.equal(la0, lb0)                  # different kernels, different rounding
+    assert (la0 - ref).abs().max().item() <= 1e-4 and (lb0 - ref).abs().max().item() <= 5e-4
+    with pytest.raises(_lib.MsauError):
+        a.set_option("no_such_option", 1)
+
+
+def test_inference_graph_survives_training_at_same_shape(golden_dir):
+    """a plan first used for inference (graph captured) and then for training reallocates its workspace; the
+    inference graph must be re-captured, not replayed on freed memory -- and the train graph stays valid afterwards."""
+    cfg = om.MsauConfig()
+    sd = om.init_state_dict(cfg, 0)
+    m = build(cfg, sd)
+    x, labels = synth_input(cfg.channels, cfg.n_class, 1, 64, 48, 3)
+    xc, lc = x.cuda(), labels.cuda()
+    m.eval()
+    with torch.no_grad():
+        c0 = m.predict_classes_graph(xc)
+    m.train()
+    l0 = float(m.train_step(xc, lc, use_graph=True))
+    filler = torch.full((1 << 24,), 7.0, device="cuda")      # reuse whatever the old workspace freed
+    m.eval()
+    with torch.no_grad():
+        c1 = m.predict_classes_graph(xc)
+        assert torch.equal(c1, m.predict_classes(xc))
+    m.train()
+    l1 = float(m.train_step(xc, lc, use_graph=True))
+    assert np.isfinite(l0) and np.isfinite(l1) and l1 != l0
+    assert float(filler.min()) == 7.0 and float(filler.max()) == 7.0
+    with pytest.raises(_lib.MsauError):
+        m.predict_classes_graph(torch.zeros((1, 64, 48), dtype=torch.int16, device="cuda"), layout=3)
+    del c0
+
+
+def test_gradient_accumulation_and_label_validation():
+    cfg = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    sd = om.init_state_dict(cfg, 5)
+    x, labels = synth_input(cfg.channels, cfg.n_class, 1, 32, 40, 6)
+    m = build(cfg, sd).train()
+    k = "msau_net.end_convs.2.custom_conv.weight"
+    m.zero_grad()
+    _, lg, ax = m(x.cuda())
+    m.loss(lg, ax, labels.cuda()).backward()
+    g1 = dict(m.named_parameters())[k].grad.clone()
+    _, lg, ax = m(x.cuda())
+    m.loss(lg, ax, labels.cuda()).backward()          # no zero_grad in between: autograd accumulates
+    g2 = dict(m.named_parameters())[k].grad
+    assert torch.allclose(g2, 2 * g1, rtol=1e-4, atol=1e-7)
+    bad = labels.clone()
+    bad[0, 3, 3] = cfg.n_class                        # torch's CrossEntropyLoss raises IndexError here
+    _, lg, ax = m(x.cuda())
+    with pytest.raises(IndexError):
+        m.loss(lg, ax, bad.cuda())
+    _, lg, ax = m(x.cuda())
+    m.loss(lg, ax, labels.cuda())                     # the flag was cleared by the failed call
+    m.train_step(x.cuda(), bad.cuda())
+    with pytest.raises(IndexError):
+        m.check_labels()
+    m.check_labels()
+
+
+def test_optimizer_state_round_trip(tmp_path):
+    cfg = om.MsauConfig(channels=12, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    sd = om.init_state_dict(cfg, 5)
+    x, labels = synth_input(cfg.channels, cfg.n_class, 2, 32, 40, 6)
+    a = build(cfg, sd).train()
+    for _ in range(3):
+        a.train_step(x.cuda(), labels.cuda())
+    path = str(tmp_path / "ck.pt")
+    train.save_checkpoint(a, path)
+    a = a.cuda()                                       # no-op move keeps the optimiser state
+    assert a._adam is not None and int(a._adam["step_dev"]) == 3
+    b = build(cfg, om.init_state_dict(cfg, 99)).train()
+    train.load_checkpoint(b, path)
+    la, lb = float(a.train_step(x.cuda(), labels.cuda())), float(b.train_step(x.cuda(), labels.cuda()))
+    assert abs(la - lb) <= 1e-6 * max(1.0, abs(la))
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert (pa.detach() - pb.detach()).abs().max().item() <= 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ drivers
+def test_bucketed_feeder_and_device_evaluate():
+    """Variable-size pages: the feeder buckets by exact grid shape (host geometry == device geometry), every bucket trains as one
+    batch from pinned records, and evaluate() counts the label x prediction matrix on the device like the host loop would."""
+    shapes = [(40, 48), (40, 48), (56, 32), (40, 48), (56, 32), (24, 64)]
+    wp, lp = [], []
+    for i, (h, w) in enumerate(shapes):
+        a, b = orr.synth_page(900 + i, h, w, 20)
+        wp.append(a); lp.append(b)
+    feeder = train.BucketedPageFeeder(wp, lp, max_pages=2, seed=3)
+    assert feeder.shapes() == sorted(set(shapes))
+    assert sorted(len(b[1]) for b in feeder.batches) == [1, 1, 2, 2]
+    for shape, idx, hw, hl in feeder.batches:           # host bucketing agrees with the device geometry kernel
+        geom = raster.BoxBatch.from_host(hw, "cuda").geometry().cpu().numpy()
+        assert all((int(g[5]), int(g[6])) == shape for g in geom)
+    cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    m = build(cfg, om.init_state_dict(cfg, 1)).train()
+    hist = train.train_pages(feeder, m, torch.eye(96, dtype=torch.float64), epochs=3, lr=1e-3)
+    assert [h["pages"] for h in hist] == [6, 6, 6] and hist[-1]["loss"] < hist[0]["loss"]
+    assert all(0.0 <= h["acc"] <= 1.0 for h in hist)
+
+    class DS(list):
+        labels = {"other": 1}
+    ds = DS()
+    for i, (h, w) in enumerate(shapes[:3]):
+        g, lab = orr.raster_word_chargrid(wp[i], lp[i], np.eye(96))
+        ds.append({"mask": torch.Tensor(g).unsqueeze(0), "label": torch.Tensor(lab).unsqueeze(0)})
+    got = train.evaluate(ds, m, None)
+    m.eval()
+    labs, preds = [], []
+    for d in ds:
+        p = m.predict_classes(d["mask"].cuda())[0].cpu().numpy()
+        l = d["label"][0].numpy().astype(np.int64)
+        labs.append(l[l != 0]); preds.append(p[l != 0])
+    labs, preds = np.hstack(labs), np.hstack(preds)
+    assert abs(got["acc"] - float((labs == preds).mean())) < 1e-12
+    assert int(got["confusion"].sum()) == labs.size
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_nccl_step_equals_single_gpu_step_on_concatenated_batch(tmp_path):
+    """the N-GPU data-parallel step equals the 1-GPU step on the concatenated batch.  Two NCCL ranks take
+    2 pages each (gradients pre-scaled 1/2, one all-reduce of the flat buffer, identical clip + Adam), rank 0 dumps its
+    parameters after 3 steps; this process runs the same 3 steps on all 4 pages.  Also: replicas stay bit-identical."""
+    out = str(tmp_path / "dp.pt")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(ROOT, "tests", "dp_worker.py"), out],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    got = torch.load(out)
+    assert got["replicas_identical"]
+    cfg = om.MsauConfig(channels=96, n_class=5, scale_space_num=3, res_depth=2, feat_root=8)
+    sd = om.init_state_dict(cfg, 7)
+    x, labels = synth_input(cfg.channels, cfg.n_class, 4, 64, 48, 8)
+    m = build(cfg, sd).train()
+    losses = [float(m.train_step(x.cuda(), labels.cuda())) for _ in range(3)]
+    # each rank reports the mean loss of ITS pages; the 1-GPU loss is the mean over all 4
+    np.testing.assert_allclose(np.mean(got["losses"], axis=0), losses, rtol=1e-5, atol=1e-6)
+    for k, p in m.state_dict().items():
+        tol = 2.5e-4 if k.endswith("attention_block.f.conv.bias") else 4e-6
+        assert (p.cpu() - got["params"][k]).abs().max().item() <= tol, k
+    for mode in ("graph",):
+        assert got["graph_matches_eager"], mode
