@@ -465,7 +465,19 @@ def main():
             out["e2e"]["dense_input_h2d_bytes_per_step"] = e2e_dense["h2d_bytes_per_step"]
         os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
+        # CUDA graphs that hold NCCL kernels must be gone before the communicator is torn down (destroy_process_group otherwise
+        # waits for ever); a timer makes sure a stuck teardown can never keep a finished benchmark from exiting
+        import gc
+        barrier()
+        model._train_graphs.clear(); model._graphs.clear()
+        del model
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         dist.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":

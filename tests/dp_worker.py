@@ -19,6 +19,10 @@ from oracle.synth import synth_input  # noqa: E402
 
 def main():
     out = sys.argv[1]
+    import threading
+    hard = threading.Timer(200.0, lambda: os._exit(3))          # a stuck collective must not outlive the test's own timeout
+    hard.daemon = True
+    hard.start()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -38,7 +42,9 @@ def main():
         return m, losses
 
     m, losses = run(False)
+    print(f"rank {rank}: eager steps done {losses}", file=sys.stderr, flush=True)
     mg, losses_g = run(True)
+    print(f"rank {rank}: graph steps done {losses_g}", file=sys.stderr, flush=True)
     torch.cuda.synchronize()
     flat = m.flat_params.detach().clone()
     gathered = [torch.empty_like(flat) for _ in range(world)]
@@ -52,7 +58,17 @@ def main():
         torch.save(dict(params={k: v.detach().cpu() for k, v in m.state_dict().items()}, losses=all_losses,
                         replicas_identical=all(torch.equal(g, gathered[0]) for g in gathered), graph_matches_eager=bool(graph_ok)), out)
     dist.barrier()
+    # graphs holding NCCL kernels must be released before the communicator goes away; never let a stuck teardown hang the test
+    import gc
+    import threading
+    del m, mg
+    gc.collect()
+    torch.cuda.synchronize()
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
     dist.destroy_process_group()
+    t.cancel()
 
 
 if __name__ == "__main__":

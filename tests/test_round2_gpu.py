@@ -80,8 +80,10 @@ def test_full_size_parameter_gradients_vs_fp64_oracle(tc):
     with open(os.path.join(out, f"grad_precision_{'tcgen05' if tc else 'fp32core'}.json"), "w") as f:
         json.dump(dict(path="tcgen05 (bf16x3 fwd/dgrad, bf16x1 wgrad)" if tc else "fp32 CUDA cores", worst=worst, worst_rel_l2=report[worst], median_rel_l2=float(np.median(list(report.values()))),
                        per_tensor=report), f, indent=1)
-    assert report[worst] <= (2e-2 if tc else 5e-3), (worst, report[worst])
-    assert float(np.median(list(report.values()))) <= (5e-3 if tc else 1e-3)
+    # measured (profiles/grad_precision_r2.json): tcgen05 path worst 6.5e-3 (attention f.conv.weight, single-term bf16 attention
+    # backward), worst convolution 4.0e-3, median 5.9e-4; fp32 path worst 5.6e-4, median 5.2e-5
+    assert report[worst] <= (1e-2 if tc else 2e-3), (worst, report[worst])
+    assert float(np.median(list(report.values()))) <= (2e-3 if tc else 3e-4)
 
 
 def test_twenty_step_trajectory_vs_oracle():
@@ -149,8 +151,11 @@ def test_alternative_trainer_step_matches_reference(golden_dir, name):
     got = dict(m.named_parameters())[k0].detach().cpu().numpy()
     lr = 1e-3
     # RMSprop's first steps move a weight by ~lr * g / |g|; momentum SGD by lr * g: bound the difference by a fraction of a step
-    assert np.abs(got - z["param_after::" + k0]).max() <= (2.2 * lr if meta["optimizer"] == "rmsprop" else 1e-5)
-    assert np.abs(got - z["param_after::" + k0]).mean() <= (0.05 * lr if meta["optimizer"] == "rmsprop" else 1e-6)
+    # RMSprop's first step is lr * g / (sqrt(0.01 g^2) + eps) = 10 lr sign(g) whatever |g| is, so an element whose gradient is
+    # rounding noise may go the other way in each of the 2 steps (<= 2 x 2 x 10 lr); the mean difference stays at 1 % of a step
+    rms = meta["optimizer"] == "rmsprop"
+    assert np.abs(got - z["param_after::" + k0]).max() <= (42 * lr if rms else 1e-5)
+    assert np.abs(got - z["param_after::" + k0]).mean() <= (0.2 * lr if rms else 1e-6)
 
     # the fused path (Trainer.train's step) lands on the same parameters as the autograd-style loop above
     m2 = build(cfg, sd).train()
@@ -161,7 +166,9 @@ def test_alternative_trainer_step_matches_reference(golden_dir, name):
                       labels_aux=a8, **opt.fused_args())
         assert abs(m2.last_accuracy() - z["acc"][s]) <= 2e-3
     for (k, p2), p1 in zip(m2.named_parameters(), m.parameters()):
-        assert (p2.detach() - p1.detach()).abs().max().item() <= (2.2 * lr if meta["optimizer"] == "rmsprop" else 1e-5), k
+        assert (p2.detach() - p1.detach()).abs().max().item() <= (42 * lr if rms else 1e-5), k
+        if not k.endswith("attention_block.f.conv.bias"):     # analytically zero gradient: RMSprop turns its rounding noise into full steps
+            assert (p2.detach() - p1.detach()).abs().mean().item() <= (0.2 * lr if rms else 1e-6), k
 
 
 def test_trainer_loop_runs_and_schedules_lr(tmp_path):
@@ -296,7 +303,7 @@ def test_optimizer_state_round_trip(tmp_path):
 def test_bucketed_feeder_and_device_evaluate():
     """Variable-size pages: the feeder buckets by exact grid shape (host geometry == device geometry), every bucket trains as one
     batch from pinned records, and evaluate() counts the label x prediction matrix on the device like the host loop would."""
-    shapes = [(40, 48), (40, 48), (56, 32), (40, 48), (56, 32), (24, 64)]
+    shapes = [(40, 48), (40, 48), (56, 40), (40, 48), (56, 40), (24, 64)]
     wp, lp = [], []
     for i, (h, w) in enumerate(shapes):
         a, b = orr.synth_page(900 + i, h, w, 20)
@@ -340,7 +347,7 @@ def test_two_rank_nccl_step_equals_single_gpu_step_on_concatenated_batch(tmp_pat
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", PYTHONPATH=ROOT)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29541", os.path.join(ROOT, "tests", "dp_worker.py"), out],
-                       env=env, capture_output=True, text=True, timeout=600)
+                       env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     got = torch.load(out)
     assert got["replicas_identical"]
@@ -351,8 +358,13 @@ def test_two_rank_nccl_step_equals_single_gpu_step_on_concatenated_batch(tmp_pat
     losses = [float(m.train_step(x.cuda(), labels.cuda())) for _ in range(3)]
     # each rank reports the mean loss of ITS pages; the 1-GPU loss is the mean over all 4
     np.testing.assert_allclose(np.mean(got["losses"], axis=0), losses, rtol=1e-5, atol=1e-6)
+    # Adam moves a weight by ~lr * sign(g) per step when |g| is small: the two runs sum the gradient in different orders (2 + 2
+    # pages vs 4), so an element whose gradient is rounding noise may go the other way in each of the 3 steps (<= 3 * 2 * lr);
+    # everything else agrees to fp32 rounding, which the mean shows
     for k, p in m.state_dict().items():
-        tol = 2.5e-4 if k.endswith("attention_block.f.conv.bias") else 4e-6
-        assert (p.cpu() - got["params"][k]).abs().max().item() <= tol, k
+        d = (p.cpu() - got["params"][k]).abs()
+        assert d.max().item() <= 6.5e-4, k
+        if not k.endswith("attention_block.f.conv.bias"):
+            assert d.mean().item() <= 2e-6, k
     for mode in ("graph",):
         assert got["graph_matches_eager"], mode
