@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--no-graph-tail", action="store_true", help="keep the all-reduce and clip + Adam outside the CUDA graph")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --pages per GPU (default 16); strong: global batch 16 split over the GPUs (16/N pages per GPU)")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE", help="engine option for A/B runs, e.g. --option pdl=0")
     ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling / configs[4] / library-GPU-baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -270,6 +271,9 @@ def main():
                                                                           scale_space_num=CFG["scale_space_num"], res_depth=CFG["res_depth"]))
     model.reset_parameters(seed=0)
     model = model.to(dev).train()
+    for kv in args.option:
+        name, val = kv.split("=")
+        model.set_option(name, int(val))
     pg = dist.group.WORLD if world > 1 else None
 
     # ---- synthetic pages for this rank: records on the host, dense grid rasterised once for the resident run

@@ -27,3 +27,17 @@ def synth_page(seed: int, gh: int = 512, gw: int = 512, n_words: int = 198, unit
     lines = dict(x=b[:, 0].copy(), y=b[:, 1].copy(), w=b[:, 2].copy(), h=b[:, 3].copy(),
                  label=(np.arange(len(boxes)) % 4).astype(np.int32))
     return words, lines
+
+
+def class_map_rects(seed: int, H: int, W: int, n_rect: int = 200, n_class: int = 5) -> np.ndarray:
+    """uint8 class map for the post-process timings (synthetic variant): ``n_rect`` random rectangles of classes
+    0..n_class-1 painted in order + 3 % salt noise (1-px gaps for the closing, thousands of tiny components for the labelling)."""
+    rng = np.random.RandomState(seed)
+    m = np.zeros((H, W), np.uint8)
+    for _ in range(n_rect):
+        h, w = rng.randint(1, max(2, H // 8)), rng.randint(1, max(2, W // 5))
+        y, x = rng.randint(0, H), rng.randint(0, W)
+        m[y:y + h, x:x + w] = rng.randint(0, n_class)
+    noise = rng.rand(H, W) < 0.03
+    m[noise] = rng.randint(0, n_class, int(noise.sum()))
+    return m

@@ -220,12 +220,17 @@ int msau_one_hot(const uint16_t* ids, int n_pages, int height, int width, int n_
 /* r_dilation / r_erosion: rectangular max / min filter, mode='constant' (zeros outside), SciPy origin. */
 int msau_rect_filter(const uint8_t* in, uint8_t* out, int n_maps, int height, int width, int size_h,
                      int size_w, int origin_h, int origin_w, int is_max, void* stream);
+/* r_closing(pred_class == cls, (1, size_w)) -- kv_model.py:175-176 -- in one pass over the uint8 class map: size_w in 1..4, width a
+ * multiple of 16, 16-byte aligned maps; identical to msau_class_equals + msau_rect_filter(max) + msau_rect_filter(min) with origin 0. */
+int msau_class_closing_row(const uint8_t* class_map, uint8_t* out, int n_maps, int height, int width, int cls, int size_w,
+                           void* stream);
 /* out = (class_map == cls) as uint8 0/1 (kv_model.py:175) */
 int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int cls, void* stream);
 /* connected_components: scipy.ndimage.label (4-connectivity, labels ordered by first raster pixel)
  * + find_objects.  labels int32 [n_maps,H,W]; n_labels int32 [n_maps]; bboxes int32
  * [n_maps, max_labels, 4] = y0,y1,x0,x1 half-open (labels beyond max_labels are counted, not boxed).
- * scratch int32 [n_maps*H*W + n_maps*(H*W/1024+2)] */
+ * scratch int32 [n_maps*H*W + n_maps*H*ceil(W/32) + n_maps*(ceil(H*ceil(W/32)/32)+2)] (parent map | candidate-root bitmap |
+ * chunk counts) */
 int msau_ccl4(const uint8_t* binary, int n_maps, int height, int width, int32_t* labels, int32_t* n_labels,
               int32_t* bboxes, int max_labels, int32_t* scratch, void* stream);
 

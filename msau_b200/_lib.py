@@ -19,7 +19,7 @@ SYMBOLS = [
     "msau_optimizer_step", "msau_onehot_argmax", "msau_confusion_counts", "msau_plan_set_option",
     "msau_raster_geometry", "msau_raster_features", "msau_raster_labels",
     "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
-    "msau_rect_filter", "msau_class_equals", "msau_ccl4", "msau_kv_select_components", "msau_kv_char_range",
+    "msau_rect_filter", "msau_class_equals", "msau_class_closing_row", "msau_ccl4", "msau_kv_select_components", "msau_kv_char_range",
     "msau_debug_layout", "msau_debug_tensor", "msau_profile_enable", "msau_profile_report",
     "msau_set_option",
     "msau_attention_scratch_bytes", "msau_attention_forward", "msau_attention_backward",
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.msau_one_hot.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp]
     L.msau_rect_filter.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]
     L.msau_class_equals.argtypes = [vp, vp, i64, i32, vp]
+    L.msau_class_closing_row.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.msau_ccl4.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     L.msau_kv_select_components.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]
     L.msau_kv_char_range.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp]

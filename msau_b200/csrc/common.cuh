@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #define MSAU_OK 0
 #define MSAU_ERR_ARG (-1)
@@ -43,6 +44,37 @@ static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 int sm_count();
 void count_launch(int n);   // bench.py's gpu_launches counter
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Kernels launched through launch_pdl() may start while their predecessor in the stream is still draining: their prologue (TMEM
+// allocation, barrier initialisation, weight images -> shared memory, index arithmetic) overlaps the predecessor's tail and the
+// launch latency disappears.  Protocol, the same in every kernel that is launched this way:
+//     prologue (touches nothing but kernel parameters, shared memory, TMEM and packed weights)
+//     pdl_wait();      // predecessor complete and its memory visible -- BEFORE the first access to any activation / gradient
+//     pdl_trigger();   // successors may now be scheduled (after the wait, so a successor's prologue only ever overlaps THIS
+//                      // kernel's body: everything older is complete, in particular the weight-packing kernels)
+// The host side decides per launch (thread-local state set by the plan): off for the first launches after the packing kernels and
+// when the engine option "pdl" is 0.  Without the launch attribute both device instructions are no-ops.
+void pdl_set(bool enabled, int hold);   // hold: number of upcoming launches that must stay fully serialised
+bool pdl_take();                        // consumes one launch's decision
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_take() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ------------------------------------------------------------------ kernel argument blocks
 // A 4-D activation in HBM: NHWC fp32, `pitch` floats per pixel (>= channels used, multiple of 4).

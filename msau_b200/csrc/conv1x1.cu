@@ -17,12 +17,14 @@ namespace msau {
 template <int CO, int PX>
 __global__ void __launch_bounds__(256, CO == 8 ? 3 : (CO == 16 ? 2 : 1)) conv1x1_kernel(const ConvArgs a, long npix) {
   extern __shared__ __align__(16) float wsm[];                 // [cin][CO]
-  if (a.skip_flag && *a.skip_flag == 0) return;
+  if (a.skip_flag) { pdl_wait(); if (*a.skip_flag == 0) return; }
   const int cin = a.c1 + a.c2;
   for (int e = threadIdx.x; e < cin * CO / 4; e += 256) reinterpret_cast<float4*>(wsm)[e] = __ldg(reinterpret_cast<const float4*>(a.w) + e);
   float* bsm = wsm + cin * CO;                                 // [CO] bias row after the weights
   if (threadIdx.x < CO) bsm[threadIdx.x] = a.bias ? __ldg(a.bias + threadIdx.x) : 0.f;
   __syncthreads();
+  pdl_wait();        // PDL protocol (common.cuh): only packed weights were read so far
+  pdl_trigger();
   for (long p0 = (long)blockIdx.x * (256 * PX) + threadIdx.x; p0 < npix; p0 += (long)gridDim.x * (256 * PX)) {
     float acc[PX][CO];
     long pp[PX];
@@ -114,7 +116,7 @@ int launch_conv1x1(const ConvArgs& a, cudaStream_t st) {
   {                                                                                                             \
     static bool attr = false;                                                                                   \
     if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv1x1_kernel<CO, PX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; } \
-    conv1x1_kernel<CO, PX><<<(unsigned)blocks, 256, smem, st>>>(a, npix);                                       \
+    MSAU_CUDA_TRY(launch_pdl(conv1x1_kernel<CO, PX>, dim3((unsigned)blocks), dim3(256), smem, st, a, npix));       \
   }
   switch (a.coutp) {
     case 8: MSAU_PW(8, 2) break;

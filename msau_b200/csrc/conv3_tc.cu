@@ -31,6 +31,7 @@
 #include "conv_tc.cuh"
 #include "prof.cuh"
 #include "tc_ptx.cuh"
+#include "tma.cuh"
 
 namespace msau {
 
@@ -53,6 +54,7 @@ struct C3Tile {
   int dgx, dgy, dgb;                  // gridDim.x decomposed in (block column, block row, page) steps
   int n_ops, ia, io, im;              // extra epilogue operands and their slot index (-1 = absent)
   int dbg;
+  int tma;                            // raw halo planes arrive by TMA tensor loads (dense [row][32 px][8 ch] slots) instead of cp.async
   uint32_t plane_bytes, in_bytes, w_bytes, w_total, raw_bytes, epi_bytes, tmem_cols;
 };
 
@@ -126,13 +128,18 @@ __device__ __forceinline__ void mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_
 
 // EPI: 0 = epilogue driven by run-time flags; 1 = bias; 2 = bias + ReLU; 3 = bias + residual + ReLU; 4 = ReLU mask; 5 = ReLU mask + add
 // LDU: raw pixels per producer thread and plane (3: T <= 4 tiles, 6: T = 8)
-template <int EPI, int LDU, int KS, int PAD>
-__global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t) {
+// TMA: the raw fp32 halo plane of a chunk is ONE cp.async.bulk.tensor load issued by one thread (map tm1 / tm2 = src1 / src2 as
+//      {channel, x, y, page}; out-of-image pixels zero-filled by the hardware = SAME padding), completion on an mbarrier
+template <int EPI, int LDU, int KS, int PAD, bool TMA>
+__global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t,
+                                                                 const __grid_constant__ CUtensorMap tm1,
+                                                                 const __grid_constant__ CUtensorMap tm2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
   __shared__ uint64_t bar_empty[C3_MAX_STAGES];   // MMA -> producers : the MMAs reading the stage have retired
   __shared__ uint64_t bar_acc_full[4];            // MMA -> epilogue  : accumulator set complete
   __shared__ uint64_t bar_acc_empty[4];           // epilogue -> MMA  : accumulator set drained
+  __shared__ uint64_t bar_raw[4];                 // TMA -> producers : raw plane of a chunk has landed (transaction bytes)
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[64];
 
@@ -150,12 +157,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
   fence_async_smem();
   if (tid == 32) {
     for (int i = 0; i < C3_MAX_STAGES; ++i) { mbar_init(&bar_full[i], C3_PROD_WARPS); mbar_init(&bar_empty[i], C3_MMA_WARPS); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS); mbar_init(&bar_raw[i], 1); }
     mbar_init_fence();
+    if (TMA) { tma_prefetch_desc(&tm1); if (a.c2) tma_prefetch_desc(&tm2); }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();        // everything above touched only parameters, packed weights, shared memory and TMEM (common.cuh: PDL protocol)
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_s;
   const int S = t.stages;
   const bool spin = !(t.dbg & 16);
@@ -173,7 +183,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     // 32-bit element offsets (every tensor here has < 2^31 elements) built from per-thread constants.
     const int lpx = lane >> 1, lhalf = (lane & 1) * 4;
     uint32_t d_issue = 0;                                          // raw slot of the next issue (bytes)
+    int i_slot = 0;                                                // ... and its index (TMA: barrier of that slot)
     auto issue = [&](const TilePos& tp, int p) {
+      if (TMA) {
+        // one thread, one instruction: the whole RI x 32 x 8 plane; coordinates may be negative / past the edge (zero-filled)
+        if (tid == 0 && tp.b < a.B && !(t.dbg & 2)) {
+          const bool from1 = p < planes1;
+          fence_async_smem();                                      // the slot was last read through the generic proxy
+          mbar_arrive_expect_tx(&bar_raw[i_slot], t.raw_bytes);
+          tma_load_4d(raw_u32 + d_issue, from1 ? &tm1 : &tm2, (from1 ? p : p - planes1) << 3, tp.bx * t.OW - t.pad, tp.by * RO - t.pad, tp.b,
+                      &bar_raw[i_slot]);
+        }
+        d_issue += t.raw_bytes;
+        if (++i_slot == t.D) { i_slot = 0; d_issue = 0; }
+        return;
+      }
       if (tp.b < a.B && !(t.dbg & 2)) {
         const int in_x0 = tp.bx * t.OW - t.pad, in_y0 = tp.by * RO - t.pad;
         const bool from1 = p < planes1;
@@ -214,9 +238,19 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     }
     int s = 0;
     uint32_t sphase = 0, d_cur = 0, c = 0;
+    int r_slot = 0;
+    uint32_t r_phase = 0;                                                        // TMA: slot / parity of the chunk being converted
     const uint32_t dimg = (uint32_t)(lpx * 16 + (lane & 1) * 8 + warp * 512);   // this thread's first half-pixel in an image
+    // raw slot addressing of this thread's half-pixels: cp.async slots are thread-private ([u][half][thread] x 16 B), a TMA slot
+    // is the dense plane [row][32 px][8 ch]: row warp + 6 u, pixel lpx + 16 j, half (lane & 1) -> consecutive lanes still read
+    // consecutive 16-byte chunks
+    const uint32_t r_base = TMA ? (uint32_t)(warp * 1024 + lane * 16) : (uint32_t)(tid * 16);
+    const uint32_t r_u = TMA ? (uint32_t)(C3_PROD_WARPS * 1024) : (uint32_t)(2 * C3_PROD_THREADS * 16);
+    const uint32_t r_j = TMA ? 512u : (uint32_t)(C3_PROD_THREADS * 16);
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
       for (int p = 0; p < t.P; ++p, ++c) {
+        // TMA: the slot about to be refilled held chunk c - 1, which every producer thread has finished reading only now
+        if (TMA) named_bar_sync(1, C3_PROD_THREADS);
         issue(ahead, p_ahead);
         if (++p_ahead == t.P) { p_ahead = 0; ahead.advance(t); }
         uint8_t* stg = img_s + (size_t)s * t.in_bytes + dimg;
@@ -224,17 +258,22 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
           if (lane == 0) wait(&bar_empty[s], sphase ^ 1u);
           __syncwarp();
         }
-        // chunk c has landed once at most D - 1 newer groups are pending (D is 2..4)
-        if (t.D == 4) cp_async_wait<3>(); else if (t.D == 3) cp_async_wait<2>(); else cp_async_wait<1>();
-        const uint8_t* rsrc = raw_s + d_cur + tid * 16;
+        if (TMA) {
+          if (!(t.dbg & 2)) mbar_wait_short(&bar_raw[r_slot], r_phase);   // (every thread acquires the plane itself)
+          if (++r_slot == t.D) { r_slot = 0; r_phase ^= 1u; }
+        } else {
+          // chunk c has landed once at most D - 1 newer groups are pending (D is 2..4)
+          if (t.D == 4) cp_async_wait<3>(); else if (t.D == 3) cp_async_wait<2>(); else cp_async_wait<1>();
+        }
+        const uint8_t* rsrc = raw_s + d_cur + r_base;
         const bool relu = a.relu1 && p < planes1;
         // this thread's two half-pixels of every row: 4 channels each -> 8 bytes of the hi image + 8 bytes of the lo image
 #pragma unroll
         for (int u = 0; u < LDU; ++u) {
           if (warp + u * C3_PROD_WARPS < t.RI) {
             float4 q[2];
-            q[0] = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16));
-            q[1] = *reinterpret_cast<const float4*>(rsrc + u * (2 * C3_PROD_THREADS * 16) + C3_PROD_THREADS * 16);
+            q[0] = *reinterpret_cast<const float4*>(rsrc + u * r_u);
+            q[1] = *reinterpret_cast<const float4*>(rsrc + u * r_u + r_j);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               float4 v = q[j];
@@ -258,7 +297,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
         if (d_cur == (uint32_t)t.D * t.raw_bytes) d_cur = 0;
       }
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
   } else if (warp < C3_PROD_WARPS + C3_MMA_WARPS) {
     // =============================================================== MMA issuers (tiles mw, mw + 2, ...)
     const int mw = warp - C3_PROD_WARPS;
@@ -480,7 +519,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
   if (warp == 0) tmem_dealloc(tmem_base, t.tmem_cols);
 }
 
-bool c3_configure(const ConvArgs& a, C3Tile& t) {
+bool c3_configure(const ConvArgs& a, C3Tile& t, bool tma = false) {
   t.CP = a.coutp;
   if (!(t.CP == 8 || t.CP == 16 || t.CP == 32 || t.CP == 64)) return false;
   t.KS = a.kh; t.pad = a.pad_l; t.OW = 32 - (t.KS - 1); t.NI = t.KS + (t.KS + 1) / 2;
@@ -491,7 +530,9 @@ bool c3_configure(const ConvArgs& a, C3Tile& t) {
   t.P = (a.c1 + a.c2) / 8;
   t.plane_bytes = (uint32_t)t.RI * 512;
   t.in_bytes = 2 * t.plane_bytes;
-  t.raw_bytes = (uint32_t)((t.RI > 18 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);    // [u][half][thread] x 16 B, rows warp + 6 u
+  t.tma = tma ? 1 : 0;
+  // cp.async: [u][half][thread] x 16 B, rows warp + 6 u;  TMA: the dense plane [RI][32 px][8 ch] fp32
+  t.raw_bytes = tma ? (uint32_t)t.RI * 1024u : (uint32_t)((t.RI > 18 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);
   t.w_bytes = (uint32_t)t.NI * (uint32_t)t.N * 32;
   t.w_total = (uint32_t)t.P * t.w_bytes;
   t.n_ops = 0; t.ia = t.io = t.im = -1;
@@ -535,10 +576,20 @@ bool conv3_tc_supported(const ConvArgs& a) {
   return c3_configure(a, t);
 }
 
-int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
+int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int use_tma) {
   MSAU_CHECK_ARG(conv3_tc_supported(a), "conv3_tc: unsupported shape");
   C3Tile t;
-  MSAU_CHECK_ARG(c3_configure(a, t), "conv3_tc: tile does not fit");
+  { static int env = -2; if (env == -2) { const char* e = getenv("MSAU_C3_TMA"); env = e ? atoi(e) : -1; } if (env >= 0) use_tma = env; }
+  CUtensorMap tm1, tm2;
+  memset(&tm1, 0, sizeof(tm1));
+  memset(&tm2, 0, sizeof(tm2));
+  bool tma = use_tma != 0 && c3_configure(a, t, true);
+  if (tma) {
+    // {channel, x, y, page} maps of the two sources; box = one 8-channel halo plane of a super-tile
+    tma = make_tmap_nhwc_f32(&tm1, a.src1, a.p1, a.Win, a.Hin, a.B, 8, 32, t.RI) &&
+          (!a.c2 || make_tmap_nhwc_f32(&tm2, a.src2, a.p2, a.Win, a.Hin, a.B, 8, 32, t.RI));
+  }
+  if (!tma) MSAU_CHECK_ARG(c3_configure(a, t, false), "conv3_tc: tile does not fit");
   const size_t smem = (size_t)t.w_total + (size_t)t.stages * t.in_bytes + (size_t)t.D * t.raw_bytes + t.epi_bytes + 1024;
   const int grid = t.n_super < sm_count() ? t.n_super : sm_count();
   t.dgx = grid % t.blocks_x;
@@ -560,12 +611,13 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   }
   { static int gen = -1; if (gen < 0) { const char* e = getenv("MSAU_C3_GENERIC"); gen = e ? atoi(e) : 0; } if (gen) epi = 0; }
   const int ldu = t.RI > 18 ? 6 : 3;
-#define MSAU_C3_LAUNCH(E, L, K, PD)                                                                                                   \
+#define MSAU_C3_LAUNCH_T(E, L, K, PD, TM)                                                                                             \
   {                                                                                                                            \
     static bool attr = false;                                                                                                  \
-    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L, K, PD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
-    conv3_tc_kernel<E, L, K, PD><<<grid, C3_THREADS, smem, st>>>(a, wtc, t);                                                          \
+    if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L, K, PD, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
+    MSAU_CUDA_TRY(launch_pdl(conv3_tc_kernel<E, L, K, PD, TM>, dim3(grid), dim3(C3_THREADS), smem, st, a, wtc, t, tm1, tm2));             \
   }
+#define MSAU_C3_LAUNCH(E, L, K, PD) { if (tma) MSAU_C3_LAUNCH_T(E, L, K, PD, true) else MSAU_C3_LAUNCH_T(E, L, K, PD, false) }
 #define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3, 1) else MSAU_C3_LAUNCH(E, 3, 3, 1) }
 #define MSAU_C3_K4(E, PD) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 4, PD) else MSAU_C3_LAUNCH(E, 3, 4, PD) }
   if (t.KS == 4) {
@@ -583,6 +635,7 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
 #undef MSAU_C3_LDU
 #undef MSAU_C3_K4
 #undef MSAU_C3_LAUNCH
+#undef MSAU_C3_LAUNCH_T
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

@@ -321,7 +321,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
   __shared__ uint32_t tap_off16[16];           // smem offset of every tap, in 16-B units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this output
+  if (a.skip_flag) {                               // (the flag is written by the kernel just before: wait for it first)
+    pdl_wait();
+    if (*a.skip_flag == 0) return;                 // one-hot input: first_layer.cu produced this output
+  }
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -340,6 +343,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();        // PDL protocol (common.cuh): nothing above reads or writes activations
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t plane_bytes = (uint32_t)t.HH * t.HW * 16;       // one of {hi, lo}
   const int S = t.stages;
@@ -632,7 +637,7 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
   {                                                                                                                    \
     static bool attr = false;                                                                                          \
     if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<SM, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
-    conv_tc_kernel<SM, EG><<<grid, TC_THREADS, smem, st>>>(a, wtc, t);                                                 \
+    MSAU_CUDA_TRY(launch_pdl(conv_tc_kernel<SM, EG>, dim3(grid), dim3(TC_THREADS), smem, st, a, wtc, t));                \
   }
   if (general) {
     switch (src_mode) {

@@ -16,7 +16,8 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st);
 int launch_pack_tc(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st);
 // 3x3 / dilation-1 convolutions with the kx taps folded into the MMA N dimension (conv3_tc.cu)
 bool conv3_tc_supported(const ConvArgs& a);
-int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st);
+// use_tma: raw halo planes by TMA tensor loads (engine option "conv3_tma"; env MSAU_C3_TMA overrides)
+int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int use_tma = 1);
 int launch_pack_tc3(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st);
 bool wgrad_tc_supported(const WgradArgs& a);
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st);

@@ -18,6 +18,7 @@
 
 #include "../../include/msau_b200.h"
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace msau {
 
@@ -89,6 +90,54 @@ __global__ void __launch_bounds__(256) class_equals_kernel(const uint8_t* __rest
   }
 }
 
+// (class_map == cls) closed with a (1, sw) window (kv_model.py:175-176: r_closing(pred_class == c, (1, 3))) in ONE pass.
+// SciPy windows (origin 0): [x - sw/2, x - sw/2 + sw - 1], zeros outside the row -- for the dilation input AND for the erosion
+// input (the dilated row), which is what clears the closing's border columns.
+// A thread owns 16 pixels: one 16-byte load + the words before and after, then everything is bit arithmetic on a 24-bit row
+// segment (bit i <-> column x - 4 + i): sw <= 4 keeps every tap inside that segment.  Width must be a multiple of 16.
+__global__ void __launch_bounds__(256) class_closing_row_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, long total16,
+                                                                 int cls, int sw) {
+  const long q = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= total16) return;
+  const int W16 = W >> 4;
+  const long row = q / W16;
+  const int x = (int)(q - row * W16) << 4;
+  const uint8_t* src = in + row * W + x;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(src));
+  const uint32_t before = x > 0 ? __ldg(reinterpret_cast<const uint32_t*>(src - 4)) : 0u;
+  const uint32_t after = x + 16 < W ? __ldg(reinterpret_cast<const uint32_t*>(src + 16)) : 0u;
+  const uint32_t words[6] = {before, v.x, v.y, v.z, v.w, after};
+  const uint32_t c = (uint32_t)cls;
+  uint32_t eq = 0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (((words[k] >> (8 * b)) & 0xffu) == c) eq |= 1u << (4 * k + b);
+  // columns outside the row hold zeros (never equal to a foreground class by SciPy's constant mode: they are simply "not set")
+  uint32_t valid = 0x00ffffffu;
+  if (x == 0) valid &= ~0xfu;
+  if (x + 16 >= W) valid &= ~0x00f00000u;
+  eq &= valid;
+  const int c0 = -(sw / 2);
+  uint32_t dil = 0;
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (d < sw) { const int sft = c0 + d; dil |= sft >= 0 ? (eq >> sft) : (eq << -sft); }
+  dil &= valid;
+  uint32_t ero = 0xffffffffu;
+#pragma unroll
+  for (int d = 0; d < 4; ++d)
+    if (d < sw) { const int sft = c0 + d; ero &= sft >= 0 ? (dil >> sft) : (dil << -sft); }
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t n4 = (ero >> (4 + 4 * k)) & 0xfu;
+    o[k] = (n4 & 1u) | ((n4 & 2u) << 7) | ((n4 & 4u) << 14) | ((n4 & 8u) << 21);
+  }
+  *reinterpret_cast<uint4*>(out + row * W + x) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ------------------------------------------------------------------------------------------- CCL
 __device__ __forceinline__ int uf_find(const int32_t* L, int a) {
   int p = L[a];
@@ -130,7 +179,8 @@ __device__ __forceinline__ void suf_union(int* L, int a, int b) {
 
 // (1) tile-local labelling.  grid = (tiles_x, tiles_y, n_maps), 256 threads: warp w owns tile rows w, w + 8, ..., a lane two
 // adjacent 32-pixel halves of the row.  L[p] = global raster index of p's tile-local root, -1 for background.
-__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint8_t* __restrict__ bin, int32_t* __restrict__ L, int H, int W) {
+__global__ void __launch_bounds__(256) ccl_tile_kernel(const uint8_t* __restrict__ bin, int32_t* __restrict__ L, int H, int W,
+                                                        uint32_t* __restrict__ cand, int Wp) {
   __shared__ int lab[CT_PIX];
   __shared__ uint32_t rowbits[CT][2];
   const long npix = (long)H * W;
@@ -177,21 +227,27 @@ __global__ void __launch_bounds__(256) ccl_tile_kernel(const uint8_t* __restrict
     }
   }
   __syncthreads();
-  // pass 3: roots -> global indices
+  // pass 3: roots -> global indices; the tile-local roots are the only pixels that can still be roots after the border links:
+  // their positions go into a bitmap (one word per 32 pixels of a row, rows padded to Wp words) that the ranking kernels walk
+  // instead of the whole parent map
+  uint32_t* cm = cand + (long)blockIdx.z * H * Wp;
   for (int r = warp; r < CT; r += 8) {
     const int gy = y0 + r;
     if (gy >= H) break;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int gx = x0 + 32 * h + lane;
-      if (gx >= W) continue;
       const int i = r * CT + 32 * h + lane;
       int out = -1;
-      if (lab[i] >= 0) {
+      bool is_root = false;
+      if (gx < W && lab[i] >= 0) {
         const int root = suf_find(lab, i);
+        is_root = root == i;
         out = (y0 + (root >> 6)) * W + x0 + (root & (CT - 1));
       }
-      Lm[(long)gy * W + gx] = out;
+      const uint32_t bits = __ballot_sync(0xffffffffu, is_root);
+      if (gx < W) Lm[(long)gy * W + gx] = out;
+      if (lane == 0 && x0 + 32 * h < W) cm[(long)gy * Wp + ((x0 + 32 * h) >> 5)] = bits;
     }
   }
 }
@@ -221,20 +277,35 @@ __global__ void __launch_bounds__(256) ccl_border_kernel(const uint8_t* __restri
   }
 }
 
-// roots per 1024-pixel chunk
-__global__ void __launch_bounds__(1024) ccl_count_kernel(const int32_t* __restrict__ L, long npix, int nchunks, int32_t* __restrict__ counts) {
-  const int m = blockIdx.y, chunk = blockIdx.x;
-  const long p = (long)chunk * 1024 + threadIdx.x;
-  const bool root = p < npix && L[(long)m * npix + p] == (int32_t)p;
-  const unsigned bal = __ballot_sync(0xffffffffu, root);
-  __shared__ int ws[32];
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = __popc(bal);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int s = 0;
-    for (int i = 0; i < 32; ++i) s += ws[i];
-    counts[(long)m * (nchunks + 1) + chunk] = s;
+// (3) ranking.  A chunk = 32 consecutive words of the candidate bitmap (row-major, so chunk order and bit order are raster
+// order); a warp per chunk, a lane per word: the lane keeps the bits whose pixel is still a root (L[p] == p).
+__device__ __forceinline__ uint32_t ccl_true_roots(const int32_t* __restrict__ Lm, uint32_t bits, int y, int x0, int W) {
+  uint32_t keep = 0;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    const int p = y * W + x0 + b;
+    if (Lm[p] == p) keep |= 1u << b;
   }
+  return keep;
+}
+
+__global__ void __launch_bounds__(256) ccl_count_kernel(const int32_t* __restrict__ L, uint32_t* __restrict__ cand, long npix, int H, int W, int Wp,
+                                                         int nchunks, int32_t* __restrict__ counts) {
+  const int m = blockIdx.y;
+  const int chunk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (chunk >= nchunks) return;
+  const long w = (long)chunk * 32 + lane;
+  uint32_t keep = 0;
+  if (w < (long)H * Wp) {
+    const int y = (int)(w / Wp), wx = (int)(w - (long)y * Wp);
+    uint32_t* cw = cand + (long)m * H * Wp + w;
+    keep = ccl_true_roots(L + (long)m * npix, *cw, y, wx * 32, W);
+    *cw = keep;                                   // the rank kernel reads the verified bits
+  }
+  int c = __popc(keep);
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) counts[(long)m * (nchunks + 1) + chunk] = c;
 }
 
 // exclusive scan of the chunk counts of one map (one block per map); last slot = total
@@ -264,21 +335,28 @@ __global__ void __launch_bounds__(1024) ccl_scan_kernel(int32_t* __restrict__ co
 }
 
 // labels[root] = rank + 1
-__global__ void __launch_bounds__(1024) ccl_rank_kernel(const int32_t* __restrict__ L, long npix, int nchunks,
-                                                         const int32_t* __restrict__ counts, int32_t* __restrict__ labels) {
-  const int m = blockIdx.y, chunk = blockIdx.x;
-  const long p = (long)chunk * 1024 + threadIdx.x;
-  const bool root = p < npix && L[(long)m * npix + p] == (int32_t)p;
-  const unsigned bal = __ballot_sync(0xffffffffu, root);
-  __shared__ int ws[32];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) ws[wid] = __popc(bal);
-  __syncthreads();
-  if (root) {
-    int before = counts[(long)m * (nchunks + 1) + chunk];
-    for (int i = 0; i < wid; ++i) before += ws[i];
-    before += __popc(bal & ((1u << lane) - 1u));
-    labels[(long)m * npix + p] = before + 1;
+__global__ void __launch_bounds__(256) ccl_rank_kernel(const uint32_t* __restrict__ cand, long npix, int H, int W, int Wp, int nchunks,
+                                                        const int32_t* __restrict__ counts, int32_t* __restrict__ labels) {
+  const int m = blockIdx.y;
+  const int chunk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (chunk >= nchunks) return;
+  const long w = (long)chunk * 32 + lane;
+  uint32_t bits = w < (long)H * Wp ? cand[(long)m * H * Wp + w] : 0u;
+  // exclusive prefix of the per-lane counts inside the warp
+  const int mine = __popc(bits);
+  int incl = mine;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int rank = counts[(long)m * (nchunks + 1) + chunk] + incl - mine;
+  if (!bits) return;
+  const int y = (int)(w / Wp), x0 = (int)(w - (long)y * Wp) * 32;
+  int32_t* lab = labels + (long)m * npix;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    lab[y * W + x0 + b] = ++rank;
   }
 }
 
@@ -340,6 +418,7 @@ extern "C" int msau_rect_filter(const uint8_t* in, uint8_t* out, int n_maps, int
                  "rect_filter: invalid origin");
   const long total = (long)n_maps * height * width;
   count_launch(1);
+  ProfScope ps("rect_filter_kernel", 0, (double)total * 2.0, (cudaStream_t)stream);
   if (size_h == 1 && origin_h == 0 && size_w <= 8 && (width & 3) == 0 && ((uintptr_t)out & 3) == 0)
     rect_filter_row4_kernel<<<cdiv(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, out, width, total / 4, size_w, -(size_w / 2) - origin_w,
                                                                                    is_max);
@@ -350,9 +429,23 @@ extern "C" int msau_rect_filter(const uint8_t* in, uint8_t* out, int n_maps, int
   return MSAU_OK;
 }
 
+extern "C" int msau_class_closing_row(const uint8_t* class_map, uint8_t* out, int n_maps, int height, int width, int cls, int size_w,
+                                      void* stream) {
+  MSAU_CHECK_ARG(class_map && out && class_map != out && n_maps >= 1 && height >= 1 && width >= 1, "class_closing_row: bad argument");
+  MSAU_CHECK_ARG(size_w >= 1 && size_w <= 4 && (width & 15) == 0 && (((uintptr_t)out | (uintptr_t)class_map) & 15) == 0 && cls >= 0 && cls <= 255,
+                 "class_closing_row: window of 1..4 columns, width a multiple of 16, 16-byte aligned maps (use class_equals + rect_filter otherwise)");
+  const long total = (long)n_maps * height * width;
+  count_launch(1);
+  ProfScope ps("class_closing_row_kernel", 0, (double)total * 2.0, (cudaStream_t)stream);
+  class_closing_row_kernel<<<cdiv(total / 16, 256), 256, 0, (cudaStream_t)stream>>>(class_map, out, width, total / 16, cls, size_w);
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
 extern "C" int msau_class_equals(const uint8_t* class_map, uint8_t* out, long long n, int cls, void* stream) {
   MSAU_CHECK_ARG(class_map && out && n >= 1, "class_equals: bad argument");
   count_launch(1);
+  ProfScope ps("class_equals_kernel", 0, (double)n * 2.0, (cudaStream_t)stream);
   class_equals_kernel<<<cdiv(cdiv(n, 16), 256), 256, 0, (cudaStream_t)stream>>>(class_map, out, n, cls);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -364,19 +457,25 @@ extern "C" int msau_ccl4(const uint8_t* binary, int n_maps, int height, int widt
   MSAU_CHECK_ARG((long)height * width < INT_MAX, "ccl4: map too large");
   cudaStream_t st = (cudaStream_t)stream;
   const long npix = (long)height * width, total = npix * n_maps;
-  const int nchunks = cdiv(npix, 1024);
+  // scratch: parent map [total] | candidate-root bitmap [n_maps][H][Wp] | chunk counts [n_maps][nchunks + 1]
+  const int Wp = cdiv(width, 32);
+  const int nchunks = cdiv((long)height * Wp, 32);
   int32_t* L = scratch;
-  int32_t* counts = scratch + total;
+  uint32_t* cand = reinterpret_cast<uint32_t*>(scratch + total);
+  int32_t* counts = scratch + total + (long)n_maps * height * Wp;
   const int tiles_x = cdiv(width, CT), tiles_y = cdiv(height, CT);
   MSAU_CHECK_ARG(n_maps <= 65535 && tiles_y <= 65535, "ccl4: at most 65535 maps per call");
   count_launch(7);
-  ccl_tile_kernel<<<dim3(tiles_x, tiles_y, n_maps), 256, 0, st>>>(binary, L, height, width);
+  // algorithmic bytes of the labelling as a whole: binary map read (1 B) + int32 label map written (4 B) + the scratch
+  // parent map written and read once (4 + 4 B): DESIGN.md section 3
+  ProfScope ps("ccl_kernels", 0, (double)total * 13.0, st);
+  ccl_tile_kernel<<<dim3(tiles_x, tiles_y, n_maps), 256, 0, st>>>(binary, L, height, width, cand, Wp);
   if (tiles_x > 1 || tiles_y > 1)
     ccl_border_kernel<<<dim3(cdiv((long)tiles_x * height + (long)tiles_y * width, 256), 1, n_maps), 256, 0, st>>>(binary, L, height, width,
                                                                                                                  tiles_x, tiles_y);
-  ccl_count_kernel<<<dim3(nchunks, n_maps), 1024, 0, st>>>(L, npix, nchunks, counts);
+  ccl_count_kernel<<<dim3(cdiv(nchunks, 8), n_maps), 256, 0, st>>>(L, cand, npix, height, width, Wp, nchunks, counts);
   ccl_scan_kernel<<<n_maps, 1024, 0, st>>>(counts, nchunks, n_labels);
-  ccl_rank_kernel<<<dim3(nchunks, n_maps), 1024, 0, st>>>(L, npix, nchunks, counts, labels);
+  ccl_rank_kernel<<<dim3(cdiv(nchunks, 8), n_maps), 256, 0, st>>>(cand, npix, height, width, Wp, nchunks, counts, labels);
   if (bboxes && max_labels > 0) ccl_bbox_init_kernel<<<cdiv((long)n_maps * max_labels * 4, 256), 256, 0, st>>>(bboxes, (long)n_maps * max_labels * 4);
   ccl_relabel_kernel<<<cdiv(total, 256), 256, 0, st>>>(L, labels, height, width, total, (bboxes && max_labels > 0) ? bboxes : nullptr,
                                                       max_labels);

@@ -48,6 +48,14 @@ int sm_count() {
   return n;
 }
 
+static thread_local bool t_pdl_on = false;
+static thread_local int t_pdl_hold = 0;
+void pdl_set(bool enabled, int hold) { t_pdl_on = enabled; t_pdl_hold = hold; }
+bool pdl_take() {
+  if (t_pdl_hold > 0) { --t_pdl_hold; return false; }
+  return t_pdl_on;
+}
+
 std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -119,7 +127,8 @@ struct EngineOpts {
   int use_c3 = 1;        // conv3_fold: kx-folded 3x3 kernel (conv3_tc.cu) where it applies
   int c3_max = 16;       // conv3_max_channels: ... for at most this many output channels
   int lrn_coop = 1;      // 0 = thread-per-pixel LRN kernels only, 1 = lane-cooperative where it wins, 2 = from 8 channels up
-  int fuse_lrn = 1;      // fuse_lrn: LRN of a dilated first conv computed in that conv's epilogue (z1 and y1 written by one kernel)
+  int c3_tma = 1;        // conv3_tma: conv3_tc's raw halo planes by TMA tensor loads (0 = cp.async ring)
+  int pdl = 1;           // pdl: programmatic dependent launch of the hot kernels (prologue overlaps the predecessor's tail)
 };
 }  // namespace msau
 
@@ -361,7 +370,8 @@ static int set_opt(EngineOpts& o, const char* name, int value) {
   if (!strcmp(name, "fuse_relu_mask")) { o.fuse_mask = value != 0; return MSAU_OK; }
   if (!strcmp(name, "lrn_coop")) { o.lrn_coop = value; return MSAU_OK; }
   if (!strcmp(name, "conv3_max_channels")) { o.c3_max = value; return MSAU_OK; }
-  if (!strcmp(name, "fuse_lrn")) { o.fuse_lrn = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "pdl")) { o.pdl = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "conv3_tma")) { o.c3_tma = value != 0; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return MSAU_ERR_ARG;
 }
@@ -395,7 +405,7 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
   a.skip_flag = skip_flag;
   count_launch(1);
   if (p->opt.use_tc && p->opt.use_pw && k == 1 && conv1x1_supported(a)) return launch_conv1x1(a, p->st);
-  if (p->opt.use_tc && p->opt.use_c3 && t3_off >= 0 && coutp <= p->opt.c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st);
+  if (p->opt.use_tc && p->opt.use_c3 && t3_off >= 0 && coutp <= p->opt.c3_max && conv3_tc_supported(a)) return launch_conv3_tc(a, p->pktc + t3_off, p->st, p->opt.c3_tma);
   if (p->opt.use_tc && tc_off >= 0 && conv_tc_supported(a)) return launch_conv_tc(a, p->pktc + tc_off, p->st);
   if (p->opt.use_tc && tc_off >= 0 && coutp == 256) {     // two launches over the two halves of the output channels (add_tc)
     ConvArgs h0 = a;
@@ -899,6 +909,9 @@ extern "C" int msau_forward(MsauPlan* p, const float* x, int x_layout, const flo
     }
   }
 
+  // the two launches after the packing kernels stay fully serialised (a PDL prologue reads packed weights: see common.cuh)
+  pdl_set(p->opt.pdl != 0, 2);
+  struct PdlOff { ~PdlOff() { pdl_set(false, 0); } } pdl_off;
   for (int b = 0; b < NB; ++b) {
     Block& blk = p->blocks[b];
     Block* prev = b > 0 ? &p->blocks[b - 1] : nullptr;
@@ -1025,6 +1038,8 @@ extern "C" int msau_loss_backward_ex(MsauPlan* p, const float* x, int x_layout, 
     p->wst = p->side;
   }
   const long npp = (long)p->H * p->W;
+  pdl_set(p->opt.pdl != 0, 0);
+  struct PdlOff { ~PdlOff() { pdl_set(false, 0); } } pdl_off;
   {
     Block& last = p->blocks[NB - 1];
     Block& auxb = p->blocks[NB - 2];

@@ -26,6 +26,8 @@ __device__ __forceinline__ float pow_m075(float d) {
 
 template <int C>
 __global__ void __launch_bounds__(256) lrn_fwd_kernel(const float* __restrict__ z, float* __restrict__ y, long npix) {
+  pdl_wait();        // PDL protocol (common.cuh)
+  pdl_trigger();
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   float v[C];
@@ -60,6 +62,8 @@ __global__ void __launch_bounds__(256) lrn_fwd_kernel(const float* __restrict__ 
 template <int C>
 __global__ void __launch_bounds__(256) lrn_bwd_kernel(const float* __restrict__ z, const float* __restrict__ gy,
                                                        float* __restrict__ gz, long npix) {
+  pdl_wait();        // PDL protocol (common.cuh)
+  pdl_trigger();
   const long pix = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   float v[C], g[C];
@@ -169,6 +173,8 @@ __device__ __forceinline__ float seg_inclusive(float v, int j) {
 template <int C, bool BWD, int UNR>
 __global__ void __launch_bounds__(256) lrn_coop_kernel(const float4* __restrict__ z, const float4* __restrict__ gy, float4* __restrict__ out,
                                                         long nquad) {
+  pdl_wait();        // PDL protocol (common.cuh)
+  pdl_trigger();
   constexpr int LP = C / 4, HALF = LP / 2;
   constexpr unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -240,8 +246,8 @@ static void lrn_coop_launch(const float* z, const float* gy, float* out, long np
   long blocks = (nchunk + 7) / 8;
   const long cap = (long)sm_count() * 16;
   if (blocks > cap) blocks = cap;
-  lrn_coop_kernel<C, BWD, UNR><<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(gy),
-                                                                 reinterpret_cast<float4*>(out), nquad);
+  launch_pdl(lrn_coop_kernel<C, BWD, UNR>, dim3((unsigned)blocks), dim3(256), 0, st, reinterpret_cast<const float4*>(z),
+             reinterpret_cast<const float4*>(gy), reinterpret_cast<float4*>(out), nquad);
 }
 
 template <bool BWD>
@@ -271,8 +277,8 @@ static int lrn_dispatch(const float* z, const float* gy, float* out, long npix, 
   }
 #define MSAU_LRN(CV)                                                             \
   case CV:                                                                       \
-    if (BWD) lrn_bwd_kernel<CV><<<grid, 256, 0, st>>>(z, gy, out, npix);         \
-    else lrn_fwd_kernel<CV><<<grid, 256, 0, st>>>(z, out, npix);                 \
+    if (BWD) launch_pdl(lrn_bwd_kernel<CV>, dim3(grid), dim3(256), 0, st, z, gy, out, npix); \
+    else launch_pdl(lrn_fwd_kernel<CV>, dim3(grid), dim3(256), 0, st, z, out, npix);         \
     break;
   switch (C) {
     MSAU_LRN(4) MSAU_LRN(8) MSAU_LRN(16) MSAU_LRN(32) MSAU_LRN(64)
@@ -291,6 +297,8 @@ int launch_lrn_bwd(const float* z, const float* gy, float* gz, long npix, int C,
 // ------------------------------------------------------------------------------------------- pool
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W,
                                                         int Ho, int Wo, int C4) {
+  pdl_wait();        // PDL protocol (common.cuh)
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Ho * Wo * C4;
   if (idx >= total) return;
@@ -327,6 +335,8 @@ __device__ __forceinline__ void pool_route(float a, float b, float c, float d, f
 // (g * (x > 0), what relu_mask_kernel would do in a separate pass) is applied here, where x is in registers anyway
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gx,
                                                         int B, int H, int W, int Ho, int Wo, int C4, int accumulate, int relu_mask) {
+  pdl_wait();        // PDL protocol (common.cuh)
+  pdl_trigger();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Ho * Wo * C4;
   if (idx >= total) return;
@@ -379,7 +389,7 @@ int launch_pool_fwd(const float* x, float* y, int B, int H, int W, int C, cudaSt
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long total = (long)B * Ho * Wo * (C / 4);
   ProfScope ps("pool_fwd_kernel", 0, ((double)B * H * W + (double)B * Ho * Wo) * C * 4.0, st);
-  pool_fwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, y, B, H, W, Ho, Wo, C / 4);
+  launch_pdl(pool_fwd_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, x, y, B, H, W, Ho, Wo, C / 4);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }
@@ -388,7 +398,7 @@ int launch_pool_bwd(const float* x, const float* gy, float* gx, int B, int H, in
   const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
   const long total = (long)B * Ho * Wo * (C / 4);
   ProfScope ps("pool_bwd_kernel", C, C, 0, 0, W, accumulate, 0, ((double)B * H * W * (accumulate ? 3 : 2) + (double)B * Ho * Wo) * C * 4.0, st);
-  pool_bwd_kernel<<<cdiv(total, 256), 256, 0, st>>>(x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate, relu_mask);
+  launch_pdl(pool_bwd_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, x, gy, gx, B, H, W, Ho, Wo, C / 4, accumulate, relu_mask);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

@@ -13,6 +13,7 @@
 //   one-hot to_categorical          inference/generic_util.py:94-95 (+ transposes kv_model.py:274-278)
 #include "../../include/msau_b200.h"
 #include "common.cuh"
+#include "prof.cuh"
 
 namespace msau {
 
@@ -361,6 +362,9 @@ extern "C" int msau_raster_features(const double* x, const double* y, const doub
     feature_owner_kernel<<<cdiv(n_boxes, 8), 256, 0, st>>>(x, y, w, h, page_ptr, n_pages, n_boxes, char_ptr, geom, use_min_scale,
                                                            out_h, out_w, owner_scratch);
   const int32_t* row_of = char_ptr ? char_feat : feat_row;
+  // algorithmic bytes: owner map read (4 B / pixel) + the grid written in its stored dtype
+  ProfScope ps(layout == 2 ? "feature_ids_kernel" : (layout == 0 ? "feature_fill_nchw_kernel" : "feature_fill_nhwc_kernel"), 0,
+               (double)total * (4.0 + (layout == 2 ? 2.0 : 4.0 * (layout == 0 ? feat_dim : round_up(feat_dim, 4)))), st);
   if (layout == 2) {
     feature_ids_kernel<<<cdiv(total, 256), 256, 0, st>>>(owner_scratch, row_of, total, reinterpret_cast<int16_t*>(grid));
   } else if (layout == 0) {
@@ -384,6 +388,7 @@ extern "C" int msau_raster_labels(const double* x, const double* y, const double
   if (n_boxes > 0)
     feature_owner_kernel<<<cdiv(n_boxes, 8), 256, 0, st>>>(x, y, w, h, page_ptr, n_pages, n_boxes, nullptr, geom, 0, out_h, out_w,
                                                            owner_scratch);
+  ProfScope ps("label_fill_kernel", 0, (double)total * 5.0, st);
   label_fill_kernel<<<cdiv(total, 256), 256, 0, st>>>(owner_scratch, labels, total, label_mask);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
@@ -409,6 +414,7 @@ extern "C" int msau_raster_kv(const double* boxes, const int32_t* page_ptr, int 
   if (n_lines > 0)
     kv_owner_kernel<<<cdiv(n_lines, 8), 256, 0, st>>>(boxes, page_ptr, n_pages, n_lines, char_ptr, geom3, out_h, out_w, owner_scratch,
                                                       owner_scratch + total, scaled_boxes);
+  ProfScope ps("kv_fill_kernel", 0, (double)total * (8.0 + 6.0), st);
   kv_fill_kernel<<<cdiv(total, 256), 256, 0, st>>>(owner_scratch, owner_scratch + total, page_ptr, char_ptr, char_ids, n_lines, npix,
                                                    total, input_mask, line_mask, char_mask);
   MSAU_CUDA_TRY(cudaGetLastError());
@@ -421,6 +427,7 @@ extern "C" int msau_one_hot(const uint16_t* ids, int n_pages, int height, int wi
   cudaStream_t st = (cudaStream_t)stream;
   const long npix = (long)height * width, total = npix * n_pages;
   count_launch(1);
+  ProfScope ps("one_hot_kernel", 0, (double)total * (2.0 + 4.0 * (layout == 0 ? n_token : round_up(n_token, 4))), st);
   if (layout == 0) {
     one_hot_kernel<0><<<cdiv(total, 256), 256, 0, st>>>(ids, npix, total, n_token, 0, out);
   } else {

@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   const int tile0 = blockIdx.x * t.tiles_per_cta;
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const bool do_bias = a.dbias != nullptr && plane == 0;
-  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
+  if (a.skip_flag) {                               // (the flag is written by an earlier kernel of this step: wait for it first)
+    pdl_wait();
+    if (*a.skip_flag == 0) return;                 // one-hot input: first_layer.cu produced this gradient
+  }
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -150,6 +153,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();        // PDL protocol (common.cuh): nothing above reads or writes activations / gradients
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_s;
   if (tile0 >= tile1) {       // nothing to do (grid rounding): still free TMEM
     __syncthreads();
@@ -396,7 +401,10 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
   const int tile0 = blockIdx.x * t.tiles_per_cta;
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const bool do_bias = a.dbias != nullptr && plane == 0;
-  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
+  if (a.skip_flag) {                               // (the flag is written by an earlier kernel of this step: wait for it first)
+    pdl_wait();
+    if (*a.skip_flag == 0) return;                 // one-hot input: first_layer.cu produced this gradient
+  }
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -413,6 +421,8 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();        // PDL protocol (common.cuh): nothing above reads or writes activations / gradients
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_s;
   if (tile0 >= tile1) {
     __syncthreads();
@@ -701,8 +711,8 @@ static int launch_wgrad_tc2(const WgradArgs& a, const Wg2Tile& t0, cudaStream_t 
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb) * (a.maskB ? 2 : 1)) * 4.0;
   ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc2_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
-  if (a.a_nchw) wgrad_tc2_kernel<true><<<grid, WG_THREADS, smem, st>>>(a, t);
-  else wgrad_tc2_kernel<false><<<grid, WG_THREADS, smem, st>>>(a, t);
+  if (a.a_nchw) MSAU_CUDA_TRY(launch_pdl(wgrad_tc2_kernel<true>, grid, dim3(WG_THREADS), smem, st, a, t));
+  else MSAU_CUDA_TRY(launch_pdl(wgrad_tc2_kernel<false>, grid, dim3(WG_THREADS), smem, st, a, t));
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }
@@ -768,7 +778,10 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const int n_my = tile1 - tile0;
   const bool do_bias = a.dbias != nullptr && plane == 0;
-  if (a.skip_flag && *a.skip_flag == 0) return;   // one-hot input: first_layer.cu produced this gradient
+  if (a.skip_flag) {                               // (the flag is written by an earlier kernel of this step: wait for it first)
+    pdl_wait();
+    if (*a.skip_flag == 0) return;                 // one-hot input: first_layer.cu produced this gradient
+  }
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
@@ -784,6 +797,8 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();        // PDL protocol (common.cuh): nothing above reads or writes activations / gradients
+  pdl_trigger();
   const uint32_t tmem_base = tmem_base_s;
   uint8_t* const stage_s = smem;                               // 2 x [X image | dY image] (bf16)
   uint8_t* const raw_s = smem + (size_t)t.S * t.stage_bytes;     // D x raw fp32 slots
@@ -1079,7 +1094,7 @@ static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t 
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * a.ca + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb)) * 4.0;
   ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc3_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, 2, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
-  wgrad_tc3_kernel<<<grid, WG3_THREADS, smem, st>>>(a, t);
+  MSAU_CUDA_TRY(launch_pdl(wgrad_tc3_kernel, grid, dim3(WG3_THREADS), smem, st, a, t));
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }
@@ -1171,7 +1186,7 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + npq * a.cb * (a.maskB ? 2 : 1)) * 4.0;
   ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
-  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(a, t);
+  MSAU_CUDA_TRY(launch_pdl(wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, a, t));
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }

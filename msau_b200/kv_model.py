@@ -112,7 +112,7 @@ class KVModel:
         Returns {c: (closed uint8 [n,H,W], labels int32 [n,H,W], n_labels int32 [n], bboxes int32 [n,max_labels,4])}."""
         out = {}
         for c in range(2, n_class):
-            closed = morph.closing_batch(morph.class_equals(pred_class, c), size)
+            closed = morph.class_closing_batch(pred_class, c, size)
             labels, n_labels, bboxes = morph.ccl_batch(closed, max_labels)
             out[c] = (closed, labels, n_labels, bboxes)
         return out

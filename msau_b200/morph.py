@@ -50,6 +50,22 @@ def closing_batch(maps: torch.Tensor, size) -> torch.Tensor:
     return rect_filter_batch(rect_filter_batch(maps, size, 0, True), size, 0, False)
 
 
+def class_closing_batch(class_map: torch.Tensor, cls: int, size) -> torch.Tensor:
+    """r_closing(pred_class == cls, size) of kv_model.py:175-176 for a batch of uint8 class maps [n, H, W].  Row windows (1, k <= 4)
+    on maps whose width is a multiple of 16 run as ONE kernel that reads the class map once; anything else falls back to
+    class_equals + dilation + erosion."""
+    assert class_map.is_cuda and class_map.dtype == torch.uint8 and class_map.dim() == 3
+    sh, sw = _pair(size)
+    n, H, W = class_map.shape
+    class_map = class_map.contiguous()
+    if sh != 1 or sw > 4 or W % 16 or class_map.data_ptr() % 16:
+        return closing_batch(class_equals(class_map, cls), size)
+    out = torch.empty_like(class_map)
+    with torch.cuda.device(class_map.device):
+        _lib.check(_lib.lib().msau_class_closing_row(class_map.data_ptr(), out.data_ptr(), n, H, W, int(cls), sw, _lib.current_stream()))
+    return out
+
+
 def class_equals(class_map: torch.Tensor, cls: int) -> torch.Tensor:
     """(class_map == cls) as uint8 0/1 -- kv_model.py:175."""
     assert class_map.is_cuda and class_map.dtype == torch.uint8
@@ -70,7 +86,8 @@ def ccl_batch(binary: torch.Tensor, max_labels: int = 4096):
     labels = torch.empty((n, H, W), dtype=torch.int32, device=dev)
     n_labels = torch.empty((n,), dtype=torch.int32, device=dev)
     bboxes = torch.empty((n, max_labels, 4), dtype=torch.int32, device=dev)
-    scratch = torch.empty((n * H * W + n * ((H * W + 1023) // 1024 + 2),), dtype=torch.int32, device=dev)
+    wp = (W + 31) // 32
+    scratch = torch.empty((n * H * W + n * H * wp + n * ((H * wp + 31) // 32 + 2),), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().msau_ccl4(binary.data_ptr(), n, H, W, labels.data_ptr(), n_labels.data_ptr(), bboxes.data_ptr(),
                                         max_labels, scratch.data_ptr(), _lib.current_stream()))

@@ -280,6 +280,11 @@ def test_ccl_batch_against_scipy_full_size():
     t = torch.from_numpy(maps).cuda()
     for c in (2, 3, 4):
         closed = morph.closing_batch(morph.class_equals(t, c), (1, 3))
+        # the one-pass (class == c) + closing kernel the inference driver uses gives the same map, also for even windows
+        assert torch.equal(closed, morph.class_closing_batch(t, c, (1, 3)))
+        if c == 2:
+            for sw in (1, 2, 4, 5, 8):
+                assert torch.equal(morph.closing_batch(morph.class_equals(t[:8], c), (1, sw)), morph.class_closing_batch(t[:8], c, (1, sw)))
         labels, n_labels, bboxes = morph.ccl_batch(closed)
         lab = labels.cpu().numpy(); nl = n_labels.cpu().numpy(); bb = bboxes.cpu().numpy(); cl = closed.cpu().numpy()
         for i in range(maps.shape[0]):
