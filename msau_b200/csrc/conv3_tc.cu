@@ -42,10 +42,16 @@ namespace {
 constexpr int C3_PROD_WARPS = 6;
 constexpr int C3_PROD_THREADS = C3_PROD_WARPS * 32;
 constexpr int C3_MMA_WARPS = 2;
-constexpr int C3_EPI_WARPS = 8;
+#ifndef MSAU_C3_EPI_WARPS
+#define MSAU_C3_EPI_WARPS 8       // measured: 16 epilogue warps are slower (117 vs 104 us at 8 -> 8 channels / 512^2): the shared-memory pipe, not latency, is the limit
+#endif
+constexpr int C3_EPI_WARPS = MSAU_C3_EPI_WARPS;      // a multiple of 4: C3_EPI_SUBS warps share each TMEM lane quarter (= tile row)
+constexpr int C3_EPI_SUBS = C3_EPI_WARPS / 4;
+constexpr int C3_EPI_HALF = C3_EPI_WARPS * 32 * 16;  // bytes of one 16-byte operand half over all epilogue threads
+constexpr int C3_EPI_OP = 2 * C3_EPI_HALF;           // ... of one 8-channel operand
 constexpr int C3_THREADS = (C3_PROD_WARPS + C3_MMA_WARPS + C3_EPI_WARPS) * 32;
 constexpr int C3_MAX_STAGES = 3;
-constexpr int C3_SLOTS = 4;          // epilogue work items per thread and super-tile
+constexpr int C3_SLOTS = (8 + C3_EPI_SUBS - 1) / C3_EPI_SUBS;   // epilogue work items per thread and super-tile (a super-tile has <= 8)
 
 struct C3Tile {
   int KS, pad, OW, NI;                // kernel size (3 or 4), SAME padding before, output columns per block (32 - KS + 1), MMAs per tile-plane
@@ -55,7 +61,7 @@ struct C3Tile {
   int n_ops, ia, io, im;              // extra epilogue operands and their slot index (-1 = absent)
   int dbg;
   int tma;                            // raw halo planes arrive by TMA tensor loads (dense [row][32 px][8 ch] slots) instead of cp.async
-  uint32_t plane_bytes, in_bytes, w_bytes, w_total, raw_bytes, epi_bytes, tmem_cols;
+  uint32_t plane_bytes, in_bytes, w_bytes, w_total, w_copy, raw_bytes, epi_bytes, tmem_cols;   // w_total: w_copy rounded up to 1 KB (slot alignment)
 };
 
 // position of a super-tile, advanced by gridDim.x super-tiles at a time without integer division
@@ -133,13 +139,17 @@ __device__ __forceinline__ void mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_
 template <int EPI, int LDU, int KS, int PAD, bool TMA>
 __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs a, const uint16_t* __restrict__ wtc, const C3Tile t,
                                                                  const __grid_constant__ CUtensorMap tm1,
-                                                                 const __grid_constant__ CUtensorMap tm2) {
+                                                                 const __grid_constant__ CUtensorMap tm2,
+                                                                 const __grid_constant__ CUtensorMap tmA,
+                                                                 const __grid_constant__ CUtensorMap tmO,
+                                                                 const __grid_constant__ CUtensorMap tmM) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_full[C3_MAX_STAGES];    // producers -> MMA : stage holds one plane (image + weights)
   __shared__ uint64_t bar_empty[C3_MAX_STAGES];   // MMA -> producers : the MMAs reading the stage have retired
   __shared__ uint64_t bar_acc_full[4];            // MMA -> epilogue  : accumulator set complete
   __shared__ uint64_t bar_acc_empty[4];           // epilogue -> MMA  : accumulator set drained
   __shared__ uint64_t bar_raw[4];                 // TMA -> producers : raw plane of a chunk has landed (transaction bytes)
+  __shared__ uint64_t bar_epi[C3_EPI_WARPS][C3_SLOTS];   // TMA -> one epilogue warp : extra operands of its work item k have landed
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[64];
 
@@ -152,12 +162,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
   uint8_t* const img_s = smem + t.w_total;
   uint8_t* const raw_s = img_s + (size_t)t.stages * t.in_bytes;
   uint8_t* const epi = raw_s + (size_t)t.D * t.raw_bytes;
-  for (int e = tid; e < (int)(t.w_total >> 4); e += C3_THREADS)
+  for (int e = tid; e < (int)(t.w_copy >> 4); e += C3_THREADS)
     reinterpret_cast<uint4*>(w_s)[e] = __ldg(reinterpret_cast<const uint4*>(wtc) + e);
   fence_async_smem();
   if (tid == 32) {
     for (int i = 0; i < C3_MAX_STAGES; ++i) { mbar_init(&bar_full[i], C3_PROD_WARPS); mbar_init(&bar_empty[i], C3_MMA_WARPS); }
     for (int i = 0; i < 4; ++i) { mbar_init(&bar_acc_full[i], C3_MMA_WARPS); mbar_init(&bar_acc_empty[i], C3_EPI_WARPS); mbar_init(&bar_raw[i], 1); }
+    if (TMA)
+      for (int i = 0; i < C3_EPI_WARPS * C3_SLOTS; ++i) mbar_init(&bar_epi[0][0] + i, 1);
     mbar_init_fence();
     if (TMA) { tma_prefetch_desc(&tm1); if (a.c2) tma_prefetch_desc(&tm2); }
   }
@@ -355,22 +367,24 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     constexpr bool G = EPI == 0;
     const int ew = warp - (C3_PROD_WARPS + C3_MMA_WARPS);   // 0..7
     const int q = warp & 3;                                  // TMEM lane quarter = tile row
-    const int sub = ew >> 2;
+    const int sub = ew >> 2;                                // 0 .. C3_EPI_SUBS-1
     const int chunks = t.CP >> 3;                            // 1, 2, 4 or 8
     const int lc = 31 - __clz(chunks);
     const int total_items = t.T << lc;                       // <= 8: item kg -> (tile kg >> lc, channel chunk kg & (chunks-1))
     const int et = ew * 32 + lane;                           // epilogue thread index 0..255
     const uint32_t epi_u32 = smem_u32(epi);
-    const uint32_t slot_stride = (uint32_t)(G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0))) * 8192u;  // bytes between consecutive items' slots
+    const uint32_t slot_stride = (uint32_t)(G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0))) * (uint32_t)C3_EPI_OP;  // bytes between consecutive items' slots
     const uint32_t my_slot = (uint32_t)et * 16u;
     const bool lane_ok = lane >= t.pad && lane < t.pad + t.OW;
     const int tile_pix = 4 * a.Wout;                         // pixel distance between consecutive tiles (4 rows)
     // position of a super-tile for this thread: pixel index of its tile-0 output, first output row, column validity
-    struct Pos { int pix; int row; bool ok; };                // (32-bit: every tensor here has < 2^31 elements)
+    struct Pos { int pix; int row; bool ok; int x0; int b; };   // (32-bit: every tensor here has < 2^31 elements)
     auto decode = [&](const TilePos& tp) -> Pos {
       Pos ps;
-      if (tp.b >= a.B) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; return ps; }
-      const int ox = tp.bx * t.OW - t.pad + lane;
+      if (tp.b >= a.B) { ps.pix = 0; ps.row = 1 << 29; ps.ok = false; ps.x0 = 0; ps.b = -1; return ps; }
+      ps.x0 = tp.bx * t.OW - t.pad;                          // column of lane 0 (warp-uniform; may be -1 / -2: zero-filled by TMA)
+      ps.b = tp.b;
+      const int ox = ps.x0 + lane;
       ps.row = tp.by * RO + q;
       ps.ok = lane_ok && ox < a.Wout;
       ps.pix = (tp.b * a.Hout + ps.row) * a.Wout + ox;
@@ -388,27 +402,50 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     const int n_ops = G ? t.n_ops : ((EPI == 3 || EPI == 4) ? 1 : (EPI == 5 ? 2 : 0));
     const float* pa = f_res ? a.res : a.add;
     const int ppa = f_res ? a.pr : a.pa;
+    // TMA variant: the extras of (this warp's tile row, item k) are ONE 1 KB box per operand -- [32 columns][8 channels] fp32 of
+    // the row, written with the 32-byte swizzle (the two 16-byte halves of the pixels 4..7 of every 8 swap places), which makes
+    // the per-lane 16-byte reads below bank-conflict free -- issued by lane 0 and completed on this warp's own mbarrier.
+    // (The cp.async form costs 8x the ideal shared-memory wavefronts: every lane's 16 bytes arrive as their own sector.)
+    const uint32_t wslot = (uint32_t)ew * 1024u;               // TMA: this warp's 1 KB inside an operand block
+    const uint32_t tslot_stride = (uint32_t)n_ops * (uint32_t)C3_EPI_OP;
+    const uint32_t rd0 = (uint32_t)((lane * 32) ^ (((lane >> 2) & 1) << 4)), rd1 = rd0 ^ 16u;   // this lane's two halves in a box
     auto prefetch = [&](const Pos& ps, int k) {
       // extras of work item k of that super-tile -> this thread's slots (one cp.async group per item, possibly empty)
-      const int kg = sub + 2 * k;
+      const int kg = sub + C3_EPI_SUBS * k;
       const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
+      if (TMA) {
+        if (n_ops > 0 && ps.b >= 0 && kg < total_items && !(t.dbg & 8)) {     // warp-uniform; rows past the image are zero-filled
+          __syncwarp();                                          // every lane is done with slot k
+          if (lane == 0) {
+            const uint32_t dst = epi_u32 + (uint32_t)k * tslot_stride + wslot;
+            uint64_t* bar = &bar_epi[ew][k];
+            const int row = ps.row + 4 * tile;
+            fence_async_smem();
+            mbar_arrive_expect_tx(bar, (uint32_t)n_ops * 1024u);
+            if (ia >= 0) tma_load_4d(dst + (uint32_t)ia * (uint32_t)C3_EPI_OP, &tmA, ch8, ps.x0, row, ps.b, bar);
+            if (io >= 0) tma_load_4d(dst + (uint32_t)io * (uint32_t)C3_EPI_OP, &tmO, ch8, ps.x0, row, ps.b, bar);
+            if (im >= 0) tma_load_4d(dst + (uint32_t)im * (uint32_t)C3_EPI_OP, &tmM, ch8, ps.x0, row, ps.b, bar);
+          }
+        }
+        return;
+      }
       if (n_ops > 0 && ps.ok && kg < total_items && ps.row + 4 * tile < a.Hout && !(t.dbg & 8)) {
         const int pix = ps.pix + tile * tile_pix;
         const uint32_t dst = epi_u32 + (uint32_t)k * slot_stride + my_slot;
         if (ia >= 0) {
           const float* ap = pa + (long)(pix * ppa + ch8);
-          cp_async16(dst + (uint32_t)ia * 8192u, ap);
-          cp_async16(dst + (uint32_t)ia * 8192u + 4096u, ap + 4);
+          cp_async16(dst + (uint32_t)ia * (uint32_t)C3_EPI_OP, ap);
+          cp_async16(dst + (uint32_t)ia * (uint32_t)C3_EPI_OP + (uint32_t)C3_EPI_HALF, ap + 4);
         }
         if (io >= 0) {
           const float* op = a.out + (long)(pix * a.po + ch8);
-          cp_async16(dst + (uint32_t)io * 8192u, op);
-          cp_async16(dst + (uint32_t)io * 8192u + 4096u, op + 4);
+          cp_async16(dst + (uint32_t)io * (uint32_t)C3_EPI_OP, op);
+          cp_async16(dst + (uint32_t)io * (uint32_t)C3_EPI_OP + (uint32_t)C3_EPI_HALF, op + 4);
         }
         if (im >= 0) {
           const float* mp = a.omask + (long)(pix * a.pom + ch8);
-          cp_async16(dst + (uint32_t)im * 8192u, mp);
-          cp_async16(dst + (uint32_t)im * 8192u + 4096u, mp + 4);
+          cp_async16(dst + (uint32_t)im * (uint32_t)C3_EPI_OP, mp);
+          cp_async16(dst + (uint32_t)im * (uint32_t)C3_EPI_OP + (uint32_t)C3_EPI_HALF, mp + 4);
         }
       }
       cp_async_commit();
@@ -417,7 +454,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
 #pragma unroll
     for (int k = 0; k < C3_SLOTS; ++k) prefetch(cur, k);
 
-    uint32_t as = 0, aphase = 0;
+    uint32_t as = 0, aphase = 0, eph = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
       tp.advance(t);
       const Pos nxt = decode(tp);
@@ -427,8 +464,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < C3_SLOTS; ++k) {
-        const int kg = sub + 2 * k;
-        cp_async_wait<C3_SLOTS - 1>();                         // this item's extras have landed
+        const int kg = sub + C3_EPI_SUBS * k;
+        if (TMA) {
+          if (n_ops > 0 && kg < total_items && !(t.dbg & 8)) mbar_wait_short(&bar_epi[ew][k], eph);
+        } else {
+          cp_async_wait<C3_SLOTS - 1>();                       // this item's extras have landed
+        }
         if (kg < total_items) {                                // warp-uniform
           const int tile = kg >> lc, ch8 = (kg & (chunks - 1)) << 3;
           float vk[KS][8];
@@ -468,11 +509,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
             }
             // out = mask( relu2( relu(acc + bias) + res ) ) + add + previous
-            const uint8_t* slot = epi + (uint32_t)k * slot_stride + my_slot;
+            // cp.async: [operand][half][thread] x 16 B; TMA: [operand][warp][32 px x 32 B, 32-byte swizzle]
+            const uint8_t* slot = TMA ? epi + (uint32_t)k * tslot_stride + wslot + rd0 : epi + (uint32_t)k * slot_stride + my_slot;
+            const int h1 = TMA ? (int)rd1 - (int)rd0 : C3_EPI_HALF;            // distance to the second half (+-16 when swizzled)
             float ev[8];
             if (ia >= 0) {
-              const float4 e0 = *reinterpret_cast<const float4*>(slot + ia * 8192);
-              const float4 e1 = *reinterpret_cast<const float4*>(slot + ia * 8192 + 4096);
+              const float4 e0 = *reinterpret_cast<const float4*>(slot + ia * C3_EPI_OP);
+              const float4 e1 = *reinterpret_cast<const float4*>(slot + ia * C3_EPI_OP + h1);
               ev[0] = e0.x; ev[1] = e0.y; ev[2] = e0.z; ev[3] = e0.w; ev[4] = e1.x; ev[5] = e1.y; ev[6] = e1.z; ev[7] = e1.w;
               if (f_res) {
 #pragma unroll
@@ -484,8 +527,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               for (int i = 0; i < 8; ++i) r[i] = fmaxf(r[i], 0.f);
             }
             if (im >= 0) {
-              const float4 m0 = *reinterpret_cast<const float4*>(slot + im * 8192);
-              const float4 m1 = *reinterpret_cast<const float4*>(slot + im * 8192 + 4096);
+              const float4 m0 = *reinterpret_cast<const float4*>(slot + im * C3_EPI_OP);
+              const float4 m1 = *reinterpret_cast<const float4*>(slot + im * C3_EPI_OP + h1);
               const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
               for (int i = 0; i < 8; ++i) r[i] = mv[i] > 0.f ? r[i] : 0.f;
@@ -495,8 +538,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
               for (int i = 0; i < 8; ++i) r[i] += ev[i];
             }
             if (io >= 0) {
-              const float4 p0 = *reinterpret_cast<const float4*>(slot + io * 8192);
-              const float4 p1 = *reinterpret_cast<const float4*>(slot + io * 8192 + 4096);
+              const float4 p0 = *reinterpret_cast<const float4*>(slot + io * C3_EPI_OP);
+              const float4 p1 = *reinterpret_cast<const float4*>(slot + io * C3_EPI_OP + h1);
               r[0] += p0.x; r[1] += p0.y; r[2] += p0.z; r[3] += p0.w; r[4] += p1.x; r[5] += p1.y; r[6] += p1.z; r[7] += p1.w;
             }
             float4* dst = reinterpret_cast<float4*>(a.out + (long)((cur.pix + tile * tile_pix) * a.po + ch8));
@@ -511,8 +554,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
       if (lane == 0) mbar_arrive(&bar_acc_empty[as]);
       if (++as == (uint32_t)t.A) { as = 0; aphase ^= 1u; }
       cur = nxt;
+      eph ^= 1u;
     }
-    cp_async_wait<0>();
+    if (!TMA) cp_async_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -534,13 +578,14 @@ bool c3_configure(const ConvArgs& a, C3Tile& t, bool tma = false) {
   // cp.async: [u][half][thread] x 16 B, rows warp + 6 u;  TMA: the dense plane [RI][32 px][8 ch] fp32
   t.raw_bytes = tma ? (uint32_t)t.RI * 1024u : (uint32_t)((t.RI > 18 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);
   t.w_bytes = (uint32_t)t.NI * (uint32_t)t.N * 32;
-  t.w_total = (uint32_t)t.P * t.w_bytes;
+  t.w_copy = (uint32_t)t.P * t.w_bytes;
+  t.w_total = (t.w_copy + 1023u) / 1024u * 1024u;
   t.n_ops = 0; t.ia = t.io = t.im = -1;
   if (a.res || a.add) t.ia = t.n_ops++;
   if (a.accumulate) t.io = t.n_ops++;
   if (a.omask) t.im = t.n_ops++;
-  const int items = (t.T * (t.CP >> 3) + 1) / 2;              // epilogue work items per thread and super-tile
-  t.epi_bytes = (uint32_t)(items * t.n_ops * 2 * 4096);
+  const int items = (t.T * (t.CP >> 3) + C3_EPI_SUBS - 1) / C3_EPI_SUBS;   // epilogue work items per thread and super-tile
+  t.epi_bytes = (uint32_t)(items * t.n_ops * C3_EPI_OP);
   t.stages = C3_MAX_STAGES; t.D = 4;
   auto total = [&]() { return (size_t)t.w_total + (size_t)t.stages * t.in_bytes + (size_t)t.D * t.raw_bytes + t.epi_bytes; };
   while (total() > 216 * 1024 && (t.D > 2 || t.stages > 2)) {
@@ -580,14 +625,22 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int
   MSAU_CHECK_ARG(conv3_tc_supported(a), "conv3_tc: unsupported shape");
   C3Tile t;
   { static int env = -2; if (env == -2) { const char* e = getenv("MSAU_C3_TMA"); env = e ? atoi(e) : -1; } if (env >= 0) use_tma = env; }
-  CUtensorMap tm1, tm2;
+  CUtensorMap tm1, tm2, tmA, tmO, tmM;
   memset(&tm1, 0, sizeof(tm1));
   memset(&tm2, 0, sizeof(tm2));
+  memset(&tmA, 0, sizeof(tmA));
+  memset(&tmO, 0, sizeof(tmO));
+  memset(&tmM, 0, sizeof(tmM));
   bool tma = use_tma != 0 && c3_configure(a, t, true);
   if (tma) {
     // {channel, x, y, page} maps of the two sources; box = one 8-channel halo plane of a super-tile
     tma = make_tmap_nhwc_f32(&tm1, a.src1, a.p1, a.Win, a.Hin, a.B, 8, 32, t.RI) &&
           (!a.c2 || make_tmap_nhwc_f32(&tm2, a.src2, a.p2, a.Win, a.Hin, a.B, 8, 32, t.RI));
+    // epilogue operands: one image row of a tile (32 columns x 8 channels) per box, 32-byte swizzle
+    const float* pa = a.res ? a.res : a.add;
+    if (tma && pa) tma = make_tmap_nhwc_f32(&tmA, pa, a.res ? a.pr : a.pa, a.Wout, a.Hout, a.B, 8, 32, 1, true);
+    if (tma && a.accumulate) tma = make_tmap_nhwc_f32(&tmO, a.out, a.po, a.Wout, a.Hout, a.B, 8, 32, 1, true);
+    if (tma && a.omask) tma = make_tmap_nhwc_f32(&tmM, a.omask, a.pom, a.Wout, a.Hout, a.B, 8, 32, 1, true);
   }
   if (!tma) MSAU_CHECK_ARG(c3_configure(a, t, false), "conv3_tc: tile does not fit");
   const size_t smem = (size_t)t.w_total + (size_t)t.stages * t.in_bytes + (size_t)t.D * t.raw_bytes + t.epi_bytes + 1024;
@@ -615,7 +668,7 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int
   {                                                                                                                            \
     static bool attr = false;                                                                                                  \
     if (!attr) { MSAU_CUDA_TRY(cudaFuncSetAttribute(conv3_tc_kernel<E, L, K, PD, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; } \
-    MSAU_CUDA_TRY(launch_pdl(conv3_tc_kernel<E, L, K, PD, TM>, dim3(grid), dim3(C3_THREADS), smem, st, a, wtc, t, tm1, tm2));             \
+    MSAU_CUDA_TRY(launch_pdl(conv3_tc_kernel<E, L, K, PD, TM>, dim3(grid), dim3(C3_THREADS), smem, st, a, wtc, t, tm1, tm2, tmA, tmO, tmM)); \
   }
 #define MSAU_C3_LAUNCH(E, L, K, PD) { if (tma) MSAU_C3_LAUNCH_T(E, L, K, PD, true) else MSAU_C3_LAUNCH_T(E, L, K, PD, false) }
 #define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3, 1) else MSAU_C3_LAUNCH(E, 3, 3, 1) }

@@ -125,7 +125,7 @@ struct EngineOpts {
   int fuse_mask = 1;     // fuse_relu_mask: gradient writers apply the ReLU mask of the tensor they feed
   int use_pw = 1;        // pointwise_conv: 1x1 convs of the narrow levels on the fp32 streaming kernel (conv1x1.cu)
   int use_c3 = 1;        // conv3_fold: kx-folded 3x3 kernel (conv3_tc.cu) where it applies
-  int c3_max = 16;       // conv3_max_channels: ... for at most this many output channels
+  int c3_max = 32;       // conv3_max_channels: ... for at most this many output channels (32: +1.3 % per step since the TMA raw ring; 64 does not fit)
   int lrn_coop = 1;      // 0 = thread-per-pixel LRN kernels only, 1 = lane-cooperative where it wins, 2 = from 8 channels up
   int c3_tma = 1;        // conv3_tma: conv3_tc's raw halo planes by TMA tensor loads (0 = cp.async ring)
   int pdl = 1;           // pdl: programmatic dependent launch of the hot kernels (prologue overlaps the predecessor's tail)

@@ -8,5 +8,7 @@
 
 namespace msau {
 // false (with set_error) when the driver entry point is missing or the encode call rejects the shape
-bool make_tmap_nhwc_f32(CUtensorMap* out, const float* base, int pitch, int W, int H, int B, int box_c, int box_w, int box_h);
+// swizzle32: CU_TENSOR_MAP_SWIZZLE_32B (byte address bit 7 XORed into bit 4 inside shared memory; box_c * 4 must be 32 bytes)
+bool make_tmap_nhwc_f32(CUtensorMap* out, const float* base, int pitch, int W, int H, int B, int box_c, int box_w, int box_h,
+                        bool swizzle32 = false);
 }  // namespace msau

@@ -1125,7 +1125,12 @@ static bool wg_config(const WgradArgs& a, WgTile& t, size_t& smem, int& ctas_out
   t.tiles_y = cdiv(a.Hq, t.TR);
   t.n_tiles = t.tiles_x * t.tiles_y * a.B;
   const int planes = a.ca >> 3;
-  int ctas = (2 * sm_count() + planes - 1) / planes;
+  // CTAs per SM (x the channel planes): the tiles of a CTA run back to back with one tile of look-ahead, so several resident CTAs
+  // are what hides the load -> convert -> issue latency on the small maps this kernel serves (env MSAU_WG_PER_SM for experiments)
+  static int per_sm_env = -1;
+  if (per_sm_env < 0) { const char* e = getenv("MSAU_WG_PER_SM"); per_sm_env = e ? atoi(e) : 0; }
+  const int per_sm = per_sm_env > 0 ? per_sm_env : 2;
+  int ctas = (per_sm * sm_count() + planes - 1) / planes;
   if (ctas > t.n_tiles) ctas = t.n_tiles;
   if (ctas < 1) ctas = 1;
   t.tiles_per_cta = cdiv(t.n_tiles, ctas);
