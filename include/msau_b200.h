@@ -266,6 +266,8 @@ int msau_profile_report(char* h_buf, size_t capacity);
 /* Debugging aids used by the parity tests: workspace layout = [packed weights | activations |
  * activation gradients (training) | scratch], all in floats; tensor `id` (allocation order) lives at
  * activations + off as [B, H, W, C] fp32. */
+/* conv3_tc role timers (env MSAU_TC_DEBUG=32): 16 cycle counters summed over the launches since the last call (conv3_tc.cu) */
+int msau_debug_c3_prof(unsigned long long* h_counters16);
 int msau_debug_layout(const MsauPlan* plan, long long* packed_floats, long long* act_floats, int* n_tensors);
 int msau_debug_tensor(const MsauPlan* plan, int id, long long* off, int* channels, int* height, int* width);
 

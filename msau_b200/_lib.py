@@ -20,7 +20,7 @@ SYMBOLS = [
     "msau_raster_geometry", "msau_raster_features", "msau_raster_labels",
     "msau_raster_kv_geometry", "msau_raster_kv", "msau_one_hot",
     "msau_rect_filter", "msau_class_equals", "msau_class_closing_row", "msau_ccl4", "msau_kv_select_components", "msau_kv_char_range",
-    "msau_debug_layout", "msau_debug_tensor", "msau_profile_enable", "msau_profile_report",
+    "msau_debug_layout", "msau_debug_tensor", "msau_debug_c3_prof", "msau_profile_enable", "msau_profile_report",
     "msau_set_option",
     "msau_attention_scratch_bytes", "msau_attention_forward", "msau_attention_backward",
 ]
@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.msau_ccl4.argtypes = [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     L.msau_kv_select_components.argtypes = [vp, vp, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp]
     L.msau_kv_char_range.argtypes = [vp, vp, i32, i32, vp, i32, vp, vp]
+    L.msau_debug_c3_prof.argtypes = [C.POINTER(C.c_ulonglong)]
     L.msau_debug_layout.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     L.msau_debug_tensor.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.msau_set_option.argtypes = [C.c_char_p, i32]

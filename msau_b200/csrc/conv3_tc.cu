@@ -37,6 +37,9 @@ namespace msau {
 
 using namespace ptx;
 
+// MSAU_TC_DEBUG bit 32: per-role wait / work cycle counters (lane 0 of every warp), read back by msau_debug_c3_prof
+__device__ unsigned long long g_c3_prof[16];
+
 namespace {
 
 constexpr int C3_PROD_WARPS = 6;
@@ -181,6 +184,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
   const uint32_t tmem_base = tmem_base_s;
   const int S = t.stages;
   const bool spin = !(t.dbg & 16);
+  const bool prof = (t.dbg & 32) != 0;
+  unsigned long long pc[4] = {0, 0, 0, 0};
+  const long long t_start = prof ? clock64() : 0;
+#define C3_TIMED(slot, stmt) { if (prof) { const long long _t0 = clock64(); stmt; pc[slot] += (unsigned long long)(clock64() - _t0); } else { stmt; } }
   auto wait = [&](uint64_t* bar, uint32_t parity) { if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); };
   const int RO = 4 * t.T;                                     // output rows per super-tile
 
@@ -262,16 +269,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x) {
       for (int p = 0; p < t.P; ++p, ++c) {
         // TMA: the slot about to be refilled held chunk c - 1, which every producer thread has finished reading only now
-        if (TMA) named_bar_sync(1, C3_PROD_THREADS);
+        if (TMA) C3_TIMED(3, named_bar_sync(1, C3_PROD_THREADS));
         issue(ahead, p_ahead);
         if (++p_ahead == t.P) { p_ahead = 0; ahead.advance(t); }
         uint8_t* stg = img_s + (size_t)s * t.in_bytes + dimg;
         if (c >= (uint32_t)S) {
-          if (lane == 0) wait(&bar_empty[s], sphase ^ 1u);
+          if (lane == 0) C3_TIMED(0, wait(&bar_empty[s], sphase ^ 1u));
           __syncwarp();
         }
         if (TMA) {
-          if (!(t.dbg & 2)) mbar_wait_short(&bar_raw[r_slot], r_phase);   // (every thread acquires the plane itself)
+          if (!(t.dbg & 2)) C3_TIMED(1, mbar_wait_short(&bar_raw[r_slot], r_phase));   // (every thread acquires the plane itself)
           if (++r_slot == t.D) { r_slot = 0; r_phase ^= 1u; }
         } else {
           // chunk c has landed once at most D - 1 newer groups are pending (D is 2..4)
@@ -324,13 +331,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     int s = 0;
     for (int st_i = blockIdx.x; st_i < t.n_super; st_i += gridDim.x, ++tcount) {
       if (tcount >= (uint32_t)t.A) {
-        if (lane == 0) wait(&bar_acc_empty[as], aphase ^ 1u);
+        if (lane == 0) C3_TIMED(1, wait(&bar_acc_empty[as], aphase ^ 1u));
         __syncwarp();
       }
       tc_fence_after();
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N);
       for (int p = 0; p < t.P; ++p) {
-        if (lane == 0) wait(&bar_full[s], sphase);
+        if (lane == 0) C3_TIMED(0, wait(&bar_full[s], sphase));
         __syncwarp();
         tc_fence_after();
         const uint32_t in16 = smem_u32(img_s + (size_t)s * t.in_bytes) >> 4;
@@ -459,14 +466,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
       tp.advance(t);
       const Pos nxt = decode(tp);
       const uint32_t acc_base = tmem_base + as * (uint32_t)(t.T * t.N) + ((uint32_t)(q * 32) << 16);
-      if (lane == 0) wait(&bar_acc_full[as], aphase);
+      if (lane == 0) C3_TIMED(0, wait(&bar_acc_full[as], aphase));
       __syncwarp();
       tc_fence_after();
 #pragma unroll
       for (int k = 0; k < C3_SLOTS; ++k) {
         const int kg = sub + C3_EPI_SUBS * k;
         if (TMA) {
-          if (n_ops > 0 && kg < total_items && !(t.dbg & 8)) mbar_wait_short(&bar_epi[ew][k], eph);
+          if (n_ops > 0 && kg < total_items && !(t.dbg & 8)) C3_TIMED(1, mbar_wait_short(&bar_epi[ew][k], eph));
         } else {
           cp_async_wait<C3_SLOTS - 1>();                       // this item's extras have landed
         }
@@ -558,6 +565,18 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     }
     if (!TMA) cp_async_wait<0>();
   }
+  if (prof && lane == 0) {
+    // role base: producers 0.., MMA 4.., epilogue 8..; slot 3 of each block = the warp's total resident cycles
+    const int role = warp < C3_PROD_WARPS ? 0 : (warp < C3_PROD_WARPS + C3_MMA_WARPS ? 4 : 8);
+    pc[role == 0 ? 2 : 3] += 0;
+    const unsigned long long total = (unsigned long long)(clock64() - t_start);
+    atomicAdd(&g_c3_prof[role + 0], pc[0]);
+    atomicAdd(&g_c3_prof[role + 1], pc[1]);
+    atomicAdd(&g_c3_prof[role + 2], role == 0 ? pc[3] : total);
+    if (role == 0) atomicAdd(&g_c3_prof[3], total);
+    if (warp == 0) atomicAdd(&g_c3_prof[12], 1ull);
+  }
+#undef C3_TIMED
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, t.tmem_cols);
@@ -569,6 +588,7 @@ bool c3_configure(const ConvArgs& a, C3Tile& t, bool tma = false) {
   t.KS = a.kh; t.pad = a.pad_l; t.OW = 32 - (t.KS - 1); t.NI = t.KS + (t.KS + 1) / 2;
   t.N = round_up(t.KS * t.CP, 16);
   t.T = 8 / (t.CP >> 3);
+  { static int tmax = -1; if (tmax < 0) { const char* e = getenv("MSAU_C3_TMAX"); tmax = e ? atoi(e) : 0; } if (tmax > 0 && t.T > tmax) t.T = tmax; }
   while (t.T > 1 && 4 * (t.T / 2) >= a.Hout) t.T /= 2;       // short maps: do not pay for rows that do not exist
   t.RI = 4 * t.T + t.KS - 1;
   t.P = (a.c1 + a.c2) / 8;
@@ -587,6 +607,10 @@ bool c3_configure(const ConvArgs& a, C3Tile& t, bool tma = false) {
   const int items = (t.T * (t.CP >> 3) + C3_EPI_SUBS - 1) / C3_EPI_SUBS;   // epilogue work items per thread and super-tile
   t.epi_bytes = (uint32_t)(items * t.n_ops * C3_EPI_OP);
   t.stages = C3_MAX_STAGES; t.D = 4;
+  { static int dmax = -1, smax = -1;
+    if (dmax < 0) { const char* e = getenv("MSAU_C3_DMAX"); dmax = e ? atoi(e) : 0; const char* f = getenv("MSAU_C3_SMAX"); smax = f ? atoi(f) : 0; }
+    if (dmax > 0 && t.D > dmax) t.D = dmax;
+    if (smax > 0 && t.stages > smax) t.stages = smax; }
   auto total = [&]() { return (size_t)t.w_total + (size_t)t.stages * t.in_bytes + (size_t)t.D * t.raw_bytes + t.epi_bytes; };
   while (total() > 216 * 1024 && (t.D > 2 || t.stages > 2)) {
     if (t.D > 2 && t.D >= t.stages) --t.D; else --t.stages;
@@ -619,6 +643,18 @@ bool conv3_tc_supported(const ConvArgs& a) {
   if (a.Win < 8 || a.Hin < 2) return false;
   C3Tile t;
   return c3_configure(a, t);
+}
+
+// MSAU_TC_DEBUG=32: cycles summed over lane 0 of every warp of every conv3_tc launch since the last call:
+// [0] producer wait stage-free  [1] producer wait raw plane  [2] producer named barrier  [3] producer warp total
+// [4] MMA wait operands  [5] MMA wait accumulator  [6] MMA warp total  [8] epilogue wait accumulator  [9] epilogue wait extras
+// [10] epilogue warp total  [12] CTAs
+int debug_c3_prof(unsigned long long* h16) {
+  MSAU_CUDA_TRY(cudaDeviceSynchronize());
+  MSAU_CUDA_TRY(cudaMemcpyFromSymbol(h16, g_c3_prof, sizeof(unsigned long long) * 16));
+  unsigned long long z[16] = {0};
+  MSAU_CUDA_TRY(cudaMemcpyToSymbol(g_c3_prof, z, sizeof(z)));
+  return MSAU_OK;
 }
 
 int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int use_tma) {

@@ -18,6 +18,7 @@ int launch_pack_tc(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, i
 bool conv3_tc_supported(const ConvArgs& a);
 // use_tma: raw halo planes by TMA tensor loads (engine option "conv3_tma"; env MSAU_C3_TMA overrides)
 int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int use_tma = 1);
+int debug_c3_prof(unsigned long long* h16);
 int launch_pack_tc3(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st);
 bool wgrad_tc_supported(const WgradArgs& a);
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st);

@@ -1246,6 +1246,11 @@ extern "C" int msau_attention_backward(const float* fg, const float* hh, const f
 
 // ---- debugging aids (tests/test_model_gpu.py compares every internal activation / activation gradient
 //      with the oracle's traced forward); not part of the reference-facing surface ----
+extern "C" int msau_debug_c3_prof(unsigned long long* h_counters16) {
+  MSAU_CHECK_ARG(h_counters16, "debug_c3_prof: null argument");
+  return debug_c3_prof(h_counters16);
+}
+
 extern "C" int msau_debug_layout(const MsauPlan* p, long long* packed_floats, long long* act_floats, int* n_tensors) {
   MSAU_CHECK_ARG(p, "debug_layout: null plan");
   if (packed_floats) *packed_floats = p->packed_floats + ((p->tc_elems + 1) / 2 + 63) / 64 * 64;
