@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmsau_b200.so")
+LIB_PATH = os.environ.get("MSAU_LIB_PATH") or os.path.join(_HERE, "lib", "libmsau_b200.so")   # (env override: kernel A/B builds)
 
 SYMBOLS = [
     "msau_last_error", "msau_version", "msau_launch_count", "msau_launch_count_add",

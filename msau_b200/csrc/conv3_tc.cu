@@ -184,10 +184,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
   const uint32_t tmem_base = tmem_base_s;
   const int S = t.stages;
   const bool spin = !(t.dbg & 16);
+#ifdef MSAU_C3_PROF      // role timers: build with -DMSAU_C3_PROF and run with MSAU_TC_DEBUG=32 (scripts/c3_roles.py)
   const bool prof = (t.dbg & 32) != 0;
   unsigned long long pc[4] = {0, 0, 0, 0};
   const long long t_start = prof ? clock64() : 0;
 #define C3_TIMED(slot, stmt) { if (prof) { const long long _t0 = clock64(); stmt; pc[slot] += (unsigned long long)(clock64() - _t0); } else { stmt; } }
+#else
+#define C3_TIMED(slot, stmt) { stmt; }
+#endif
   auto wait = [&](uint64_t* bar, uint32_t parity) { if (spin) mbar_wait_spin(bar, parity); else mbar_wait(bar, parity); };
   const int RO = 4 * t.T;                                     // output rows per super-tile
 
@@ -565,6 +569,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     }
     if (!TMA) cp_async_wait<0>();
   }
+#ifdef MSAU_C3_PROF
   if (prof && lane == 0) {
     // role base: producers 0.., MMA 4.., epilogue 8..; slot 3 of each block = the warp's total resident cycles
     const int role = warp < C3_PROD_WARPS ? 0 : (warp < C3_PROD_WARPS + C3_MMA_WARPS ? 4 : 8);
@@ -576,6 +581,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) conv3_tc_kernel(const ConvArgs 
     if (role == 0) atomicAdd(&g_c3_prof[3], total);
     if (warp == 0) atomicAdd(&g_c3_prof[12], 1ull);
   }
+#endif
 #undef C3_TIMED
   tc_fence_before();
   __syncthreads();
@@ -645,7 +651,7 @@ bool conv3_tc_supported(const ConvArgs& a) {
   return c3_configure(a, t);
 }
 
-// MSAU_TC_DEBUG=32: cycles summed over lane 0 of every warp of every conv3_tc launch since the last call:
+// built with -DMSAU_C3_PROF and run with MSAU_TC_DEBUG=32: cycles summed over lane 0 of every warp of every conv3_tc launch since the last call:
 // [0] producer wait stage-free  [1] producer wait raw plane  [2] producer named barrier  [3] producer warp total
 // [4] MMA wait operands  [5] MMA wait accumulator  [6] MMA warp total  [8] epilogue wait accumulator  [9] epilogue wait extras
 // [10] epilogue warp total  [12] CTAs

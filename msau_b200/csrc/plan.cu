@@ -72,6 +72,11 @@ struct ConvLayer {
   long pk_w = -1, pk_b = -1, pk_d1 = -1, pk_d2 = -1;    // packed: fwd weights, bias, dgrad wrt src1 / src2
   long tc_w = -1, tc_d1 = -1, tc_d2 = -1;               // bf16 tensor-core weight images (bf16 element offsets)
   long t3_w = -1, t3_d1 = -1, t3_d2 = -1;               // same for the kx-folded 3x3 kernel (conv3_tc.cu)
+  // dilation >= map size in both directions (the deepest levels of the S5 / S6 models: dilation 16 / 32 on <= 16 x 16 maps):
+  // every tap but the centre reads SAME padding only, so the layer IS a 1x1 conv with the centre-tap weights (tc images of that
+  // slab: tc_wc / tc_dc) and only the centre tap has a weight gradient -- the other 8 are exactly zero
+  bool center = false;
+  long tc_wc = -1, tc_dc = -1;
   int pad() const { return ((k - 1) * dil) / 2; }       // SAME "before" padding, model/layers/utils.py:13-18
 };
 
@@ -427,6 +432,9 @@ static int conv_same(MsauPlan* p, const float* src1, int c1, int p1, int nchw, i
 }
 
 static int layer_fwd(MsauPlan* p, const ConvLayer& L, const Tensor& s1, const Tensor* s2, const Tensor& out, const ConvOpt& o) {
+  if (L.center)      // centre tap only (see ConvLayer::center): a 1x1 conv on the centre slab of the packed weights
+    return conv_same(p, p->A(s1), L.c1p, s1.C, 0, L.c1p, nullptr, 0, 0, p->pk + L.pk_w + 4L * (L.c1p + L.c2p) * L.coutp, p->pk + L.pk_b,
+                     p->A(out), out.C, L.coutp, out.H, out.W, 1, 1, 0, o, L.tc_wc, -1);
   return conv_same(p, p->A(s1), L.c1p, s1.C, 0, L.c1p, s2 ? p->A(*s2) : nullptr, s2 ? L.c2p : 0, s2 ? s2->C : 0, p->pk + L.pk_w,
                    p->pk + L.pk_b, p->A(out), out.C, L.coutp, out.H, out.W, L.k, L.dil, L.pad(), o, L.tc_w, L.t3_w);
 }
@@ -439,6 +447,9 @@ static int layer_dgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   if (pkd < 0) { set_error("internal: dgrad weights missing"); return MSAU_ERR_ARG; }
   o.mask1 = dymask; o.pm1 = pm;
   o.accumulate = p->touch(dst);
+  if (L.center && which == 1)
+    return conv_same(p, dy, L.coutp, pdy, 0, L.coutp, nullptr, 0, 0, p->pk + pkd + 4L * L.coutp * cs, nullptr, p->G(dst), dst.C, cs, dst.H, dst.W,
+                     1, 1, 0, o, L.tc_dc, -1);
   const int padd = (L.k - 1) * L.dil - L.pad();
   return conv_same(p, dy, L.coutp, pdy, 0, L.coutp, nullptr, 0, 0, p->pk + pkd, nullptr, p->G(dst), dst.C, cs, dst.H, dst.W, L.k,
                    L.dil, padd, o, which == 1 ? L.tc_d1 : L.tc_d2, which == 1 ? L.t3_d1 : L.t3_d2);
@@ -472,6 +483,10 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
   a.skip_flag = skip_flag;
+  if (L.center) {     // only the centre tap (index 4 of the 3x3) sees anything but padding
+    a.kh = a.kw = 1; a.dila = 1; a.pada_t = a.pada_l = 0;
+    a.dW += 4;
+  }
   if (p->opt.use_tc && a.cb == 256 && cb < 0 && !wgrad_tc_supported(a)) {
     // the tensor-core kernels take up to 128 output channels: run the two halves of a 256-channel dY separately
     WgradArgs h = a;
@@ -748,6 +763,12 @@ extern "C" int msau_plan_create(const MsauConfig* cfg, int batch, int height, in
       const int cin = l == 0 ? cin0 : (cfg->feat_root << (l - 1));
       // blocks >= 1 read the previous block's logits, stored with pitch lp
       setup_conv(p, blk.down[l].conv1, f, cin, 0, 3, 1 << l, !(b == 0 && l == 0), false, (b > 0 && l == 0) ? p->lp : 0);
+      ConvLayer& K1 = blk.down[l].conv1;
+      if (l > 0 && (1 << l) >= p->Hl[l] && (1 << l) >= p->Wl[l]) {
+        K1.center = true;
+        K1.tc_wc = add_tc(p, K1.pk_w + 4L * (K1.c1p + K1.c2p) * K1.coutp, 1, K1.c1p + K1.c2p, K1.coutp);
+        if (K1.pk_d1 >= 0) K1.tc_dc = add_tc(p, K1.pk_d1 + 4L * K1.coutp * K1.c1p, 1, K1.coutp, K1.c1p);
+      }
     }
     if (b > 0)
       for (int l = 0; l < S; ++l) {

@@ -119,7 +119,10 @@ struct WgTile {
 };
 
 static constexpr int WG_THREADS = 256;
-static constexpr int WU = 4;          // pixels whose global loads are in flight per thread
+#ifndef MSAU_WG_WU
+#define MSAU_WG_WU 4
+#endif
+static constexpr int WU = MSAU_WG_WU;   // pixels whose global loads are in flight per thread
 
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a, const WgTile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
