@@ -136,7 +136,7 @@ __device__ __forceinline__ void mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_
 
 
 // EPI: 0 = epilogue driven by run-time flags; 1 = bias; 2 = bias + ReLU; 3 = bias + residual + ReLU; 4 = ReLU mask; 5 = ReLU mask + add
-// LDU: raw pixels per producer thread and plane (3: T <= 4 tiles, 6: T = 8)
+// LDU: halo rows per producer warp and plane (6: T = 8 tiles, the 8-channel levels; 3: T = 4, 16 channels; 2: T <= 2, 32 channels)
 // TMA: the raw fp32 halo plane of a chunk is ONE cp.async.bulk.tensor load issued by one thread (map tm1 / tm2 = src1 / src2 as
 //      {channel, x, y, page}; out-of-image pixels zero-filled by the hardware = SAME padding), completion on an mbarrier
 template <int EPI, int LDU, int KS, int PAD, bool TMA>
@@ -602,7 +602,7 @@ bool c3_configure(const ConvArgs& a, C3Tile& t, bool tma = false) {
   t.in_bytes = 2 * t.plane_bytes;
   t.tma = tma ? 1 : 0;
   // cp.async: [u][half][thread] x 16 B, rows warp + 6 u;  TMA: the dense plane [RI][32 px][8 ch] fp32
-  t.raw_bytes = tma ? (uint32_t)t.RI * 1024u : (uint32_t)((t.RI > 18 ? 6 : 3) * 2 * C3_PROD_THREADS * 16);
+  t.raw_bytes = tma ? (uint32_t)t.RI * 1024u : (uint32_t)((t.RI > 18 ? 6 : (t.RI > 12 ? 3 : 2)) * 2 * C3_PROD_THREADS * 16);
   t.w_bytes = (uint32_t)t.NI * (uint32_t)t.N * 32;
   t.w_copy = (uint32_t)t.P * t.w_bytes;
   t.w_total = (t.w_copy + 1023u) / 1024u * 1024u;
@@ -694,7 +694,9 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int
   const double npix = (double)a.B * a.Hin * a.Win;
   double bytes = npix * (a.c1 + a.c2) * 4.0;
   bytes += npix * a.coutp * 4.0 * (1 + (a.res ? 1 : 0) + (a.omask ? 1 : 0) + (a.add ? 1 : 0) + (a.accumulate ? 1 : 0));
-  ProfScope ps("conv3_tc_kernel", a.c1 + a.c2, a.coutp, a.kh, 1, a.Wout, (a.relu1 ? 2 : 0) + (general ? 1 : 0),
+  // (the 32-channel launches -- maps <= 128^2, latency-sized, on conv_tc until round 2 -- are booked as their own row, so that
+  //  the 8/16-channel family stays the launch set round 1 reported)
+  ProfScope ps(a.coutp >= 32 ? "conv3_tc_kernel_c32" : "conv3_tc_kernel", a.c1 + a.c2, a.coutp, a.kh, 1, a.Wout, (a.relu1 ? 2 : 0) + (general ? 1 : 0),
                2.0 * npix * a.kh * a.kw * (a.c1 + a.c2) * a.coutp, bytes, st);
   // epilogue specialisation (the flag-driven variant covers everything else, e.g. accumulation into a touched gradient)
   int epi = 0;
@@ -705,7 +707,7 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int
     else if (!bias && a.omask && !a.res && !a.relu && !a.relu2) epi = a.add ? 5 : 4;
   }
   { static int gen = -1; if (gen < 0) { const char* e = getenv("MSAU_C3_GENERIC"); gen = e ? atoi(e) : 0; } if (gen) epi = 0; }
-  const int ldu = t.RI > 18 ? 6 : 3;
+  const int ldu = t.RI > 18 ? 6 : (t.RI > 12 ? 3 : 2);
 #define MSAU_C3_LAUNCH_T(E, L, K, PD, TM)                                                                                             \
   {                                                                                                                            \
     static bool attr = false;                                                                                                  \
@@ -713,7 +715,7 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int
     MSAU_CUDA_TRY(launch_pdl(conv3_tc_kernel<E, L, K, PD, TM>, dim3(grid), dim3(C3_THREADS), smem, st, a, wtc, t, tm1, tm2, tmA, tmO, tmM)); \
   }
 #define MSAU_C3_LAUNCH(E, L, K, PD) { if (tma) MSAU_C3_LAUNCH_T(E, L, K, PD, true) else MSAU_C3_LAUNCH_T(E, L, K, PD, false) }
-#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3, 1) else MSAU_C3_LAUNCH(E, 3, 3, 1) }
+#define MSAU_C3_LDU(E) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 3, 1) else if (ldu == 3) MSAU_C3_LAUNCH(E, 3, 3, 1) else MSAU_C3_LAUNCH(E, 2, 3, 1) }
 #define MSAU_C3_K4(E, PD) { if (ldu == 6) MSAU_C3_LAUNCH(E, 6, 4, PD) else MSAU_C3_LAUNCH(E, 3, 4, PD) }
   if (t.KS == 4) {
     if (t.pad == 1) { if (epi == 1) MSAU_C3_K4(1, 1) else MSAU_C3_K4(0, 1) }
