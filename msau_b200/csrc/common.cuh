@@ -104,6 +104,7 @@ struct ConvArgs {
   //  d2s: the output is the depth-to-space view of [B, Hout, Wout, cph]: virtual output channel (py, px, c) of
   //       virtual pixel (y, x) is stored at physical pixel (2y+py, 2x+px), channel c;  coutp = 4*cph
   int s2d, d2s, cph, Hs, Ws;
+  int d2s_col0;                    // d2s: this launch produces the virtual output columns [d2s_col0, d2s_col0 + coutp) of the 4 * cph
   // tensor-core kernels return at once when *skip_flag == 0 (the structured first-layer kernels did the work)
   const int* skip_flag;
 };
@@ -120,6 +121,7 @@ struct WgradArgs {
   // b_s2d (tensor-core path): Bm is the space-to-depth view of a physical [B, Hb, Wb, cph] tensor (cb = 4*cph) and the
   // result is the weight gradient of a ConvTranspose2d(k3, s2, p1): virtual tap (ty, tx) x phase (py, px) -> (ky, kx)
   int b_s2d, cph;
+  int b_col0;                                       // b_s2d: first virtual column of this launch's window (cb columns) inside the 4 * cph
   const int* skip_flag;                             // as in ConvArgs
 };
 

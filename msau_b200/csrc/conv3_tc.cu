@@ -44,7 +44,10 @@ namespace {
 
 constexpr int C3_PROD_WARPS = 6;
 constexpr int C3_PROD_THREADS = C3_PROD_WARPS * 32;
-constexpr int C3_MMA_WARPS = 2;
+#ifndef MSAU_C3_MMA_WARPS
+#define MSAU_C3_MMA_WARPS 2
+#endif
+constexpr int C3_MMA_WARPS = MSAU_C3_MMA_WARPS;
 #ifndef MSAU_C3_EPI_WARPS
 #define MSAU_C3_EPI_WARPS 8       // measured: 16 epilogue warps are slower (117 vs 104 us at 8 -> 8 channels / 512^2): the shared-memory pipe, not latency, is the limit
 #endif

@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const ConvArgs a
             const int ox = x0 + tile * 8 + colx;
             if (!EPI_GENERAL && a.d2s) {
               // depth-to-space store (all four sub-pixel phases of a transposed conv in one accumulator)
-              const int ph = (ch * 8) / a.cph, c = ch * 8 - ph * a.cph;
+              const int vc = a.d2s_col0 + ch * 8, ph = vc / a.cph, c = vc - ph * a.cph;
               const int oyp = 2 * oy + (ph >> 1), oxp = 2 * ox + (ph & 1);
               if (oy < a.Hq && ox < a.Wq && oyp < a.Hout && oxp < a.Wout && !(t.dbg & 4)) {
                 float b8[8];
@@ -588,7 +588,7 @@ bool conv_tc_supported(const ConvArgs& a) {
   if (a.stride != 1 || a.osy != 1 || a.oy0 != 0 || a.ox0 != 0) return false;
   if (a.Hq != a.Hin || a.Wq != a.Win) return false;
   if (a.d2s) {
-    if (a.coutp != 4 * a.cph || (a.cph & 7) || !a.bias || a.res || a.omask || a.add || a.accumulate || a.relu2) return false;
+    if (a.d2s_col0 < 0 || (a.d2s_col0 & 7) || a.d2s_col0 + a.coutp > 4 * a.cph || (a.cph & 7) || !a.bias || a.res || a.omask || a.add || a.accumulate || a.relu2) return false;
     if (a.Hout > 2 * a.Hq || a.Hout < 2 * a.Hq - 1 || a.Wout > 2 * a.Wq || a.Wout < 2 * a.Wq - 1) return false;
   } else if (a.Hout != a.Hin || a.Wout != a.Win) return false;
   if (a.s2d) {

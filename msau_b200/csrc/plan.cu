@@ -235,8 +235,9 @@ static void add_desc(MsauPlan* p, long dst, int TH, int TW, int I, int O, int i_
 static long add_tc(MsauPlan* p, long src_off, int taps, int cin, int coutp) {
   // conv_tc takes up to 128 output columns per launch; a 256-column layer (the S6 model's deepest level) gets two images back
   // to back (tc_half_elems apart) and runs as two launches on the two halves of the output channels
-  if (cin % 8 != 0 || (coutp > 128 && coutp != 256)) return -1;
-  const int halves = coutp > 128 ? 2 : 1, cw = coutp / halves;
+  // (the merged transposed conv of the S6 model has 4 * 128 = 512 phase-major columns: four images)
+  if (cin % 8 != 0 || (coutp > 128 && coutp % 128 != 0) || coutp > 512) return -1;
+  const int halves = coutp > 128 ? coutp / 128 : 1, cw = coutp / halves;
   long first = -1;
   for (int h = 0; h < halves; ++h) {
     TcPackDesc d;
@@ -322,7 +323,7 @@ static void setup_deconv(MsauPlan* p, DeconvLayer& L, int cin, int cout) {
   // dgrad: d_in[iy] = sum_ky dOut[2 iy - 1 + ky] W[ci][co][ky]: stride-2 conv over dOut (rows = co, cols = ci)
   L.pk_d = p->alloc_packed(9L * L.coutp * L.cinp);
   add_desc(p, L.pk_d, 3, 3, L.coutp, L.cinp, 0, 0, cout, cin, L.w_off, 0, 0, 9, (long)cout * 9, 0, 1, 0, 1, 3);
-  if (L.cinp % 8 == 0 && L.coutp % 8 == 0 && 4 * L.coutp <= 128 && L.cinp <= 128) {
+  if (L.cinp % 8 == 0 && L.coutp % 8 == 0 && (4 * L.coutp <= 128 || (4 * L.coutp) % 128 == 0) && 4 * L.coutp <= 512 && L.cinp <= 256) {
     // forward: Wm[ty][tx][ci][(py,px,co)], tap (ty,tx) reads input pixel (q+ty, q'+tx)
     L.pk_m = p->alloc_packed(4L * L.cinp * 4 * L.coutp);
     // dgrad: Wdm[ty][tx][(py,px,co)][ci], tap (ty,tx) reads virtual dOut pixel (q-1+ty, q'-1+tx):
@@ -593,6 +594,22 @@ static int deconv_fwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
       count_launch(1);
       return launch_conv_tc(a, p->pktc + L.tc_m, p->st);
     }
+    if (a.coutp > 128) {
+      // more than 128 phase-major columns (64- / 128-channel transposed convs of the S5 / S6 models): windows of 128 columns,
+      // one weight image each (add_tc); the depth-to-space store maps a window's columns back to (phase, channel)
+      ConvArgs w0 = a;
+      w0.coutp = 128;
+      if (conv_tc_supported(w0)) {
+        const int nw = a.coutp / 128;
+        for (int w = 0; w < nw; ++w) {
+          ConvArgs aw = w0;
+          aw.d2s_col0 = 128 * w;
+          count_launch(1);
+          MSAU_TRY(launch_conv_tc(aw, p->pktc + L.tc_m + (long)w * tc_half_elems(4, L.cinp), p->st));
+        }
+        return MSAU_OK;
+      }
+    }
   }
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
@@ -633,6 +650,19 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
       MSAU_TRY(wgrad_fork(p));
       MSAU_TRY(launch_wgrad_tc(a, p->wst));
       w_done = true;
+    } else if (a.cb > 128 && a.cb % 128 == 0) {
+      WgradArgs w0 = a;            // windows of 128 of the 4 * coutp phase-major dY columns (tensor-core kernels take <= 128)
+      w0.cb = 128;
+      if (wgrad_tc_supported(w0)) {
+        for (int w = 0; w < a.cb / 128; ++w) {
+          WgradArgs aw = w0;
+          aw.b_col0 = 128 * w;
+          count_launch(1);
+          MSAU_TRY(wgrad_fork(p));
+          MSAU_TRY(launch_wgrad_tc(aw, p->wst));
+        }
+        w_done = true;
+      }
     }
   }
   if (!w_done) {
@@ -668,6 +698,19 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
       a.accumulate = p->touch(in);
       count_launch(1);
       return launch_conv_tc(a, p->pktc + L.tc_dm, p->st);
+    }
+    if (a.coutp == 256) {          // 256 input channels of the transposed conv: two launches over the two halves (add_tc)
+      ConvArgs h0 = a;
+      h0.coutp = 128;
+      if (conv_tc_supported(h0)) {
+        h0.accumulate = p->touch(in);
+        ConvArgs h1 = h0;
+        h1.out += 128;
+        if (h1.omask) h1.omask += 128;
+        count_launch(2);
+        MSAU_TRY(launch_conv_tc(h0, p->pktc + L.tc_dm, p->st));
+        return launch_conv_tc(h1, p->pktc + L.tc_dm + tc_half_elems(4, 4 * L.coutp), p->st);
+      }
     }
   }
   // data: stride-2 gather over dOut

@@ -234,9 +234,9 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       const int total = y_px * t.ny_planes;
       const int pl = tid % t.ny_planes;            // constant per thread (256 % ny_planes == 0)
       // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
-      const int sph = a.b_s2d ? (pl << 3) / a.cph : 0;
+      const int sph = a.b_s2d ? (a.b_col0 + (pl << 3)) / a.cph : 0;
       const int spy = sph >> 1, spx = sph & 1, smul = a.b_s2d ? 2 : 1;
-      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? (pl << 3) - sph * a.cph : (pl << 3));
+      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? a.b_col0 + (pl << 3) - sph * a.cph : (pl << 3));
       const float* msrc = a.maskB ? a.maskB + (long)b * a.Hb * a.Wb * a.pmb + (pl << 3) : nullptr;
       uint8_t* ydst = yh + (size_t)pl * t.y_plane_bytes;
       int yr_ = (tid / t.ny_planes) / t.TC, yc_ = (tid / t.ny_planes) - yr_ * t.TC;   // pixel of element tid + k * 256
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
             const int co = c0 + j;
             if (a.b_s2d) {
               // transposed conv: virtual tap (ty, tx) x phase (py, px) -> real tap: (0,0)->1, (0,1)->2, (1,1)->0, (1,0)->none
-              const int ph = co / a.cph, c = co - ph * a.cph;
+              const int vco = a.b_col0 + co, ph = vco / a.cph, c = vco - ph * a.cph;
               const int py = ph >> 1, px = ph & 1;
               const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
               const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   __syncthreads();
   if (do_bias) {
     if (a.b_s2d) {
-      if (tid < a.cb && (tid % a.cph) < a.cb_lim) atomicAdd(a.dbias + (tid % a.cph), sbias[tid]);
+      if (tid < a.cb && ((a.b_col0 + tid) % a.cph) < a.cb_lim) atomicAdd(a.dbias + ((a.b_col0 + tid) % a.cph), sbias[tid]);
     } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -534,9 +534,9 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
       const bool two = lane + 32 < t.TC;
       for (int pl = pl0; pl < nyp; pl += 8) {
         // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
-        const int sph = a.b_s2d ? (pl << 3) / a.cph : 0;
+        const int sph = a.b_s2d ? (a.b_col0 + (pl << 3)) / a.cph : 0;
         const int spy = sph >> 1, spx = sph & 1;
-        const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? (pl << 3) - sph * a.cph : (pl << 3));
+        const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? a.b_col0 + (pl << 3) - sph * a.cph : (pl << 3));
         const int vx0 = qx0 + lane, vx1 = vx0 + 32;
         const int gx0 = vx0 * smul + spx, gx1 = vx1 * smul + spx;
         const bool okx0 = lane < t.TC && vx0 < a.Wq && gx0 < a.Wb && !(t.dbg & 2), okx1 = two && vx1 < a.Wq && gx1 < a.Wb && !(t.dbg & 2);
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
         for (int j = 0; j < 8; ++j) {
           const int co = cb0 + j;
           if (a.b_s2d) {
-            const int ph = co / a.cph, c = co - ph * a.cph;
+            const int vco = a.b_col0 + co, ph = vco / a.cph, c = vco - ph * a.cph;
             const int py = ph >> 1, px = ph & 1;
             const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
             const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(WG_THREADS, 3) wgrad_tc2_kernel(const WgradArg
   __syncthreads();
   if (do_bias) {
     if (a.b_s2d) {
-      if (tid < a.cb && (tid % a.cph) < a.cb_lim) atomicAdd(a.dbias + (tid % a.cph), sbias[tid]);
+      if (tid < a.cb && ((a.b_col0 + tid) % a.cph) < a.cb_lim) atomicAdd(a.dbias + ((a.b_col0 + tid) % a.cph), sbias[tid]);
     } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1021,7 +1021,7 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
         for (int j = 0; j < 8; ++j) {
           const int co = cb0 + j;
           if (a.b_s2d) {
-            const int ph = co / a.cph, c = co - ph * a.cph;
+            const int vco = a.b_col0 + co, ph = vco / a.cph, c = vco - ph * a.cph;
             const int py = ph >> 1, px = ph & 1;
             const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
             const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
@@ -1035,7 +1035,7 @@ __global__ void __launch_bounds__(WG3_THREADS, 1) wgrad_tc3_kernel(const WgradAr
   __syncthreads();
   if (do_bias && n_my > 0) {
     if (a.b_s2d) {
-      if (tid < a.cb && (tid % a.cph) < a.cb_lim) atomicAdd(a.dbias + (tid % a.cph), sbias[tid]);
+      if (tid < a.cb && ((a.b_col0 + tid) % a.cph) < a.cb_lim) atomicAdd(a.dbias + ((a.b_col0 + tid) % a.cph), sbias[tid]);
     } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, sbias[tid]);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -1150,7 +1150,8 @@ bool wgrad_tc_supported(const WgradArgs& a) {
   if (a.sa != 1 || a.sb != 1 || a.dilb != 0 || a.padb_t != 0 || a.padb_l != 0) return false;
   if (a.Ha != a.Hq || a.Wa != a.Wq) return false;
   if (a.b_s2d) {
-    if (a.cb != 4 * a.cph || (a.cph & 7) || a.maskB || a.kh != 2 || a.kw != 2) return false;
+    // (b_col0: this launch covers the virtual columns [b_col0, b_col0 + cb) of the 4 * cph phase-major columns)
+    if (a.b_col0 < 0 || (a.b_col0 & 7) || a.b_col0 + a.cb > 4 * a.cph || (a.cph & 7) || a.maskB || a.kh != 2 || a.kw != 2) return false;
     if (a.Hb > 2 * a.Hq || a.Hb < 2 * a.Hq - 1 || a.Wb > 2 * a.Wq || a.Wb < 2 * a.Wq - 1) return false;
   } else if (a.Hb != a.Hq || a.Wb != a.Wq) return false;
   if ((a.ca & 7) || (a.cb & 7) || a.cb > 128 || a.kw > 4 || a.kh > 4) return false;
