@@ -114,7 +114,6 @@ __device__ __forceinline__ uint4 wpack8(const float* x) {
 struct WgTile {
   int TR, TC, HHx, HWx, N, ny_planes;       // tile rows/cols, X halo extent, MMA N, dY channel planes
   int xq, xr, yq, yr;                       // 256 elements ahead = (xq rows, xr cols) of the X tile / (yq, yr) of the dY tile
-  int xq2, xr2;                             // 128 pixels (256 16-byte units) ahead in the X tile
   int tiles_x, tiles_y, n_tiles, tiles_per_cta;
   uint32_t x_plane_bytes, y_plane_bytes, stage_bytes, tmem_cols;
 };
@@ -125,8 +124,6 @@ static constexpr int WG_THREADS = 256;
 #endif
 static constexpr int WU = MSAU_WG_WU;   // pixels whose global loads are in flight per thread
 
-// MASK: dY is multiplied by (maskB > 0) on load (compile-time: the mask operand and its selects cost registers and instructions)
-template <bool MASK>
 __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a, const WgTile t) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_free[2];
@@ -196,36 +193,6 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       const int plane_stride = a.Ha * a.Wa;
       const float* xsrc = a.a_nchw ? a.A + ((long)b * a.ca_logical + ca0) * plane_stride : a.A + (long)b * plane_stride * a.pa + ca0;
       const int n_valid = a.ca_logical - ca0;
-      if (!a.a_nchw) {
-        // 16-byte units in memory order (see the dY loader): lanes 2 i and 2 i + 1 take the two halves of one pixel's 8 channels,
-        // so a warp instruction touches 16 cache lines instead of 32
-        const int hf = tid & 1;
-        int iy = (tid >> 1) / t.HWx, ix = (tid >> 1) - iy * t.HWx;      // pixel of unit tid + k * 256, advanced without divisions
-        constexpr int XU = 2 * WU;
-        for (int e0 = tid; e0 < 2 * x_px; e0 += WG_THREADS * XU) {
-          float4 v[XU];
-          int so[XU];
-#pragma unroll
-          for (int u = 0; u < XU; ++u) {
-            const int e = e0 + u * WG_THREADS;
-            const int gy = in_y0 + iy, gx = in_x0 + ix;
-            so[u] = e >> 1;
-            iy += t.xq2; ix += t.xr2;
-            if (ix >= t.HWx) { ix -= t.HWx; ++iy; }
-            const bool inb = e < 2 * x_px && (unsigned)gy < (unsigned)a.Ha && (unsigned)gx < (unsigned)a.Wa;
-            v[u] = inb ? __ldg(reinterpret_cast<const float4*>(xsrc + (gy * a.Wa + gx) * a.pa + hf * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < XU; ++u) {
-            const int e = e0 + u * WG_THREADS;
-            if (e >= 2 * x_px) break;
-            float4 q = v[u];
-            if (a.reluA) { q.x = fmaxf(q.x, 0.f); q.y = fmaxf(q.y, 0.f); q.z = fmaxf(q.z, 0.f); q.w = fmaxf(q.w, 0.f); }
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(q.x, q.y), h1 = __floats2bfloat162_rn(q.z, q.w);
-            *reinterpret_cast<uint2*>(xh + so[u] * 16 + hf * 8) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-          }
-        }
-      } else {
       int iy = tid / t.HWx, ix = tid - iy * t.HWx;        // element tid + k * 256 of the halo tile, advanced without divisions
       for (int e0 = tid; e0 < x_px; e0 += WG_THREADS * WU) {
         float v[WU][8];
@@ -260,58 +227,25 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
           *reinterpret_cast<uint4*>(xh + e * 16) = wpack8(v[u]);
         }
       }
-      }
     }
     // ---- dY tile: [planes], each plane TR x TC pixels of 16 B ----
-    // Work unit = 16 bytes (4 channels = half a plane-pixel), units in MEMORY order: consecutive lanes read consecutive 16-byte
-    // chunks of a pixel's channels, so a warp instruction covers 512 contiguous bytes (4 cache lines) instead of 32 strided
-    // 32-byte pieces of 32 different lines -- the strided form cost one L1TEX wavefront per lane and made this kernel
-    // L1TEX-bound on the 32/64-channel levels.  The transposed-conv view (b_s2d) is contiguous within a phase.
     {
       uint8_t* yh = st + t.x_plane_bytes;
-      const int upp = 2 * t.ny_planes;             // units per pixel; 256 % upp == 0, so a thread's (plane, half) never changes
-      const int total = y_px * upp;
-      const int cu = tid % upp, pl = cu >> 1, hf = cu & 1;
+      const int total = y_px * t.ny_planes;
+      const int pl = tid % t.ny_planes;            // constant per thread (256 % ny_planes == 0)
       // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
       const int sph = a.b_s2d ? (a.b_col0 + (pl << 3)) / a.cph : 0;
       const int spy = sph >> 1, spx = sph & 1, smul = a.b_s2d ? 2 : 1;
-      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? a.b_col0 + (pl << 3) - sph * a.cph : (pl << 3)) + hf * 4;
-      const float* msrc = MASK ? a.maskB + (long)b * a.Hb * a.Wb * a.pmb + (pl << 3) + hf * 4 : nullptr;
-      uint8_t* ydst = yh + (size_t)pl * t.y_plane_bytes + hf * 8;
-      constexpr int YU = 2 * WU;                   // 16-byte units in flight per thread (same bytes as WU pixels)
-      const int upr = t.TC * upp;                  // units per tile row
-      // interior tiles of an ordinary dY (the common case): unit e -> row e / upr, column (e % upr) / upp with shifts only, the
-      // address is the tile origin + row * row stride + column * pixel pitch, and nothing needs a bounds check
-      if (!MASK && !a.b_s2d && (upr & (upr - 1)) == 0 && qy0 + t.TR <= a.Hq && qx0 + t.TC <= a.Wq) {
-        const int sh = 31 - __clz(upr), lu = 31 - __clz(upp);
-        const float* base = a.Bm + ((long)(b * a.Hb + qy0) * a.Wb + qx0) * a.pb + cu * 4;
-        const int rowstride = a.Wb * a.pb;
-        for (int e0 = tid; e0 < total; e0 += WG_THREADS * YU) {
-          float4 v[YU];
+      const float* ysrc = a.Bm + (long)b * a.Hb * a.Wb * a.pb + (a.b_s2d ? a.b_col0 + (pl << 3) - sph * a.cph : (pl << 3));
+      const float* msrc = a.maskB ? a.maskB + (long)b * a.Hb * a.Wb * a.pmb + (pl << 3) : nullptr;
+      uint8_t* ydst = yh + (size_t)pl * t.y_plane_bytes;
+      int yr_ = (tid / t.ny_planes) / t.TC, yc_ = (tid / t.ny_planes) - yr_ * t.TC;   // pixel of element tid + k * 256
+      for (int e0 = tid; e0 < total; e0 += WG_THREADS * WU) {
+        float v[WU][8];
+        float4 mk[WU][2];
+        int so[WU];
 #pragma unroll
-          for (int u = 0; u < YU; ++u) {
-            const int e = e0 + u * WG_THREADS;
-            const int r = e >> sh, c = (e & (upr - 1)) >> lu;
-            v[u] = e < total ? __ldg(reinterpret_cast<const float4*>(base + r * rowstride + c * a.pb)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < YU; ++u) {
-            const int e = e0 + u * WG_THREADS;
-            if (e >= total) break;
-            const int r = e >> sh, c = (e & (upr - 1)) >> lu;
-            const float4 q = v[u];
-            if (do_bias) { bacc[0] += q.x; bacc[1] += q.y; bacc[2] += q.z; bacc[3] += q.w; }
-            const __nv_bfloat162 h0 = __floats2bfloat162_rn(q.x, q.y), h1 = __floats2bfloat162_rn(q.z, q.w);
-            *reinterpret_cast<uint2*>(ydst + (r * t.TC + c) * 16) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
-          }
-        }
-      } else {
-      int yr_ = (tid / upp) / t.TC, yc_ = (tid / upp) - yr_ * t.TC;   // pixel of unit tid + k * 256
-      for (int e0 = tid; e0 < total; e0 += WG_THREADS * YU) {
-        float4 v[YU], mk[YU];
-        int so[YU];
-#pragma unroll
-        for (int u = 0; u < YU; ++u) {
+        for (int u = 0; u < WU; ++u) {
           const int e = e0 + u * WG_THREADS;
           const int r = yr_, c = yc_;
           so[u] = r * t.TC + c;
@@ -322,22 +256,32 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
           const bool inb = e < total && vy < a.Hq && vx < a.Wq && gy < a.Hb && gx < a.Wb;
           const int lin = gy * a.Wb + gx;
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          v[u] = inb ? __ldg(reinterpret_cast<const float4*>(ysrc + lin * a.pb)) : z4;
-          if (MASK) mk[u] = inb ? __ldg(reinterpret_cast<const float4*>(msrc + lin * a.pmb)) : z4;
+          const float4* sp = reinterpret_cast<const float4*>(ysrc + lin * a.pb);
+          const float4 q0 = inb ? __ldg(sp) : z4;
+          const float4 q1 = inb ? __ldg(sp + 1) : z4;
+          v[u][0] = q0.x; v[u][1] = q0.y; v[u][2] = q0.z; v[u][3] = q0.w;
+          v[u][4] = q1.x; v[u][5] = q1.y; v[u][6] = q1.z; v[u][7] = q1.w;
+          if (msrc) {
+            const float4* mp = reinterpret_cast<const float4*>(msrc + lin * a.pmb);
+            mk[u][0] = inb ? __ldg(mp) : z4;
+            mk[u][1] = inb ? __ldg(mp + 1) : z4;
+          }
         }
 #pragma unroll
-        for (int u = 0; u < YU; ++u) {
+        for (int u = 0; u < WU; ++u) {
           const int e = e0 + u * WG_THREADS;
           if (e >= total) break;
-          float4 q = v[u];
-          if (MASK) {
-            q.x = mk[u].x > 0.f ? q.x : 0.f; q.y = mk[u].y > 0.f ? q.y : 0.f; q.z = mk[u].z > 0.f ? q.z : 0.f; q.w = mk[u].w > 0.f ? q.w : 0.f;
+          if (msrc) {
+            const float m[8] = {mk[u][0].x, mk[u][0].y, mk[u][0].z, mk[u][0].w, mk[u][1].x, mk[u][1].y, mk[u][1].z, mk[u][1].w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = m[k] > 0.f ? v[u][k] : 0.f;
           }
-          if (do_bias) { bacc[0] += q.x; bacc[1] += q.y; bacc[2] += q.z; bacc[3] += q.w; }
-          const __nv_bfloat162 h0 = __floats2bfloat162_rn(q.x, q.y), h1 = __floats2bfloat162_rn(q.z, q.w);
-          *reinterpret_cast<uint2*>(ydst + so[u] * 16) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+          if (do_bias) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) bacc[k] += v[u][k];
+          }
+          *reinterpret_cast<uint4*>(ydst + so[u] * 16) = wpack8(v[u]);
         }
-      }
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -381,11 +325,11 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       __syncwarp();
     }
   }
-  // ---- bias gradient partials: a thread owns 4 channels (plane cu >> 1, half cu & 1) ----
+  // ---- bias gradient partials ----
   if (do_bias) {
-    const int cu = tid % (2 * t.ny_planes);
+    const int pl = tid % t.ny_planes;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) atomicAdd(&sbias[cu * 4 + k], bacc[k]);
+    for (int k = 0; k < 8; ++k) atomicAdd(&sbias[pl * 8 + k], bacc[k]);
   }
   // ---- reduce the resident accumulators into dW ----
   if (tid == 0) wmbar_wait(&bar_done, 0);
@@ -1179,8 +1123,7 @@ static bool wg_config(const WgradArgs& a, WgTile& t, size_t& smem, int& ctas_out
   const uint32_t y_bytes = (uint32_t)t.ny_planes * t.y_plane_bytes;
   t.stage_bytes = (t.x_plane_bytes + y_bytes + 1023) / 1024 * 1024;
   t.xq = WG_THREADS / t.HWx; t.xr = WG_THREADS % t.HWx;
-  t.xq2 = (WG_THREADS / 2) / t.HWx; t.xr2 = (WG_THREADS / 2) % t.HWx;
-  { const int dpx = WG_THREADS / (2 * t.ny_planes); t.yq = dpx / t.TC; t.yr = dpx % t.TC; }    // pixels a thread advances per 256 16-byte units
+  { const int dpx = WG_THREADS / t.ny_planes; t.yq = dpx / t.TC; t.yr = dpx % t.TC; }
   t.tiles_x = cdiv(a.Wq, t.TC);
   t.tiles_y = cdiv(a.Hq, t.TR);
   t.n_tiles = t.tiles_x * t.tiles_y * a.B;
@@ -1245,16 +1188,14 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   MSAU_CHECK_ARG(fits, "wgrad_tc: tile does not fit (smem %zu B, tmem %u cols)", smem, t.tmem_cols);
   static bool attr = false;
   if (!attr) {
-    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   dim3 grid(ctas, planes);
   const double npq = (double)a.B * a.Hq * a.Wq;
   const double wbytes = (npq * (a.a_nchw ? a.ca_logical : a.ca) + npq * a.cb * (a.maskB ? 2 : 1)) * 4.0;
   ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw, a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
-  if (a.maskB) MSAU_CUDA_TRY(launch_pdl(wgrad_tc_kernel<true>, grid, dim3(WG_THREADS), smem, st, a, t));
-  else MSAU_CUDA_TRY(launch_pdl(wgrad_tc_kernel<false>, grid, dim3(WG_THREADS), smem, st, a, t));
+  MSAU_CUDA_TRY(launch_pdl(wgrad_tc_kernel, grid, dim3(WG_THREADS), smem, st, a, t));
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;
 }
