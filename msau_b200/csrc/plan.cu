@@ -1237,8 +1237,13 @@ extern "C" int msau_loss_backward(MsauPlan* p, const float* x, int x_layout, con
 
 extern "C" int msau_plan_error_flags(MsauPlan* p, int* h_flags) {
   MSAU_CHECK_ARG(p && h_flags, "plan_error_flags: null argument");
-  MSAU_CUDA_TRY(cudaMemcpy(h_flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost));
-  if (*h_flags) MSAU_CUDA_TRY(cudaMemset(p->d_flags, 0, sizeof(int)));
+  // on the stream of the plan's last call (a non-blocking stream does not synchronise with the NULL stream)
+  MSAU_CUDA_TRY(cudaMemcpyAsync(h_flags, p->d_flags, sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  MSAU_CUDA_TRY(cudaStreamSynchronize(p->st));
+  if (*h_flags) {
+    MSAU_CUDA_TRY(cudaMemsetAsync(p->d_flags, 0, sizeof(int), p->st));
+    MSAU_CUDA_TRY(cudaStreamSynchronize(p->st));
+  }
   return MSAU_OK;
 }
 

@@ -116,6 +116,7 @@ struct WgTile {
   int xq, xr, yq, yr;                       // 256 elements ahead = (xq rows, xr cols) of the X tile / (yq, yr) of the dY tile
   int tiles_x, tiles_y, n_tiles, tiles_per_cta;
   uint32_t x_plane_bytes, y_plane_bytes, stage_bytes, tmem_cols;
+  int dbg;                                  // MSAU_WG_DBG (timing experiments only): 1 = skip the loads after the first two tiles, 2 = skip the MMAs
 };
 
 static constexpr int WG_THREADS = 256;
@@ -187,7 +188,8 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
     const int b = rest / t.tiles_y;
     const int qy0 = ty * t.TR, qx0 = tx * t.TC;
     // ---- X halo tile of this plane: (HHx x HWx) pixels of 16 B.  WU pixels' loads are in flight per thread ----
-    {
+    const bool dbg_skip_ld = (t.dbg & 1) && it >= 2;
+    if (!dbg_skip_ld) {
       const int in_y0 = qy0 - a.pada_t, in_x0 = qx0 - a.pada_l;
       uint8_t* xh = st;
       const int plane_stride = a.Ha * a.Wa;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
       }
     }
     // ---- dY tile: [planes], each plane TR x TC pixels of 16 B ----
-    {
+    if (!dbg_skip_ld) {
       uint8_t* yh = st + t.x_plane_bytes;
       const int total = y_px * t.ny_planes;
       const int pl = tid % t.ny_planes;            // constant per thread (256 % ny_planes == 0)
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
         uint32_t a_lo = (((xh >> 4) + (uint32_t)(ky * a.dila * t.HWx)) & 0x3FFF) | lbo;
         uint32_t b_lo = ((yh >> 4) & 0x3FFF) | lbo;
         const uint32_t xrow16 = (uint32_t)t.HWx - (uint32_t)chunks * 16;   // row advance after the chunks, 16-B units
-        for (int r = 0; r < t.TR; ++r) {
+        for (int r = 0; r < ((t.dbg & 2) ? 0 : t.TR); ++r) {
           if (chunks == 4) {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
     }
   }
   // ---- bias gradient partials ----
-  if (do_bias) {
+  if (do_bias && !(t.dbg & 4)) {
     const int pl = tid % t.ny_planes;
 #pragma unroll
     for (int k = 0; k < 8; ++k) atomicAdd(&sbias[pl * 8 + k], bacc[k]);
@@ -335,7 +337,7 @@ __global__ void __launch_bounds__(WG_THREADS) wgrad_tc_kernel(const WgradArgs a,
   if (tid == 0) wmbar_wait(&bar_done, 0);
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  if (warp < 2) {
+  if (warp < 2 && !(t.dbg & 8)) {
     // M = 64 accumulator: row m lives in TMEM lane (m % 16) + 32 * (m / 16)  (cute tmem_frg, "half subpartition"
     // atom).  row m = kx * 8 + channel-in-plane -> warp 0 (lanes 0..15) holds kx 0,1 ; warp 1 (lanes 32..47) kx 2,3.
     const int kx = warp * 2 + (lane >> 3), ci = ca0 + (lane & 7);
@@ -1103,6 +1105,451 @@ static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t 
 }
 
 // tile geometry of the generic kernel; false when it does not fit shared memory / TMEM (large dilation on a wide dY)
+
+// =====================================================================================================
+// Warp-specialised kernel for the <= 128^2 levels (more than 16 output channels; dilation 1 or a single tap).
+// What the per-plane kernels above cost there, measured (profiles/README.md, round 2): every 8-channel plane of X had its own
+// CTAs, each re-reading ALL of dY through L2 (c32 -> c32: 640 B per pixel instead of 256, ~5.9 TB/s of L2 -> SM traffic for 30
+// of the 68 us); the warps that issue the MMAs were also loaders, so the 14 us of instruction issue added to the load time
+// instead of hiding under it; and 296 CTAs x 2304 scalar atomics + 2048 same-address shared atomics per CTA made a 12 us tail.
+// Here one CTA per SM (576 threads) owns `ppc` planes of X at once:
+//   16 loader warps   fp32 global -> bf16 operand images ([plane][row][col][8 ch] for X, [row][plane][col][8 ch] with kh-1 halo
+//                     rows for dY, as in wgrad_tc2), S stages, one (plane, row) or (row, plane) item per warp, four items in flight
+//    2 MMA warps      one elected lane each; warp w owns the accumulators w, w + 2: (X plane) or, for few planes, (row-interleaved copy)
+//   dil = 1, k x k:   M = 64 rows = (kx, ci) of ONE plane, N = kh * cout columns = (ky, co): one instruction per 16 pixels and plane
+//   1 x 1 ("gemm"):   M = 64 / 128 rows = (plane, ci) of ALL the CTA's planes, N = cout: one instruction per 16 pixels
+//   epilogue          TMEM -> shared memory in dW order -> 16-byte vector reductions (red.global.add.v4.f32) into dW; the bias
+//                     gradient is reduced by warp shuffles before it touches shared memory, its planes spread over the CTA groups
+struct Wg4Tile {
+  int TR, TC, HWx, TRy, nyp, N, M;           // X rows / columns per tile, X row pitch (px), staged dY rows, dY planes, MMA N and M
+  int ppc, n_groups, gemm, S, copies;        // X planes per CTA, plane groups (grid.y), 1x1 mode, stages, accumulator copies per item
+  int tiles_x, tiles_y, n_tiles, tiles_per_cta;
+  uint32_t x_plane_bytes, x_bytes, stage_bytes, tmem_cols;
+  int vec;                                   // dW layout / alignment allow 16-byte reductions (checked on the host)
+  uint32_t m_tr, m_nyp, m_nh;                // ceil(2^20 / d) for d = TR, nyp, HWx - TC: j / d = (j * m) >> 20 for the item indices (j < 4096)
+  int dbg;
+};
+static constexpr int WG4_LOAD_WARPS = 16;
+static constexpr int WG4_U = 2;                 // items (two pixels per lane each) whose loads are in flight per warp
+static constexpr int WG4_MMA_WARPS = 2;         // (576 threads: 112 registers each)
+static constexpr int WG4_THREADS = (WG4_LOAD_WARPS + WG4_MMA_WARPS) * 32;
+static constexpr int WG4_MAX_S = 4;
+
+__device__ __forceinline__ void wred_v4(float* p, const float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradArgs a, const Wg4Tile t) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_full[WG4_MAX_S];   // loaders -> MMA : operand images of the stage are written
+  __shared__ uint64_t bar_free[WG4_MAX_S];   // MMA -> loaders : the instructions reading the stage have retired
+  __shared__ uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sbias[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int group = blockIdx.y;
+  const int pl0 = group * t.ppc;                                 // first X plane of this CTA
+  const int np = min(t.ppc, (a.ca >> 3) - pl0);                  // its X planes
+  const int tile0 = blockIdx.x * t.tiles_per_cta;
+  const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
+  const int n_my = tile1 - tile0;
+  const int items = t.gemm ? 1 : np;                             // accumulators = items x copies; copy c takes the rows r = c (mod copies)
+  const int n_acc = items * t.copies;
+  const int n_iss = min(WG4_MMA_WARPS, n_acc);
+  if (a.skip_flag) {                               // (the flag is written by an earlier kernel of this step: wait for it first)
+    pdl_wait();
+    if (*a.skip_flag == 0) return;
+  }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(wsmem_u32(&tmem_base_s)), "r"(t.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    for (int i = 0; i < WG4_MAX_S; ++i) { wmbar_init(&bar_full[i], WG4_LOAD_WARPS); wmbar_init(&bar_free[i], n_iss); }
+    wmbar_init(&bar_done, n_iss);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid >= 64 && tid < 192) sbias[tid - 64] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();        // PDL protocol (common.cuh): nothing above reads or writes activations / gradients
+  pdl_trigger();
+  const uint32_t tmem_base = tmem_base_s;
+  if (n_my <= 0) {
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+    return;
+  }
+
+  if (warp < WG4_LOAD_WARPS) {
+    // =============================================================== loaders
+    // Items of a tile, each at most two pixels per lane: X rows (plane, row: columns lane and lane + 32), X halo columns (one
+    // item per plane: the TR x (kw-1) pixels right of column TC), dY rows (staged row, plane).  Warp w takes the items
+    // w, w + 16, ...; ALL of a round's loads (WG4_U items = 16 x 16 B per lane) are issued before the first conversion, so a
+    // tile costs one memory latency, not one per pair of items (measured: 2 items per round made the loaders the critical path).
+    const int nh = t.HWx - t.TC;                                 // X halo columns per row
+    const int n_x = np * t.TR;
+    const int n_h = nh > 0 ? np : 0;
+    const int n_items = n_x + n_h + t.TRy * t.nyp;
+    const int smul = a.b_s2d ? 2 : 1;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // the dY plane of this warp's items never changes when the warp count is a multiple of the plane count: the bias gradient
+    // then stays in registers for the whole kernel
+    const bool fixed_pl = (WG4_LOAD_WARPS % t.nyp) == 0;
+    float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int bacc_pl = -1;
+    struct Item { const float* sA; const float* sB; uint8_t* dA; uint8_t* dB; bool okA, okB, stA, stB, relu, bias; int pl; };
+    int tx = tile0 % t.tiles_x, ty = (tile0 / t.tiles_x) % t.tiles_y, b = (tile0 / t.tiles_x) / t.tiles_y;
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % t.S;
+      if (it >= t.S) {
+        if (lane == 0) wmbar_wait_spin(&bar_free[s], ((it / t.S) - 1) & 1);
+        __syncwarp();
+      }
+      uint8_t* const st = smem + (size_t)s * t.stage_bytes;
+      uint8_t* const yh = st + t.x_bytes;
+      const int qy0 = ty * t.TR, qx0 = tx * t.TC;
+      const int in_x0 = qx0 - a.pada_l;
+      const int vy0 = qy0 + a.pada_t - (a.kh - 1);
+      const float* const ximg = a.A + (long)b * a.Ha * a.Wa * a.pa + (pl0 << 3);
+      const float* const yimg = a.Bm + (long)b * a.Hb * a.Wb * a.pb;
+      auto decode = [&](int j) {
+        Item I;
+        I.relu = false; I.bias = false; I.pl = 0;
+        if (j < n_x) {
+          const int p = (int)(((uint32_t)j * t.m_tr) >> 20), r = j - p * t.TR;
+          const int gy = qy0 + r, gx0 = in_x0 + lane, gx1 = gx0 + 32;
+          const bool oky = gy < a.Ha;
+          I.stA = lane < t.TC; I.stB = lane + 32 < t.TC;
+          I.okA = oky && I.stA && (unsigned)gx0 < (unsigned)a.Wa;
+          I.okB = oky && I.stB && (unsigned)gx1 < (unsigned)a.Wa;
+          I.sA = ximg + (gy * a.Wa + gx0) * a.pa + (p << 3);
+          I.sB = I.sA + 32 * a.pa;
+          I.dA = st + (size_t)p * t.x_plane_bytes + (size_t)(r * t.HWx + lane) * 16;
+          I.dB = I.dA + 512;
+          I.relu = a.reluA != 0;
+        } else if (j < n_x + n_h) {
+          const int p = j - n_x;
+          const int e0 = lane, e1 = lane + 32;
+          const int r0 = (int)(((uint32_t)e0 * t.m_nh) >> 20), c0 = t.TC + (e0 - r0 * nh);
+          const int r1 = (int)(((uint32_t)e1 * t.m_nh) >> 20), c1 = t.TC + (e1 - r1 * nh);
+          I.stA = r0 < t.TR; I.stB = r1 < t.TR;
+          const int gy0 = qy0 + r0, gy1 = qy0 + r1, gx0 = in_x0 + c0, gx1 = in_x0 + c1;
+          I.okA = I.stA && gy0 < a.Ha && (unsigned)gx0 < (unsigned)a.Wa;
+          I.okB = I.stB && gy1 < a.Ha && (unsigned)gx1 < (unsigned)a.Wa;
+          I.sA = ximg + (gy0 * a.Wa + gx0) * a.pa + (p << 3);
+          I.sB = ximg + (gy1 * a.Wa + gx1) * a.pa + (p << 3);
+          I.dA = st + (size_t)p * t.x_plane_bytes + (size_t)(r0 * t.HWx + c0) * 16;
+          I.dB = st + (size_t)p * t.x_plane_bytes + (size_t)(r1 * t.HWx + c1) * 16;
+          I.relu = a.reluA != 0;
+        } else {
+          const int jj = j - n_x - n_h;
+          const int r = (int)(((uint32_t)jj * t.m_nyp) >> 20), pl = jj - r * t.nyp;
+          // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
+          const int sph = a.b_s2d ? (a.b_col0 + (pl << 3)) / a.cph : 0;
+          const int spy = sph >> 1, spx = sph & 1;
+          const int vy = vy0 + r, gy = vy * smul + spy;
+          const int vx0 = qx0 + lane, vx1 = vx0 + 32;
+          const int gx0 = vx0 * smul + spx, gx1 = vx1 * smul + spx;
+          const bool oky = (unsigned)vy < (unsigned)a.Hq && gy < a.Hb;
+          I.stA = lane < t.TC; I.stB = lane + 32 < t.TC;
+          I.okA = oky && I.stA && vx0 < a.Wq && gx0 < a.Wb;
+          I.okB = oky && I.stB && vx1 < a.Wq && gx1 < a.Wb;
+          I.sA = yimg + (gy * a.Wb + gx0) * a.pb + (a.b_s2d ? a.b_col0 + (pl << 3) - sph * a.cph : (pl << 3));
+          I.sB = I.sA + 32 * smul * a.pb;
+          I.dA = yh + (size_t)((r * t.nyp + pl) * t.TC + lane) * 16;
+          I.dB = I.dA + 512;
+          // bias gradient: rows of this tile only (halo rows belong to the neighbours); the planes are spread over the groups
+          I.bias = a.dbias != nullptr && (pl % t.n_groups) == group && vy >= qy0 && vy < qy0 + t.TR;
+          I.pl = pl;
+        }
+        return I;
+      };
+      const bool skip_ld = (t.dbg & 1) != 0;
+      for (int j0 = warp; j0 < n_items && !skip_ld; j0 += WG4_U * WG4_LOAD_WARPS) {
+        float4 q[WG4_U][2][2];
+#pragma unroll
+        for (int u = 0; u < WG4_U; ++u) {
+          const int j = j0 + u * WG4_LOAD_WARPS;
+          if (j < n_items) {
+            const Item I = decode(j);
+            const float4* sp0 = reinterpret_cast<const float4*>(I.sA);
+            const float4* sp1 = reinterpret_cast<const float4*>(I.sB);
+            q[u][0][0] = I.okA ? __ldg(sp0) : z4; q[u][0][1] = I.okA ? __ldg(sp0 + 1) : z4;
+            q[u][1][0] = I.okB ? __ldg(sp1) : z4; q[u][1][1] = I.okB ? __ldg(sp1 + 1) : z4;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < WG4_U; ++u) {
+          const int j = j0 + u * WG4_LOAD_WARPS;
+          if (j < n_items) {
+            const Item I = decode(j);
+            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              float v[8] = {q[u][k][0].x, q[u][k][0].y, q[u][k][0].z, q[u][k][0].w, q[u][k][1].x, q[u][k][1].y, q[u][k][1].z, q[u][k][1].w};
+              if (I.relu) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
+              }
+              if (I.bias) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) bsum[c] += v[c];
+              }
+              if (k == 0 ? I.stA : I.stB) *reinterpret_cast<uint4*>(k == 0 ? I.dA : I.dB) = wpack8(v);
+            }
+            if (I.bias) {                                          // (warp-uniform)
+              if (fixed_pl) {
+                bacc_pl = I.pl;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) bacc[c] += bsum[c];
+              } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  float sum = bsum[c];
+#pragma unroll
+                  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                  if (lane == 0) atomicAdd(&sbias[I.pl * 8 + c], sum);
+                }
+              }
+            }
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) wmbar_arrive(&bar_full[s]);
+      if (++tx == t.tiles_x) { tx = 0; if (++ty == t.tiles_y) { ty = 0; ++b; } }
+    }
+    if (bacc_pl >= 0) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float sum = bacc[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) atomicAdd(&sbias[bacc_pl * 8 + c], sum);
+      }
+    }
+  } else if (warp - WG4_LOAD_WARPS < n_iss) {
+    // =============================================================== MMA issue
+    const int w = warp - WG4_LOAD_WARPS;
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(t.N >> 3) << 17) |
+                           ((uint32_t)(t.M >> 4) << 24);
+    const int chunks = t.TC >> 4;
+    const uint32_t lbo = (128u >> 4) << 16;
+    // row groups of the X operand: the kx taps (one pixel apart) or, 1x1, the channel planes; column groups of dY: (ky, plane)
+    const uint32_t a_hi = ((t.gemm ? (t.x_plane_bytes >> 4) : 1u) & 0x3FFF) | (1u << 14);
+    const uint32_t b_hi = ((uint32_t)t.TC & 0x3FFF) | (1u << 14);
+    const uint32_t yrow16 = (uint32_t)(t.nyp * t.TC);            // staged dY row pitch, 16-B units
+    for (int it = 0; it < n_my; ++it) {
+      const int s = it % t.S;
+      if (lane == 0) wmbar_wait_spin(&bar_full[s], (it / t.S) & 1);
+      __syncwarp();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (welect_one()) {
+        const uint32_t xh = wsmem_u32(smem + (size_t)s * t.stage_bytes);
+        const uint32_t yh = xh + t.x_bytes;
+        for (int acc = w; acc < n_acc; acc += WG4_MMA_WARPS) {
+          const int item = acc % items, copy = acc / items;
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * t.N);
+          const uint32_t a16 = (xh >> 4) + (t.gemm ? 0u : (uint32_t)item * (t.x_plane_bytes >> 4));
+          uint32_t first = (it == 0) ? 0u : 1u;
+          for (int r = copy; r < ((t.dbg & 2) ? 0 : t.TR); r += t.copies) {
+            uint32_t a_lo = ((a16 + (uint32_t)(r * t.HWx)) & 0x3FFF) | lbo;
+            uint32_t b_lo = (((yh >> 4) + (uint32_t)r * yrow16) & 0x3FFF) | lbo;
+            for (int cc = 0; cc < chunks; ++cc) {
+              wtc_mma2(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first);
+              first = 1u;
+              a_lo += 16; b_lo += 16;
+            }
+          }
+        }
+        wtc_commit(&bar_free[s]);
+        if (it == n_my - 1) wtc_commit(&bar_done);
+      }
+      __syncwarp();
+    }
+  }
+
+  // =============================================================== accumulators -> dW
+  if (lane == 0) wmbar_wait_spin(&bar_done, 0);
+  __syncwarp();
+  __syncthreads();                                               // (the operand stages are dead: their memory becomes the dW block)
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  float* const blk = reinterpret_cast<float*>(smem);             // [co][ci of this CTA][ky][kx] = dW order
+  const int KK = a.kh * a.kw;
+  const int seg = np * 8 * KK;
+  {
+    // row m of an M = 64 accumulator lives in TMEM lane (m % 16) + 32 * (m / 16), of an M = 128 one in lane m; the warps
+    // w, w + 4, ... share the lane quarter w & 3 and split the (item, 8-column chunk) pairs
+    const int qd = warp & 3, slot = warp >> 2;
+    const int n_slots = (WG4_THREADS / 32 - qd + 3) >> 2;        // warps of this lane quarter
+    const int m = t.M == 64 ? 16 * qd + lane : 32 * qd + lane;
+    const int g = m >> 3, ci = m & 7;                            // row group: kx tap, or (1x1) channel plane
+    const bool mine = (t.M == 64 ? lane < 16 : true) && (t.gemm ? g < np : g < a.kw);
+    const int n_chunks = t.N >> 3;
+    const int pairs = items * n_chunks;
+    for (int k = slot; k < pairs && !(t.dbg & 8); k += n_slots) {
+      const int item = k / n_chunks, c0 = (k - item * n_chunks) << 3;
+      float v[8];
+      wtmem_ld8(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(item * t.N + c0), v);
+      for (int cp = 1; cp < t.copies; ++cp) {
+        float w8[8];
+        wtmem_ld8(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)((cp * items + item) * t.N + c0), w8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w8[j];
+      }
+      if (mine) {
+        const int kyi = c0 / a.cb, cb0 = c0 - kyi * a.cb;        // column group = (kyi, 8-channel plane); ky = kh-1-kyi
+        const int ky = a.kh - 1 - kyi;
+        const int row = t.gemm ? (g * 8 + ci) : ((item * 8 + ci) * KK + ky * a.kw + g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) blk[(cb0 + j) * seg + row] = v[j];
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int total = a.cb * seg;
+    const int ci0 = pl0 << 3;
+    if (t.vec && ci0 + np * 8 <= a.ca_lim && !(t.dbg & 8)) {
+      float* const base = a.dW + (long)ci0 * a.s_ca;
+      for (int e = tid * 4; e < total; e += WG4_THREADS * 4) {
+        const int co = e / seg, i = e - co * seg;
+        wred_v4(base + (long)co * a.s_cb + i, *reinterpret_cast<const float4*>(blk + e));
+      }
+    } else if (!(t.dbg & 8)) {
+      for (int e = tid; e < total; e += WG4_THREADS) {
+        const int co = e / seg, rem = e - co * seg;
+        const int cil = rem / KK, tap = rem - cil * KK;
+        const int ci = ci0 + cil;
+        if (ci >= a.ca_lim) continue;
+        const float v = blk[e];
+        if (a.b_s2d) {
+          // transposed conv: virtual tap (ty, tx) x phase (py, px) -> real tap: (0,0)->1, (0,1)->2, (1,1)->0, (1,0)->none
+          const int ky = tap / a.kw, kx = tap - ky * a.kw;
+          const int vco = a.b_col0 + co, ph = vco / a.cph, c = vco - ph * a.cph;
+          const int py = ph >> 1, px = ph & 1;
+          const int rky = ky == 0 ? (py ? 2 : 1) : (py ? 0 : -1);
+          const int rkx = kx == 0 ? (px ? 2 : 1) : (px ? 0 : -1);
+          if (ph < 4 && c < a.cb_lim && rky >= 0 && rkx >= 0) atomicAdd(a.dW + (long)ci * a.s_ca + (long)c * a.s_cb + (rky * 3 + rkx), v);
+        } else if (co < a.cb_lim) atomicAdd(a.dW + (long)ci * a.s_ca + (long)co * a.s_cb + tap, v);
+      }
+    }
+  }
+  if (a.dbias != nullptr && tid < a.cb) {
+    const float v = sbias[tid];
+    if (v != 0.f) {
+      if (a.b_s2d) {
+        if (((a.b_col0 + tid) % a.cph) < a.cb_lim) atomicAdd(a.dbias + ((a.b_col0 + tid) % a.cph), v);
+      } else if (tid < a.cb_lim) atomicAdd(a.dbias + tid, v);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(t.tmem_cols) : "memory");
+}
+
+static bool wgrad_tc4_config(const WgradArgs& a, Wg4Tile& t, size_t& smem, int& ctas) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("MSAU_WG4_OFF"); off = e ? atoi(e) : 0; }
+  if (off) return false;
+  const bool one = a.kh == 1 && a.kw == 1;
+  if (a.a_nchw || a.maskB || a.cb <= 16 || a.cb > 128 || (a.cb & 7) || (a.ca & 7)) return false;
+  if (!one && a.dila != 1) return false;
+  if (one && (a.pada_t != 0 || a.pada_l != 0)) return false;
+  memset(&t, 0, sizeof(t));
+  const int planes = a.ca >> 3;
+  t.gemm = one;
+  t.nyp = a.cb >> 3;
+  t.N = a.kh * a.cb;
+  if (t.N > 256) return false;
+  int ppc_max;
+  if (one) { t.M = planes > 8 ? 128 : 64; ppc_max = t.M >> 3; }
+  else { t.M = 64; ppc_max = 512 / t.N; }
+  if (ppc_max < 1) return false;
+  t.n_groups = cdiv(planes, ppc_max);
+  t.ppc = cdiv(planes, t.n_groups);
+  const int items = one ? 1 : t.ppc;
+  t.copies = WG4_MMA_WARPS / items;
+  if (t.copies > 512 / (items * t.N)) t.copies = 512 / (items * t.N);
+  if (t.copies < 1) t.copies = 1;
+  t.TC = round_up(a.Wq, 16);
+  if (t.TC > 64) t.TC = 64;
+  t.HWx = t.TC + (a.kw - 1);
+  t.tiles_x = cdiv(a.Wq, t.TC);
+  int cx = sm_count() / t.n_groups;
+  if (cx < 1) cx = 1;
+  const size_t budget = 200 * 1024;
+  const int KK = a.kh * a.kw;
+  const size_t blk_bytes = (size_t)a.cb * t.ppc * 8 * KK * 4;
+  // tile rows: the cheapest schedule per CTA.  A tile costs one memory latency per loader round (WG4_U x WG4_LOAD_WARPS items),
+  // the conversion of its items and a hand-shake; the kh-1 halo rows of the staged dY tile favour tall tiles, the balance over
+  // the CTAs short ones (constants in microseconds, from the role timings in profiles/README.md)
+  double best = 1e300;
+  int best_tr = 0, best_s = 0;
+  for (int tr = 1; tr <= 16 && tr <= a.Hq; ++tr) {
+    const uint32_t xpb = one ? (uint32_t)(tr * t.TC * 16) : (uint32_t)((tr * t.HWx + 23) * 16 + 127) / 128 * 128;
+    const uint32_t yb = (uint32_t)((tr + a.kh - 1) * t.nyp * t.TC * 16);
+    const size_t stage = ((size_t)t.ppc * xpb + yb + 1023) / 1024 * 1024;
+    const size_t tail = one ? (size_t)(t.M >> 3) * xpb : 0;      // 1x1: the row groups past the CTA's planes are read (and ignored)
+    int S = (int)((budget - tail) / stage);
+    if (budget < tail || S < 2) continue;
+    if (S > WG4_MAX_S) S = WG4_MAX_S;
+    if ((size_t)S * stage + tail < blk_bytes) continue;
+    const long n_tiles = (long)t.tiles_x * cdiv(a.Hq, tr) * a.B;
+    const long tpc = (n_tiles + cx - 1) / cx;
+    const int n_items = t.ppc * tr + (a.kw > 1 ? t.ppc : 0) + (tr + a.kh - 1) * t.nyp;
+    const int rounds = cdiv(n_items, WG4_U * WG4_LOAD_WARPS);
+    double cost = (double)tpc * (1.2 * rounds + 0.017 * n_items + 0.3) * (S >= 3 ? 1.0 : 1.06);
+    if (t.copies > tr) cost *= 4.0;
+    if (cost < best) { best = cost; best_tr = tr; best_s = S; }
+  }
+  if (!best_tr) return false;
+  t.TR = best_tr; t.S = best_s;
+  if (t.copies > t.TR) t.copies = t.TR;
+  t.TRy = t.TR + a.kh - 1;
+  t.x_plane_bytes = one ? (uint32_t)(t.TR * t.TC * 16) : (uint32_t)((t.TR * t.HWx + 23) * 16 + 127) / 128 * 128;
+  t.x_bytes = (uint32_t)t.ppc * t.x_plane_bytes;
+  t.stage_bytes = (uint32_t)((t.x_bytes + (size_t)t.TRy * t.nyp * t.TC * 16 + 1023) / 1024 * 1024);
+  smem = (size_t)t.S * t.stage_bytes + (one ? (size_t)(t.M >> 3) * t.x_plane_bytes : 0) + 1024;
+  const int cols = items * t.copies * t.N;
+  t.tmem_cols = 32;
+  while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
+  if (t.tmem_cols > 512) return false;
+  t.tiles_y = cdiv(a.Hq, t.TR);
+  t.n_tiles = t.tiles_x * t.tiles_y * a.B;
+  ctas = cx < t.n_tiles ? cx : t.n_tiles;
+  t.tiles_per_cta = cdiv(t.n_tiles, ctas);
+  ctas = cdiv(t.n_tiles, t.tiles_per_cta);
+  t.m_tr = ((1u << 20) + t.TR - 1) / t.TR;
+  t.m_nyp = ((1u << 20) + t.nyp - 1) / t.nyp;
+  { const int nh = t.HWx - t.TC; t.m_nh = nh > 0 ? ((1u << 20) + nh - 1) / nh : 0; }
+  t.vec = !a.b_s2d && a.s_ca == KK && (a.s_cb & 3) == 0 && (((uintptr_t)a.dW) & 15) == 0 && a.cb_lim >= a.cb;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_WG_DBG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
+  return true;
+}
+
+static int launch_wgrad_tc4(const WgradArgs& a, const Wg4Tile& t, size_t smem, int ctas, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    MSAU_CUDA_TRY(cudaFuncSetAttribute(wgrad_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
+    attr = true;
+  }
+  dim3 grid(ctas, t.n_groups);
+  const double npq = (double)a.B * a.Hq * a.Wq;
+  const double wbytes = (npq * a.ca + (double)a.B * a.Hb * a.Wb * (a.b_s2d ? a.cph : a.cb)) * 4.0;
+  ProfScope ps(a.skip_flag ? "dense_first_layer_skippable" : "wgrad_tc4_kernel", a.ca, a.cb, a.kh, a.dila, a.Wq, a.a_nchw,
+               a.skip_flag ? 0.0 : 2.0 * npq * a.kh * a.kw * a.ca * a.cb, a.skip_flag ? 0.0 : wbytes, st);
+  MSAU_CUDA_TRY(launch_pdl(wgrad_tc4_kernel, grid, dim3(WG4_THREADS), smem, st, a, t));
+  MSAU_CUDA_TRY(cudaGetLastError());
+  return MSAU_OK;
+}
+
 static bool wg_config(const WgradArgs& a, WgTile& t, size_t& smem, int& ctas_out) {
   t.N = a.cb;                           // M = 64 allows any multiple of 8
   t.ny_planes = a.cb >> 3;
@@ -1142,6 +1589,7 @@ static bool wg_config(const WgradArgs& a, WgTile& t, size_t& smem, int& ctas_out
   t.tmem_cols = 32;
   while ((int)t.tmem_cols < cols) t.tmem_cols <<= 1;
   smem = (size_t)t.stage_bytes * 2 + 1024;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_WG_DBG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
   ctas_out = ctas;
   return smem <= 200 * 1024 && t.tmem_cols <= 512;
 }
@@ -1177,6 +1625,10 @@ int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   {
     Wg3Tile t3;
     if (wgrad_tc3_config(a, t3)) return launch_wgrad_tc3(a, t3, st);
+    Wg4Tile t4;
+    size_t smem4 = 0;
+    int ctas4 = 0;
+    if (wgrad_tc4_config(a, t4, smem4, ctas4)) return launch_wgrad_tc4(a, t4, smem4, ctas4, st);
     Wg2Tile t2;
     if (wgrad_tc2_config(a, t2)) return launch_wgrad_tc2(a, t2, st);
   }

@@ -1,6 +1,6 @@
 """Per-layer-shape kernel timing of one train step (MSAU_PROF_DETAIL=1)."""
 import os, sys
-os.environ["MSAU_PROF_DETAIL"] = "1"
+os.environ.setdefault("MSAU_PROF_DETAIL", "1")      # MSAU_PROF_DETAIL=0: per-kernel-family totals (cheaper host side)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import msau_b200
