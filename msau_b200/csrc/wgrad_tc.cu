@@ -1123,14 +1123,19 @@ static int launch_wgrad_tc3(const WgradArgs& a, const Wg3Tile& t0, cudaStream_t 
 struct Wg4Tile {
   int TR, TC, HWx, TRy, nyp, N, M;           // X rows / columns per tile, X row pitch (px), staged dY rows, dY planes, MMA N and M
   int ppc, n_groups, gemm, S, copies;        // X planes per CTA, plane groups (grid.y), 1x1 mode, stages, accumulator copies per item
+  int pmode, TRx;                            // per-ky accumulators (dilated / wide layers): X tile has the (kh-1)*dil halo rows, dY none
   int tiles_x, tiles_y, n_tiles, tiles_per_cta;
   uint32_t x_plane_bytes, x_bytes, stage_bytes, tmem_cols;
   int vec;                                   // dW layout / alignment allow 16-byte reductions (checked on the host)
-  uint32_t m_tr, m_nyp, m_nh;                // ceil(2^20 / d) for d = TR, nyp, HWx - TC: j / d = (j * m) >> 20 for the item indices (j < 4096)
+  // loaders: lanes per pixel (log2) / pixels per load instruction / items per tile row, for X and dY; dY plane groups (s2d: phases)
+  int lg_lpp_x, pxi_x, spr_x, lg_lpp_y, pxi_y, spr_y, ppg, ngrp, lg_ngrp;
+  uint32_t y_pitch;                          // bytes between the channel planes of a staged dY row (TC pixels + bank padding)
+  uint32_t m_sx, m_sy;                       // ceil(2^20 / d) for d = spr_x, spr_y: j / d = (j * m) >> 20 for the item indices (j < 4096)
   int dbg;
 };
 static constexpr int WG4_LOAD_WARPS = 16;
-static constexpr int WG4_U = 2;                 // items (two pixels per lane each) whose loads are in flight per warp
+static constexpr int WG4_U = 2;                 // items whose loads are in flight per warp
+static constexpr int WG4_K = 4;                 // load instructions (16 B per lane) per item
 static constexpr int WG4_MMA_WARPS = 2;         // (576 threads: 112 registers each)
 static constexpr int WG4_THREADS = (WG4_LOAD_WARPS + WG4_MMA_WARPS) * 32;
 static constexpr int WG4_MAX_S = 4;
@@ -1154,7 +1159,7 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
   const int tile0 = blockIdx.x * t.tiles_per_cta;
   const int tile1 = min(t.n_tiles, tile0 + t.tiles_per_cta);
   const int n_my = tile1 - tile0;
-  const int items = t.gemm ? 1 : np;                             // accumulators = items x copies; copy c takes the rows r = c (mod copies)
+  const int items = t.gemm ? 1 : (t.pmode ? np * a.kh : np);     // accumulators = items x copies; copy c takes the rows r = c (mod copies)
   const int n_acc = items * t.copies;
   const int n_iss = min(WG4_MMA_WARPS, n_acc);
   if (a.skip_flag) {                               // (the flag is written by an earlier kernel of this step: wait for it first)
@@ -1187,22 +1192,26 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
 
   if (warp < WG4_LOAD_WARPS) {
     // =============================================================== loaders
-    // Items of a tile, each at most two pixels per lane: X rows (plane, row: columns lane and lane + 32), X halo columns (one
-    // item per plane: the TR x (kw-1) pixels right of column TC), dY rows (staged row, plane).  Warp w takes the items
-    // w, w + 16, ...; ALL of a round's loads (WG4_U items = 16 x 16 B per lane) are issued before the first conversion, so a
-    // tile costs one memory latency, not one per pair of items (measured: 2 items per round made the loaders the critical path).
-    const int nh = t.HWx - t.TC;                                 // X halo columns per row
-    const int n_x = np * t.TR;
-    const int n_h = nh > 0 ? np : 0;
-    const int n_items = n_x + n_h + t.TRy * t.nyp;
+    // Every warp-level load instruction reads whole pixels: the channels of ALL the CTA's X planes (or of all the dY planes of
+    // one memory-contiguous group) are consecutive in an NHWC pixel, so lane = (pixel in the instruction, 16-byte chunk of the
+    // pixel) touches 32 / lanes-per-pixel cache lines per instruction instead of 32 (one lane per pixel: measured L1-wavefront
+    // bound, 128 wavefronts per 2 KB).  An item = WG4_K such instructions = 2 KB: a run of pixels of one tile row.  Warp w takes
+    // the items w, w + 16, ...; the loads of WG4_U items are in flight before the first conversion (deeper measured slower).
+    // Each lane converts its 4 floats to 4 bf16 = one 8-byte store into the [8 ch] slot of its (plane, pixel).
+    const int n_xi = t.TRx * t.spr_x;                            // X items: (row, run of pixels), all planes of the CTA
+    const int n_items = n_xi + t.TRy * t.spr_y * t.ngrp;         // dY items: (staged row, run of pixels, plane group)
     const int smul = a.b_s2d ? 2 : 1;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    // the dY plane of this warp's items never changes when the warp count is a multiple of the plane count: the bias gradient
-    // then stays in registers for the whole kernel
-    const bool fixed_pl = (WG4_LOAD_WARPS % t.nyp) == 0;
-    float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int pxl_x = lane >> t.lg_lpp_x, ch_x = lane & ((1 << t.lg_lpp_x) - 1);
+    const int pxl_y = lane >> t.lg_lpp_y, ch_y = lane & ((1 << t.lg_lpp_y) - 1);
+    const bool act_x = ch_x < np * 2, act_y = ch_y < t.ppg * 2;
+    const uint32_t lane_dx = (uint32_t)(ch_x >> 1) * t.x_plane_bytes + (uint32_t)(ch_x & 1) * 8u;
+    const uint32_t lane_dy = (uint32_t)(ch_y >> 1) * t.y_pitch + (uint32_t)(ch_y & 1) * 8u;
+    // dY items of this warp always belong to the same plane group (16 % ngrp == 0): a lane's 4 bias-gradient channels stay in
+    // registers for the whole kernel
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
     int bacc_pl = -1;
-    struct Item { const float* sA; const float* sB; uint8_t* dA; uint8_t* dB; bool okA, okB, stA, stB, relu, bias; int pl; };
+    struct Item { const float* src; uint32_t dst; int step, px0, lim; bool row_ok, is_x, bias; };
     int tx = tile0 % t.tiles_x, ty = (tile0 / t.tiles_x) % t.tiles_y, b = (tile0 / t.tiles_x) / t.tiles_y;
     for (int it = 0; it < n_my; ++it) {
       const int s = it % t.S;
@@ -1210,77 +1219,70 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
         if (lane == 0) wmbar_wait_spin(&bar_free[s], ((it / t.S) - 1) & 1);
         __syncwarp();
       }
-      uint8_t* const st = smem + (size_t)s * t.stage_bytes;
-      uint8_t* const yh = st + t.x_bytes;
+      const uint32_t st = wsmem_u32(smem + (size_t)s * t.stage_bytes);
+      const uint32_t yh = st + t.x_bytes;
       const int qy0 = ty * t.TR, qx0 = tx * t.TC;
       const int in_x0 = qx0 - a.pada_l;
-      const int vy0 = qy0 + a.pada_t - (a.kh - 1);
+      const int in_y0 = t.pmode ? qy0 - a.pada_t : qy0;           // the vertical taps live in the dY rows unless pmode
+      const int vy0 = t.pmode ? qy0 : qy0 + a.pada_t - (a.kh - 1);
       const float* const ximg = a.A + (long)b * a.Ha * a.Wa * a.pa + (pl0 << 3);
       const float* const yimg = a.Bm + (long)b * a.Hb * a.Wb * a.pb;
+      // px0 = tile column of this lane's first pixel; pixel k of the item is px0 + k * pxi (global: + k * step floats); a pixel is
+      // loaded when px < lim (inside the tile and the image) and stored (zero-filled) when it is inside the tile
       auto decode = [&](int j) {
         Item I;
-        I.relu = false; I.bias = false; I.pl = 0;
-        if (j < n_x) {
-          const int p = (int)(((uint32_t)j * t.m_tr) >> 20), r = j - p * t.TR;
-          const int gy = qy0 + r, gx0 = in_x0 + lane, gx1 = gx0 + 32;
-          const bool oky = gy < a.Ha;
-          I.stA = lane < t.TC; I.stB = lane + 32 < t.TC;
-          I.okA = oky && I.stA && (unsigned)gx0 < (unsigned)a.Wa;
-          I.okB = oky && I.stB && (unsigned)gx1 < (unsigned)a.Wa;
-          I.sA = ximg + (gy * a.Wa + gx0) * a.pa + (p << 3);
-          I.sB = I.sA + 32 * a.pa;
-          I.dA = st + (size_t)p * t.x_plane_bytes + (size_t)(r * t.HWx + lane) * 16;
-          I.dB = I.dA + 512;
-          I.relu = a.reluA != 0;
-        } else if (j < n_x + n_h) {
-          const int p = j - n_x;
-          const int e0 = lane, e1 = lane + 32;
-          const int r0 = (int)(((uint32_t)e0 * t.m_nh) >> 20), c0 = t.TC + (e0 - r0 * nh);
-          const int r1 = (int)(((uint32_t)e1 * t.m_nh) >> 20), c1 = t.TC + (e1 - r1 * nh);
-          I.stA = r0 < t.TR; I.stB = r1 < t.TR;
-          const int gy0 = qy0 + r0, gy1 = qy0 + r1, gx0 = in_x0 + c0, gx1 = in_x0 + c1;
-          I.okA = I.stA && gy0 < a.Ha && (unsigned)gx0 < (unsigned)a.Wa;
-          I.okB = I.stB && gy1 < a.Ha && (unsigned)gx1 < (unsigned)a.Wa;
-          I.sA = ximg + (gy0 * a.Wa + gx0) * a.pa + (p << 3);
-          I.sB = ximg + (gy1 * a.Wa + gx1) * a.pa + (p << 3);
-          I.dA = st + (size_t)p * t.x_plane_bytes + (size_t)(r0 * t.HWx + c0) * 16;
-          I.dB = st + (size_t)p * t.x_plane_bytes + (size_t)(r1 * t.HWx + c1) * 16;
-          I.relu = a.reluA != 0;
+        I.bias = false;
+        if (j < n_xi) {
+          const int r = (int)(((uint32_t)j * t.m_sx) >> 20), seg = j - r * t.spr_x;
+          const int gy = in_y0 + r;
+          I.is_x = true;
+          I.px0 = seg * WG4_K * t.pxi_x + pxl_x;
+          I.row_ok = act_x && (unsigned)gy < (unsigned)a.Ha;
+          I.lim = min(t.HWx, a.Wa - in_x0);                      // (the left image border: gx >= 0, checked per pixel)
+          I.src = ximg + ((long)gy * a.Wa + in_x0 + I.px0) * a.pa + ch_x * 4;
+          I.step = t.pxi_x * a.pa;
+          I.dst = st + lane_dx + (uint32_t)(r * t.HWx + I.px0) * 16u;
         } else {
-          const int jj = j - n_x - n_h;
-          const int r = (int)(((uint32_t)jj * t.m_nyp) >> 20), pl = jj - r * t.nyp;
-          // b_s2d: plane pl of the virtual tensor = phase (py, px), channels [c0, c0+8) of the physical one
-          const int sph = a.b_s2d ? (a.b_col0 + (pl << 3)) / a.cph : 0;
+          const int jj = j - n_xi;
+          const int g = jj & (t.ngrp - 1), rest = jj >> t.lg_ngrp;
+          const int r = (int)(((uint32_t)rest * t.m_sy) >> 20), seg = rest - r * t.spr_y;
+          // b_s2d: the planes of group g are one phase (py, px) of the physical tensor, channels [choff, choff + 8 ppg)
+          const int col0 = a.b_col0 + g * t.ppg * 8;
+          const int sph = a.b_s2d ? col0 / a.cph : 0;
+          const int choff = a.b_s2d ? col0 - sph * a.cph : g * t.ppg * 8;
           const int spy = sph >> 1, spx = sph & 1;
           const int vy = vy0 + r, gy = vy * smul + spy;
-          const int vx0 = qx0 + lane, vx1 = vx0 + 32;
-          const int gx0 = vx0 * smul + spx, gx1 = vx1 * smul + spx;
-          const bool oky = (unsigned)vy < (unsigned)a.Hq && gy < a.Hb;
-          I.stA = lane < t.TC; I.stB = lane + 32 < t.TC;
-          I.okA = oky && I.stA && vx0 < a.Wq && gx0 < a.Wb;
-          I.okB = oky && I.stB && vx1 < a.Wq && gx1 < a.Wb;
-          I.sA = yimg + (gy * a.Wb + gx0) * a.pb + (a.b_s2d ? a.b_col0 + (pl << 3) - sph * a.cph : (pl << 3));
-          I.sB = I.sA + 32 * smul * a.pb;
-          I.dA = yh + (size_t)((r * t.nyp + pl) * t.TC + lane) * 16;
-          I.dB = I.dA + 512;
+          I.is_x = false;
+          I.px0 = seg * WG4_K * t.pxi_y + pxl_y;
+          I.row_ok = act_y && (unsigned)vy < (unsigned)a.Hq && gy < a.Hb;
+          // vx = qx0 + px < Wq and gx = vx * smul + spx < Wb
+          I.lim = min(t.TC, min(a.Wq - qx0, (a.Wb - spx + smul - 1) / smul - qx0));
+          I.src = yimg + ((long)gy * a.Wb + (qx0 + I.px0) * smul + spx) * a.pb + choff + ch_y * 4;
+          I.step = t.pxi_y * smul * a.pb;
+          const int pl = g * t.ppg + (ch_y >> 1);
+          I.dst = yh + lane_dy + (uint32_t)(r * t.nyp + g * t.ppg) * t.y_pitch + (uint32_t)I.px0 * 16u;
           // bias gradient: rows of this tile only (halo rows belong to the neighbours); the planes are spread over the groups
-          I.bias = a.dbias != nullptr && (pl % t.n_groups) == group && vy >= qy0 && vy < qy0 + t.TR;
-          I.pl = pl;
+          I.bias = a.dbias != nullptr && act_y && (pl % t.n_groups) == group && vy >= qy0 && vy < qy0 + t.TR;
+          if (I.bias) bacc_pl = pl;
         }
         return I;
       };
       const bool skip_ld = (t.dbg & 1) != 0;
       for (int j0 = warp; j0 < n_items && !skip_ld; j0 += WG4_U * WG4_LOAD_WARPS) {
-        float4 q[WG4_U][2][2];
+        float4 q[WG4_U][WG4_K];
 #pragma unroll
         for (int u = 0; u < WG4_U; ++u) {
           const int j = j0 + u * WG4_LOAD_WARPS;
           if (j < n_items) {
             const Item I = decode(j);
-            const float4* sp0 = reinterpret_cast<const float4*>(I.sA);
-            const float4* sp1 = reinterpret_cast<const float4*>(I.sB);
-            q[u][0][0] = I.okA ? __ldg(sp0) : z4; q[u][0][1] = I.okA ? __ldg(sp0 + 1) : z4;
-            q[u][1][0] = I.okB ? __ldg(sp1) : z4; q[u][1][1] = I.okB ? __ldg(sp1 + 1) : z4;
+            const int pxi = I.is_x ? t.pxi_x : t.pxi_y;
+            const int gx0 = I.is_x ? in_x0 + I.px0 : 0;         // X: global column of pixel 0 (may be negative: left padding)
+#pragma unroll
+            for (int k = 0; k < WG4_K; ++k) {
+              const int px = I.px0 + k * pxi;
+              const bool ok = I.row_ok && px < I.lim && gx0 + k * pxi >= 0;
+              q[u][k] = ok ? __ldg(reinterpret_cast<const float4*>(I.src + (long)k * I.step)) : z4;
+            }
           }
         }
 #pragma unroll
@@ -1288,33 +1290,19 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
           const int j = j0 + u * WG4_LOAD_WARPS;
           if (j < n_items) {
             const Item I = decode(j);
-            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const int pxi = I.is_x ? t.pxi_x : t.pxi_y;
+            const int ext = I.is_x ? t.HWx : t.TC;
+            const bool act = I.is_x ? act_x : act_y;
+            const bool relu = I.is_x && a.reluA;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              float v[8] = {q[u][k][0].x, q[u][k][0].y, q[u][k][0].z, q[u][k][0].w, q[u][k][1].x, q[u][k][1].y, q[u][k][1].z, q[u][k][1].w};
-              if (I.relu) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
-              }
-              if (I.bias) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) bsum[c] += v[c];
-              }
-              if (k == 0 ? I.stA : I.stB) *reinterpret_cast<uint4*>(k == 0 ? I.dA : I.dB) = wpack8(v);
-            }
-            if (I.bias) {                                          // (warp-uniform)
-              if (fixed_pl) {
-                bacc_pl = I.pl;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) bacc[c] += bsum[c];
-              } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  float sum = bsum[c];
-#pragma unroll
-                  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                  if (lane == 0) atomicAdd(&sbias[I.pl * 8 + c], sum);
-                }
+            for (int k = 0; k < WG4_K; ++k) {
+              float4 v = q[u][k];
+              if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (I.bias) { bacc[0] += v.x; bacc[1] += v.y; bacc[2] += v.z; bacc[3] += v.w; }
+              if (act && I.px0 + k * pxi < ext) {
+                const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+                const uint32_t u0 = *reinterpret_cast<const uint32_t*>(&h0), u1 = *reinterpret_cast<const uint32_t*>(&h1);
+                asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(I.dst + (uint32_t)(k * pxi) * 16u), "r"(u0), "r"(u1) : "memory");
               }
             }
           }
@@ -1325,13 +1313,13 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
       if (lane == 0) wmbar_arrive(&bar_full[s]);
       if (++tx == t.tiles_x) { tx = 0; if (++ty == t.tiles_y) { ty = 0; ++b; } }
     }
-    if (bacc_pl >= 0) {
+    if (a.dbias != nullptr) {
+      // lanes with the same chunk (= channel quadruple) hold partial sums of different pixels
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float sum = bacc[c];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) atomicAdd(&sbias[bacc_pl * 8 + c], sum);
+        for (int o = 16; o >= (1 << t.lg_lpp_y); o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (pxl_y == 0 && bacc_pl >= 0) atomicAdd(&sbias[bacc_pl * 8 + (ch_y & 1) * 4 + c], sum);
       }
     }
   } else if (warp - WG4_LOAD_WARPS < n_iss) {
@@ -1342,9 +1330,9 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
     const int chunks = t.TC >> 4;
     const uint32_t lbo = (128u >> 4) << 16;
     // row groups of the X operand: the kx taps (one pixel apart) or, 1x1, the channel planes; column groups of dY: (ky, plane)
-    const uint32_t a_hi = ((t.gemm ? (t.x_plane_bytes >> 4) : 1u) & 0x3FFF) | (1u << 14);
-    const uint32_t b_hi = ((uint32_t)t.TC & 0x3FFF) | (1u << 14);
-    const uint32_t yrow16 = (uint32_t)(t.nyp * t.TC);            // staged dY row pitch, 16-B units
+    const uint32_t a_hi = ((t.gemm ? (t.x_plane_bytes >> 4) : (uint32_t)a.dila) & 0x3FFF) | (1u << 14);
+    const uint32_t b_hi = ((t.y_pitch >> 4) & 0x3FFF) | (1u << 14);
+    const uint32_t yrow16 = (uint32_t)t.nyp * (t.y_pitch >> 4);   // staged dY row pitch, 16-B units
     for (int it = 0; it < n_my; ++it) {
       const int s = it % t.S;
       if (lane == 0) wmbar_wait_spin(&bar_full[s], (it / t.S) & 1);
@@ -1356,7 +1344,9 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
         for (int acc = w; acc < n_acc; acc += WG4_MMA_WARPS) {
           const int item = acc % items, copy = acc / items;
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * t.N);
-          const uint32_t a16 = (xh >> 4) + (t.gemm ? 0u : (uint32_t)item * (t.x_plane_bytes >> 4));
+          // item = X plane, or (pmode) plane * kh + ky: the same plane image, ky * dil rows further down
+          const int ipl = t.pmode ? item / a.kh : item, iky = t.pmode ? item - ipl * a.kh : 0;
+          const uint32_t a16 = (xh >> 4) + (t.gemm ? 0u : (uint32_t)ipl * (t.x_plane_bytes >> 4) + (uint32_t)(iky * a.dila * t.HWx));
           uint32_t first = (it == 0) ? 0u : 1u;
           for (int r = copy; r < ((t.dbg & 2) ? 0 : t.TR); r += t.copies) {
             uint32_t a_lo = ((a16 + (uint32_t)(r * t.HWx)) & 0x3FFF) | lbo;
@@ -1405,8 +1395,9 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
       }
       if (mine) {
         const int kyi = c0 / a.cb, cb0 = c0 - kyi * a.cb;        // column group = (kyi, 8-channel plane); ky = kh-1-kyi
-        const int ky = a.kh - 1 - kyi;
-        const int row = t.gemm ? (g * 8 + ci) : ((item * 8 + ci) * KK + ky * a.kw + g);
+        const int ipl = t.pmode ? item / a.kh : item;
+        const int ky = t.pmode ? item - ipl * a.kh : a.kh - 1 - kyi;
+        const int row = t.gemm ? (g * 8 + ci) : ((ipl * 8 + ci) * KK + ky * a.kw + g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) blk[(cb0 + j) * seg + row] = v[j];
       }
@@ -1459,42 +1450,74 @@ static bool wgrad_tc4_config(const WgradArgs& a, Wg4Tile& t, size_t& smem, int& 
   if (off < 0) { const char* e = getenv("MSAU_WG4_OFF"); off = e ? atoi(e) : 0; }
   if (off) return false;
   const bool one = a.kh == 1 && a.kw == 1;
-  if (a.a_nchw || a.maskB || a.cb <= 16 || a.cb > 128 || (a.cb & 7) || (a.ca & 7)) return false;
-  if (!one && a.dila != 1) return false;
+  if (a.a_nchw || a.maskB || a.cb > 128 || (a.cb & 7) || (a.ca & 7)) return false;
   if (one && (a.pada_t != 0 || a.pada_l != 0)) return false;
+  // per-ky accumulators when the taps cannot ride in the dY column groups: dilation, or kh * cout beyond one instruction
+  const bool pmode = !one && (a.dila != 1 || a.kh * a.cb > 256);
+  if (!pmode && a.cb <= 16) return false;                        // (wgrad_tc3 / wgrad_tc2 own the <= 16-channel streaming levels)
+  if (pmode && a.b_s2d) return false;
   memset(&t, 0, sizeof(t));
   const int planes = a.ca >> 3;
   t.gemm = one;
+  t.pmode = pmode;
   t.nyp = a.cb >> 3;
-  t.N = a.kh * a.cb;
+  t.N = pmode ? a.cb : a.kh * a.cb;
   if (t.N > 256) return false;
   int ppc_max;
   if (one) { t.M = planes > 8 ? 128 : 64; ppc_max = t.M >> 3; }
-  else { t.M = 64; ppc_max = 512 / t.N; }
+  else { t.M = 64; ppc_max = 512 / (a.kh * a.cb); if (ppc_max > 16) ppc_max = 16; }
   if (ppc_max < 1) return false;
   t.n_groups = cdiv(planes, ppc_max);
   t.ppc = cdiv(planes, t.n_groups);
-  const int items = one ? 1 : t.ppc;
+  const int items = one ? 1 : (pmode ? t.ppc * a.kh : t.ppc);
   t.copies = WG4_MMA_WARPS / items;
   if (t.copies > 512 / (items * t.N)) t.copies = 512 / (items * t.N);
   if (t.copies < 1) t.copies = 1;
   t.TC = round_up(a.Wq, 16);
   if (t.TC > 64) t.TC = 64;
-  t.HWx = t.TC + (a.kw - 1);
+  t.HWx = t.TC + (a.kw - 1) * a.dila;
   t.tiles_x = cdiv(a.Wq, t.TC);
+  const int xhalo = pmode ? (a.kh - 1) * a.dila : 0, yhalo = pmode ? 0 : a.kh - 1;     // halo rows of the X / dY tile
+  // loader geometry: lanes per pixel = the 16-byte chunks of the pixel's channel run, rounded up to a power of two
+  auto lg_pow2_at_least = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  t.lg_lpp_x = lg_pow2_at_least(t.ppc * 2);
+  if (a.b_s2d) {
+    // the window [b_col0, b_col0 + cb) of the phase-major virtual columns is either inside one phase or made of whole phases
+    if (a.cph >= a.cb) {
+      if ((a.b_col0 % a.cph) + a.cb > a.cph) return false;
+      t.ngrp = 1; t.ppg = t.nyp;
+    } else {
+      if ((a.b_col0 % a.cph) || (a.cb % a.cph) || (a.cph & 7)) return false;
+      t.ngrp = a.cb / a.cph; t.ppg = a.cph >> 3;
+    }
+  } else { t.ngrp = 1; t.ppg = t.nyp; }
+  if (t.ngrp & (t.ngrp - 1)) return false;
+  if (WG4_LOAD_WARPS % t.ngrp) return false;
+  t.lg_ngrp = lg_pow2_at_least(t.ngrp);
+  t.lg_lpp_y = lg_pow2_at_least(t.ppg * 2);
+  if (t.lg_lpp_x > 5 || t.lg_lpp_y > 5) return false;
+  t.pxi_x = 32 >> t.lg_lpp_x;
+  t.pxi_y = 32 >> t.lg_lpp_y;
+  t.spr_x = cdiv(cdiv(t.HWx, t.pxi_x), WG4_K);
+  t.spr_y = cdiv(cdiv(t.TC, t.pxi_y), WG4_K);
+  // bank padding: the planes' pxi-pixel runs of one store instruction tile the 128-byte bank window
+  const uint32_t pad_x = (uint32_t)(t.pxi_x * 16) % 128u, pad_y = (uint32_t)(t.pxi_y * 16) % 128u;
+  t.y_pitch = (uint32_t)t.TC * 16u + pad_y;
   int cx = sm_count() / t.n_groups;
   if (cx < 1) cx = 1;
   const size_t budget = 200 * 1024;
   const int KK = a.kh * a.kw;
   const size_t blk_bytes = (size_t)a.cb * t.ppc * 8 * KK * 4;
-  // tile rows: the cheapest schedule per CTA.  A tile costs one memory latency per loader round (WG4_U x WG4_LOAD_WARPS items),
-  // the conversion of its items and a hand-shake; the kh-1 halo rows of the staged dY tile favour tall tiles, the balance over
-  // the CTAs short ones (constants in microseconds, from the role timings in profiles/README.md)
+  // tile rows: the cheapest schedule per CTA.  A tile costs its items (2 KB of loads + conversion each) and a hand-shake; the kh-1
+  // halo rows of the staged dY tile favour tall tiles, the balance over the CTAs short ones (constants in microseconds)
+  auto x_plane = [&](int tr) {      // (row groups kw..7 of the instruction read up to 7 * dil + 16 pixels past the useful ones)
+    return (one ? (uint32_t)(tr * t.TC * 16) : (uint32_t)(((tr + xhalo) * t.HWx + 7 * a.dila + 16) * 16 + 127) / 128 * 128) + pad_x;
+  };
   double best = 1e300;
   int best_tr = 0, best_s = 0;
   for (int tr = 1; tr <= 16 && tr <= a.Hq; ++tr) {
-    const uint32_t xpb = one ? (uint32_t)(tr * t.TC * 16) : (uint32_t)((tr * t.HWx + 23) * 16 + 127) / 128 * 128;
-    const uint32_t yb = (uint32_t)((tr + a.kh - 1) * t.nyp * t.TC * 16);
+    const uint32_t xpb = x_plane(tr);
+    const size_t yb = (size_t)(tr + yhalo) * t.nyp * t.y_pitch;
     const size_t stage = ((size_t)t.ppc * xpb + yb + 1023) / 1024 * 1024;
     const size_t tail = one ? (size_t)(t.M >> 3) * xpb : 0;      // 1x1: the row groups past the CTA's planes are read (and ignored)
     int S = (int)((budget - tail) / stage);
@@ -1503,19 +1526,19 @@ static bool wgrad_tc4_config(const WgradArgs& a, Wg4Tile& t, size_t& smem, int& 
     if ((size_t)S * stage + tail < blk_bytes) continue;
     const long n_tiles = (long)t.tiles_x * cdiv(a.Hq, tr) * a.B;
     const long tpc = (n_tiles + cx - 1) / cx;
-    const int n_items = t.ppc * tr + (a.kw > 1 ? t.ppc : 0) + (tr + a.kh - 1) * t.nyp;
-    const int rounds = cdiv(n_items, WG4_U * WG4_LOAD_WARPS);
-    double cost = (double)tpc * (1.2 * rounds + 0.017 * n_items + 0.3) * (S >= 3 ? 1.0 : 1.06);
+    const int n_items = (tr + xhalo) * t.spr_x + (tr + yhalo) * t.spr_y * t.ngrp;
+    double cost = (double)tpc * (0.05 * n_items + 0.3) * (S >= 3 ? 1.0 : 1.06);
     if (t.copies > tr) cost *= 4.0;
     if (cost < best) { best = cost; best_tr = tr; best_s = S; }
   }
   if (!best_tr) return false;
   t.TR = best_tr; t.S = best_s;
   if (t.copies > t.TR) t.copies = t.TR;
-  t.TRy = t.TR + a.kh - 1;
-  t.x_plane_bytes = one ? (uint32_t)(t.TR * t.TC * 16) : (uint32_t)((t.TR * t.HWx + 23) * 16 + 127) / 128 * 128;
+  t.TRy = t.TR + yhalo;
+  t.TRx = t.TR + xhalo;
+  t.x_plane_bytes = x_plane(t.TR);
   t.x_bytes = (uint32_t)t.ppc * t.x_plane_bytes;
-  t.stage_bytes = (uint32_t)((t.x_bytes + (size_t)t.TRy * t.nyp * t.TC * 16 + 1023) / 1024 * 1024);
+  t.stage_bytes = (uint32_t)((t.x_bytes + (size_t)t.TRy * t.nyp * t.y_pitch + 1023) / 1024 * 1024);
   smem = (size_t)t.S * t.stage_bytes + (one ? (size_t)(t.M >> 3) * t.x_plane_bytes : 0) + 1024;
   const int cols = items * t.copies * t.N;
   t.tmem_cols = 32;
@@ -1526,9 +1549,8 @@ static bool wgrad_tc4_config(const WgradArgs& a, Wg4Tile& t, size_t& smem, int& 
   ctas = cx < t.n_tiles ? cx : t.n_tiles;
   t.tiles_per_cta = cdiv(t.n_tiles, ctas);
   ctas = cdiv(t.n_tiles, t.tiles_per_cta);
-  t.m_tr = ((1u << 20) + t.TR - 1) / t.TR;
-  t.m_nyp = ((1u << 20) + t.nyp - 1) / t.nyp;
-  { const int nh = t.HWx - t.TC; t.m_nh = nh > 0 ? ((1u << 20) + nh - 1) / nh : 0; }
+  t.m_sx = ((1u << 20) + t.spr_x - 1) / t.spr_x;
+  t.m_sy = ((1u << 20) + t.spr_y - 1) / t.spr_y;
   t.vec = !a.b_s2d && a.s_ca == KK && (a.s_cb & 3) == 0 && (((uintptr_t)a.dW) & 15) == 0 && a.cb_lim >= a.cb;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("MSAU_WG_DBG"); dbg = e ? atoi(e) : 0; } t.dbg = dbg; }
   return true;
