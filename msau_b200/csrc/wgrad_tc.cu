@@ -1454,7 +1454,11 @@ static bool wgrad_tc4_config(const WgradArgs& a, Wg4Tile& t, size_t& smem, int& 
   if (one && (a.pada_t != 0 || a.pada_l != 0)) return false;
   // per-ky accumulators when the taps cannot ride in the dY column groups: dilation, or kh * cout beyond one instruction
   const bool pmode = !one && (a.dila != 1 || a.kh * a.cb > 256);
-  if (!pmode && a.cb <= 16) return false;                        // (wgrad_tc3 / wgrad_tc2 own the <= 16-channel streaming levels)
+  // measured (profiles/README.md): with one X plane (8 input channels, the 512^2 level) the cp.async pipeline of wgrad_tc3 is faster
+  // (82 vs 110 us); from two planes on this kernel wins because every operand byte is loaded once (16 -> 16 at 256^2: 50 vs 60 us)
+  static int min_ca = -1;
+  if (min_ca < 0) { const char* e = getenv("MSAU_WG4_MIN_CA"); min_ca = e ? atoi(e) : 16; }
+  if (!pmode && a.ca < min_ca) return false;
   if (pmode && a.b_s2d) return false;
   memset(&t, 0, sizeof(t));
   const int planes = a.ca >> 3;
@@ -1645,12 +1649,12 @@ bool wgrad_tc_supported(const WgradArgs& a) {
 int launch_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   MSAU_CHECK_ARG(wgrad_tc_supported(a), "wgrad_tc: unsupported shape");
   {
-    Wg3Tile t3;
-    if (wgrad_tc3_config(a, t3)) return launch_wgrad_tc3(a, t3, st);
     Wg4Tile t4;
     size_t smem4 = 0;
     int ctas4 = 0;
     if (wgrad_tc4_config(a, t4, smem4, ctas4)) return launch_wgrad_tc4(a, t4, smem4, ctas4, st);
+    Wg3Tile t3;
+    if (wgrad_tc3_config(a, t3)) return launch_wgrad_tc3(a, t3, st);
     Wg2Tile t2;
     if (wgrad_tc2_config(a, t2)) return launch_wgrad_tc2(a, t2, st);
   }
