@@ -442,7 +442,7 @@ def main():
     barrier()
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # (rank 0 at N = 1 only: under torchrun the other ranks share the host cores)
         times, threads = cpu_train_pages(3, 1)
         cpu = dict(value=len(times) / sum(times), unit="pages/s", cores=threads, kind="port",
                    sample="3 pages (after 1 warm-up) of the same workload: R1 rasterise + fwd + loss + bwd + clip + Adam, "

@@ -20,7 +20,7 @@ TAG = os.environ.get("MSAU_ROUND", "r2")          # file-name tag of the round t
 FAMILY = [("feature_fill", "feature_fill_kernels"), ("feature_ids", "feature_ids_kernel"), ("ccl_", "ccl_kernels"), ("class_closing", "class_closing_row_kernel"),
           ("conv3_tc_kernel<0, 2,", "conv3_tc_kernel_c32"), ("conv3_tc_kernel<1, 2,", "conv3_tc_kernel_c32"), ("conv3_tc_kernel<2, 2,", "conv3_tc_kernel_c32"),
           ("conv3_tc_kernel<3, 2,", "conv3_tc_kernel_c32"), ("conv3_tc_kernel<4, 2,", "conv3_tc_kernel_c32"), ("conv3_tc_kernel<5, 2,", "conv3_tc_kernel_c32"),
-          ("wgrad_tc3", "wgrad_tc3_kernel"), ("wgrad_tc2", "wgrad_tc2_kernel"), ("wgrad_tc", "wgrad_tc_kernel"), ("conv3_tc", "conv3_tc_kernel"),
+          ("wgrad_tc4", "wgrad_tc4_kernel"), ("wgrad_tc3", "wgrad_tc3_kernel"), ("wgrad_tc2", "wgrad_tc2_kernel"), ("wgrad_tc", "wgrad_tc_kernel"), ("conv3_tc", "conv3_tc_kernel"),
           ("conv_tc", "conv_tc_kernel"), ("conv1x1", "conv1x1_kernel"), ("relu_mask", "relu_mask_kernel"), ("attn_tc", "attn_kernels")]
 
 
