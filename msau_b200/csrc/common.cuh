@@ -123,6 +123,7 @@ struct WgradArgs {
   int b_s2d, cph;
   int b_col0;                                       // b_s2d: first virtual column of this launch's window (cb columns) inside the 4 * cph
   const int* skip_flag;                             // as in ConvArgs
+  int no_tc4;                                       // engine option wgrad_multi_plane = 0: keep this launch off wgrad_tc4 (tests of the other kernels)
 };
 
 int launch_conv(const ConvArgs& a, cudaStream_t st);

@@ -134,6 +134,7 @@ struct EngineOpts {
   int lrn_coop = 1;      // 0 = thread-per-pixel LRN kernels only, 1 = lane-cooperative where it wins, 2 = from 8 channels up
   int c3_tma = 1;        // conv3_tma: conv3_tc's raw halo planes by TMA tensor loads (0 = cp.async ring)
   int pdl = 1;           // pdl: programmatic dependent launch of the hot kernels (prologue overlaps the predecessor's tail)
+  int use_wg4 = 1;       // wgrad_multi_plane: weight gradients of the >= 16-channel layers on wgrad_tc4 (0 = the per-plane kernels)
 };
 }  // namespace msau
 
@@ -378,6 +379,7 @@ static int set_opt(EngineOpts& o, const char* name, int value) {
   if (!strcmp(name, "conv3_max_channels")) { o.c3_max = value; return MSAU_OK; }
   if (!strcmp(name, "pdl")) { o.pdl = value != 0; return MSAU_OK; }
   if (!strcmp(name, "conv3_tma")) { o.c3_tma = value != 0; return MSAU_OK; }
+  if (!strcmp(name, "wgrad_multi_plane")) { o.use_wg4 = value != 0; return MSAU_OK; }
   set_error("set_option: unknown option '%s'", name);
   return MSAU_ERR_ARG;
 }
@@ -484,6 +486,7 @@ static int layer_wgrad(MsauPlan* p, const ConvLayer& L, int which, const float* 
   a.cb_lim = cb_lim < 0 ? L.cout : cb_lim;
   a.dbias = which == 1 ? p->gparams + (b_off_override >= 0 ? b_off_override : L.b_off) : nullptr;
   a.skip_flag = skip_flag;
+  a.no_tc4 = !p->opt.use_wg4;
   if (L.center) {     // only the centre tap (index 4 of the 3x3) sees anything but padding
     a.kh = a.kw = 1; a.dila = 1; a.pada_t = a.pada_l = 0;
     a.dW += 4;
@@ -645,6 +648,7 @@ static int deconv_bwd(MsauPlan* p, const DeconvLayer& L, const Tensor& in, const
     a.B = p->B; a.Hq = in.H; a.Wq = in.W; a.kh = 2; a.kw = 2;
     a.dW = p->gparams + L.w_off; a.s_ca = (long)L.cout * 9; a.s_cb = 9; a.ca_lim = L.cin; a.cb_lim = L.cout;
     a.dbias = p->gparams + L.b_off;
+    a.no_tc4 = !p->opt.use_wg4;
     if (wgrad_tc_supported(a)) {
       count_launch(1);
       MSAU_TRY(wgrad_fork(p));

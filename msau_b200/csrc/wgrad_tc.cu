@@ -1448,7 +1448,7 @@ __global__ void __launch_bounds__(WG4_THREADS, 1) wgrad_tc4_kernel(const WgradAr
 static bool wgrad_tc4_config(const WgradArgs& a, Wg4Tile& t, size_t& smem, int& ctas) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("MSAU_WG4_OFF"); off = e ? atoi(e) : 0; }
-  if (off) return false;
+  if (off || a.no_tc4) return false;
   const bool one = a.kh == 1 && a.kw == 1;
   if (a.a_nchw || a.maskB || a.cb > 128 || (a.cb & 7) || (a.ca & 7)) return false;
   if (one && (a.pada_t != 0 || a.pada_l != 0)) return false;

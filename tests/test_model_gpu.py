@@ -206,12 +206,14 @@ def test_param_grads_and_train_step_match_golden(golden_dir, name, tc):
         assert torch.equal(dict(m2.named_parameters())[k].detach().cpu(), sd[k])
 
 
-@pytest.mark.parametrize("option,value", [("conv3_fold", 0), ("structured_first_layer", 0), ("lrn_coop", 0), ("lrn_coop", 2), ("fuse_relu_mask", 0)])
+@pytest.mark.parametrize("option,value", [("conv3_fold", 0), ("structured_first_layer", 0), ("lrn_coop", 0), ("lrn_coop", 2), ("fuse_relu_mask", 0),
+                                          ("wgrad_multi_plane", 0)])
 def test_alternative_kernel_paths_match_oracle(golden_dir, option, value):
     """The default tensor-core path uses the kx-folded 3x3 kernel (conv3_tc.cu) and, for one-hot inputs, the id-gather first
     layer (first_layer.cu).  With either switched off the generic implicit-GEMM kernels do the same work; with a dense
     (not one-hot) input the structured first layer must step aside on its own (device flag).  LRN: thread-per-pixel kernels
-    only (0) / lane-cooperative kernels at every width (2) instead of the measured per-width choice."""
+    only (0) / lane-cooperative kernels at every width (2) instead of the measured per-width choice.  wgrad_multi_plane = 0: the
+    per-plane weight-gradient kernels (wgrad_tc3 / wgrad_tc) instead of wgrad_tc4 for the >= 16-channel layers."""
     z, meta, cfg = load(golden_dir, "model_s4r2_c96")
     sd = om.init_state_dict(cfg, meta["seed"])
     x, labels = synth_input(cfg.channels, cfg.n_class, meta["B"], meta["H"], meta["W"], meta["seed"] + 1)
