@@ -745,7 +745,8 @@ int launch_conv3_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st, int
 // row n = kx * coutp + co:  images 0..2 = {Whi(ky), Whi(ky)},  image 3 = {Wlo(0), Wlo(1)},  image 4 = {Wlo(2), 0}
 __global__ void __launch_bounds__(256) pack_tc3_kernel(const float* __restrict__ pk, uint16_t* __restrict__ pktc,
                                                         const TcPackDesc* __restrict__ descs, int n_desc) {
-  const long blk = blockIdx.x;
+  // one thread per [8 ch] slot of an image row (16 bytes out; consecutive threads = consecutive output channels: coalesced reads)
+  const int blk = (int)blockIdx.x;
   int lo = 0, hi = n_desc - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -754,15 +755,14 @@ __global__ void __launch_bounds__(256) pack_tc3_kernel(const float* __restrict__
   const TcPackDesc d = descs[lo];
   const int N = d.N;
   const int KS = d.taps == 16 ? 4 : 3, NI = KS + (KS + 1) / 2;
-  const long per_plane = (long)NI * N * 16;
-  const long total = (long)(d.cin / 8) * per_plane;
-  const long e = (blk - d.blk0) * 256 + threadIdx.x;
+  const int per_plane = NI * N * 2;                              // slots per 8-channel plane: images x 2 chunks x N rows
+  const int total = (d.cin / 8) * per_plane;
+  const int e = (blk - (int)d.blk0) * 256 + (int)threadIdx.x;
   if (e >= total) return;
-  const int p = (int)(e / per_plane);
-  long r = e - (long)p * per_plane;
-  const int img = (int)(r / (N * 16)); r -= (long)img * N * 16;
-  const int chunk = (int)(r / (N * 8)); r -= (long)chunk * N * 8;
-  const int n = (int)(r / 8), k = (int)(r - (long)n * 8);
+  const int p = e / per_plane;
+  int r = e - p * per_plane;
+  const int img = r / (2 * N); r -= img * 2 * N;
+  const int chunk = r / N, n = r - chunk * N;
   const int kx = n / d.coutp, co = n - kx * d.coutp;
   int ky = -1;
   bool want_lo = false;
@@ -772,16 +772,25 @@ __global__ void __launch_bounds__(256) pack_tc3_kernel(const float* __restrict__
     ky = 2 * (img - KS) + chunk;
     if (ky >= KS) ky = -1;
   }
-  float w = 0.f;
-  if (ky >= 0 && kx < KS) w = pk[d.src_off + ((long)(ky * KS + kx) * d.cin + 8 * p + k) * d.coutp + co];
-  const __nv_bfloat16 h = __float2bfloat16_rn(w);
-  const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w - __bfloat162float(h)) : h;
-  pktc[d.dst_off + e] = __bfloat16_as_ushort(out);
+  uint32_t h2[4] = {0u, 0u, 0u, 0u};
+  if (ky >= 0 && kx < KS) {
+    const float* src = pk + d.src_off + ((long)(ky * KS + kx) * d.cin + 8 * p) * d.coutp + co;
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(src + (long)k * d.coutp);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(w[k]);
+      const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w[k] - __bfloat162float(h)) : h;
+      h2[k >> 1] |= (uint32_t)__bfloat16_as_ushort(out) << (16 * (k & 1));
+    }
+  }
+  *reinterpret_cast<uint4*>(pktc + d.dst_off + (long)e * 8) = make_uint4(h2[0], h2[1], h2[2], h2[3]);     // (dst_off is a multiple of 128)
 }
 
 int launch_pack_tc3(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st) {
   if (n_desc == 0) return MSAU_OK;
-  ProfScope ps("pack_tc_kernel", 0, (double)total_blocks * 256 * 6.0, st);
+  ProfScope ps("pack_tc_kernel", 0, (double)total_blocks * 256 * 48.0, st);
   pack_tc3_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(pk, pktc, d_descs, n_desc);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;

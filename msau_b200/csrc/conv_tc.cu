@@ -668,7 +668,8 @@ int launch_conv_tc(const ConvArgs& a, const uint16_t* wtc, cudaStream_t st) {
 // one B image = [chunk0: N x 16 B][chunk1: N x 16 B]
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ pk, uint16_t* __restrict__ pktc,
                                                        const TcPackDesc* __restrict__ descs, int n_desc) {
-  const long blk = blockIdx.x;
+  // one thread per [8 ch] slot of an image row (16 bytes out; consecutive threads = consecutive output channels: coalesced reads)
+  const int blk = (int)blockIdx.x;
   int lo = 0, hi = n_desc - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
@@ -676,16 +677,14 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
   }
   const TcPackDesc d = descs[lo];
   const int N = d.N, taps = d.taps, n3 = (taps + 1) / 2;
-  const long per_plane = (long)(taps + n3) * N * 16;             // bf16 elements
-  const long total = (long)(d.cin / 8) * per_plane;
-  const long e = (blk - d.blk0) * 256 + threadIdx.x;
+  const int per_plane = (taps + n3) * N * 2;                     // slots per 8-channel plane: images x 2 chunks x N rows
+  const int total = (d.cin / 8) * per_plane;
+  const int e = (blk - (int)d.blk0) * 256 + (int)threadIdx.x;
   if (e >= total) return;
-  const int p = (int)(e / per_plane);
-  long r = e - (long)p * per_plane;
-  const int img = (int)(r / (N * 16)); r -= (long)img * N * 16;
-  const int chunk = (int)(r / (N * 8)); r -= (long)chunk * N * 8;
-  const int n = (int)(r / 8), k = (int)(r - (long)n * 8);
-  float w = 0.f;
+  const int p = e / per_plane;
+  int r = e - p * per_plane;
+  const int img = r / (2 * N); r -= img * 2 * N;
+  const int chunk = r / N, n = r - chunk * N;
   bool want_lo = false;
   int tap = -1;
   if (img < taps) { tap = img; }
@@ -694,15 +693,25 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
     tap = 2 * (img - taps) + chunk;
     if (tap >= taps) tap = -1;
   }
-  if (tap >= 0 && n < d.coutp) w = pk[d.src_off + ((long)tap * d.cin + 8 * p + k) * d.src_pitch + d.col0 + n];
-  const __nv_bfloat16 h = __float2bfloat16_rn(w);
-  const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w - __bfloat162float(h)) : h;
-  pktc[d.dst_off + e] = __bfloat16_as_ushort(out);
+  uint32_t h2[4] = {0u, 0u, 0u, 0u};
+  if (tap >= 0 && n < d.coutp) {
+    const float* src = pk + d.src_off + ((long)tap * d.cin + 8 * p) * d.src_pitch + d.col0 + n;
+    float w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w[k] = __ldg(src + (long)k * d.src_pitch);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(w[k]);
+      const __nv_bfloat16 out = want_lo ? __float2bfloat16_rn(w[k] - __bfloat162float(h)) : h;
+      h2[k >> 1] |= (uint32_t)__bfloat16_as_ushort(out) << (16 * (k & 1));
+    }
+  }
+  *reinterpret_cast<uint4*>(pktc + d.dst_off + (long)e * 8) = make_uint4(h2[0], h2[1], h2[2], h2[3]);     // (dst_off is a multiple of 128)
 }
 
 int launch_pack_tc(const float* pk, uint16_t* pktc, const TcPackDesc* d_descs, int n_desc, long total_blocks, cudaStream_t st) {
   if (n_desc == 0) return MSAU_OK;
-  ProfScope ps("pack_tc_kernel", 0, (double)total_blocks * 256 * 6.0, st);
+  ProfScope ps("pack_tc_kernel", 0, (double)total_blocks * 256 * 48.0, st);
   pack_tc_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(pk, pktc, d_descs, n_desc);
   MSAU_CUDA_TRY(cudaGetLastError());
   return MSAU_OK;

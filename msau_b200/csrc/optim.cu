@@ -21,14 +21,16 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ par
     if (descs[mid].blk0 <= blk) lo = mid; else hi = mid - 1;
   }
   const PackDesc d = descs[lo];
-  const long e = (blk - d.blk0) * 256 + threadIdx.x;
-  const long total = (long)d.TH * d.TW * d.I_log * d.O_log;
+  // (32-bit index arithmetic: a layer has < 2^31 weights; the 64-bit divisions were most of this kernel's time)
+  const int e = (int)(blk - d.blk0) * 256 + (int)threadIdx.x;
+  const int total = d.TH * d.TW * d.I_log * d.O_log;
   if (e >= total) return;
-  const int o = (int)(e % d.O_log);
-  long r = e / d.O_log;
-  const int i = (int)(r % d.I_log); r /= d.I_log;
-  const int tx = (int)(r % d.TW);
-  const int ty = (int)(r / d.TW);
+  int r = e / d.O_log;
+  const int o = e - r * d.O_log;
+  const int r2 = r / d.I_log;
+  const int i = r - r2 * d.I_log;
+  const int ty = r2 / d.TW;
+  const int tx = r2 - ty * d.TW;
   const int ky = d.ky0 + d.kys * ty, kx = d.kx0 + d.kxs * tx;
   const float v = params[d.src_off + (long)(i + d.i_off) * d.s_i + (long)(o + d.o_off) * d.s_o + ky * d.KW + kx];
   packed[d.dst_off + ((long)((ty + d.ty_d0) * d.TWd + tx + d.tx_d0) * d.I + d.i_dst0 + i) * d.O + d.o_dst0 + o] = v;

@@ -247,7 +247,7 @@ static long add_tc(MsauPlan* p, long src_off, int taps, int cin, int coutp) {
     d.N = cw < 16 ? 16 : round_up(cw, 16);
     const long elems = (long)(cin / 8) * (taps + (taps + 1) / 2) * d.N * 16;
     d.blk0 = p->tc_blocks;
-    p->tc_blocks += cdiv(elems, 256);
+    p->tc_blocks += cdiv(elems / 8, 256);       // one thread per [8 ch] slot (16 bytes)
     p->tc_elems += (elems + 127) / 128 * 128;
     p->tc_descs.push_back(d);
     if (h == 0) first = d.dst_off;
@@ -263,7 +263,7 @@ static long add_tc3(MsauPlan* p, long src_off, int cin, int coutp, int ks = 3) {
   d.N = round_up(ks * coutp, 16);
   const long elems = (long)(cin / 8) * (ks + (ks + 1) / 2) * d.N * 16;
   d.blk0 = p->t3_blocks;
-  p->t3_blocks += cdiv(elems, 256);
+  p->t3_blocks += cdiv(elems / 8, 256);
   p->tc_elems += (elems + 127) / 128 * 128;
   p->t3_descs.push_back(d);
   return d.dst_off;
