@@ -15,6 +15,13 @@
 // (measured relative error of dW ~1e-4, far below the ReLU-mask noise of the data-gradient path); the hi/lo
 // split that the forward convolutions need would triple the operand traffic for nothing here.
 // grid = (pixel-tile ranges, input-channel planes).
+//
+// Four kernels share this contraction; launch_wgrad_tc() picks, in this order:
+//   wgrad_tc4_kernel  >= 16 input channels (and every dilated / > 85-column layer): several X planes per CTA, warp-specialised,
+//                     whole-pixel loads, all taps (or all planes, 1x1) per instruction, vector reductions into dW     [round 2]
+//   wgrad_tc3_kernel  one X plane, <= 16 output channels, NHWC: cp.async raw ring + converter warps (the 512^2 level)
+//   wgrad_tc2_kernel  all taps per instruction with register-staged loads (NCHW first layer, narrow maps)
+//   wgrad_tc_kernel   the round-1 kernel described above (one accumulator per ky, one CTA per plane): masked dY and leftovers
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
